@@ -1,0 +1,1287 @@
+// dcdf_oracle.hpp -- CPU restatement of the dcdf Heuristic T-k^2-raster hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  This file is the parity oracle and the "port"
+// CPU baseline.  Nothing under dcdf_b200/ (the product) may include, link or
+// call it; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs do.
+//
+// Parity status: PINNED by the reference's own known-answer tests
+// (fixed.rs:209-401, bitmap.rs:262-284, dac.rs:164-171, snapshot.rs:539-572,
+// log.rs:902-955 ...) which tests/test_oracle_golden.py replays.  The
+// reference itself (Rust) cannot be compiled in this image (no cargo/rustc),
+// so serialized byte strings and heuristic block boundaries are anchored on
+// this restatement alone (the reference's tests do not pin them either).
+//
+// Every function cites the reference file:line it follows (paths relative to
+// /root/reference/dcdf/src).  The recursion/BFS/byte-at-a-time structure of
+// the reference is kept on purpose so that timing this code is an honest
+// stand-in for the reference's CPU path.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <limits>
+#include <memory>
+#include <optional>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace orc {
+
+// ---------------------------------------------------------------- errors
+// Data errors are panics in the reference (fixed.rs:40,51,66; block.rs:27-32;
+// mmbuffer.rs:606; superchunk.rs:105-110; mmarray.rs:218-229).  Here they are
+// exceptions carrying the C-ABI status code.
+enum Status : int32_t {
+  OK = 0,
+  NONFINITE = 1,
+  PRECISION_LOSS = 2,
+  OVERFLOW_ = 3,
+  BAD_LEVELS = 4,
+  OUT_OF_BOUNDS = 5,
+  BAD_FORMAT = 6,
+  CUDA = 7,
+  BAD_ARG = 8,
+};
+struct Error {
+  int32_t code;
+  std::string msg;
+};
+[[noreturn]] inline void fail(int32_t code, const std::string& msg) { throw Error{code, msg}; }
+
+using i64 = int64_t;
+using u64 = uint64_t;
+using u32 = uint32_t;
+using u8 = uint8_t;
+using usize = size_t;
+using OptI = std::optional<i64>;
+
+// ---------------------------------------------------------------- fixed.rs
+// to_fixed  fixed.rs:31-71.  Arithmetic is done in the input float type F.
+template <class F>
+inline i64 to_fixed(F n, usize fractional_bits, bool round) {
+  if (std::isnan(n)) return 0;                                  // :35-37
+  if (!std::isfinite(n)) fail(NONFINITE, "cannot convert non-finite to fixed point");  // :39-41
+  F shifted = n * static_cast<F>(i64(1) << fractional_bits);   // :44
+  F fract = shifted - std::trunc(shifted);                      // Rust fract(): keeps sign
+  if (fract > F(0)) {                                           // :47 (positive only)
+    if (round) {
+      shifted = std::round(shifted);                            // :49 half away from zero
+    } else {
+      fail(PRECISION_LOSS, "loss of precision converting to fixed point");  // :51-57
+    }
+  }
+  shifted = shifted * F(2);                                     // :61
+  // num-traits ToPrimitive::to_i64 for floats: Some iff -2^63 <= x < 2^63, truncating.
+  const F lim = static_cast<F>(9223372036854775808.0);
+  if (!(shifted >= -lim && shifted < lim)) fail(OVERFLOW_, "overflow converting to fixed point");  // :66-69
+  return static_cast<i64>(shifted) + 1;                         // :64
+}
+
+// from_fixed  fixed.rs:81-86
+template <class F>
+inline F from_fixed(i64 n, usize fractional_bits) {
+  if (n == 0) return std::numeric_limits<F>::quiet_NaN();
+  return static_cast<F>(n - 1) / static_cast<F>(i64(1) << (fractional_bits + 1));
+}
+
+struct Fraction {
+  bool round;  // false = Precise(bits), true = Round(bits)   fixed.rs:88-92
+  usize bits;
+};
+
+// Rust `f as usize` / `f as i64` saturating casts.
+inline usize sat_usize(double v) {
+  if (std::isnan(v) || v <= 0.0) return 0;
+  if (v >= 18446744073709551616.0) return std::numeric_limits<usize>::max();
+  return static_cast<usize>(v);
+}
+inline i64 sat_i64(double v) {
+  if (std::isnan(v)) return 0;
+  if (v >= 9223372036854775808.0) return std::numeric_limits<i64>::max();
+  if (v <= -9223372036854775808.0) return std::numeric_limits<i64>::min();
+  return static_cast<i64>(v);
+}
+inline unsigned trailing_zeros64(i64 v) { return v == 0 ? 64u : (unsigned)__builtin_ctzll((u64)v); }
+
+// A strided read-only [instants, rows, cols] view (ndarray ArrayView3 stand-in).
+template <class T>
+struct View3 {
+  const T* base;
+  i64 shape[3];
+  i64 strides[3];  // in elements
+  const T& at(usize i, usize r, usize c) const {
+    return base[(i64)i * strides[0] + (i64)r * strides[1] + (i64)c * strides[2]];
+  }
+  View3 slice(usize start, usize end, usize top, usize bottom, usize left, usize right) const {
+    View3 v = *this;
+    v.base = &at(start, top, left);
+    v.shape[0] = end - start;
+    v.shape[1] = bottom - top;
+    v.shape[2] = right - left;
+    return v;
+  }
+  usize len() const { return (usize)(shape[0] * shape[1] * shape[2]); }
+};
+
+// suggest_fraction  fixed.rs:96-159
+template <class F>
+inline Fraction suggest_fraction(const View3<F>& data) {
+  const usize TOTAL_BITS = 62;                                  // :102
+  if (data.len() == 0) fail(BAD_ARG, "empty array");            // values.next().unwrap() would panic
+  bool have = false;
+  F max_value = std::numeric_limits<F>::quiet_NaN();
+  for (i64 i = 0; i < data.shape[0]; i++)                       // :106-120, NaN skipped
+    for (i64 r = 0; r < data.shape[1]; r++)
+      for (i64 c = 0; c < data.shape[2]; c++) {
+        F n = data.at(i, r, c);
+        if (std::isnan(n)) continue;
+        if (!have || n > max_value) { max_value = n; have = true; }
+      }
+  if (!have) return Fraction{false, 0};                         // :121-124 all NaN
+  usize whole_bits = 1 + sat_usize(std::floor(std::log2((double)max_value)));  // :126
+  if (whole_bits > TOTAL_BITS) fail(OVERFLOW_, "value too large for fixed point");  // :130 underflow panic
+  usize max_fraction_bits = TOTAL_BITS - whole_bits;
+  usize fraction_bits = 0;
+  const double scale = (double)(i64(1) << max_fraction_bits);
+  for (i64 i = 0; i < data.shape[0]; i++)                       // :136-156
+    for (i64 r = 0; r < data.shape[1]; r++)
+      for (i64 c = 0; c < data.shape[2]; c++) {
+        double n = (double)data.at(i, r, c);
+        if (std::isnan(n)) continue;
+        double shifted = n * scale;
+        if (shifted - std::trunc(shifted) != 0.0) return Fraction{true, max_fraction_bits};  // :146-148
+        i64 s = sat_i64(shifted);                               // :150
+        usize tz = trailing_zeros64(s);
+        usize these = max_fraction_bits > tz ? max_fraction_bits - tz : 0;  // saturating_sub :152
+        if (these > fraction_bits) fraction_bits = these;
+      }
+  return Fraction{false, fraction_bits};
+}
+
+// MMBuffer3F32::compute_fractional_bits  mmbuffer.rs:596-613 (f64 twin :654-671)
+template <class F>
+inline usize compute_fractional_bits(const View3<F>& data, usize fractional_bits, bool round) {
+  Fraction s = suggest_fraction(data);
+  if (round) return std::min(s.bits, fractional_bits);
+  if (s.round) fail(PRECISION_LOSS, "loss of precision");
+  return s.bits;
+}
+
+// min_max_float  mmbuffer.rs:465-499 (note the NaN quirk at :485-487)
+template <class F>
+inline std::vector<std::pair<F, F>> min_max_float(const View3<F>& a) {
+  std::vector<std::pair<F, F>> out;
+  for (i64 i = 0; i < a.shape[0]; i++) {
+    usize n_cells = (usize)(a.shape[1] * a.shape[2]);
+    if (n_cells == 0) fail(BAD_ARG, "empty instant");
+    usize pos = 0;
+    auto next = [&](F& v) -> bool {
+      if (pos >= n_cells) return false;
+      v = a.at(i, pos / a.shape[2], pos % a.shape[2]);
+      pos++;
+      return true;
+    };
+    F mn, mx, v;
+    next(v);
+    mn = mx = v;
+    while (std::isnan(mn)) {
+      if (next(v)) { mn = v; mx = v; } else break;
+    }
+    while (next(v)) {
+      if (std::isnan(v)) {
+        mn = v;
+      } else {
+        if (v < mn) mn = v;
+        else if (v > mx) mx = v;
+      }
+    }
+    out.emplace_back(mn, mx);
+  }
+  return out;
+}
+// min_max (integers)  mmbuffer.rs:434-463
+template <class N>
+inline std::vector<std::pair<N, N>> min_max_int(const View3<N>& a) {
+  std::vector<std::pair<N, N>> out;
+  for (i64 i = 0; i < a.shape[0]; i++) {
+    N mn = a.at(i, 0, 0), mx = mn;
+    for (i64 r = 0; r < a.shape[1]; r++)
+      for (i64 c = 0; c < a.shape[2]; c++) {
+        N v = a.at(i, r, c);
+        if (v < mn) mn = v;
+        if (v > mx) mx = v;
+      }
+    out.emplace_back(mn, mx);
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------- MMBuffer3 (typed adaptor)
+// mmbuffer.rs:255-432: `get` converts a cell to i64 on every access, `set` converts back.
+enum Encoding : u8 { ENC_I32 = 4, ENC_I64 = 8, ENC_F32 = 32, ENC_F64 = 64 };  // mmstruct.rs:36-43
+
+struct Buffer3 {
+  Encoding enc;
+  const void* base;
+  i64 shape[3];
+  i64 strides[3];
+  usize fractional_bits = 0;
+  bool round = false;
+
+  template <class T>
+  View3<T> view() const {
+    View3<T> v;
+    v.base = static_cast<const T*>(base);
+    for (int i = 0; i < 3; i++) { v.shape[i] = shape[i]; v.strides[i] = strides[i]; }
+    return v;
+  }
+  i64 get(usize i, usize r, usize c) const {                    // mmbuffer.rs:303-310
+    switch (enc) {
+      case ENC_I32: return (i64)view<int32_t>().at(i, r, c);
+      case ENC_I64: return view<i64>().at(i, r, c);
+      case ENC_F32: return to_fixed<float>(view<float>().at(i, r, c), fractional_bits, round);   // :565-571
+      default: return to_fixed<double>(view<double>().at(i, r, c), fractional_bits, round);      // :623-629
+    }
+  }
+  Buffer3 slice(usize s, usize e, usize t, usize b, usize l, usize r) const {  // :263-278
+    Buffer3 o = *this;
+    i64 off = (i64)s * strides[0] + (i64)t * strides[1] + (i64)l * strides[2];
+    usize esz = enc == ENC_I32 || enc == ENC_F32 ? 4 : 8;
+    o.base = static_cast<const char*>(base) + off * (i64)esz;
+    o.shape[0] = e - s; o.shape[1] = b - t; o.shape[2] = r - l;
+    return o;
+  }
+  void compute_fractional_bits() {                              // :424-431
+    if (enc == ENC_F32) fractional_bits = orc::compute_fractional_bits(view<float>(), fractional_bits, round);
+    else if (enc == ENC_F64) fractional_bits = orc::compute_fractional_bits(view<double>(), fractional_bits, round);
+  }
+  std::vector<std::pair<i64, i64>> min_max() const {            // :366-395
+    std::vector<std::pair<i64, i64>> out;
+    switch (enc) {
+      case ENC_I32: for (auto& p : min_max_int(view<int32_t>())) out.emplace_back(p.first, p.second); break;
+      case ENC_I64: for (auto& p : min_max_int(view<i64>())) out.emplace_back(p.first, p.second); break;
+      case ENC_F32:
+        for (auto& p : min_max_float(view<float>()))
+          out.emplace_back(to_fixed<float>(p.first, fractional_bits, round), to_fixed<float>(p.second, fractional_bits, round));
+        break;
+      default:
+        for (auto& p : min_max_float(view<double>()))
+          out.emplace_back(to_fixed<double>(p.first, fractional_bits, round), to_fixed<double>(p.second, fractional_bits, round));
+    }
+    return out;
+  }
+  usize frac_bits_reported() const { return (enc == ENC_F32 || enc == ENC_F64) ? fractional_bits : 0; }  // :397-403
+};
+
+// ---------------------------------------------------------------- extio.rs (big-endian)
+struct Writer {
+  std::vector<u8> buf;
+  void byte(u8 b) { buf.push_back(b); }                         // extio.rs:196-201
+  void u32be(u32 w) {                                           // extio.rs:228-233
+    buf.push_back(u8(w >> 24)); buf.push_back(u8(w >> 16)); buf.push_back(u8(w >> 8)); buf.push_back(u8(w));
+  }
+  void bytes(const std::vector<u8>& b) { buf.insert(buf.end(), b.begin(), b.end()); }
+};
+struct Reader {
+  const u8* p;
+  usize n;
+  usize pos = 0;
+  u8 byte() {
+    if (pos + 1 > n) fail(BAD_FORMAT, "unexpected end of stream");
+    return p[pos++];
+  }
+  u32 u32be() {
+    if (pos + 4 > n) fail(BAD_FORMAT, "unexpected end of stream");
+    u32 w = (u32(p[pos]) << 24) | (u32(p[pos + 1]) << 16) | (u32(p[pos + 2]) << 8) | u32(p[pos + 3]);
+    pos += 4;
+    return w;
+  }
+  std::vector<u8> take(usize k) {
+    if (pos + k > n) fail(BAD_FORMAT, "unexpected end of stream");
+    std::vector<u8> v(p + pos, p + pos + k);
+    pos += k;
+    return v;
+  }
+};
+
+// ---------------------------------------------------------------- bitmap.rs
+struct BitMap {
+  usize length = 0;
+  usize k = 4;
+  std::vector<u32> index;
+  std::vector<u32> bitmap;
+  mutable std::vector<usize>* touched = nullptr;  // instrumentation hook (unused by default)
+
+  bool get(usize i) const {                                     // bitmap.rs:176-183
+    usize word_index = i / 32;
+    if (word_index >= bitmap.size()) fail(OUT_OF_BOUNDS, "bitmap index out of bounds");
+    return ((bitmap[word_index] >> (31 - i % 32)) & 1u) != 0;
+  }
+  usize rank(usize i) const {                                   // bitmap.rs:186-212
+    if (i > length) fail(OUT_OF_BOUNDS, "rank index out of bounds");
+    usize block = i / 32 / k;
+    u32 count = block > 0 ? index[block - 1] : 0;
+    usize start = block * k, end = i / 32;
+    for (usize w = start; w < end; w++) count += (u32)__builtin_popcount(bitmap[w]);
+    usize leftover = i - end * 32;
+    if (leftover > 0) count += (u32)__builtin_popcount(bitmap[end] >> (32 - leftover));
+    return count;
+  }
+  usize rank0(usize i) const { return i - rank(i); }            // bitmap.rs:215-217
+  u64 size() const { return 4 + 4 + index.size() * 4 + bitmap.size() * 4; }  // :166-172
+  void write_to(Writer& w) const {                              // :128-138
+    w.u32be((u32)length);
+    w.u32be((u32)k);
+    for (u32 v : index) w.u32be(v);
+    for (u32 v : bitmap) w.u32be(v);
+  }
+  static BitMap read_from(Reader& r) {                          // :142-164
+    BitMap b;
+    b.length = r.u32be();
+    b.k = r.u32be();
+    if (b.k == 0) fail(BAD_FORMAT, "bitmap k == 0");
+    usize blocks = b.length / 32 / b.k;
+    for (usize i = 0; i < blocks; i++) b.index.push_back(r.u32be());
+    usize words = (b.length + 31) / 32;
+    for (usize i = 0; i < words; i++) b.bitmap.push_back(r.u32be());
+    return b;
+  }
+};
+
+struct BitMapBuilder {
+  usize length = 0;
+  std::vector<u8> bytes;
+  void push(bool bit) {                                         // bitmap.rs:44-62 (bit at a time)
+    usize position = length % 8;
+    unsigned shift = 7 - position;
+    if (position == 0) bytes.push_back(bit ? u8(1u << shift) : u8(0));
+    else if (bit) bytes.back() = u8(bytes.back() + (1u << shift));
+    length++;
+  }
+  BitMap finish() const {                                       // bitmap.rs:66-113
+    BitMap b;
+    b.length = length;
+    b.k = 4;                                                    // :69
+    usize blocks = length / 32 / b.k;
+    usize words = (length + 31) / 32;
+    b.bitmap.assign(words, 0);
+    if (words > 0) {
+      unsigned shift = 24;
+      usize wi = 0;
+      for (u8 byte : bytes) {
+        b.bitmap[wi] |= u32(byte) << shift;
+        if (shift == 0) { wi++; shift = 24; } else shift -= 8;
+      }
+    }
+    u32 count = 0;
+    for (usize i = 0; i < blocks; i++) {                        // :97-104
+      for (usize j = 0; j < b.k; j++) count += (u32)__builtin_popcount(b.bitmap[i * b.k + j]);
+      b.index.push_back(count);
+    }
+    return b;
+  }
+};
+
+// ---------------------------------------------------------------- dac.rs
+inline u64 zigzag_encode(i64 n) { return (u64)((n >> 63) ^ (i64)((u64)n << 1)); }  // dac.rs:134-137
+inline i64 zigzag_decode(u64 zz) { return (i64)((zz >> 1) ^ ((zz & 1) ? ~u64(0) : u64(0))); }  // :139-142
+
+struct Dac {
+  std::vector<std::pair<BitMap, std::vector<u8>>> levels;
+
+  i64 get(usize index) const {                                  // dac.rs:80-93
+    u64 n = 0;
+    usize i = 0;
+    for (auto& lv : levels) {
+      if (index >= lv.second.size()) fail(OUT_OF_BOUNDS, "dac index out of bounds");
+      n |= u64(lv.second[index]) << (i * 8);
+      if (lv.first.get(index)) index = lv.first.rank(index);
+      else break;
+      i++;
+    }
+    return zigzag_decode(n);
+  }
+  static Dac from(const std::vector<i64>& data) {               // dac.rs:96-132 (byte at a time)
+    std::vector<std::pair<BitMapBuilder, std::vector<u8>>> lv(8);
+    for (i64 datum_ : data) {
+      u64 datum = zigzag_encode(datum_);
+      for (auto& l : lv) {
+        l.second.push_back(u8(datum & 0xff));
+        datum >>= 8;
+        if (datum == 0) { l.first.push(false); break; }
+        l.first.push(true);
+      }
+    }
+    Dac d;
+    for (auto& l : lv) {                                        // take_while non-empty :124-128
+      if (l.first.length == 0) break;
+      d.levels.emplace_back(l.first.finish(), std::move(l.second));
+    }
+    return d;
+  }
+  usize len() const { return levels.empty() ? 0 : levels[0].first.length; }  // dac.rs:152-154 (test helper)
+  std::vector<i64> collect() const {                            // dac.rs:157-159 (test helper)
+    std::vector<i64> v;
+    for (usize i = 0; i < len(); i++) v.push_back(get(i));
+    return v;
+  }
+  u64 size() const {                                            // dac.rs:66-75
+    u64 s = 1;
+    for (auto& l : levels) s += l.first.size() + l.second.size();
+    return s;
+  }
+  void write_to(Writer& w) const {                              // dac.rs:37-44
+    w.byte((u8)levels.size());
+    for (auto& l : levels) { l.first.write_to(w); w.bytes(l.second); }
+  }
+  static Dac read_from(Reader& r) {                             // dac.rs:48-63
+    Dac d;
+    usize n = r.byte();
+    for (usize i = 0; i < n; i++) {
+      BitMap b = BitMap::read_from(r);
+      std::vector<u8> bytes = r.take(b.length);
+      d.levels.emplace_back(std::move(b), std::move(bytes));
+    }
+    return d;
+  }
+};
+
+// ---------------------------------------------------------------- geom.rs / helpers.rs
+template <class N>
+inline void rearrange(N& lower, N& upper) { if (lower > upper) std::swap(lower, upper); }  // helpers.rs:7-16
+struct Rect {                                                   // geom.rs:4-42
+  usize top, bottom, left, right;
+  Rect(usize t, usize b, usize l, usize r) : top(t), bottom(b), left(l), right(r) {
+    rearrange(top, bottom);
+    rearrange(left, right);
+  }
+  usize rows() const { return bottom - top; }
+  usize cols() const { return right - left; }
+};
+struct Cube {                                                   // geom.rs:72-120
+  usize start, end, top, bottom, left, right;
+  Cube(usize s, usize e, usize t, usize b, usize l, usize r) : start(s), end(e), top(t), bottom(b), left(l), right(r) {
+    rearrange(start, end);
+    rearrange(top, bottom);
+    rearrange(left, right);
+  }
+  usize instants() const { return end - start; }
+  usize rows() const { return bottom - top; }
+  usize cols() const { return right - left; }
+  Rect rect() const { return Rect(top, bottom, left, right); }
+};
+
+// sidelen = k^ceil(log_k(max(rows, cols)))  snapshot.rs:118-119, log.rs:124-125
+inline u32 levels_for(usize longest, int k) {
+  double s = (double)longest;
+  double l = std::ceil(std::log(s) / std::log((double)k));     // f64::log(self, base)
+  if (!(l >= 0)) l = 0;                                         // `as u32` saturates
+  return (u32)l;
+}
+inline usize ipow(int k, u32 e) {
+  usize r = 1;
+  for (u32 i = 0; i < e; i++) r *= (usize)k;
+  return r;
+}
+
+// ---------------------------------------------------------------- snapshot.rs
+struct K2TreeNode {                                             // snapshot.rs:425-429
+  OptI max, min;
+  std::vector<K2TreeNode> children;
+};
+
+template <class G>
+K2TreeNode k2_build(const G& get, usize rows, usize cols, usize k, usize sidelen, usize row, usize col) {  // :439-500
+  if (sidelen == 1) {
+    OptI v;
+    if (row < rows && col < cols) v = get(row, col);
+    return K2TreeNode{v, v, {}};
+  }
+  K2TreeNode node;
+  node.children.reserve(k * k);
+  sidelen /= k;
+  for (usize i = 0; i < k; i++)
+    for (usize j = 0; j < k; j++)
+      node.children.push_back(k2_build(get, rows, cols, k, sidelen, row + i * sidelen, col + j * sidelen));
+  OptI mx = node.children[0].max, mn = node.children[0].min;
+  for (usize c = 1; c < node.children.size(); c++) {
+    const K2TreeNode& ch = node.children[c];
+    if (ch.max) { if (mx) { if (*ch.max > *mx) mx = ch.max; } else mx = ch.max; }
+    if (ch.min) { if (mn) { if (*ch.min < *mn) mn = ch.min; } else mn = ch.min; }
+  }
+  node.max = mx;
+  node.min = mn;
+  return node;
+}
+
+struct Snapshot {
+  BitMap nodemap;
+  Dac max, min;
+  int k = 2;
+  usize shape[2] = {0, 0};
+  usize sidelen = 0;
+
+  template <class G>
+  static Snapshot build(const G& get, usize rows, usize cols, int k) {  // snapshot.rs:108-156
+    BitMapBuilder nodemap;
+    std::vector<i64> max, min;
+    usize sidelen = ipow(k, levels_for(std::max(rows, cols), k));
+    K2TreeNode root = k2_build(get, rows, cols, (usize)k, sidelen, 0, 0);
+    struct Item { i64 diff_max, diff_min; const K2TreeNode* node; };
+    std::deque<Item> q;
+    q.push_back({root.max.value_or(0), root.min.value_or(0), &root});
+    while (!q.empty()) {
+      Item it = q.front();
+      q.pop_front();
+      i64 child_max = it.node->max.value_or(0), child_min = it.node->min.value_or(0);
+      max.push_back(it.diff_max);
+      if (!it.node->children.empty()) {
+        bool elide = child_min == child_max;
+        nodemap.push(!elide);
+        if (!elide) {
+          min.push_back(it.diff_min);
+          for (auto& d : it.node->children)
+            q.push_back({child_max - d.max.value_or(0), d.min.value_or(0) - child_min, &d});
+        }
+      }
+    }
+    Snapshot s;
+    s.nodemap = nodemap.finish();
+    s.max = Dac::from(max);
+    s.min = Dac::from(min);
+    s.k = k;
+    s.shape[0] = rows; s.shape[1] = cols;
+    s.sidelen = sidelen;
+    return s;
+  }
+
+  i64 get(usize row, usize col) const {                         // snapshot.rs:165-172
+    if (!nodemap.get(0)) return max.get(0);
+    return _get(sidelen, row, col, 0, max.get(0));
+  }
+  i64 _get(usize sl, usize row, usize col, usize index, i64 max_value) const {  // :174-188
+    usize kk = (usize)k;
+    sl /= kk;
+    index = 1 + nodemap.rank(index) * kk * kk;
+    index += row / sl * kk + col / sl;
+    max_value -= max.get(index);
+    if (index >= nodemap.length || !nodemap.get(index)) return max_value;
+    return _get(sl, row % sl, col % sl, index, max_value);
+  }
+
+  template <class S>
+  void fill_window(S&& set, const Rect& b) const {              // snapshot.rs:204-236
+    if (!nodemap.get(0)) {
+      i64 v = max.get(0);
+      for (usize r = 0; r < b.rows(); r++)
+        for (usize c = 0; c < b.cols(); c++) set(r, c, v);
+    } else {
+      _fill_window(set, sidelen, b.top, b.bottom - 1, b.left, b.right - 1, 0, max.get(0), b.top, b.left, 0, 0);
+    }
+  }
+  template <class S>
+  void _fill_window(S& set, usize sl, usize top, usize bottom, usize left, usize right, usize index, i64 max_value,
+                    usize window_top, usize window_left, usize top_offset, usize left_offset) const {  // :238-301
+    usize kk = (usize)k;
+    sl /= kk;
+    index = 1 + nodemap.rank(index) * kk * kk;
+    for (usize i = top / sl; i <= bottom / sl; i++) {
+      usize top_ = top > i * sl ? top - i * sl : 0;
+      usize bottom_ = std::min(sl - 1, bottom - i * sl);
+      usize top_offset_ = top_offset + i * sl;
+      for (usize j = left / sl; j <= right / sl; j++) {
+        usize left_ = left > j * sl ? left - j * sl : 0;
+        usize right_ = std::min(sl - 1, right - j * sl);
+        usize left_offset_ = left_offset + j * sl;
+        usize index_ = index + i * kk + j;
+        i64 max_value_ = max_value - max.get(index_);
+        if (index_ >= nodemap.length || !nodemap.get(index_)) {
+          for (usize r = top_; r <= bottom_; r++)
+            for (usize c = left_; c <= right_; c++) set(top_offset_ + r - window_top, left_offset_ + c - window_left, max_value_);
+        } else {
+          _fill_window(set, sl, top_, bottom_, left_, right_, index_, max_value_, window_top, window_left, top_offset_, left_offset_);
+        }
+      }
+    }
+  }
+
+  std::vector<std::pair<usize, usize>> search_window(const Rect& b, i64 lower, i64 upper) const {  // :310-346
+    std::vector<std::pair<usize, usize>> cells;
+    if (!nodemap.get(0)) {
+      i64 v = max.get(0);
+      if (lower <= v && v <= upper)
+        for (usize r = b.top; r < b.bottom; r++)
+          for (usize c = b.left; c < b.right; c++) cells.emplace_back(r, c);
+    } else {
+      _search_window(sidelen, b.top, b.bottom - 1, b.left, b.right - 1, lower, upper, 0, min.get(0), max.get(0), cells, 0, 0);
+    }
+    return cells;
+  }
+  void _search_window(usize sl, usize top, usize bottom, usize left, usize right, i64 lower, i64 upper, usize index,
+                      i64 min_value, i64 max_value, std::vector<std::pair<usize, usize>>& cells, usize top_offset,
+                      usize left_offset) const {                // :348-421
+    usize kk = (usize)k;
+    sl /= kk;
+    index = 1 + nodemap.rank(index) * kk * kk;
+    for (usize i = top / sl; i <= bottom / sl; i++) {
+      usize top_ = top > i * sl ? top - i * sl : 0;
+      usize bottom_ = std::min(sl - 1, bottom - i * sl);
+      usize top_offset_ = top_offset + i * sl;
+      for (usize j = left / sl; j <= right / sl; j++) {
+        usize left_ = left > j * sl ? left - j * sl : 0;
+        usize right_ = std::min(sl - 1, right - j * sl);
+        usize left_offset_ = left_offset + j * sl;
+        usize index_ = index + i * kk + j;
+        i64 max_value_ = max_value - max.get(index_);
+        if (index_ >= nodemap.length || !nodemap.get(index_)) {
+          if (lower <= max_value_ && max_value_ <= upper)
+            for (usize r = top_; r <= bottom_; r++)
+              for (usize c = left_; c <= right_; c++) cells.emplace_back(top_offset_ + r, left_offset_ + c);
+        } else {
+          i64 min_value_ = min_value + min.get(nodemap.rank(index_));
+          if (lower <= min_value && max_value_ <= upper) {      // :392 uses the *parent* min (sic)
+            for (usize r = top_; r <= bottom_; r++)
+              for (usize c = left_; c <= right_; c++) cells.emplace_back(top_offset_ + r, left_offset_ + c);
+          } else if (upper >= min_value_ && lower <= max_value_) {
+            _search_window(sl, top_, bottom_, left_, right_, lower, upper, index_, min_value_, max_value_, cells, top_offset_, left_offset_);
+          }
+        }
+      }
+    }
+  }
+
+  u64 size() const { return 1 + 4 + 4 + 4 + nodemap.size() + max.size() + min.size(); }  // :84-93
+  void write_to(Writer& w) const {                              // :48-58
+    w.byte((u8)k);
+    w.u32be((u32)shape[0]);
+    w.u32be((u32)shape[1]);
+    w.u32be((u32)sidelen);
+    nodemap.write_to(w);
+    max.write_to(w);
+    min.write_to(w);
+  }
+  static Snapshot read_from(Reader& r) {                        // :62-81
+    Snapshot s;
+    s.k = r.byte();
+    s.shape[0] = r.u32be();
+    s.shape[1] = r.u32be();
+    s.sidelen = r.u32be();
+    s.nodemap = BitMap::read_from(r);
+    s.max = Dac::read_from(r);
+    s.min = Dac::read_from(r);
+    return s;
+  }
+};
+
+// ---------------------------------------------------------------- log.rs
+struct K2PTreeNode {                                            // log.rs:705-713
+  OptI max_t, min_t, max_s, min_s;
+  i64 diff = 0;
+  bool equal = true;
+  std::vector<K2PTreeNode> children;
+};
+inline bool opt_lt(const OptI& l, const OptI& r) { return l && r && *l < *r; }  // log.rs:782-789
+
+template <class GS, class GT>
+K2PTreeNode k2p_build(const GS& get_s, const GT& get_t, usize rows, usize cols, usize k, usize sidelen, usize row, usize col) {  // :725-817
+  if (sidelen == 1) {
+    OptI vs, vt;
+    if (row < rows && col < cols) vs = get_s(row, col);
+    if (row < rows && col < cols) vt = get_t(row, col);
+    K2PTreeNode n;
+    n.max_t = n.min_t = vt;
+    n.max_s = n.min_s = vs;
+    n.diff = vt.value_or(0) - vs.value_or(0);
+    n.equal = true;
+    return n;
+  }
+  K2PTreeNode node;
+  node.children.reserve(k * k);
+  sidelen /= k;
+  for (usize i = 0; i < k; i++)
+    for (usize j = 0; j < k; j++)
+      node.children.push_back(k2p_build(get_s, get_t, rows, cols, k, sidelen, row + i * sidelen, col + j * sidelen));
+  node.max_t = node.children[0].max_t;
+  node.min_t = node.children[0].min_t;
+  node.max_s = node.children[0].max_s;
+  node.min_s = node.children[0].min_s;
+  bool equal = true;
+  for (auto& c : node.children) equal = equal && c.equal;
+  node.diff = node.children[0].diff;
+  for (usize c = 1; c < node.children.size(); c++) {
+    const K2PTreeNode& ch = node.children[c];
+    if (opt_lt(node.max_t, ch.max_t)) node.max_t = ch.max_t;
+    if (opt_lt(ch.min_t, node.min_t)) node.min_t = ch.min_t;
+    if (opt_lt(node.max_s, ch.max_s)) node.max_s = ch.max_s;
+    if (opt_lt(ch.min_s, node.min_s)) node.min_s = ch.min_s;
+    equal = equal && ch.diff == node.diff;
+  }
+  node.equal = equal;
+  return node;
+}
+
+struct Log {
+  BitMap nodemap, equal;
+  Dac max, min;
+  int k = 2;
+  usize shape[2] = {0, 0};
+  usize sidelen = 0;
+
+  template <class GS, class GT>
+  static Log build(const GS& get_s, const GT& get_t, usize rows, usize cols, int k) {  // log.rs:112-165
+    BitMapBuilder nodemap, equal;
+    std::vector<i64> max, min;
+    usize sidelen = ipow(k, levels_for(std::max(rows, cols), k));
+    K2PTreeNode root = k2p_build(get_s, get_t, rows, cols, (usize)k, sidelen, 0, 0);
+    std::deque<const K2PTreeNode*> q;
+    q.push_back(&root);
+    while (!q.empty()) {
+      const K2PTreeNode* node = q.front();
+      q.pop_front();
+      max.push_back(node->max_t.value_or(0) - node->max_s.value_or(0));
+      if (!node->children.empty()) {
+        if (node->min_t == node->max_t) {                       // Option equality :137
+          nodemap.push(false);
+          equal.push(false);
+        } else if (node->equal) {
+          nodemap.push(false);
+          equal.push(true);
+        } else {
+          nodemap.push(true);
+          min.push_back(*node->min_t - *node->min_s);
+          for (auto& c : node->children) q.push_back(&c);
+        }
+      }
+    }
+    Log l;
+    l.nodemap = nodemap.finish();
+    l.equal = equal.finish();
+    l.max = Dac::from(max);
+    l.min = Dac::from(min);
+    l.k = k;
+    l.shape[0] = rows; l.shape[1] = cols;
+    l.sidelen = sidelen;
+    return l;
+  }
+
+  // NOTE log.rs:240,245 test `index > length`; for k=2 length = 1 (mod 4) so the padding bit that
+  // is read when index == length is always an in-range zero.  `>=` is the bounds-safe equivalent.
+  bool leaf_t_(usize index) const { return index >= nodemap.length || !nodemap.get(index); }
+
+  i64 get(const Snapshot& s, usize row, usize col) const {      // log.rs:176-205
+    i64 max_t = max.get(0), max_s = s.max.get(0);
+    bool single_t = !nodemap.get(0), single_s = !s.nodemap.get(0);
+    if (single_t && single_s) return max_t + max_s;
+    if (single_t && !equal.get(0)) return max_t + max_s;
+    return _get(s, sidelen, row, col, single_t ? std::optional<usize>() : std::optional<usize>(0),
+                single_s ? std::optional<usize>() : std::optional<usize>(0), max_t, max_s);
+  }
+  i64 _get(const Snapshot& s, usize sl, usize row, usize col, std::optional<usize> index_t, std::optional<usize> index_s,
+           i64 max_t, i64 max_s) const {                        // log.rs:207-293
+    usize kk = (usize)k;
+    sl /= kk;
+    if (index_s) {
+      usize idx = 1 + s.nodemap.rank(*index_s) * kk * kk + row / sl * kk + col / sl;
+      max_s -= s.max.get(idx);
+      index_s = idx;
+    }
+    if (index_t) {
+      usize idx = 1 + nodemap.rank(*index_t) * kk * kk + row / sl * kk + col / sl;
+      max_t = max.get(idx);
+      index_t = idx;
+    }
+    bool leaf_t = index_t ? leaf_t_(*index_t) : true;
+    bool leaf_s = index_s ? (*index_s >= s.nodemap.length || !s.nodemap.get(*index_s)) : true;
+    if (leaf_t && leaf_s) return max_t + max_s;
+    if (leaf_s) return _get(s, sl, row % sl, col % sl, index_t, std::nullopt, max_t, max_s);
+    if (leaf_t) {
+      if (index_t && *index_t < nodemap.length) {
+        bool eq = equal.get(nodemap.rank0(*index_t + 1) - 1);
+        if (!eq) return max_t + max_s;
+      }
+      return _get(s, sl, row % sl, col % sl, std::nullopt, index_s, max_t, max_s);
+    }
+    return _get(s, sl, row % sl, col % sl, index_t, index_s, max_t, max_s);
+  }
+
+  template <class S>
+  void fill_window(S&& set, const Snapshot& s, const Rect& b) const {  // log.rs:311-349
+    bool single_t = !nodemap.get(0), single_s = !s.nodemap.get(0);
+    if (single_t && (single_s || !equal.get(0))) {
+      i64 v = max.get(0) + s.max.get(0);
+      for (usize r = 0; r < b.rows(); r++)
+        for (usize c = 0; c < b.cols(); c++) set(r, c, v);
+    } else {
+      _fill_window(set, s, sidelen, b.top, b.bottom - 1, b.left, b.right - 1,
+                   single_t ? std::optional<usize>() : std::optional<usize>(0),
+                   single_s ? std::optional<usize>() : std::optional<usize>(0), max.get(0), s.max.get(0), b.top, b.left, 0, 0);
+    }
+  }
+  template <class S>
+  void _fill_window(S& set, const Snapshot& s, usize sl, usize top, usize bottom, usize left, usize right,
+                    std::optional<usize> index_t, std::optional<usize> index_s, i64 max_t, i64 max_s, usize window_top,
+                    usize window_left, usize top_offset, usize left_offset) const {  // log.rs:351-508
+    usize kk = (usize)k;
+    sl /= kk;
+    if (index_t) index_t = 1 + nodemap.rank(*index_t) * kk * kk;
+    if (index_s) index_s = 1 + s.nodemap.rank(*index_s) * kk * kk;
+    for (usize i = top / sl; i <= bottom / sl; i++) {
+      usize top_ = top > i * sl ? top - i * sl : 0;
+      usize bottom_ = std::min(sl - 1, bottom - i * sl);
+      usize top_offset_ = top_offset + i * sl;
+      for (usize j = left / sl; j <= right / sl; j++) {
+        usize left_ = left > j * sl ? left - j * sl : 0;
+        usize right_ = std::min(sl - 1, right - j * sl);
+        usize left_offset_ = left_offset + j * sl;
+        std::optional<usize> index_t_, index_s_;
+        if (index_t) index_t_ = *index_t + i * kk + j;
+        i64 max_t_ = index_t_ ? max.get(*index_t_) : max_t;
+        bool leaf_t = index_t_ ? leaf_t_(*index_t_) : true;
+        if (index_s) index_s_ = *index_s + i * kk + j;
+        i64 max_s_ = index_s_ ? max_s - s.max.get(*index_s_) : max_s;
+        bool leaf_s = index_s_ ? (*index_s_ >= s.nodemap.length || !s.nodemap.get(*index_s_)) : true;
+        auto fill = [&](i64 value) {
+          for (usize r = top_; r <= bottom_; r++)
+            for (usize c = left_; c <= right_; c++) set(top_offset_ + r - window_top, left_offset_ + c - window_left, value);
+        };
+        if (leaf_t && leaf_s) {
+          fill(max_t_ + max_s_);
+        } else if (leaf_s) {
+          _fill_window(set, s, sl, top_, bottom_, left_, right_, index_t_, std::nullopt, max_t_, max_s_, window_top, window_left, top_offset_, left_offset_);
+        } else if (leaf_t) {
+          // log.rs:444 tests `!nodemap.get(index)` (true for every in-range leaf, and for index == length
+          // it reads a zero padding bit and then an out-of-range `equal` bit); restated bounds-safe as in get().
+          if (index_t_ && *index_t_ < nodemap.length) {
+            bool eq = equal.get(nodemap.rank0(*index_t_ + 1) - 1);
+            if (!eq) { fill(max_t_ + max_s_); continue; }
+          }
+          _fill_window(set, s, sl, top_, bottom_, left_, right_, std::nullopt, index_s_, max_t_, max_s_, window_top, window_left, top_offset_, left_offset_);
+        } else {
+          _fill_window(set, s, sl, top_, bottom_, left_, right_, index_t_, index_s_, max_t_, max_s_, window_top, window_left, top_offset_, left_offset_);
+        }
+      }
+    }
+  }
+
+  std::vector<std::pair<usize, usize>> search_window(const Snapshot& s, const Rect& b, i64 lower, i64 upper) const {  // log.rs:519-555
+    std::vector<std::pair<usize, usize>> cells;
+    bool single_t = !nodemap.get(0), single_s = !s.nodemap.get(0);
+    _search_window(s, sidelen, b.top, b.bottom - 1, b.left, b.right - 1, lower, upper,
+                   single_t ? std::optional<usize>() : std::optional<usize>(0),
+                   single_s ? std::optional<usize>() : std::optional<usize>(0), min.get(0), s.min.get(0), max.get(0),
+                   s.max.get(0), cells, 0, 0);
+    return cells;
+  }
+  void _search_window(const Snapshot& s, usize sl, usize top, usize bottom, usize left, usize right, i64 lower, i64 upper,
+                      std::optional<usize> index_t, std::optional<usize> index_s, i64 min_t, i64 min_s, i64 max_t, i64 max_s,
+                      std::vector<std::pair<usize, usize>>& cells, usize top_offset, usize left_offset) const {  // log.rs:557-702
+    i64 max_value = max_s + max_t, min_value = min_s + min_t;
+    if (min_value >= lower && max_value <= upper) {
+      for (usize r = top; r <= bottom; r++)
+        for (usize c = left; c <= right; c++) cells.emplace_back(top_offset + r, left_offset + c);
+      return;
+    } else if (min_value > upper || max_value < lower) {
+      return;
+    }
+    usize kk = (usize)k;
+    sl /= kk;
+    if (sl == 0) return;  // unreachable for consistent data (leaf min==max); guards malformed input
+    if (index_t) index_t = 1 + nodemap.rank(*index_t) * kk * kk;
+    if (index_s) index_s = 1 + s.nodemap.rank(*index_s) * kk * kk;
+    for (usize i = top / sl; i <= bottom / sl; i++) {
+      usize top_ = top > i * sl ? top - i * sl : 0;
+      usize bottom_ = std::min(sl - 1, bottom - i * sl);
+      usize top_offset_ = top_offset + i * sl;
+      for (usize j = left / sl; j <= right / sl; j++) {
+        usize left_ = left > j * sl ? left - j * sl : 0;
+        usize right_ = std::min(sl - 1, right - j * sl);
+        usize left_offset_ = left_offset + j * sl;
+        std::optional<usize> index_t_, index_s_;
+        if (index_t) index_t_ = *index_t + i * kk + j;
+        if (index_s) index_s_ = *index_s + i * kk + j;
+        i64 max_t_ = index_t_ ? max.get(*index_t_) : max_t;
+        i64 max_s_ = index_s_ ? max_s - s.max.get(*index_s_) : max_s;
+        bool leaf_t = index_t_ ? (*index_t_ >= nodemap.length || !nodemap.get(*index_t_)) : true;
+        bool leaf_s = index_s_ ? (*index_s_ >= s.nodemap.length || !s.nodemap.get(*index_s_)) : true;
+        i64 min_t_ = index_t_ ? (leaf_t ? min_t : min.get(nodemap.rank(*index_t_))) : min_t;
+        i64 min_s_ = index_s_ ? (leaf_s ? min_s : min_s + s.min.get(s.nodemap.rank(*index_s_))) : min_s;
+        if (leaf_s) { min_s_ = max_s_; index_s_ = std::nullopt; }
+        if (leaf_t) {
+          min_t_ = max_t_;
+          if (index_t_ && *index_t_ < nodemap.length && !equal.get(nodemap.rank0(*index_t_ + 1) - 1))
+            min_t_ = max_s_ + max_t_ - min_s_;
+          index_t_ = std::nullopt;
+        }
+        _search_window(s, sl, top_, bottom_, left_, right_, lower, upper, index_t_, index_s_, min_t_, min_s_, max_t_, max_s_, cells, top_offset_, left_offset_);
+      }
+    }
+  }
+
+  u64 size() const { return 1 + 4 + 4 + 4 + nodemap.size() + equal.size() + max.size() + min.size(); }  // log.rs:92-98
+  void write_to(Writer& w) const {                              // log.rs:53-64
+    w.byte((u8)k);
+    w.u32be((u32)shape[0]);
+    w.u32be((u32)shape[1]);
+    w.u32be((u32)sidelen);
+    nodemap.write_to(w);
+    equal.write_to(w);
+    max.write_to(w);
+    min.write_to(w);
+  }
+  static Log read_from(Reader& r) {                             // log.rs:68-89
+    Log l;
+    l.k = r.byte();
+    l.shape[0] = r.u32be();
+    l.shape[1] = r.u32be();
+    l.sidelen = r.u32be();
+    l.nodemap = BitMap::read_from(r);
+    l.equal = BitMap::read_from(r);
+    l.max = Dac::read_from(r);
+    l.min = Dac::read_from(r);
+    return l;
+  }
+};
+
+// ---------------------------------------------------------------- block.rs
+struct Block {
+  Snapshot snapshot;
+  std::vector<Log> logs;
+  Block(Snapshot s, std::vector<Log> l) : snapshot(std::move(s)), logs(std::move(l)) {  // block.rs:26-38
+    if (logs.size() > 254) fail(BAD_ARG, "too many logs in one block");
+  }
+  i64 get(usize instant, usize row, usize col) const {          // block.rs:42-47
+    return instant == 0 ? snapshot.get(row, col) : logs[instant - 1].get(snapshot, row, col);
+  }
+  template <class S>
+  void fill_window(S&& set, usize instant, const Rect& b) const {  // block.rs:56-64
+    if (instant == 0) snapshot.fill_window(set, b);
+    else logs[instant - 1].fill_window(set, snapshot, b);
+  }
+  std::vector<std::pair<usize, usize>> search_window(usize instant, const Rect& b, i64 lower, i64 upper) const {  // :70-81
+    return instant == 0 ? snapshot.search_window(b, lower, upper) : logs[instant - 1].search_window(snapshot, b, lower, upper);
+  }
+  u64 size() const {                                            // block.rs:112-118
+    u64 s = 1 + snapshot.size();
+    for (auto& l : logs) s += l.size();
+    return s;
+  }
+  void write_to(Writer& w) const {                              // block.rs:88-95
+    w.byte((u8)(logs.size() + 1));
+    snapshot.write_to(w);
+    for (auto& l : logs) l.write_to(w);
+  }
+  static Block read_from(Reader& r) {                           // block.rs:99-109
+    usize n = r.byte();
+    if (n == 0) fail(BAD_FORMAT, "block with zero instants");
+    Snapshot s = Snapshot::read_from(r);
+    std::vector<Log> logs;
+    for (usize i = 0; i + 1 < n; i++) logs.push_back(Log::read_from(r));
+    return Block(std::move(s), std::move(logs));
+  }
+};
+
+// ---------------------------------------------------------------- chunk.rs
+struct BuildStats {                                             // mmstruct.rs:24-34 (MMStruct3Build)
+  u64 size = 0;
+  usize elided = 0, local = 0, external = 0, snapshots = 0, logs = 0;
+};
+
+struct Chunk {
+  std::vector<Block> blocks;
+  std::vector<usize> index;
+  Encoding encoding = ENC_I64;
+  usize fractional_bits = 0;
+
+  Chunk(std::vector<Block> b, Encoding e, usize fb) : blocks(std::move(b)), encoding(e), fractional_bits(fb) {  // chunk.rs:100-114
+    usize count = 0;
+    for (auto& blk : blocks) { count += blk.logs.size() + 1; index.push_back(count); }
+  }
+
+  // Chunk::build  chunk.rs:42-96 -- the heuristic.
+  static Chunk build(const Buffer3& buffer, usize instants, usize rows, usize cols, int k, BuildStats* stats) {
+    if (instants == 0 || rows == 0 || cols == 0) fail(BAD_ARG, "empty shape");
+    usize count_snapshots = 0, count_logs = 0;
+    std::vector<Block> blocks;
+    auto first_get = [&](usize r, usize c) { return buffer.get(0, r, c); };
+    Snapshot snapshot = Snapshot::build(first_get, rows, cols, k);
+    usize snapshot_index = 0;
+    std::vector<Log> logs;
+    for (usize i = 1; i < instants; i++) {
+      auto get_t = [&](usize r, usize c) { return buffer.get(i, r, c); };
+      Snapshot new_snapshot = Snapshot::build(get_t, rows, cols, k);
+      auto get_s = [&](usize r, usize c) { return buffer.get(snapshot_index, r, c); };
+      Log new_log = Log::build(get_s, get_t, rows, cols, k);
+      if (logs.size() == 254 || new_snapshot.size() <= new_log.size()) {  // :62
+        count_snapshots++;
+        count_logs += logs.size();
+        blocks.emplace_back(std::move(snapshot), std::move(logs));
+        snapshot = std::move(new_snapshot);
+        logs.clear();
+        snapshot_index = i;
+      } else {
+        logs.push_back(std::move(new_log));
+      }
+    }
+    count_snapshots++;
+    count_logs += logs.size();
+    blocks.emplace_back(std::move(snapshot), std::move(logs));
+    Chunk chunk(std::move(blocks), buffer.enc, buffer.frac_bits_reported());
+    if (stats) {
+      stats->size = chunk.size();
+      stats->elided = stats->local = stats->external = 0;
+      stats->logs = count_logs;
+      stats->snapshots = count_snapshots;
+    }
+    return chunk;
+  }
+
+  void shape(usize out[3]) const {                              // chunk.rs:119-123
+    out[1] = blocks[0].snapshot.shape[0];
+    out[2] = blocks[0].snapshot.shape[1];
+    out[0] = 0;
+    for (auto& b : blocks) out[0] += 1 + b.logs.size();
+  }
+  std::pair<usize, usize> find_block(usize instant) const {     // chunk.rs:164-191
+    if (instant < index[0]) return {0, instant};
+    usize lower = 0, upper = blocks.size(), idx = upper / 2;
+    for (;;) {
+      if (idx >= index.size()) fail(OUT_OF_BOUNDS, "instant out of bounds");
+      usize here = index[idx];
+      if (here == instant) { idx += 1; break; }
+      else if (here < instant) lower = idx;
+      else { if (index[idx - 1] <= instant) break; else upper = idx; }
+      idx = (lower + upper) / 2;
+    }
+    if (idx >= blocks.size()) fail(OUT_OF_BOUNDS, "instant out of bounds");
+    return {idx, instant - index[idx - 1]};
+  }
+  // ChunkIter  chunk.rs:284-313
+  struct Iter {
+    const Chunk* chunk;
+    usize block, instant, remaining;
+    bool next(usize& b, usize& i) {
+      if (remaining == 0) return false;
+      b = block; i = instant;
+      if (block >= chunk->blocks.size()) fail(OUT_OF_BOUNDS, "instant out of bounds");
+      if (instant == chunk->blocks[block].logs.size()) { instant = 0; block++; } else instant++;
+      remaining--;
+      return true;
+    }
+  };
+  Iter iter(usize start, usize end) const {                     // chunk.rs:197-206
+    auto p = find_block(start);
+    return Iter{this, p.first, p.second, end - start};
+  }
+  i64 get(usize instant, usize row, usize col) const {          // chunk.rs:127-131
+    auto p = find_block(instant);
+    return blocks[p.first].get(p.second, row, col);
+  }
+  template <class S1>
+  void fill_cell(usize start, usize end, usize row, usize col, S1&& set) const {  // chunk.rs:135-148
+    Iter it = iter(start, end);
+    usize b, i, n = 0;
+    while (it.next(b, i)) set(n++, blocks[b].get(i, row, col));
+  }
+  template <class S3>
+  void fill_window(const Cube& bounds, S3&& set) const {        // chunk.rs:152-158
+    Iter it = iter(bounds.start, bounds.end);
+    usize b, i, n = 0;
+    Rect rect = bounds.rect();
+    while (it.next(b, i)) {
+      auto set2d = [&](usize r, usize c, i64 v) { set(n, r, c, v); };
+      blocks[b].fill_window(set2d, i, rect);
+      n++;
+    }
+  }
+  // iter_search + SearchIter  chunk.rs:213-228,336-383 : (instant,row,col) in instant order,
+  // within an instant in the Snapshot/Log traversal order.
+  std::vector<std::array<usize, 3>> search(const Cube& bounds, i64 lower, i64 upper) const {
+    rearrange(lower, upper);                                    // chunk.rs:214
+    std::vector<std::array<usize, 3>> out;
+    Iter it = iter(bounds.start, bounds.end);
+    usize b, i, instant = bounds.start;
+    Rect rect = bounds.rect();
+    while (it.next(b, i)) {
+      for (auto& rc : blocks[b].search_window(i, rect, lower, upper)) out.push_back({instant, rc.first, rc.second});
+      instant++;
+    }
+    return out;
+  }
+  u64 size() const {                                            // chunk.rs:269-278
+    u64 s = 1 + 1 + 4;
+    for (auto& b : blocks) s += b.size();
+    return s;
+  }
+  void write_to(Writer& w) const {                              // chunk.rs:235-243
+    w.byte((u8)encoding);
+    w.byte((u8)fractional_bits);
+    w.u32be((u32)blocks.size());
+    for (auto& b : blocks) b.write_to(w);
+  }
+  static Chunk read_from(Reader& r) {                           // chunk.rs:247-266
+    u8 e = r.byte();
+    if (e != ENC_I32 && e != ENC_I64 && e != ENC_F32 && e != ENC_F64) fail(BAD_FORMAT, "bad encoding byte");  // mmstruct.rs:45-59
+    usize fb = r.byte();
+    usize n = r.u32be();
+    if (n == 0) fail(BAD_FORMAT, "chunk with zero blocks");
+    std::vector<Block> blocks;
+    for (usize i = 0; i < n; i++) blocks.push_back(Block::read_from(r));
+    return Chunk(std::move(blocks), (Encoding)e, fb);
+  }
+};
+
+// ---------------------------------------------------------------- superchunk.rs (compute part)
+// Superchunk::build  superchunk.rs:88-270 minus CIDs / resolver.save / Links (host storage side).
+struct SuperNode;
+struct SubRef {
+  int kind = 0;  // 0 = Elided, 2 = External (superchunk.rs:827-831; Local is never produced by build)
+  std::shared_ptr<Chunk> chunk;        // leaf subchunk
+  std::shared_ptr<SuperNode> super;    // nested superchunk
+};
+struct SuperNode {
+  usize shape[3];
+  usize sidelen = 0;
+  u32 levels = 0;
+  usize chunks_sidelen = 0, subsidelen = 0;
+  usize fractional_bits = 0;
+  Encoding encoding = ENC_F32;
+  std::vector<SubRef> refs;
+  Dac max, min;
+  BuildStats stats;
+
+  static std::shared_ptr<SuperNode> build(Buffer3& buffer, usize instants, usize rows, usize cols, const u32* levels,
+                                          usize n_levels, int k) {
+    if (n_levels < 2) fail(BAD_LEVELS, "need at least two level entries");
+    usize longest = std::max(rows, cols);
+    u32 total_levels = levels_for(longest, k);                  // :96-101
+    u32 user_levels = 0;
+    for (usize i = 0; i < n_levels; i++) user_levels += levels[i];
+    if (user_levels != total_levels) fail(BAD_LEVELS, "tree levels passed in do not match levels needed");  // :105-110
+    usize sidelen = ipow(k, total_levels);
+    const u32* sublevels = levels + 1;
+    usize n_sub = n_levels - 1;
+    bool at_bottom = n_sub == 1;
+    u32 lv = levels[0];
+    usize subsidelen = ipow(k, lv);
+    usize chunks_sidelen = sidelen / subsidelen;
+
+    auto node = std::make_shared<SuperNode>();
+    std::vector<bool> elided;
+    std::vector<std::vector<std::pair<i64, i64>>> min_max;
+    std::vector<SubRef> built;  // results of the FuturesOrdered, in push order
+    std::vector<BuildStats> built_stats;
+    for (usize row = 0; row < subsidelen; row++) {              // :127-181
+      usize top = row * chunks_sidelen, bottom = std::min(top + chunks_sidelen, rows);
+      for (usize col = 0; col < subsidelen; col++) {
+        usize left = col * chunks_sidelen, right = std::min(left + chunks_sidelen, cols);
+        if (top >= rows || left >= cols) {
+          elided.push_back(true);
+          min_max.emplace_back(instants, std::make_pair<i64, i64>(0, 0));
+          continue;
+        }
+        Buffer3 sub = buffer.slice(0, instants, top, bottom, left, right);
+        usize srows = bottom - top, scols = right - left;
+        auto mm = sub.min_max();                                // :144 (parent's fractional bits)
+        bool can_elide = true;
+        for (auto& p : mm) can_elide = can_elide && p.first == p.second;
+        min_max.push_back(mm);
+        if (can_elide) { elided.push_back(true); continue; }
+        bool build_subchunk = at_bottom || levels_for(std::max(srows, scols), k) <= sublevels[0];  // :153-163
+        sub.compute_fractional_bits();                          // :167
+        SubRef ref;
+        ref.kind = 2;
+        BuildStats st;
+        if (build_subchunk) {
+          ref.chunk = std::make_shared<Chunk>(Chunk::build(sub, instants, srows, scols, k, &st));
+        } else {
+          ref.super = build(sub, instants, srows, scols, sublevels, n_sub, k);
+          st = ref.super->stats;
+        }
+        built.push_back(ref);
+        built_stats.push_back(st);
+        elided.push_back(false);
+      }
+    }
+    std::vector<i64> mins, maxs;                                // :190-198 instant-major, subchunk-minor
+    for (usize i = 0; i < instants; i++)
+      for (auto& sc : min_max) { mins.push_back(sc[i].first); maxs.push_back(sc[i].second); }
+    usize n_subchunks = subsidelen * subsidelen, next = 0;
+    BuildStats st;
+    u64 sizes = 0;
+    for (usize i = 0; i < n_subchunks; i++) {                   // :206-240
+      if (elided[i]) { st.elided++; node->refs.push_back(SubRef{}); continue; }
+      SubRef ref = built[next];
+      BuildStats bs = built_stats[next];
+      next++;
+      bool can_elide = true;
+      for (usize n = i; n < n_subchunks * instants; n += n_subchunks) can_elide = can_elide && maxs[n] == mins[n];
+      if (can_elide) { st.elided++; node->refs.push_back(SubRef{}); continue; }
+      sizes += bs.size;
+      node->refs.push_back(ref);
+      st.external++;  // the reference de-duplicates by CID (:222-232); the oracle counts every stored subchunk
+      st.snapshots += bs.snapshots;
+      st.logs += bs.logs;
+    }
+    node->shape[0] = instants; node->shape[1] = rows; node->shape[2] = cols;
+    node->sidelen = sidelen;
+    node->levels = lv;
+    node->chunks_sidelen = chunks_sidelen;
+    node->subsidelen = subsidelen;
+    node->fractional_bits = buffer.frac_bits_reported();
+    node->encoding = buffer.enc;
+    node->max = Dac::from(maxs);
+    node->min = Dac::from(mins);
+    st.size = sizes + node->max.size() + node->min.size();     // node/link sizes carry CIDs: host side, excluded
+    node->stats = st;
+    return node;
+  }
+
+  // Superchunk::get  superchunk.rs:313-351.  Returns fixed value and the fractional bits to decode it with.
+  i64 get(usize instant, usize row, usize col, usize* bits) const {
+    usize chunk_row = row / chunks_sidelen, local_row = row % chunks_sidelen;
+    usize chunk_col = col / chunks_sidelen, local_col = col % chunks_sidelen;
+    usize ci = chunk_row * subsidelen + chunk_col;
+    const SubRef& ref = refs[ci];
+    if (ref.kind == 0) { *bits = fractional_bits; return max.get(ci + instant * subsidelen * subsidelen); }
+    if (ref.chunk) { *bits = ref.chunk->fractional_bits; return ref.chunk->get(instant, local_row, local_col); }
+    return ref.super->get(instant, local_row, local_col, bits);
+  }
+  // Superchunk::fill_window  superchunk.rs:403-457 with subchunks_for :589-633
+  using Set5 = std::function<void(usize, usize, usize, i64, usize)>;
+  void fill_window(const Cube& w, const Set5& set) const {      // set(i, r, c, fixed, bits)
+    usize r0 = w.top / chunks_sidelen, r1 = (w.bottom - 1) / chunks_sidelen;
+    usize c0 = w.left / chunks_sidelen, c1 = (w.right - 1) / chunks_sidelen;
+    for (usize row = r0; row <= r1; row++) {
+      usize chunk_top = row * chunks_sidelen;
+      usize wt = std::max(chunk_top, w.top), wb = std::min(chunk_top + chunks_sidelen, w.bottom);
+      for (usize col = c0; col <= c1; col++) {
+        usize chunk_left = col * chunks_sidelen;
+        usize wl = std::max(chunk_left, w.left), wr = std::min(chunk_left + chunks_sidelen, w.right);
+        usize ci = row * subsidelen + col;
+        Cube local(w.start, w.end, wt - chunk_top, wb - chunk_top, wl - chunk_left, wr - chunk_left);
+        usize st = wt - w.top, sl = wl - w.left;
+        const SubRef& ref = refs[ci];
+        if (ref.kind == 0) {
+          usize stride = subsidelen * subsidelen;
+          for (usize i = 0; i < local.instants(); i++) {
+            i64 v = max.get(ci + (w.start + i) * stride);
+            for (usize r = 0; r < local.rows(); r++)
+              for (usize c = 0; c < local.cols(); c++) set(i, st + r, sl + c, v, fractional_bits);
+          }
+        } else if (ref.chunk) {
+          usize fb = ref.chunk->fractional_bits;
+          ref.chunk->fill_window(local, [&](usize i, usize r, usize c, i64 v) { set(i, st + r, sl + c, v, fb); });
+        } else {
+          ref.super->fill_window(local, [&](usize i, usize r, usize c, i64 v, usize fb) { set(i, st + r, sl + c, v, fb); });
+        }
+      }
+    }
+  }
+};
+
+}  // namespace orc
