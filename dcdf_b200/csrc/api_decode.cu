@@ -1,0 +1,584 @@
+// api_decode.cu -- C-ABI entry points for the query half of the path (Chunk::read_from, get / fill_cell /
+// fill_window / iter_search at chunk and superchunk level, flat to_fixed / from_fixed).
+#include <algorithm>
+
+#include "decode.cuh"
+#include "host.hpp"
+
+using namespace dcdf;
+
+namespace {
+
+template <typename Fn>
+int32_t guarded(dcdf_ctx* ctx, Fn&& fn) {
+  if (!ctx) return DCDF_ERR_BAD_ARG;
+  try {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) throw CudaFail{std::string("cudaSetDevice: ") + cudaGetErrorString(e)};
+    fn();
+    return DCDF_OK;
+  } catch (const ApiFail& f) {
+    ctx->last_error = f.msg;
+    return f.code;
+  } catch (const CudaFail& f) {
+    ctx->last_error = f.msg;
+    cudaGetLastError();
+    return DCDF_ERR_CUDA;
+  } catch (const std::bad_alloc&) {
+    ctx->last_error = "host out of memory";
+    return DCDF_ERR_BAD_ARG;
+  }
+}
+
+size_t enc_size(int enc) { return (enc == DCDF_ENC_I32 || enc == DCDF_ENC_F32) ? 4 : 8; }
+
+// Device-side metadata of a queryable object.
+struct DevMeta {
+  UnitMeta* units = nullptr;
+  SliceMeta* slices = nullptr;
+  int32_t* slot_unit = nullptr;
+  u32* err = nullptr;
+};
+
+// Everything the query kernels need for one handle; owned by the handle (dev_meta / dir pointers).
+struct MetaBlock {
+  DevMeta d;
+  QuerySet Q;
+  u64 n_dir = 0;
+};
+
+void check_err_word(dcdf_ctx* ctx, u32* d_err, const char* what) {
+  u32 f = 0;
+  CK(cudaMemcpyAsync(&f, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (f & EF_BAD_FORMAT) api_fail(DCDF_ERR_BAD_FORMAT, "%s: malformed chunk bytes", what);
+  if (f & EF_NONFINITE) api_fail(DCDF_ERR_NONFINITE, "%s: non-finite input", what);
+  if (f & EF_OVERFLOW) api_fail(DCDF_ERR_OVERFLOW, "%s: overflow", what);
+  if (f & EF_PRECISION) api_fail(DCDF_ERR_PRECISION_LOSS, "%s: loss of precision", what);
+  if (f) api_fail(DCDF_ERR_CUDA, "%s: device error flags %u", what, f);
+}
+
+MetaBlock* make_meta(dcdf_ctx* ctx, const u8* blob, std::vector<UnitMeta>& units, const std::vector<SliceMeta>& slices,
+                     const std::vector<int32_t>& slot_unit, u32 n_slots, i64 chunk_size, int chunks_sidelen, int subsidelen,
+                     int encoding, const i64* shape, const i64* tbl_max, void** dir_out, bool count_first) {
+  cudaStream_t st = ctx->stream;
+  MetaBlock* mb = new MetaBlock();
+  try {
+    const size_t ub = sizeof(UnitMeta) * units.size(), sb = sizeof(SliceMeta) * slices.size(), mbytes = sizeof(int32_t) * slot_unit.size();
+    u8* raw = nullptr;
+    CK(cudaMalloc(&raw, ub + sb + mbytes + 64));
+    mb->d.units = reinterpret_cast<UnitMeta*>(raw);
+    mb->d.slices = reinterpret_cast<SliceMeta*>(raw + ub);
+    mb->d.slot_unit = reinterpret_cast<int32_t*>(raw + ub + sb);
+    mb->d.err = reinterpret_cast<u32*>(raw + ub + sb + ((mbytes + 15) & ~size_t(15)));
+    CK(cudaMemsetAsync(mb->d.err, 0, 16, st));
+    CK(cudaMemcpyAsync(mb->d.units, units.data(), ub, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(mb->d.slices, slices.data(), sb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(mb->d.slot_unit, slot_unit.data(), mbytes, cudaMemcpyHostToDevice, st));
+    DirParams DP;
+    DP.blob = blob;
+    DP.units = mb->d.units;
+    DP.dir = nullptr;
+    DP.n_units = (u32)units.size();
+    DP.err = mb->d.err;
+    const u32 grid = ((u32)units.size() + 63) / 64;
+    if (count_first) {
+      DP.count_only = 1;
+      k_build_dir<<<grid, 64, 0, st>>>(DP);
+      CK(cudaGetLastError());
+      ctx->launches++;
+      check_err_word(ctx, mb->d.err, "chunk open");
+      CK(cudaMemcpyAsync(units.data(), mb->d.units, ub, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      u64 n = 0;
+      for (auto& u : units) { u.dir_base = (u32)n; n += (u64)u.instants; }
+      CK(cudaMemcpyAsync(mb->d.units, units.data(), ub, cudaMemcpyHostToDevice, st));
+    }
+    u64 n_dir = 0;
+    for (auto& u : units) if (u.stored) n_dir = std::max<u64>(n_dir, (u64)u.dir_base + (u64)u.instants);
+    InstDir* dir = nullptr;
+    CK(cudaMalloc(&dir, sizeof(InstDir) * std::max<u64>(n_dir, 1)));
+    *dir_out = dir;
+    DP.dir = dir;
+    DP.count_only = 0;
+    k_build_dir<<<grid, 64, 0, st>>>(DP);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    check_err_word(ctx, mb->d.err, "chunk directory");
+    CK(cudaMemcpyAsync(units.data(), mb->d.units, ub, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    mb->n_dir = n_dir;
+    QuerySet& Q = mb->Q;
+    Q.blob = blob;
+    Q.units = mb->d.units;
+    Q.dir = dir;
+    Q.slices = mb->d.slices;
+    Q.slot_unit = mb->d.slot_unit;
+    Q.tbl_max = tbl_max;
+    Q.n_slices = (u32)slices.size();
+    Q.n_slots = n_slots;
+    Q.chunk_size = chunk_size;
+    Q.chunks_sidelen = chunks_sidelen;
+    Q.subsidelen = subsidelen;
+    Q.encoding = encoding;
+    for (int i = 0; i < 3; i++) Q.shape[i] = shape[i];
+    return mb;
+  } catch (...) {
+    if (mb->d.units) cudaFree(mb->d.units);
+    delete mb;
+    throw;
+  }
+}
+
+// ---- handle -> MetaBlock (lazily for built objects)
+MetaBlock* chunk_meta(dcdf_ctx* ctx, const dcdf_chunk* cc) {
+  dcdf_chunk* c = const_cast<dcdf_chunk*>(cc);
+  if (c->dir) return static_cast<MetaBlock*>(c->dir);
+  std::vector<UnitMeta> units(1);
+  memset(&units[0], 0, sizeof(UnitMeta));
+  units[0].blob_off = 0; units[0].size = c->size; units[0].dir_base = 0; units[0].instants = (int)c->shape[0];
+  units[0].stored = 1;
+  std::vector<SliceMeta> slices(1);
+  memset(&slices[0], 0, sizeof(SliceMeta));
+  slices[0].t0 = 0; slices[0].instants = (int)c->shape[0]; slices[0].bits = c->fractional_bits;
+  std::vector<int32_t> slot_unit(1, 0);
+  void* dir = nullptr;
+  const bool count_first = c->shape[0] == 0;
+  MetaBlock* mb = make_meta(ctx, c->bytes, units, slices, slot_unit, 1, 0, 1 << 30, 1, c->encoding, c->shape, nullptr, &dir, count_first);
+  if (count_first) {
+    c->shape[0] = units[0].instants; c->shape[1] = units[0].rows; c->shape[2] = units[0].cols;
+    c->fractional_bits = units[0].bits;
+    c->encoding = units[0].enc;
+    mb->Q.encoding = c->encoding;
+    for (int i = 0; i < 3; i++) mb->Q.shape[i] = c->shape[i];
+  }
+  mb->Q.chunk_size = std::max<i64>(c->shape[0], 1);
+  c->dir = mb;
+  return mb;
+}
+
+MetaBlock* super_meta(dcdf_ctx* ctx, const dcdf_superchunk* scc) {
+  dcdf_superchunk* sc = const_cast<dcdf_superchunk*>(scc);
+  if (sc->dev_meta) return static_cast<MetaBlock*>(sc->dev_meta);
+  std::vector<UnitMeta> units(sc->units.size());
+  for (size_t u = 0; u < units.size(); u++) {
+    UnitMeta& m = units[u];
+    memset(&m, 0, sizeof m);
+    m.stored = sc->stored[u];
+    m.blob_off = sc->chunk_off[u];
+    m.size = m.stored ? sc->results[u].bytes : 0;
+    m.dir_base = sc->units[u].piece_base;
+    m.instants = sc->units[u].instants;
+  }
+  std::vector<SliceMeta> slices(sc->slices.size());
+  for (size_t s = 0; s < slices.size(); s++) {
+    SliceMeta& m = slices[s];
+    memset(&m, 0, sizeof m);
+    m.t0 = sc->slices[s].t0;
+    m.instants = (int)sc->slices[s].info.shape[0];
+    m.bits = sc->slices[s].info.fractional_bits;
+    m.table_base = sc->slices[s].table_base;
+    m.slot_base = (u32)(s * sc->n_slots);
+  }
+  void* dir = nullptr;
+  const auto& i0 = sc->slices[0].info;
+  MetaBlock* mb = make_meta(ctx, sc->chunk_blob, units, slices, sc->slot_unit, sc->n_slots, sc->chunk_size, (int)i0.chunks_sidelen,
+                            (int)i0.subsidelen, sc->encoding, sc->shape, sc->tbl_max, &dir, false);
+  sc->dir = dir;
+  sc->dev_meta = mb;
+  return mb;
+}
+
+void free_meta(void* p, bool free_dir) {
+  MetaBlock* mb = static_cast<MetaBlock*>(p);
+  if (!mb) return;
+  if (free_dir && mb->Q.dir) cudaFree(const_cast<InstDir*>(mb->Q.dir));
+  if (mb->d.units) cudaFree(mb->d.units);
+  delete mb;
+}
+
+// ---- query plumbing
+struct OutSpec {
+  int raw;        // 1 = fixed i64
+  size_t esize;
+};
+OutSpec out_spec(int out_encoding, int obj_encoding) {
+  if (out_encoding == DCDF_ENC_I64 && obj_encoding != DCDF_ENC_I64) return {1, 8};
+  if (out_encoding == obj_encoding) return {obj_encoding == DCDF_ENC_I64 ? 1 : 0, enc_size(obj_encoding)};
+  api_fail(DCDF_ERR_BAD_ARG, "out_encoding must be DCDF_ENC_I64 (raw fixed point) or the object's own encoding");
+}
+
+const void* to_device(dcdf_ctx* ctx, DevBuf& buf, const void* src, size_t bytes, int mem) {
+  if (mem == DCDF_MEM_DEVICE) return src;
+  buf.reserve(bytes);
+  CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return buf.p;
+}
+
+struct OutTarget {
+  void* dev;
+  void* user;
+  size_t bytes;
+  int mem;
+};
+OutTarget out_begin(dcdf_ctx* ctx, void* user, size_t bytes, int mem) {
+  if (!user && bytes) api_fail(DCDF_ERR_BAD_ARG, "null output");
+  if (mem == DCDF_MEM_DEVICE) return {user, user, bytes, mem};
+  ctx->query_out.reserve(bytes);
+  return {ctx->query_out.p, user, bytes, mem};
+}
+void out_end(dcdf_ctx* ctx, const OutTarget& t) {
+  if (t.mem != DCDF_MEM_DEVICE && t.bytes) CK(cudaMemcpyAsync(t.user, t.dev, t.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+}
+
+void tbegin(dcdf_ctx* ctx, int which) { CK(cudaEventRecord(ctx->ev[2 * which], ctx->stream)); }
+void tend(dcdf_ctx* ctx, int which) { CK(cudaEventRecord(ctx->ev[2 * which + 1], ctx->stream)); }
+void tcollect(dcdf_ctx* ctx, int which) {
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, ctx->ev[2 * which], ctx->ev[2 * which + 1]) == cudaSuccess) ctx->kernel_ms[which] = ms;
+  else cudaGetLastError();
+}
+
+dcdf_cube order_cube(const dcdf_cube& c) {  // Cube::new re-orders swapped bounds (geom.rs:83-107)
+  dcdf_cube o = c;
+  if (o.start > o.end) std::swap(o.start, o.end);
+  if (o.top > o.bottom) std::swap(o.top, o.bottom);
+  if (o.left > o.right) std::swap(o.left, o.right);
+  return o;
+}
+void check_cube(const dcdf_cube& c, const i64* shape) {  // mmarray.rs:218-229
+  if (c.start < 0 || c.top < 0 || c.left < 0 || c.end > shape[0] || c.bottom > shape[1] || c.right > shape[2])
+    api_fail(DCDF_ERR_OUT_OF_BOUNDS, "window [%lld:%lld, %lld:%lld, %lld:%lld] out of bounds for shape [%lld, %lld, %lld]",
+             (long long)c.start, (long long)c.end, (long long)c.top, (long long)c.bottom, (long long)c.left, (long long)c.right,
+             (long long)shape[0], (long long)shape[1], (long long)shape[2]);
+}
+
+void do_get_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const int64_t* irc, void* out, int32_t out_encoding, int32_t mem) {
+  if (n == 0) return;
+  if (!irc) api_fail(DCDF_ERR_BAD_ARG, "null queries");
+  const OutSpec os = out_spec(out_encoding, mb->Q.encoding);
+  if (mem == DCDF_MEM_HOST) {
+    for (uint64_t i = 0; i < n; i++)
+      for (int d = 0; d < 3; d++)
+        if (irc[3 * i + d] < 0 || irc[3 * i + d] >= mb->Q.shape[d]) api_fail(DCDF_ERR_OUT_OF_BOUNDS, "cell query %llu out of bounds", (unsigned long long)i);
+  }
+  const i64* d_q = static_cast<const i64*>(to_device(ctx, ctx->query_in, irc, sizeof(i64) * 3 * n, mem));
+  OutTarget ot = out_begin(ctx, out, os.esize * n, mem);
+  tbegin(ctx, KT_CELL);
+  k_get_batch<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(mb->Q, d_q, n, ot.dev, os.raw);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  tend(ctx, KT_CELL);
+  out_end(ctx, ot);
+  tcollect(ctx, KT_CELL);
+}
+
+void do_cell_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const int64_t* q, const uint64_t* out_off, void* out,
+                   int32_t out_encoding, int32_t mem) {
+  if (n == 0) return;
+  if (!q || !out_off) api_fail(DCDF_ERR_BAD_ARG, "null queries");
+  const OutSpec os = out_spec(out_encoding, mb->Q.encoding);
+  if (mem != DCDF_MEM_HOST) api_fail(DCDF_ERR_BAD_ARG, "cell_batch takes host query arrays (results may stay on the device via window_batch)");
+  std::vector<i64> qq(q, q + 4 * n);
+  i64 longest = 1;
+  for (uint64_t i = 0; i < n; i++) {
+    if (qq[4 * i] > qq[4 * i + 1]) std::swap(qq[4 * i], qq[4 * i + 1]);
+    const i64 s = qq[4 * i], e = qq[4 * i + 1], r = qq[4 * i + 2], c = qq[4 * i + 3];
+    if (s < 0 || e > mb->Q.shape[0] || r < 0 || r >= mb->Q.shape[1] || c < 0 || c >= mb->Q.shape[2])
+      api_fail(DCDF_ERR_OUT_OF_BOUNDS, "cell series %llu out of bounds", (unsigned long long)i);
+    if ((uint64_t)(e - s) != out_off[i + 1] - out_off[i]) api_fail(DCDF_ERR_BAD_ARG, "out_off does not match the series lengths");
+    longest = std::max(longest, e - s);
+  }
+  const size_t total = out_off[n];
+  ctx->query_in.reserve(sizeof(i64) * 4 * n + sizeof(u64) * (n + 1));
+  i64* d_q = ctx->query_in.as<i64>();
+  u64* d_off = reinterpret_cast<u64*>(d_q + 4 * n);
+  CK(cudaMemcpyAsync(d_q, qq.data(), sizeof(i64) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_off, out_off, sizeof(u64) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+  OutTarget ot = out_begin(ctx, out, os.esize * total, mem);
+  dim3 grid((unsigned)std::min<i64>((longest + 127) / 128, 1024), (unsigned)std::min<uint64_t>(n, 65535));
+  tbegin(ctx, KT_CELL);
+  k_cell_batch<<<grid, 128, 0, ctx->stream>>>(mb->Q, d_q, d_off, n, ot.dev, os.raw);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  tend(ctx, KT_CELL);
+  out_end(ctx, ot);  // qq stays alive until here
+  tcollect(ctx, KT_CELL);
+}
+
+void do_window_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* bounds, const uint64_t* out_off, void* out,
+                     int32_t out_encoding, int32_t mem) {
+  if (n == 0) return;
+  if (!bounds || !out_off) api_fail(DCDF_ERR_BAD_ARG, "null windows");
+  const OutSpec os = out_spec(out_encoding, mb->Q.encoding);
+  std::vector<CubeDev> cubes(n);
+  i64 biggest = 1;
+  for (uint64_t i = 0; i < n; i++) {
+    const dcdf_cube c = order_cube(bounds[i]);
+    check_cube(c, mb->Q.shape);
+    cubes[i] = {c.start, c.end, c.top, c.bottom, c.left, c.right};
+    const i64 cells = (c.end - c.start) * (c.bottom - c.top) * (c.right - c.left);
+    if ((uint64_t)cells != out_off[i + 1] - out_off[i]) api_fail(DCDF_ERR_BAD_ARG, "out_off does not match the window sizes");
+    biggest = std::max(biggest, cells);
+  }
+  const size_t total = out_off[n];
+  ctx->query_in.reserve(sizeof(CubeDev) * n + sizeof(u64) * (n + 1));
+  CubeDev* d_c = ctx->query_in.as<CubeDev>();
+  u64* d_off = reinterpret_cast<u64*>(d_c + n);
+  CK(cudaMemcpyAsync(d_c, cubes.data(), sizeof(CubeDev) * n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_off, out_off, sizeof(u64) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+  OutTarget ot = out_begin(ctx, out, os.esize * total, mem);
+  const unsigned gy = (unsigned)std::min<uint64_t>(n, 65535);
+  const unsigned gx = (unsigned)std::max<i64>(1, std::min<i64>((biggest + 255) / 256, std::max<i64>(1, (i64)ctx->sm_count * 16 / gy)));
+  tbegin(ctx, KT_WINDOW);
+  k_window_cells<<<dim3(gx, gy), 256, 0, ctx->stream>>>(mb->Q, d_c, d_off, n, ot.dev, os.raw);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  tend(ctx, KT_WINDOW);
+  out_end(ctx, ot);
+  tcollect(ctx, KT_WINDOW);
+}
+
+void do_search_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* bounds, const int64_t* lower, const int64_t* upper,
+                     uint64_t* counts, int64_t* out_irc, uint64_t cap, uint64_t* n_found, int32_t mem) {
+  if (n_found) *n_found = 0;
+  if (n == 0) return;
+  if (!bounds || !lower || !upper) api_fail(DCDF_ERR_BAD_ARG, "null search arguments");
+  cudaStream_t st = ctx->stream;
+  std::vector<CubeDev> cubes(n);
+  std::vector<u64> job_base(n + 1);
+  u64 n_jobs = 0;
+  const i64 cs = mb->Q.chunks_sidelen;
+  for (uint64_t i = 0; i < n; i++) {
+    const dcdf_cube c = order_cube(bounds[i]);
+    check_cube(c, mb->Q.shape);
+    cubes[i] = {c.start, c.end, c.top, c.bottom, c.left, c.right};
+    job_base[i] = n_jobs;
+    if (c.end > c.start && c.bottom > c.top && c.right > c.left) {
+      const u64 nsub = (u64)((c.bottom - 1) / cs - c.top / cs + 1) * (u64)((c.right - 1) / cs - c.left / cs + 1);
+      n_jobs += nsub * (u64)(c.end - c.start);
+    }
+  }
+  job_base[n] = n_jobs;
+  if (n_jobs == 0) {
+    if (counts) std::fill(counts, counts + n, 0);
+    return;
+  }
+  const size_t in_bytes = sizeof(CubeDev) * n + sizeof(u64) * (n + 1) + 2 * sizeof(i64) * n;
+  ctx->query_in.reserve(in_bytes);
+  CubeDev* d_c = ctx->query_in.as<CubeDev>();
+  u64* d_jb = reinterpret_cast<u64*>(d_c + n);
+  i64* d_lo = reinterpret_cast<i64*>(d_jb + n + 1);
+  i64* d_hi = d_lo + n;
+  CK(cudaMemcpyAsync(d_c, cubes.data(), sizeof(CubeDev) * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_jb, job_base.data(), sizeof(u64) * (n + 1), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_lo, lower, sizeof(i64) * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_hi, upper, sizeof(i64) * n, cudaMemcpyHostToDevice, st));
+  ctx->query_aux.reserve(sizeof(u64) * (2 * n_jobs + 2) + sizeof(u64) * (n + 1));
+  u64* d_counts = ctx->query_aux.as<u64>();
+  u64* d_offsets = d_counts + n_jobs;
+  u64* d_pick = d_offsets + n_jobs + 1;
+  SearchParams SP;
+  SP.Q = mb->Q;
+  SP.cubes = d_c; SP.job_base = d_jb; SP.n_queries = n; SP.n_jobs = n_jobs;
+  SP.lower = d_lo; SP.upper = d_hi;
+  SP.counts = d_counts; SP.offsets = d_offsets;
+  SP.out = nullptr; SP.cap = 0;
+  const unsigned grid = (unsigned)((n_jobs + 127) / 128);
+  tbegin(ctx, KT_SEARCH);
+  k_search<<<grid, 128, 0, st>>>(SP, 0);
+  CK(cudaGetLastError());
+  k_scan_u64<<<1, 1024, 0, st>>>(d_counts, n_jobs, d_offsets);
+  CK(cudaGetLastError());
+  k_pick_u64<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(d_offsets, d_jb, n + 1, d_pick);
+  CK(cudaGetLastError());
+  ctx->launches += 3;
+  std::vector<u64> pick(n + 1);
+  CK(cudaMemcpyAsync(pick.data(), d_pick, sizeof(u64) * (n + 1), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const u64 total = pick[n];
+  if (n_found) *n_found = total;
+  if (counts) for (uint64_t i = 0; i < n; i++) counts[i] = pick[i + 1] - pick[i];
+  if (out_irc && total) {
+    if (cap < total) api_fail(DCDF_ERR_BAD_ARG, "search output too small: need %llu triplets", (unsigned long long)total);
+    OutTarget ot = out_begin(ctx, out_irc, sizeof(i64) * 3 * total, mem);
+    SP.out = static_cast<i64*>(ot.dev);
+    SP.cap = total;
+    k_search<<<grid, 128, 0, st>>>(SP, 1);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    tend(ctx, KT_SEARCH);
+    out_end(ctx, ot);
+  } else {
+    tend(ctx, KT_SEARCH);
+    CK(cudaStreamSynchronize(st));
+  }
+  tcollect(ctx, KT_SEARCH);
+}
+
+}  // namespace
+
+namespace dcdf {
+void free_chunk_meta(void* p) { free_meta(p, true); }
+void free_super_meta(void* p) { free_meta(p, false); }
+}  // namespace dcdf
+
+extern "C" {
+
+// ===================================================================================== Chunk::read_from
+int32_t dcdf_chunk_open(dcdf_ctx* ctx, const uint8_t* bytes, uint64_t len, int32_t mem, dcdf_chunk** out) {
+  return guarded(ctx, [&] {
+    if (!out) api_fail(DCDF_ERR_BAD_ARG, "null out");
+    *out = nullptr;
+    if (!bytes || len < 6) api_fail(DCDF_ERR_BAD_FORMAT, "chunk bytes too short");
+    dcdf_chunk* c = new dcdf_chunk();
+    c->device = ctx->device;
+    try {
+      CK(cudaMalloc(&c->bytes, len + 16));
+      CK(cudaMemsetAsync(c->bytes + len, 0, 16, ctx->stream));
+      CK(cudaMemcpyAsync(c->bytes, bytes, len, mem == DCDF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+      c->size = len;
+      c->owner = true;
+      c->shape[0] = 0;  // unknown until the directory pass has counted the instants
+      MetaBlock* mb = chunk_meta(ctx, c);
+      // block table from the directory (snap indices)
+      std::vector<InstDir> dir(c->shape[0]);
+      CK(cudaMemcpyAsync(dir.data(), mb->Q.dir, sizeof(InstDir) * dir.size(), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      uint32_t run = 0;
+      for (size_t i = 0; i < dir.size(); i++) {
+        if (dir[i].snap == i && i > 0) { c->block_instants.push_back(run); run = 0; }
+        run++;
+      }
+      c->block_instants.push_back(run);
+      c->n_blocks = (uint32_t)c->block_instants.size();
+    } catch (...) {
+      if (c->dir) free_chunk_meta(c->dir);
+      c->dir = nullptr;
+      if (c->bytes) cudaFree(c->bytes);
+      delete c;
+      throw;
+    }
+    *out = c;
+  });
+}
+
+int32_t dcdf_chunk_get_batch(dcdf_ctx* ctx, const dcdf_chunk* chunk, uint64_t n, const int64_t* irc, void* out,
+                             int32_t out_encoding, int32_t mem) {
+  return guarded(ctx, [&] {
+    if (!chunk) api_fail(DCDF_ERR_BAD_ARG, "null chunk");
+    do_get_batch(ctx, chunk_meta(ctx, chunk), n, irc, out, out_encoding, mem);
+  });
+}
+
+int32_t dcdf_chunk_cell_batch(dcdf_ctx* ctx, const dcdf_chunk* chunk, uint64_t n, const int64_t* q, const uint64_t* out_off,
+                              void* out, int32_t out_encoding, int32_t mem) {
+  return guarded(ctx, [&] {
+    if (!chunk) api_fail(DCDF_ERR_BAD_ARG, "null chunk");
+    do_cell_batch(ctx, chunk_meta(ctx, chunk), n, q, out_off, out, out_encoding, mem);
+  });
+}
+
+int32_t dcdf_chunk_window(dcdf_ctx* ctx, const dcdf_chunk* chunk, const dcdf_cube* bounds, void* out, int32_t out_encoding,
+                          int32_t mem) {
+  return guarded(ctx, [&] {
+    if (!chunk || !bounds) api_fail(DCDF_ERR_BAD_ARG, "null argument");
+    const dcdf_cube c = order_cube(*bounds);
+    const uint64_t off[2] = {0, (uint64_t)((c.end - c.start) * (c.bottom - c.top) * (c.right - c.left))};
+    do_window_batch(ctx, chunk_meta(ctx, chunk), 1, bounds, off, out, out_encoding, mem);
+  });
+}
+
+int32_t dcdf_chunk_search(dcdf_ctx* ctx, const dcdf_chunk* chunk, const dcdf_cube* bounds, int64_t lower, int64_t upper,
+                          int64_t* out_irc, uint64_t cap, uint64_t* n_found, int32_t mem) {
+  return guarded(ctx, [&] {
+    if (!chunk || !bounds) api_fail(DCDF_ERR_BAD_ARG, "null argument");
+    do_search_batch(ctx, chunk_meta(ctx, chunk), 1, bounds, &lower, &upper, nullptr, out_irc, cap, n_found, mem);
+  });
+}
+
+// ===================================================================================== Superchunk queries
+int32_t dcdf_superchunk_get_batch(dcdf_ctx* ctx, const dcdf_superchunk* sc, uint64_t n, const int64_t* irc, void* out,
+                                  int32_t out_encoding, int32_t mem) {
+  return guarded(ctx, [&] {
+    if (!sc) api_fail(DCDF_ERR_BAD_ARG, "null superchunk");
+    do_get_batch(ctx, super_meta(ctx, sc), n, irc, out, out_encoding, mem);
+  });
+}
+
+int32_t dcdf_superchunk_cell_batch(dcdf_ctx* ctx, const dcdf_superchunk* sc, uint64_t n, const int64_t* q, const uint64_t* out_off,
+                                   void* out, int32_t out_encoding, int32_t mem) {
+  return guarded(ctx, [&] {
+    if (!sc) api_fail(DCDF_ERR_BAD_ARG, "null superchunk");
+    do_cell_batch(ctx, super_meta(ctx, sc), n, q, out_off, out, out_encoding, mem);
+  });
+}
+
+int32_t dcdf_superchunk_window(dcdf_ctx* ctx, const dcdf_superchunk* sc, const dcdf_cube* bounds, void* out, int32_t out_encoding,
+                               int32_t mem) {
+  return guarded(ctx, [&] {
+    if (!sc || !bounds) api_fail(DCDF_ERR_BAD_ARG, "null argument");
+    const dcdf_cube c = order_cube(*bounds);
+    const uint64_t off[2] = {0, (uint64_t)((c.end - c.start) * (c.bottom - c.top) * (c.right - c.left))};
+    do_window_batch(ctx, super_meta(ctx, sc), 1, bounds, off, out, out_encoding, mem);
+  });
+}
+
+int32_t dcdf_superchunk_window_batch(dcdf_ctx* ctx, const dcdf_superchunk* sc, uint64_t n, const dcdf_cube* bounds,
+                                     const uint64_t* out_off, void* out, int32_t out_encoding, int32_t mem) {
+  return guarded(ctx, [&] {
+    if (!sc) api_fail(DCDF_ERR_BAD_ARG, "null superchunk");
+    do_window_batch(ctx, super_meta(ctx, sc), n, bounds, out_off, out, out_encoding, mem);
+  });
+}
+
+int32_t dcdf_superchunk_search_batch(dcdf_ctx* ctx, const dcdf_superchunk* sc, uint64_t n, const dcdf_cube* bounds,
+                                     const int64_t* lower, const int64_t* upper, uint64_t* counts, int64_t* out_irc, uint64_t cap,
+                                     uint64_t* n_found, int32_t mem) {
+  return guarded(ctx, [&] {
+    if (!sc) api_fail(DCDF_ERR_BAD_ARG, "null superchunk");
+    do_search_batch(ctx, super_meta(ctx, sc), n, bounds, lower, upper, counts, out_irc, cap, n_found, mem);
+  });
+}
+
+// ===================================================================================== flat conversions
+int32_t dcdf_to_fixed(dcdf_ctx* ctx, const void* in, int32_t encoding, uint64_t n, int32_t fractional_bits, int32_t round,
+                      int64_t* out, int32_t mem) {
+  return guarded(ctx, [&] {
+    if (n == 0) return;
+    if (!in || !out) api_fail(DCDF_ERR_BAD_ARG, "null argument");
+    if (encoding != DCDF_ENC_F32 && encoding != DCDF_ENC_F64) api_fail(DCDF_ERR_BAD_ARG, "to_fixed needs a float encoding");
+    const void* d_in = to_device(ctx, ctx->query_in, in, enc_size(encoding) * n, mem);
+    OutTarget ot = out_begin(ctx, out, sizeof(i64) * n, mem);
+    ctx->small.reserve(256);
+    u32* d_err = ctx->small.as<u32>() + 32;
+    CK(cudaMemsetAsync(d_err, 0, 4, ctx->stream));
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 32);
+    if (encoding == DCDF_ENC_F32) k_to_fixed<float><<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(d_in), n, fractional_bits, round, static_cast<i64*>(ot.dev), d_err);
+    else k_to_fixed<double><<<grid, 256, 0, ctx->stream>>>(static_cast<const double*>(d_in), n, fractional_bits, round, static_cast<i64*>(ot.dev), d_err);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    out_end(ctx, ot);
+    check_err_word(ctx, d_err, "to_fixed");
+  });
+}
+
+int32_t dcdf_from_fixed(dcdf_ctx* ctx, const int64_t* in, uint64_t n, int32_t fractional_bits, void* out, int32_t encoding,
+                        int32_t mem) {
+  return guarded(ctx, [&] {
+    if (n == 0) return;
+    if (!in || !out) api_fail(DCDF_ERR_BAD_ARG, "null argument");
+    if (encoding != DCDF_ENC_F32 && encoding != DCDF_ENC_F64) api_fail(DCDF_ERR_BAD_ARG, "from_fixed needs a float encoding");
+    const i64* d_in = static_cast<const i64*>(to_device(ctx, ctx->query_in, in, sizeof(i64) * n, mem));
+    OutTarget ot = out_begin(ctx, out, enc_size(encoding) * n, mem);
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 32);
+    if (encoding == DCDF_ENC_F32) k_from_fixed<float><<<grid, 256, 0, ctx->stream>>>(d_in, n, fractional_bits, static_cast<float*>(ot.dev));
+    else k_from_fixed<double><<<grid, 256, 0, ctx->stream>>>(d_in, n, fractional_bits, static_cast<double*>(ot.dev));
+    CK(cudaGetLastError());
+    ctx->launches++;
+    out_end(ctx, ot);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,930 @@
+// api_encode.cu -- C-ABI entry points for the encode half of the path (context, a1/a2/a3, Chunk::build,
+// Superchunk::build).  Host logic only orchestrates: every data pass is a kernel in encode_tile.cuh,
+// stats.cuh, gather.cuh.  No CPU fallback exists: without a device every call returns DCDF_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+
+#include "gather.cuh"
+#include "host.hpp"
+#include "stats.cuh"
+
+using namespace dcdf;
+
+namespace dcdf {
+void free_chunk_meta(void* p);
+void free_super_meta(void* p);
+}  // namespace dcdf
+
+namespace {
+
+int32_t status_from_flags(u32 f, std::string& msg) {
+  if (f & EF_NONFINITE) { msg = "cannot convert a non-finite value to fixed point (fixed.rs:39-41)"; return DCDF_ERR_NONFINITE; }
+  if (f & EF_OVERFLOW) { msg = "overflow converting to fixed point (fixed.rs:66-69)"; return DCDF_ERR_OVERFLOW; }
+  if (f & EF_PRECISION) { msg = "loss of precision converting to fixed point (fixed.rs:51-57)"; return DCDF_ERR_PRECISION_LOSS; }
+  if (f & EF_BAD_FORMAT) { msg = "internal consistency check failed in the encoder"; return DCDF_ERR_BAD_FORMAT; }
+  if (f & EF_OUT_CAP) { msg = "output buffer too small"; return DCDF_ERR_BAD_ARG; }
+  return DCDF_OK;
+}
+
+size_t elem_size(int enc) { return (enc == DCDF_ENC_I32 || enc == DCDF_ENC_F32) ? 4 : 8; }
+
+template <typename Fn>
+int32_t guarded(dcdf_ctx* ctx, Fn&& fn) {
+  if (!ctx) return DCDF_ERR_BAD_ARG;
+  try {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) throw CudaFail{std::string("cudaSetDevice: ") + cudaGetErrorString(e)};
+    fn();
+    return DCDF_OK;
+  } catch (const ApiFail& f) {
+    ctx->last_error = f.msg;
+    return f.code;
+  } catch (const CudaFail& f) {
+    ctx->last_error = f.msg;
+    cudaGetLastError();
+    return DCDF_ERR_CUDA;
+  } catch (const std::bad_alloc&) {
+    ctx->last_error = "host out of memory";
+    return DCDF_ERR_BAD_ARG;
+  }
+}
+
+// sidelen exponent: ceil(log_k(longest)) computed in f64 exactly as the reference does
+// (snapshot.rs:118-119, superchunk.rs:96-101).
+uint32_t levels_for(int64_t longest, int k) {
+  double l = std::ceil(std::log((double)longest) / std::log((double)k));
+  if (!(l >= 0)) l = 0;
+  return (uint32_t)l;
+}
+
+void validate_array(const dcdf_array3* a) {
+  if (!a || !a->base) api_fail(DCDF_ERR_BAD_ARG, "null array");
+  if (a->encoding != DCDF_ENC_I32 && a->encoding != DCDF_ENC_I64 && a->encoding != DCDF_ENC_F32 && a->encoding != DCDF_ENC_F64)
+    api_fail(DCDF_ERR_BAD_ARG, "bad encoding %d", a->encoding);
+  for (int i = 0; i < 3; i++) {
+    if (a->shape[i] <= 0) api_fail(DCDF_ERR_BAD_ARG, "empty array axis %d", i);
+    if (a->strides[i] < 0) api_fail(DCDF_ERR_BAD_ARG, "negative strides are not supported");
+  }
+  if (a->mem != DCDF_MEM_HOST && a->mem != DCDF_MEM_DEVICE) api_fail(DCDF_ERR_BAD_ARG, "bad mem kind");
+}
+
+// Returns a device pointer for the array (copying a host view's spanned extent if needed).
+const void* stage_input(dcdf_ctx* ctx, const dcdf_array3* a) {
+  if (a->mem == DCDF_MEM_DEVICE) return a->base;
+  size_t span = 1;
+  for (int i = 0; i < 3; i++) span += (size_t)(a->shape[i] - 1) * (size_t)a->strides[i];
+  size_t bytes = span * elem_size(a->encoding);
+  ctx->input_copy.reserve(bytes);
+  CK(cudaMemcpyAsync(ctx->input_copy.p, a->base, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return ctx->input_copy.p;
+}
+
+struct EncodeJob {
+  const void* dev_data = nullptr;
+  int encoding = 0;
+  int64_t strides[3] = {0, 0, 0};
+  std::vector<EncUnit> units;
+  std::vector<SliceDesc> slices;
+  std::vector<uint64_t> table_len;
+  uint32_t n_slots = 1;
+  uint32_t t_max = 1;
+  int plain = 0, req_bits = 0, round = 0, compute_bits = 0;
+  int64_t rows = 0, cols = 0;  // full raster (exact pass)
+  size_t input_bytes = 0;
+};
+
+struct EncodeOut {
+  std::vector<EncUnit> units;  // with bits / flags
+  std::vector<UnitResult> results;
+  std::vector<uint8_t> stored;
+  std::vector<uint64_t> chunk_off;
+  std::vector<SliceState> states;
+  std::vector<Piece> dac_pieces;
+  std::vector<Piece> pieces;  // only fetched on request
+  uint8_t* blob = nullptr;
+  uint64_t blob_size = 0;
+  uint8_t* dac_blob = nullptr;
+  uint64_t dac_blob_size = 0;
+  std::vector<uint64_t> dac_off;  // [n_slices][2]
+  int64_t* tbl_max = nullptr;
+  int64_t* tbl_min = nullptr;
+  uint64_t tbl_total = 0;
+};
+
+template <typename InT, typename V>
+void launch_encode(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
+  if (grid == 0) return;
+  const size_t smem = sizeof(EncSmem<V>);
+  CK(cudaFuncSetAttribute(k_encode_tiles<InT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_encode_tiles<InT, V><<<grid, ENC_THREADS, smem, ctx->stream>>>(P);
+  CK(cudaGetLastError());
+  ctx->launches++;
+}
+
+template <typename InT, bool IS_FLOAT>
+void launch_stats(dcdf_ctx* ctx, const StatParams& P) {
+  k_unit_stats<InT, IS_FLOAT><<<P.n_units, STAT_THREADS, 0, ctx->stream>>>(P);
+  CK(cudaGetLastError());
+  ctx->launches++;
+}
+
+void time_begin(dcdf_ctx* ctx, int which) { CK(cudaEventRecord(ctx->ev[2 * which], ctx->stream)); }
+void time_end(dcdf_ctx* ctx, int which) { CK(cudaEventRecord(ctx->ev[2 * which + 1], ctx->stream)); }
+void time_collect(dcdf_ctx* ctx, int which) {
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, ctx->ev[2 * which], ctx->ev[2 * which + 1]) == cudaSuccess) ctx->kernel_ms[which] = ms;
+  else cudaGetLastError();
+}
+
+// The whole encode pipeline for a list of <=64x64 units grouped in slices.
+void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces) {
+  cudaStream_t st = ctx->stream;
+  const u32 n_units = (u32)job.units.size();
+  const u32 n_slices = (u32)job.slices.size();
+  if (n_units == 0) api_fail(DCDF_ERR_BAD_ARG, "nothing to encode");
+  u64 n_pieces = 0;
+  for (auto& u : job.units) { u.piece_base = (u32)n_pieces; n_pieces += (u64)u.instants; }
+  if (n_pieces > 0xfffffff0ull) api_fail(DCDF_ERR_BAD_ARG, "too many (unit, instant) pairs for one call");
+  u64 tbl_total = 0;
+  std::vector<uint64_t> table_base(n_slices);
+  for (u32 s = 0; s < n_slices; s++) {
+    table_base[s] = tbl_total;
+    job.slices[s].table_base = tbl_total;
+    tbl_total += job.plain ? 0 : job.table_len[s];
+  }
+
+  // ---- device scratch
+  ctx->units.reserve(sizeof(EncUnit) * n_units);
+  ctx->ustats.reserve(sizeof(UnitStats) * n_units);
+  ctx->istats.reserve(sizeof(InstStats) * (size_t)n_units * job.t_max);
+  ctx->slices.reserve(sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_slices);
+  ctx->sstate.reserve(sizeof(SliceState) * n_slices);
+  ctx->order.reserve(sizeof(u32) * (2 * (size_t)n_units + 8));
+  ctx->pieces.reserve(sizeof(Piece) * (n_pieces + 2 * (size_t)n_slices));
+  ctx->results.reserve(sizeof(UnitResult) * n_units);
+  ctx->stored.reserve(n_units);
+  ctx->chunk_off.reserve(sizeof(u64) * ((size_t)n_units + 1));
+  ctx->small.reserve(256);
+  if (!job.plain) ctx->tbl_scratch.reserve(sizeof(u64) * 2 * tbl_total);
+  int64_t *d_tbl_max = nullptr, *d_tbl_min = nullptr;
+  if (!job.plain && tbl_total) {
+    CK(cudaMalloc(&d_tbl_max, sizeof(i64) * tbl_total));
+    CK(cudaMalloc(&d_tbl_min, sizeof(i64) * tbl_total));
+  }
+  out.tbl_max = d_tbl_max;
+  out.tbl_min = d_tbl_min;
+  out.tbl_total = tbl_total;
+
+  // small: [0] err (u32) | [8] arena_head (u64) | [16] order counts (2 x u32)
+  u32* d_err = ctx->small.as<u32>();
+  unsigned long long* d_head = reinterpret_cast<unsigned long long*>(ctx->small.as<u8>() + 8);
+  u32* d_counts = reinterpret_cast<u32*>(ctx->small.as<u8>() + 16);
+
+  ctx->pin.reserve(sizeof(EncUnit) * n_units + sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_slices + 64);
+  EncUnit* h_units = ctx->pin.as<EncUnit>();
+  memcpy(h_units, job.units.data(), sizeof(EncUnit) * n_units);
+  SliceDesc* h_slices = reinterpret_cast<SliceDesc*>(h_units + n_units);
+  memcpy(h_slices, job.slices.data(), sizeof(SliceDesc) * n_slices);
+  u64* h_tb = reinterpret_cast<u64*>(h_slices + n_slices);
+  for (u32 s = 0; s < n_slices; s++) { h_tb[s] = table_base[s]; h_tb[n_slices + s] = job.plain ? 0 : job.table_len[s]; }
+  CK(cudaMemcpyAsync(ctx->units.p, h_units, sizeof(EncUnit) * n_units, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->slices.p, h_slices, sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_slices, cudaMemcpyHostToDevice, st));
+  const u64* d_table_base = reinterpret_cast<const u64*>(ctx->slices.as<SliceDesc>() + n_slices);
+  const u64* d_table_len = d_table_base + n_slices;
+
+  // ---- K1: per-unit statistics
+  StatParams SP;
+  SP.data = job.dev_data;
+  SP.stride_t = job.strides[0]; SP.stride_r = job.strides[1]; SP.stride_c = job.strides[2];
+  SP.units = ctx->units.as<EncUnit>();
+  SP.n_units = n_units;
+  SP.t_max = job.t_max;
+  SP.ustats = ctx->ustats.as<UnitStats>();
+  SP.istats = ctx->istats.as<InstStats>();
+  time_begin(ctx, KT_STATS);
+  switch (job.encoding) {
+    case DCDF_ENC_F32: launch_stats<float, true>(ctx, SP); break;
+    case DCDF_ENC_F64: launch_stats<double, true>(ctx, SP); break;
+    case DCDF_ENC_I32: launch_stats<int32_t, false>(ctx, SP); break;
+    default: launch_stats<i64, false>(ctx, SP); break;
+  }
+  time_end(ctx, KT_STATS);
+
+  // ---- K1b: slice finalisation
+  FinalizeParams FP;
+  FP.slices = ctx->slices.as<SliceDesc>();
+  FP.state = ctx->sstate.as<SliceState>();
+  FP.units_in = ctx->units.as<EncUnit>();
+  FP.units = ctx->units.as<EncUnit>();
+  FP.ustats = SP.ustats;
+  FP.istats = SP.istats;
+  FP.t_max = job.t_max;
+  FP.n_slots = job.n_slots;
+  FP.encoding = job.encoding;
+  FP.req_bits = job.req_bits; FP.round = job.round; FP.compute_bits = job.compute_bits; FP.plain = job.plain;
+  FP.tbl_min = d_tbl_min; FP.tbl_max = d_tbl_max;
+  FP.order_narrow = ctx->order.as<u32>();
+  FP.order_wide = ctx->order.as<u32>() + n_units;
+  FP.order_counts = d_counts;
+  FP.stored = ctx->stored.as<u8>();
+  FP.err = d_err;
+  CK(cudaMemsetAsync(ctx->small.p, 0, 64, st));
+  k_finalize_phase1<<<n_slices, 256, 0, st>>>(FP, n_slices);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  const bool is_float = job.encoding == DCDF_ENC_F32 || job.encoding == DCDF_ENC_F64;
+  if (is_float && job.compute_bits) {
+    // Exact slice-level pass, needed only when a negative value may hit the saturating cast of
+    // fixed.rs:150 (rare).  The flags are a few bytes per slice, read back once per call.
+    SliceState* ss = ctx->sstate.as<SliceState>();
+    std::vector<SliceState> hs(n_slices);
+    CK(cudaMemcpyAsync(hs.data(), ss, sizeof(SliceState) * n_slices, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    bool any = false;
+    for (auto& s : hs) any = any || s.need_exact;
+    if (any) {
+      ctx->exact.reserve((sizeof(i64) + 5 * sizeof(int)) * n_slices + 64);
+      std::vector<i64> t0(n_slices);
+      std::vector<int> inst(n_slices);
+      for (u32 s = 0; s < n_slices; s++) { t0[s] = job.slices[s].t0; inst[s] = job.slices[s].instants; }
+      i64* d_t0 = ctx->exact.as<i64>();
+      int* d_inst = reinterpret_cast<int*>(d_t0 + n_slices);
+      CK(cudaMemcpyAsync(d_t0, t0.data(), sizeof(i64) * n_slices, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(d_inst, inst.data(), sizeof(int) * n_slices, cudaMemcpyHostToDevice, st));
+      ExactParams XP;
+      XP.data = job.dev_data;
+      XP.stride_t = job.strides[0]; XP.stride_r = job.strides[1]; XP.stride_c = job.strides[2];
+      XP.rows = job.rows; XP.cols = job.cols;
+      XP.slice_t0 = d_t0; XP.slice_instants = d_inst;
+      std::vector<int> need(n_slices), maxfb(n_slices);
+      for (u32 s = 0; s < n_slices; s++) { need[s] = hs[s].need_exact; maxfb[s] = hs[s].maxfb; }
+      int* d_need = d_inst + n_slices;
+      int* d_maxfb = d_need + n_slices;
+      int* d_f = d_maxfb + n_slices;
+      int* d_round = d_f + n_slices;
+      CK(cudaMemcpyAsync(d_need, need.data(), sizeof(int) * n_slices, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(d_maxfb, maxfb.data(), sizeof(int) * n_slices, cudaMemcpyHostToDevice, st));
+      CK(cudaMemsetAsync(d_f, 0, 2 * sizeof(int) * n_slices, st));
+      XP.slice_need = d_need; XP.slice_maxfb = d_maxfb; XP.slice_f = d_f; XP.slice_round = d_round;
+      dim3 grid((unsigned)std::min<int64_t>(4 * ctx->sm_count, 65535), n_slices);
+      if (job.encoding == DCDF_ENC_F32) k_fraction_exact<float><<<grid, 256, 0, st>>>(XP, n_slices);
+      else k_fraction_exact<double><<<grid, 256, 0, st>>>(XP, n_slices);
+      CK(cudaGetLastError());
+      ctx->launches++;
+      std::vector<int> f(n_slices), r(n_slices);
+      CK(cudaMemcpyAsync(f.data(), d_f, sizeof(int) * n_slices, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(r.data(), d_round, sizeof(int) * n_slices, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      for (u32 s = 0; s < n_slices; s++) { hs[s].f_exact = f[s]; hs[s].round_exact = r[s]; }
+      CK(cudaMemcpyAsync(ss, hs.data(), sizeof(SliceState) * n_slices, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  }
+  k_finalize_phase2<<<n_slices, 256, 0, st>>>(FP, n_slices);
+  CK(cudaGetLastError());
+  ctx->launches++;
+
+  // ---- K_enc (+ table DACs), with arena growth on overflow
+  if (ctx->arena_hint == 0) ctx->arena_hint = std::max<size_t>(job.input_bytes / 2 + (8u << 20), 16u << 20);
+  std::vector<uint8_t> head_buf(64);
+  for (int attempt = 0;; attempt++) {
+    ctx->arena.reserve(ctx->arena_hint);
+    const u64 arena_cap = ctx->arena.cap;
+    CK(cudaMemsetAsync(d_head, 0, 8, st));
+    EncParams EP;
+    EP.data = job.dev_data;
+    EP.stride_t = job.strides[0]; EP.stride_r = job.strides[1]; EP.stride_c = job.strides[2];
+    EP.units = ctx->units.as<EncUnit>();
+    EP.pieces = ctx->pieces.as<Piece>();
+    EP.results = ctx->results.as<UnitResult>();
+    EP.arena = ctx->arena.as<u8>();
+    EP.arena_cap = arena_cap;
+    EP.arena_head = d_head;
+    EP.err = d_err;
+    time_begin(ctx, KT_ENCODE);
+    for (int wide = 0; wide < 2; wide++) {
+      EP.order = wide ? FP.order_wide : FP.order_narrow;
+      EP.order_count = d_counts + wide;
+      switch (job.encoding) {
+        case DCDF_ENC_F32:
+          if (wide) launch_encode<float, i64>(ctx, EP, n_units); else launch_encode<float, int32_t>(ctx, EP, n_units);
+          break;
+        case DCDF_ENC_F64:
+          if (wide) launch_encode<double, i64>(ctx, EP, n_units); else launch_encode<double, int32_t>(ctx, EP, n_units);
+          break;
+        case DCDF_ENC_I32:
+          if (wide) launch_encode<int32_t, i64>(ctx, EP, n_units); else launch_encode<int32_t, int32_t>(ctx, EP, n_units);
+          break;
+        default:
+          if (wide) launch_encode<i64, i64>(ctx, EP, n_units); else launch_encode<i64, int32_t>(ctx, EP, n_units);
+          break;
+      }
+    }
+    time_end(ctx, KT_ENCODE);
+    if (!job.plain) {
+      TableDacParams TP;
+      TP.tbl_min = d_tbl_min; TP.tbl_max = d_tbl_max;
+      TP.table_base = d_table_base; TP.table_len = d_table_len;
+      TP.scratch = ctx->tbl_scratch.as<u64>();
+      TP.total = tbl_total;
+      TP.pieces = ctx->pieces.as<Piece>() + n_pieces;
+      TP.arena = ctx->arena.as<u8>(); TP.arena_cap = arena_cap; TP.arena_head = d_head; TP.err = d_err;
+      k_table_dac<<<dim3(n_slices, 2), ENC_THREADS, 0, st>>>(TP);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+    k_scan_units<<<1, 1024, 0, st>>>(ctx->results.as<UnitResult>(), ctx->stored.as<u8>(), n_units, ctx->chunk_off.as<u64>());
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaMemcpyAsync(head_buf.data(), ctx->small.p, 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    u32 flags;
+    u64 head;
+    memcpy(&flags, head_buf.data(), 4);
+    memcpy(&head, head_buf.data() + 8, 8);
+    if (flags & EF_ARENA_FULL) {
+      if (attempt >= 2) api_fail(DCDF_ERR_CUDA, "arena overflow persisted after growth");
+      ctx->arena_hint = (size_t)head + (size_t)head / 16 + (1u << 20);
+      CK(cudaMemsetAsync(d_err, 0, 4, st));
+      // phase-2 outputs (order lists, unit bits) are still valid; only the emission is repeated
+      continue;
+    }
+    std::string msg;
+    int32_t code = status_from_flags(flags, msg);
+    if (code != DCDF_OK) {
+      if (d_tbl_max) cudaFree(d_tbl_max);
+      if (d_tbl_min) cudaFree(d_tbl_min);
+      out.tbl_max = out.tbl_min = nullptr;
+      throw ApiFail{code, msg};
+    }
+    break;
+  }
+  time_collect(ctx, KT_STATS);
+  time_collect(ctx, KT_ENCODE);
+
+  // ---- read back the small per-unit tables
+  out.units.resize(n_units);
+  out.results.resize(n_units);
+  out.stored.resize(n_units);
+  out.chunk_off.resize((size_t)n_units + 1);
+  out.states.resize(n_slices);
+  CK(cudaMemcpyAsync(out.units.data(), ctx->units.p, sizeof(EncUnit) * n_units, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out.results.data(), ctx->results.p, sizeof(UnitResult) * n_units, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out.stored.data(), ctx->stored.p, n_units, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out.chunk_off.data(), ctx->chunk_off.p, sizeof(u64) * ((size_t)n_units + 1), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out.states.data(), ctx->sstate.p, sizeof(SliceState) * n_slices, cudaMemcpyDeviceToHost, st));
+  if (!job.plain) {
+    out.dac_pieces.resize(2 * (size_t)n_slices);
+    CK(cudaMemcpyAsync(out.dac_pieces.data(), ctx->pieces.as<Piece>() + n_pieces, sizeof(Piece) * 2 * n_slices, cudaMemcpyDeviceToHost, st));
+  }
+  if (want_pieces) {
+    out.pieces.resize(n_pieces);
+    CK(cudaMemcpyAsync(out.pieces.data(), ctx->pieces.p, sizeof(Piece) * n_pieces, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+
+  // ---- final blobs
+  out.blob_size = out.chunk_off[n_units];
+  CK(cudaMalloc(&out.blob, out.blob_size + 16));  // +16: decoders read aligned words past the last byte
+  CK(cudaMemsetAsync(out.blob + out.blob_size, 0, 16, st));
+  GatherParams GP;
+  GP.units = ctx->units.as<EncUnit>();
+  GP.results = ctx->results.as<UnitResult>();
+  GP.stored = ctx->stored.as<u8>();
+  GP.pieces = ctx->pieces.as<Piece>();
+  GP.chunk_off = ctx->chunk_off.as<u64>();
+  GP.arena = ctx->arena.as<u8>();
+  GP.out = out.blob;
+  GP.out_cap = out.blob_size;
+  GP.encoding = job.encoding;
+  GP.n_units = n_units;
+  GP.err = d_err;
+  time_begin(ctx, KT_GATHER);
+  k_gather_chunks<<<n_units, 256, 0, st>>>(GP);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (!job.plain) {
+    out.dac_off.resize(2 * (size_t)n_slices);
+    u64 off = 0;
+    for (u32 i = 0; i < 2 * n_slices; i++) { out.dac_off[i] = off; off += out.dac_pieces[i].size; }
+    out.dac_blob_size = off;
+    CK(cudaMalloc(&out.dac_blob, off + 16));
+    ctx->query_aux.reserve(sizeof(u64) * 2 * n_slices);
+    CK(cudaMemcpyAsync(ctx->query_aux.p, out.dac_off.data(), sizeof(u64) * 2 * n_slices, cudaMemcpyHostToDevice, st));
+    GatherDacParams DP;
+    DP.pieces = ctx->pieces.as<Piece>() + n_pieces;
+    DP.dst_off = ctx->query_aux.as<u64>();
+    DP.arena = ctx->arena.as<u8>();
+    DP.out = out.dac_blob;
+    k_gather_dacs<<<2 * n_slices, 256, 0, st>>>(DP);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  time_end(ctx, KT_GATHER);
+  CK(cudaMemcpyAsync(head_buf.data(), ctx->small.p, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  time_collect(ctx, KT_GATHER);
+  u32 flags;
+  memcpy(&flags, head_buf.data(), 4);
+  std::string msg;
+  int32_t code = status_from_flags(flags, msg);
+  if (code != DCDF_OK) throw ApiFail{code, msg};
+}
+
+void copy_out(dcdf_ctx* ctx, const uint8_t* dev_src, uint64_t n, uint8_t* dst, uint64_t cap, int32_t mem) {
+  if (!dst) api_fail(DCDF_ERR_BAD_ARG, "null destination");
+  if (cap < n) api_fail(DCDF_ERR_BAD_ARG, "destination too small: need %llu bytes", (unsigned long long)n);
+  if (n == 0) return;
+  CK(cudaMemcpyAsync(dst, dev_src, n, mem == DCDF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace
+
+// ===================================================================================== context
+extern "C" {
+
+int32_t dcdf_abi_version(void) { return DCDF_ABI_VERSION; }
+
+int32_t dcdf_ctx_create(int32_t device, dcdf_ctx** out) {
+  if (!out) return DCDF_ERR_BAD_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0 || device < 0 || device >= n) {
+    cudaGetLastError();
+    return DCDF_ERR_CUDA;  // no CPU fallback
+  }
+  dcdf_ctx* ctx = new dcdf_ctx();
+  ctx->device = device;
+  try {
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (auto& ev : ctx->ev) CK(cudaEventCreate(&ev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+  } catch (const CudaFail&) {
+    delete ctx;
+    cudaGetLastError();
+    return DCDF_ERR_CUDA;
+  }
+  *out = ctx;
+  return DCDF_OK;
+}
+
+int32_t dcdf_ctx_destroy(dcdf_ctx* ctx) {
+  if (!ctx) return DCDF_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->input_copy, &ctx->units, &ctx->ustats, &ctx->istats, &ctx->slices, &ctx->sstate, &ctx->tbl_scratch,
+                    &ctx->order, &ctx->pieces, &ctx->results, &ctx->stored, &ctx->chunk_off, &ctx->arena, &ctx->small,
+                    &ctx->exact, &ctx->query_in, &ctx->query_out, &ctx->query_aux};
+  for (auto* b : bufs) b->release();
+  ctx->pin.release();
+  ctx->pin2.release();
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return DCDF_OK;
+}
+
+int32_t dcdf_ctx_set_stream(dcdf_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return DCDF_ERR_BAD_ARG;
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return DCDF_OK;
+}
+
+int32_t dcdf_ctx_synchronize(dcdf_ctx* ctx) {
+  return guarded(ctx, [&] { CK(cudaStreamSynchronize(ctx->stream)); });
+}
+
+const char* dcdf_last_error(const dcdf_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+uint64_t dcdf_ctx_launch_count(const dcdf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int32_t dcdf_ctx_last_kernel_ms(const dcdf_ctx* ctx, int32_t which, float* ms) {
+  if (!ctx || !ms || which < 0 || which >= KT_COUNT) return DCDF_ERR_BAD_ARG;
+  *ms = ctx->kernel_ms[which];
+  return DCDF_OK;
+}
+
+// ===================================================================================== a1 / a2
+// Tile an arbitrary [T,R,C] array into <=64x64 units that span all instants (statistics only).
+static void tile_units(const dcdf_array3* a, std::vector<EncUnit>& units) {
+  const int64_t rows = a->shape[1], cols = a->shape[2];
+  for (int64_t top = 0; top < rows; top += 64)
+    for (int64_t left = 0; left < cols; left += 64) {
+      EncUnit u;
+      memset(&u, 0, sizeof u);
+      u.base = top * a->strides[1] + left * a->strides[2];
+      u.rows = (int)std::min<int64_t>(64, rows - top);
+      u.cols = (int)std::min<int64_t>(64, cols - left);
+      u.instants = (int)a->shape[0];
+      u.row0 = (int)top; u.col0 = (int)left;
+      units.push_back(u);
+    }
+}
+
+static void run_unit_stats(dcdf_ctx* ctx, const dcdf_array3* a, const void* dev, const std::vector<EncUnit>& units) {
+  const u32 n_units = (u32)units.size();
+  ctx->units.reserve(sizeof(EncUnit) * n_units);
+  ctx->ustats.reserve(sizeof(UnitStats) * n_units);
+  ctx->istats.reserve(sizeof(InstStats) * (size_t)n_units * (size_t)a->shape[0]);
+  CK(cudaMemcpyAsync(ctx->units.p, units.data(), sizeof(EncUnit) * n_units, cudaMemcpyHostToDevice, ctx->stream));
+  StatParams SP;
+  SP.data = dev;
+  SP.stride_t = a->strides[0]; SP.stride_r = a->strides[1]; SP.stride_c = a->strides[2];
+  SP.units = ctx->units.as<EncUnit>();
+  SP.n_units = n_units;
+  SP.t_max = (u32)a->shape[0];
+  SP.ustats = ctx->ustats.as<UnitStats>();
+  SP.istats = ctx->istats.as<InstStats>();
+  switch (a->encoding) {
+    case DCDF_ENC_F32: launch_stats<float, true>(ctx, SP); break;
+    case DCDF_ENC_F64: launch_stats<double, true>(ctx, SP); break;
+    case DCDF_ENC_I32: launch_stats<int32_t, false>(ctx, SP); break;
+    default: launch_stats<i64, false>(ctx, SP); break;
+  }
+}
+
+int32_t dcdf_suggest_fraction(dcdf_ctx* ctx, const dcdf_array3* a, int32_t* kind, int32_t* bits) {
+  return guarded(ctx, [&] {
+    validate_array(a);
+    if (!kind || !bits) api_fail(DCDF_ERR_BAD_ARG, "null out");
+    if (a->encoding != DCDF_ENC_F32 && a->encoding != DCDF_ENC_F64) api_fail(DCDF_ERR_BAD_ARG, "suggest_fraction needs a float array");
+    if (a->shape[0] > 0x7fffffff) api_fail(DCDF_ERR_BAD_ARG, "too many instants");
+    cudaStream_t st = ctx->stream;
+    const void* dev = stage_input(ctx, a);
+    std::vector<EncUnit> units;
+    tile_units(a, units);
+    run_unit_stats(ctx, a, dev, units);
+    const u32 n_units = (u32)units.size();
+    ctx->slices.reserve(sizeof(SliceDesc));
+    ctx->sstate.reserve(sizeof(SliceState));
+    ctx->small.reserve(256);
+    SliceDesc sd;
+    memset(&sd, 0, sizeof sd);
+    sd.instants = (int)a->shape[0]; sd.n_units = n_units;
+    CK(cudaMemcpyAsync(ctx->slices.p, &sd, sizeof sd, cudaMemcpyHostToDevice, st));
+    FinalizeParams FP;
+    memset(&FP, 0, sizeof FP);
+    FP.slices = ctx->slices.as<SliceDesc>();
+    FP.state = ctx->sstate.as<SliceState>();
+    FP.ustats = ctx->ustats.as<UnitStats>();
+    FP.encoding = a->encoding;
+    FP.compute_bits = 1;
+    k_finalize_phase1<<<1, 256, 0, st>>>(FP, 1);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    SliceState hs;
+    CK(cudaMemcpyAsync(&hs, ctx->sstate.p, sizeof hs, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hs.err & EF_OVERFLOW) api_fail(DCDF_ERR_OVERFLOW, "value too large for fixed point (fixed.rs:130)");
+    if (!hs.need_exact) { *kind = hs.sug_round; *bits = hs.sug_bits; return; }
+    ctx->exact.reserve(64);
+    i64 t0 = 0;
+    int vals[5] = {(int)a->shape[0], 1, hs.maxfb, 0, 0};  // instants, need, maxfb, f, round
+    i64* d_t0 = ctx->exact.as<i64>();
+    int* d_vals = reinterpret_cast<int*>(d_t0 + 1);
+    CK(cudaMemcpyAsync(d_t0, &t0, sizeof t0, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_vals, vals, sizeof vals, cudaMemcpyHostToDevice, st));
+    ExactParams XP;
+    XP.data = dev;
+    XP.stride_t = a->strides[0]; XP.stride_r = a->strides[1]; XP.stride_c = a->strides[2];
+    XP.rows = a->shape[1]; XP.cols = a->shape[2];
+    XP.slice_t0 = d_t0; XP.slice_instants = d_vals; XP.slice_need = d_vals + 1; XP.slice_maxfb = d_vals + 2;
+    XP.slice_f = d_vals + 3; XP.slice_round = d_vals + 4;
+    dim3 grid((unsigned)(4 * ctx->sm_count), 1);
+    if (a->encoding == DCDF_ENC_F32) k_fraction_exact<float><<<grid, 256, 0, st>>>(XP, 1);
+    else k_fraction_exact<double><<<grid, 256, 0, st>>>(XP, 1);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaMemcpyAsync(vals, d_vals, sizeof vals, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *kind = vals[4] ? 1 : 0;
+    *bits = vals[4] ? hs.maxfb : vals[3];
+  });
+}
+
+int32_t dcdf_min_max(dcdf_ctx* ctx, const dcdf_array3* a, int32_t fractional_bits, int32_t round, int64_t* min_out,
+                     int64_t* max_out) {
+  return guarded(ctx, [&] {
+    validate_array(a);
+    if (!min_out || !max_out) api_fail(DCDF_ERR_BAD_ARG, "null out");
+    if (a->shape[0] > 0x7fffffff) api_fail(DCDF_ERR_BAD_ARG, "too many instants");
+    cudaStream_t st = ctx->stream;
+    const void* dev = stage_input(ctx, a);
+    std::vector<EncUnit> units;
+    tile_units(a, units);
+    run_unit_stats(ctx, a, dev, units);
+    const int T = (int)a->shape[0];
+    ctx->query_out.reserve(sizeof(i64) * 2 * (size_t)T);
+    ctx->small.reserve(256);
+    CK(cudaMemsetAsync(ctx->small.p, 0, 64, st));
+    RegionMinMaxParams RP;
+    RP.units = ctx->units.as<EncUnit>();
+    RP.n_units = (u32)units.size();
+    RP.istats = ctx->istats.as<InstStats>();
+    RP.t_max = (u32)T;
+    RP.region_cols = a->shape[2];
+    RP.encoding = a->encoding; RP.bits = fractional_bits; RP.round = round;
+    RP.instants = T;
+    RP.out_min = ctx->query_out.as<i64>();
+    RP.out_max = RP.out_min + T;
+    RP.err = ctx->small.as<u32>();
+    k_region_minmax<<<(T + 127) / 128, 128, 0, st>>>(RP);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    u32 flags = 0;
+    CK(cudaMemcpyAsync(min_out, RP.out_min, sizeof(i64) * T, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(max_out, RP.out_max, sizeof(i64) * T, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&flags, RP.err, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::string msg;
+    const int32_t code = status_from_flags(flags, msg);
+    if (code != DCDF_OK) throw ApiFail{code, msg};
+  });
+}
+
+// ===================================================================================== Chunk::build
+int32_t dcdf_chunk_build(dcdf_ctx* ctx, const dcdf_array3* a, int32_t k, int32_t fractional_bits, int32_t round,
+                         dcdf_chunk** out, dcdf_build_stats* stats) {
+  return guarded(ctx, [&] {
+    if (!out) api_fail(DCDF_ERR_BAD_ARG, "null out");
+    *out = nullptr;
+    validate_array(a);
+    if (k != 2) api_fail(DCDF_ERR_BAD_ARG, "only k = 2 is supported (dataset.rs:848 hard-codes it)");
+    if (fractional_bits < 0 || fractional_bits > 62) api_fail(DCDF_ERR_BAD_ARG, "fractional_bits out of range");
+    const int64_t rows = a->shape[1], cols = a->shape[2];
+    const int64_t longest = std::max(rows, cols);
+    if (longest < 2) api_fail(DCDF_ERR_BAD_ARG, "1x1 rasters have an empty nodemap (snapshot.rs:166)");
+    const uint32_t L = levels_for(longest, 2);
+    if (L > 6) api_fail(DCDF_ERR_BAD_ARG, "Chunk::build on the GPU handles sides up to 64; use dcdf_superchunk_build for larger rasters");
+    EncodeJob job;
+    job.dev_data = stage_input(ctx, a);
+    job.encoding = a->encoding;
+    for (int i = 0; i < 3; i++) job.strides[i] = a->strides[i];
+    job.rows = rows; job.cols = cols;
+    job.plain = 1;
+    job.req_bits = fractional_bits;
+    job.round = round ? 1 : 0;
+    job.t_max = (uint32_t)a->shape[0];
+    job.input_bytes = (size_t)a->shape[0] * rows * cols * elem_size(a->encoding);
+    EncUnit u;
+    memset(&u, 0, sizeof u);
+    u.base = 0; u.rows = (int)rows; u.cols = (int)cols; u.instants = (int)a->shape[0];
+    u.lo = 6 - (int)L;
+    job.units.push_back(u);
+    SliceDesc sd;
+    memset(&sd, 0, sizeof sd);
+    sd.t0 = 0; sd.instants = (int)a->shape[0]; sd.unit_base = 0; sd.n_units = 1;
+    job.slices.push_back(sd);
+    job.table_len.push_back(0);
+    EncodeOut eo;
+    run_encode(ctx, job, eo, true);
+    dcdf_chunk* c = new dcdf_chunk();
+    c->device = ctx->device;
+    c->bytes = eo.blob;
+    c->size = eo.blob_size;
+    c->owner = true;
+    for (int i = 0; i < 3; i++) c->shape[i] = a->shape[i];
+    c->encoding = a->encoding;
+    c->fractional_bits = eo.units[0].bits;
+    c->n_blocks = eo.results[0].snapshots;
+    uint32_t run = 0;
+    for (size_t i = 0; i < eo.pieces.size(); i++) {
+      if (eo.pieces[i].kind == 1u && i > 0) { c->block_instants.push_back(run); run = 0; }
+      run++;
+    }
+    c->block_instants.push_back(run);
+    if (stats) {
+      stats->size = eo.results[0].bytes;
+      stats->elided = stats->local = stats->external = 0;
+      stats->snapshots = eo.results[0].snapshots;
+      stats->logs = eo.results[0].logs;
+    }
+    *out = c;
+  });
+}
+
+int32_t dcdf_chunk_free(dcdf_chunk* c) {
+  if (!c) return DCDF_OK;
+  cudaSetDevice(c->device);
+  if (c->dir) free_chunk_meta(c->dir);
+  if (c->owner && c->bytes) cudaFree(c->bytes);
+  delete c;
+  return DCDF_OK;
+}
+
+int32_t dcdf_chunk_size(const dcdf_chunk* c, uint64_t* len) {
+  if (!c || !len) return DCDF_ERR_BAD_ARG;
+  *len = c->size;
+  return DCDF_OK;
+}
+
+int32_t dcdf_chunk_bytes(dcdf_ctx* ctx, const dcdf_chunk* c, uint8_t* dst, uint64_t cap, int32_t mem) {
+  return guarded(ctx, [&] {
+    if (!c) api_fail(DCDF_ERR_BAD_ARG, "null chunk");
+    copy_out(ctx, c->bytes, c->size, dst, cap, mem);
+  });
+}
+
+int32_t dcdf_chunk_info(const dcdf_chunk* c, int64_t shape[3], int32_t* encoding, int32_t* fractional_bits, uint32_t* n_blocks) {
+  if (!c) return DCDF_ERR_BAD_ARG;
+  if (shape) for (int i = 0; i < 3; i++) shape[i] = c->shape[i];
+  if (encoding) *encoding = c->encoding;
+  if (fractional_bits) *fractional_bits = c->fractional_bits;
+  if (n_blocks) *n_blocks = c->n_blocks;
+  return DCDF_OK;
+}
+
+int32_t dcdf_chunk_block_instants(dcdf_ctx* ctx, const dcdf_chunk* c, uint32_t* out) {
+  return guarded(ctx, [&] {
+    if (!c || !out) api_fail(DCDF_ERR_BAD_ARG, "null argument");
+    if (c->block_instants.size() != c->n_blocks) api_fail(DCDF_ERR_BAD_FORMAT, "block table missing");
+    for (size_t i = 0; i < c->block_instants.size(); i++) out[i] = c->block_instants[i];
+  });
+}
+
+// ===================================================================================== Superchunk::build
+int32_t dcdf_superchunk_build(dcdf_ctx* ctx, const dcdf_array3* a, const uint32_t* levels, uint32_t n_levels, int32_t k,
+                              int32_t fractional_bits, int32_t round, int32_t compute_bits, int64_t chunk_size,
+                              dcdf_superchunk** out) {
+  return guarded(ctx, [&] {
+    if (!out) api_fail(DCDF_ERR_BAD_ARG, "null out");
+    *out = nullptr;
+    validate_array(a);
+    if (k != 2) api_fail(DCDF_ERR_BAD_ARG, "only k = 2 is supported (dataset.rs:848 hard-codes it)");
+    if (!levels || n_levels < 2) api_fail(DCDF_ERR_BAD_LEVELS, "need at least two k2_levels entries");
+    if (fractional_bits < 0 || fractional_bits > 62) api_fail(DCDF_ERR_BAD_ARG, "fractional_bits out of range");
+    const int64_t T = a->shape[0], rows = a->shape[1], cols = a->shape[2];
+    const uint32_t total_levels = levels_for(std::max(rows, cols), 2);
+    uint32_t user_levels = 0;
+    for (uint32_t i = 0; i < n_levels; i++) user_levels += levels[i];
+    if (user_levels != total_levels)
+      api_fail(DCDF_ERR_BAD_LEVELS, "Need %u tree levels to encode array, but %u levels passed in (superchunk.rs:105-110)", total_levels, user_levels);
+    if (n_levels != 2) api_fail(DCDF_ERR_BAD_ARG, "nested superchunks (more than two k2_levels entries) are not built on the GPU yet");
+    if (levels[1] > 6) api_fail(DCDF_ERR_BAD_ARG, "leaf subchunks larger than 64x64 are not built on the GPU yet");
+    const int64_t sidelen = (int64_t)1 << total_levels;
+    const int64_t subsidelen = (int64_t)1 << levels[0];
+    const int64_t chunks_sidelen = sidelen / subsidelen;
+    if (chunks_sidelen < 2 && false) api_fail(DCDF_ERR_BAD_ARG, "unreachable");
+    const int64_t cs = chunk_size > 0 ? chunk_size : T;
+    const uint32_t n_slices = (uint32_t)((T + cs - 1) / cs);
+    const uint32_t n_slots = (uint32_t)(subsidelen * subsidelen);
+
+    EncodeJob job;
+    job.dev_data = stage_input(ctx, a);
+    job.encoding = a->encoding;
+    for (int i = 0; i < 3; i++) job.strides[i] = a->strides[i];
+    job.rows = rows; job.cols = cols;
+    job.plain = 0;
+    job.req_bits = fractional_bits;
+    job.round = round ? 1 : 0;
+    job.compute_bits = compute_bits ? 1 : 0;
+    job.n_slots = n_slots;
+    job.t_max = (uint32_t)std::min<int64_t>(cs, T);
+    job.input_bytes = (size_t)T * rows * cols * elem_size(a->encoding);
+    const int lo = 6 - (int)levels[1];
+    std::vector<int32_t> slot_unit((size_t)n_slices * n_slots, -1);
+    for (uint32_t s = 0; s < n_slices; s++) {
+      const int64_t t0 = (int64_t)s * cs, t1 = std::min<int64_t>(t0 + cs, T);
+      SliceDesc sd;
+      memset(&sd, 0, sizeof sd);
+      sd.t0 = t0; sd.instants = (int)(t1 - t0); sd.unit_base = (uint32_t)job.units.size();
+      for (int64_t r = 0; r < subsidelen; r++) {
+        const int64_t top = r * chunks_sidelen;
+        if (top >= rows) break;
+        const int64_t bottom = std::min(top + chunks_sidelen, rows);
+        for (int64_t c = 0; c < subsidelen; c++) {
+          const int64_t left = c * chunks_sidelen;
+          if (left >= cols) break;
+          const int64_t right = std::min(left + chunks_sidelen, cols);
+          EncUnit u;
+          memset(&u, 0, sizeof u);
+          u.base = t0 * a->strides[0] + top * a->strides[1] + left * a->strides[2];
+          u.rows = (int)(bottom - top); u.cols = (int)(right - left); u.instants = sd.instants;
+          u.lo = lo;
+          u.slot = (uint32_t)(r * subsidelen + c);
+          u.row0 = (int)top; u.col0 = (int)left;
+          slot_unit[(size_t)s * n_slots + u.slot] = (int32_t)job.units.size();
+          job.units.push_back(u);
+        }
+      }
+      sd.n_units = (uint32_t)job.units.size() - sd.unit_base;
+      job.slices.push_back(sd);
+      job.table_len.push_back((uint64_t)sd.instants * n_slots);
+    }
+    // a 1x1 leaf subchunk cannot be a Chunk (snapshot.rs:166); it can only appear elided
+    EncodeOut eo;
+    run_encode(ctx, job, eo, false);
+
+    dcdf_superchunk* sc = new dcdf_superchunk();
+    sc->device = ctx->device;
+    sc->encoding = a->encoding;
+    for (int i = 0; i < 3; i++) sc->shape[i] = a->shape[i];
+    sc->chunk_size = cs;
+    sc->n_slots = n_slots;
+    sc->units = std::move(eo.units);
+    sc->stored = std::move(eo.stored);
+    sc->chunk_off = std::move(eo.chunk_off);
+    sc->results = std::move(eo.results);
+    sc->slot_unit = std::move(slot_unit);
+    sc->chunk_blob = eo.blob; sc->chunk_blob_size = eo.blob_size;
+    sc->dac_blob = eo.dac_blob; sc->dac_blob_size = eo.dac_blob_size;
+    sc->tbl_max = eo.tbl_max; sc->tbl_min = eo.tbl_min; sc->tbl_len = eo.tbl_total;
+    const bool is_float = a->encoding == DCDF_ENC_F32 || a->encoding == DCDF_ENC_F64;
+    for (uint32_t s = 0; s < n_slices; s++) {
+      dcdf_superchunk::Slice sl;
+      memset(&sl.info, 0, sizeof sl.info);
+      const SliceDesc& sd = job.slices[s];
+      sl.t0 = sd.t0; sl.unit_base = sd.unit_base; sl.n_units = sd.n_units;
+      sl.table_base = sd.table_base;
+      sl.info.shape[0] = sd.instants; sl.info.shape[1] = rows; sl.info.shape[2] = cols;
+      sl.info.sidelen = sidelen; sl.info.chunks_sidelen = chunks_sidelen; sl.info.subsidelen = subsidelen;
+      sl.info.levels = levels[0];
+      sl.info.encoding = a->encoding;
+      sl.info.fractional_bits = is_float ? eo.states[s].bits : 0;
+      sl.info.n_refs = n_slots;
+      sl.dac_off[0] = eo.dac_off[2 * s]; sl.dac_off[1] = eo.dac_off[2 * s + 1];
+      sl.dac_size[0] = eo.dac_pieces[2 * s].size; sl.dac_size[1] = eo.dac_pieces[2 * s + 1].size;
+      sl.info.max_dac_bytes = sl.dac_size[0]; sl.info.min_dac_bytes = sl.dac_size[1];
+      sl.chunk_blob_off = sc->chunk_off[sd.unit_base];
+      sl.info.chunk_bytes = sc->chunk_off[sd.unit_base + sd.n_units] - sc->chunk_off[sd.unit_base];
+      dcdf_build_stats& bs = sl.info.stats;
+      uint32_t stored = 0;
+      for (uint32_t i = 0; i < sd.n_units; i++) {
+        const uint32_t u = sd.unit_base + i;
+        if (!sc->stored[u]) continue;
+        stored++;
+        bs.snapshots += sc->results[u].snapshots;
+        bs.logs += sc->results[u].logs;
+      }
+      bs.external = stored;
+      bs.local = 0;
+      bs.elided = n_slots - stored;
+      bs.size = sl.info.chunk_bytes + sl.dac_size[0] + sl.dac_size[1];
+      sc->slices.push_back(sl);
+    }
+    *out = sc;
+  });
+}
+
+int32_t dcdf_superchunk_free(dcdf_superchunk* sc) {
+  if (!sc) return DCDF_OK;
+  cudaSetDevice(sc->device);
+  if (sc->chunk_blob) cudaFree(sc->chunk_blob);
+  if (sc->dac_blob) cudaFree(sc->dac_blob);
+  if (sc->tbl_max) cudaFree(sc->tbl_max);
+  if (sc->tbl_min) cudaFree(sc->tbl_min);
+  if (sc->dev_meta) free_super_meta(sc->dev_meta);
+  if (sc->dir) cudaFree(sc->dir);
+  delete sc;
+  return DCDF_OK;
+}
+
+int32_t dcdf_superchunk_count(const dcdf_superchunk* sc, uint32_t* n) {
+  if (!sc || !n) return DCDF_ERR_BAD_ARG;
+  *n = (uint32_t)sc->slices.size();
+  return DCDF_OK;
+}
+
+int32_t dcdf_superchunk_get_info(const dcdf_superchunk* sc, uint32_t slice, dcdf_superchunk_info* info) {
+  if (!sc || !info || slice >= sc->slices.size()) return DCDF_ERR_BAD_ARG;
+  *info = sc->slices[slice].info;
+  return DCDF_OK;
+}
+
+int32_t dcdf_superchunk_refs(dcdf_ctx* ctx, const dcdf_superchunk* sc, uint32_t slice, int32_t* kinds, uint64_t* chunk_off,
+                             uint64_t* chunk_size, int32_t* chunk_bits) {
+  return guarded(ctx, [&] {
+    if (!sc || slice >= sc->slices.size()) api_fail(DCDF_ERR_BAD_ARG, "bad slice");
+    const auto& sl = sc->slices[slice];
+    for (uint32_t i = 0; i < sc->n_slots; i++) {
+      const int32_t u = sc->slot_unit[(size_t)slice * sc->n_slots + i];
+      const bool st = u >= 0 && sc->stored[u];
+      if (kinds) kinds[i] = st ? DCDF_REF_EXTERNAL : DCDF_REF_ELIDED;
+      if (chunk_off) chunk_off[i] = st ? sc->chunk_off[u] - sl.chunk_blob_off : 0;
+      if (chunk_size) chunk_size[i] = st ? sc->results[u].bytes : 0;
+      if (chunk_bits) chunk_bits[i] = st ? sc->units[u].bits : 0;
+    }
+  });
+}
+
+int32_t dcdf_superchunk_bytes(dcdf_ctx* ctx, const dcdf_superchunk* sc, uint32_t slice, int32_t which, uint8_t* dst,
+                              uint64_t cap, int32_t mem) {
+  return guarded(ctx, [&] {
+    if (!sc || slice >= sc->slices.size() || which < 0 || which > 2) api_fail(DCDF_ERR_BAD_ARG, "bad slice / which");
+    const auto& sl = sc->slices[slice];
+    if (which == 0) copy_out(ctx, sc->chunk_blob + sl.chunk_blob_off, sl.info.chunk_bytes, dst, cap, mem);
+    else copy_out(ctx, sc->dac_blob + sl.dac_off[which - 1], sl.dac_size[which - 1], dst, cap, mem);
+  });
+}
+
+int32_t dcdf_superchunk_total_bytes(const dcdf_superchunk* sc, uint64_t* n) {
+  if (!sc || !n) return DCDF_ERR_BAD_ARG;
+  *n = sc->chunk_blob_size + sc->dac_blob_size;
+  return DCDF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+// host.hpp -- host-side plumbing shared by the C-ABI translation units (context, buffers, handles).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dcdf_cuda.h"
+#include "common.cuh"
+#include "encode_tile.cuh"
+
+namespace dcdf {
+
+struct CudaFail {
+  std::string msg;
+};
+struct ApiFail {
+  int32_t code;
+  std::string msg;
+};
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+  if (e != cudaSuccess) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+    throw CudaFail{buf};
+  }
+}
+#define CK(x) ::dcdf::cuda_check((x), #x, __FILE__, __LINE__)
+[[noreturn]] inline void api_fail(int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw ApiFail{code, buf};
+}
+
+// Grow-only device buffer owned by a context (scratch that survives between calls).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t n) {
+    if (n <= cap) return;
+    if (p) CK(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 256;
+    CK(cudaMalloc(&p, want));
+    cap = want;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+// Pinned host staging buffer.
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t n) {
+    if (n <= cap) return;
+    if (p) CK(cudaFreeHost(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 256;
+    CK(cudaMallocHost(&p, want));
+    cap = want;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+enum { KT_ENCODE = 0, KT_STATS = 1, KT_GATHER = 2, KT_WINDOW = 3, KT_CELL = 4, KT_SEARCH = 5, KT_COUNT = 6 };
+
+}  // namespace dcdf
+
+struct dcdf_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  uint64_t launches = 0;
+  float kernel_ms[dcdf::KT_COUNT] = {0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev[2 * dcdf::KT_COUNT] = {};
+  int sm_count = 148;
+  // scratch
+  dcdf::DevBuf input_copy, units, ustats, istats, slices, sstate, tbl_scratch, order, pieces, results, stored, chunk_off,
+      arena, small, exact, query_in, query_out, query_aux;
+  dcdf::PinBuf pin, pin2;
+  size_t arena_hint = 0;
+};
+
+// One Chunk resident on the device.  `bytes` may point into a superchunk's blob (owner == false).
+struct dcdf_chunk {
+  int device = 0;
+  uint8_t* bytes = nullptr;
+  uint64_t size = 0;
+  bool owner = true;
+  int64_t shape[3] = {0, 0, 0};
+  int32_t encoding = 0, fractional_bits = 0;
+  uint32_t n_blocks = 0;
+  // decode directory (built lazily / at open): one entry per instant
+  void* dir = nullptr;  // device: InstantDir[shape[0]]
+  std::vector<uint32_t> block_instants;
+};
+
+struct dcdf_superchunk {
+  int device = 0;
+  int32_t encoding = 0;
+  int64_t shape[3] = {0, 0, 0};  // whole array
+  int64_t chunk_size = 0;
+  struct Slice {
+    dcdf_superchunk_info info;
+    int64_t t0;
+    uint32_t unit_base, n_units;
+    uint64_t chunk_blob_off, dac_off[2], dac_size[2];
+    uint64_t table_base;
+  };
+  std::vector<Slice> slices;
+  uint32_t n_slots = 0;
+  // host mirrors (small)
+  std::vector<dcdf::EncUnit> units;
+  std::vector<uint8_t> stored;
+  std::vector<uint64_t> chunk_off;  // [n_units + 1] into chunk_blob
+  std::vector<dcdf::UnitResult> results;
+  std::vector<int32_t> slot_unit;   // [n_slices][n_slots] -> unit index or -1
+  // device blobs
+  uint8_t* chunk_blob = nullptr;
+  uint64_t chunk_blob_size = 0;
+  uint8_t* dac_blob = nullptr;
+  uint64_t dac_blob_size = 0;
+  int64_t* tbl_max = nullptr;  // fixed-point max table (values of elided subchunks), all slices
+  int64_t* tbl_min = nullptr;
+  uint64_t tbl_len = 0;
+  void* dir = nullptr;         // device decode directory over all stored units
+  void* dev_meta = nullptr;    // device copies of unit / slot tables for the query kernels
+};

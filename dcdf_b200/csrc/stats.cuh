@@ -1,0 +1,569 @@
+// stats.cuh -- the scan passes that precede encoding (one CTA per subchunk x time-slice unit):
+//   suggest_fraction                      fixed.rs:96-159
+//   MMBuffer3F32::compute_fractional_bits mmbuffer.rs:596-613
+//   MMBuffer3::min_max / min_max_float    mmbuffer.rs:366-395, 434-499
+// and the per-slice finalisation of Superchunk::build (superchunk.rs:127-198): parent/sub fractional
+// bits, fixed-point (min,max) tables in instant-major order, elision flags, narrow/wide work lists.
+#pragma once
+#include "common.cuh"
+#include "encode_tile.cuh"
+
+namespace dcdf {
+
+constexpr int STAT_THREADS = 256;
+
+struct UnitStats {
+  double vmax;      // max over non-NaN values (floats) -- suggest_fraction uses max, not max-abs
+  double vneg;      // most negative value (<= 0), 0 if none
+  i64 imax, imin;   // integer encodings: exact extrema over the unit
+  int has_value;    // any non-NaN value
+  int frac_nonneg;  // max fractional bits over values >= 0
+  int frac_neg;     // max fractional bits over values < 0
+  int nonfinite;    // saw +-inf
+  int sug_round;    // unit-level suggest_fraction: 1 = Round(bits), 0 = Precise(bits)
+  int sug_bits;
+  int sug_err;      // EF_* raised while computing the suggestion (whole part too large)
+};
+
+// per (unit, instant): raw extrema as 64-bit patterns (double for float inputs, i64 for integers)
+struct InstStats {
+  u64 mn, mx;
+  u32 first;  // tile-local row-major index (r * cols + c) of the first non-NaN cell, 0xffffffff if none
+  u32 last;   // 1 + index of the last NaN cell, 0 if none
+  // all NaN  <=> first == 0xffffffff ; NaN quirk (mmbuffer.rs:485-487: a NaN after the first non-NaN makes
+  // min NaN) <=> last > first
+  DCDF_DEVINL u32 flags() const {
+    const bool all_nan = first == 0xffffffffu;
+    return (all_nan ? 1u : 0u) | ((!all_nan && last > first) ? 2u : 0u);
+  }
+};
+
+template <typename T>
+struct FloatBits;
+template <>
+struct FloatBits<int32_t> {
+  static DCDF_DEVINL int fracbits(int32_t) { return 0; }
+};
+template <>
+struct FloatBits<i64> {
+  static DCDF_DEVINL int fracbits(i64) { return 0; }
+};
+template <>
+struct FloatBits<float> {
+  static DCDF_DEVINL int fracbits(float v) {
+    u32 b = __float_as_uint(v);
+    int E = (b >> 23) & 0xff;
+    u32 M = b & 0x7fffffu;
+    int e_odd;
+    if (E == 0) {
+      if (M == 0) return 0;
+      e_odd = -149 + (__ffs((int)M) - 1);
+    } else {
+      e_odd = E - 150 + (__ffs((int)(M | 0x800000u)) - 1);
+    }
+    return e_odd < 0 ? -e_odd : 0;
+  }
+};
+template <>
+struct FloatBits<double> {
+  static DCDF_DEVINL int fracbits(double v) {
+    u64 b = (u64)__double_as_longlong(v);
+    int E = (int)((b >> 52) & 0x7ff);
+    u64 M = b & 0xfffffffffffffull;
+    int e_odd;
+    if (E == 0) {
+      if (M == 0) return 0;
+      e_odd = -1074 + (__ffsll((long long)M) - 1);
+    } else {
+      e_odd = E - 1075 + (__ffsll((long long)(M | (1ull << 52))) - 1);
+    }
+    return e_odd < 0 ? -e_odd : 0;
+  }
+};
+
+// whole_bits = 1 + (floor(log2(max)) as usize)  (fixed.rs:126; `as` saturates: NaN / negatives -> 0)
+DCDF_DEVINL int whole_bits_of(double vmax) {
+  if (!(vmax > 0.0)) return 1;
+  int e = ilogb(vmax);
+  return 1 + (e > 0 ? e : 0);
+}
+
+// Evaluate suggest_fraction from a (max, frac_nonneg, frac_neg, most-negative) summary.
+// Returns false when negatives may hit the saturating cast (fixed.rs:150) and an exact pass is needed.
+DCDF_DEVINL bool suggest_from_summary(bool has_value, double vmax, double vneg, int frac_nonneg, int frac_neg, int& round_,
+                                      int& bits, int& err) {
+  err = 0;
+  if (!has_value) { round_ = 0; bits = 0; return true; }  // all NaN -> Precise(0)  (fixed.rs:121-124)
+  int whole = whole_bits_of(vmax);
+  if (whole > 62) { err = EF_OVERFLOW; round_ = 0; bits = 0; return true; }
+  int maxfb = 62 - whole;
+  if (vneg < 0.0 && -vneg >= ldexp(1.0, 63 - maxfb)) return false;  // some negative saturates `as i64`
+  int f = frac_nonneg > frac_neg ? frac_nonneg : frac_neg;
+  if (f > maxfb) { round_ = 1; bits = maxfb; }  // fixed.rs:146-148
+  else { round_ = 0; bits = f; }
+  return true;
+}
+
+struct StatParams {
+  const void* data;
+  i64 stride_t, stride_r, stride_c;
+  const EncUnit* units;
+  u32 n_units;
+  u32 t_max;  // row pitch of the per-instant tables
+  UnitStats* ustats;
+  InstStats* istats;  // [n_units][t_max]
+};
+
+template <typename InT, bool IS_FLOAT>
+__global__ void __launch_bounds__(STAT_THREADS) k_unit_stats(const StatParams P) {
+  const u32 u = blockIdx.x;
+  if (u >= P.n_units) return;
+  const EncUnit unit = P.units[u];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const InT* base = static_cast<const InT*>(P.data) + unit.base;
+  const int rows = unit.rows, cols = unit.cols;
+  const int cells = rows * cols;
+  __shared__ double s_mn[8], s_mx[8];
+  __shared__ i64 s_imn[8], s_imx[8];
+  __shared__ u32 s_first[8], s_last[8];
+  __shared__ int s_i[8][4];
+  __shared__ int s_redo, s_maxfb;
+
+  double vmax = -INFINITY, vneg = 0.0;
+  i64 imax = INT64_MIN, imin = INT64_MAX;
+  int has = 0, fnn = 0, fng = 0, nonfinite = 0;
+
+  for (int inst = 0; inst < unit.instants; inst++) {
+    const InT* p = base + (i64)inst * P.stride_t;
+    double mn = INFINITY, mx = -INFINITY;
+    i64 lmn = INT64_MAX, lmx = INT64_MIN;
+    u32 first = 0xffffffffu, last = 0;  // row-major position (+1 for last) of first non-NaN / last NaN
+    bool any_nan = false;
+    for (int idx = tid; idx < cells; idx += STAT_THREADS) {
+      const int r = idx / cols, c = idx - r * cols;
+      const InT v = __ldg(p + (i64)r * P.stride_r + (i64)c * P.stride_c);
+      if (IS_FLOAT) {
+        const double d = (double)v;
+        if (d != d) {
+          any_nan = true;
+          last = (u32)idx + 1u;  // idx ascends within a thread
+        } else {
+          if (fabs(d) == INFINITY) nonfinite = 1;
+          if (first == 0xffffffffu) first = (u32)idx;
+          mn = fmin(mn, d);
+          mx = fmax(mx, d);
+          const int fb = FloatBits<InT>::fracbits(v);
+          if (d < 0.0) { fng = fb > fng ? fb : fng; vneg = fmin(vneg, d); }
+          else fnn = fb > fnn ? fb : fnn;
+        }
+      } else {
+        const i64 x = (i64)v;
+        lmn = x < lmn ? x : lmn;
+        lmx = x > lmx ? x : lmx;
+      }
+    }
+    (void)any_nan;
+    // warp reduce
+    for (int o = 16; o > 0; o >>= 1) {
+      if (IS_FLOAT) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+      } else {
+        i64 a = __shfl_xor_sync(0xffffffffu, lmn, o), b = __shfl_xor_sync(0xffffffffu, lmx, o);
+        lmn = a < lmn ? a : lmn;
+        lmx = b > lmx ? b : lmx;
+      }
+    }
+    if (lane == 0) {
+      s_mn[warp] = mn; s_mx[warp] = mx; s_first[warp] = first; s_last[warp] = last;
+      s_imn[warp] = lmn; s_imx[warp] = lmx;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      InstStats st;
+      if (IS_FLOAT) {
+        for (int w = 1; w < 8; w++) {
+          mn = fmin(mn, s_mn[w]); mx = fmax(mx, s_mx[w]);
+          first = min(first, s_first[w]); last = max(last, s_last[w]);
+        }
+        const bool all_nan = first == 0xffffffffu;
+        st.first = first; st.last = last;
+        st.mn = (u64)__double_as_longlong(mn);
+        st.mx = (u64)__double_as_longlong(mx);
+        if (!all_nan) { has = 1; vmax = fmax(vmax, mx); }
+      } else {
+        for (int w = 1; w < 8; w++) {
+          lmn = s_imn[w] < lmn ? s_imn[w] : lmn;
+          lmx = s_imx[w] > lmx ? s_imx[w] : lmx;
+        }
+        st.first = 0; st.last = 0;
+        st.mn = (u64)lmn; st.mx = (u64)lmx;
+        imin = lmn < imin ? lmn : imin;
+        imax = lmx > imax ? lmx : imax;
+        has = 1;
+      }
+      P.istats[(size_t)u * P.t_max + inst] = st;
+    }
+    __syncthreads();
+  }
+
+  // unit-level reductions of the thread-local accumulators
+  for (int o = 16; o > 0; o >>= 1) {
+    fnn = max(fnn, __shfl_xor_sync(0xffffffffu, fnn, o));
+    fng = max(fng, __shfl_xor_sync(0xffffffffu, fng, o));
+    nonfinite |= __shfl_xor_sync(0xffffffffu, nonfinite, o);
+    vneg = fmin(vneg, __shfl_xor_sync(0xffffffffu, vneg, o));
+  }
+  if (lane == 0) { s_i[warp][0] = fnn; s_i[warp][1] = fng; s_i[warp][2] = nonfinite; s_mn[warp] = vneg; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; w++) {
+      fnn = max(fnn, s_i[w][0]); fng = max(fng, s_i[w][1]); nonfinite |= s_i[w][2];
+      vneg = fmin(vneg, s_mn[w]);
+    }
+    UnitStats us;
+    us.vmax = vmax; us.vneg = vneg; us.imax = imax; us.imin = imin;
+    us.has_value = has; us.frac_nonneg = fnn; us.frac_neg = fng; us.nonfinite = nonfinite;
+    us.sug_round = 0; us.sug_bits = 0; us.sug_err = 0;
+    int redo = 0;
+    if (IS_FLOAT) {
+      if (!suggest_from_summary(has, vmax, vneg, fnn, fng, us.sug_round, us.sug_bits, us.sug_err)) redo = 1;
+    }
+    P.ustats[u] = us;
+    s_redo = redo;
+    s_maxfb = 62 - whole_bits_of(vmax);
+  }
+  __syncthreads();
+  if (IS_FLOAT && s_redo) {
+    // Exact second pass (rare): some negative value saturates the `as i64` cast of fixed.rs:150, so its
+    // contribution is maxfb - 63 -> 0 bits instead of its own fractional bits.
+    const int maxfb = s_maxfb;
+    const double sat = ldexp(1.0, 63 - maxfb);
+    int f = 0, rnd = 0;
+    for (int inst = 0; inst < unit.instants; inst++) {
+      const InT* p = base + (i64)inst * P.stride_t;
+      for (int idx = tid; idx < cells; idx += STAT_THREADS) {
+        const int r = idx / cols, c = idx - r * cols;
+        const InT v = __ldg(p + (i64)r * P.stride_r + (i64)c * P.stride_c);
+        const double d = (double)v;
+        if (d != d) continue;
+        const int fb = FloatBits<InT>::fracbits(v);
+        if (fb > maxfb) rnd = 1;
+        if (!(d < 0.0 && -d >= sat)) f = fb > f ? fb : f;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      f = max(f, __shfl_xor_sync(0xffffffffu, f, o));
+      rnd |= __shfl_xor_sync(0xffffffffu, rnd, o);
+    }
+    if (lane == 0) { s_i[warp][0] = f; s_i[warp][1] = rnd; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; w++) { f = max(f, s_i[w][0]); rnd |= s_i[w][1]; }
+      P.ustats[u].sug_round = rnd;
+      P.ustats[u].sug_bits = rnd ? maxfb : f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Exact region-level suggest_fraction pass with a known maxfb, launched only when needed (device flag).
+struct ExactParams {
+  const void* data;
+  i64 stride_t, stride_r, stride_c;
+  i64 rows, cols;
+  const i64* slice_t0;       // [n_slices] first instant
+  const int* slice_instants; // [n_slices]
+  const int* slice_need;     // [n_slices] 1 = run
+  const int* slice_maxfb;    // [n_slices]
+  int* slice_f;              // [n_slices] out: max bits (atomicMax)
+  int* slice_round;          // [n_slices] out: any fractional overflow (atomicOr)
+};
+template <typename InT>
+__global__ void __launch_bounds__(256) k_fraction_exact(const ExactParams P, u32 n_slices) {
+  const u32 s = blockIdx.y;
+  if (s >= n_slices || !P.slice_need[s]) return;
+  const int maxfb = P.slice_maxfb[s];
+  const double sat = ldexp(1.0, 63 - maxfb);
+  const i64 n = (i64)P.slice_instants[s] * P.rows * P.cols;
+  const InT* base = static_cast<const InT*>(P.data) + P.slice_t0[s] * P.stride_t;
+  int f = 0, rnd = 0;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    const i64 t = i / (P.rows * P.cols), rem = i - t * P.rows * P.cols;
+    const i64 r = rem / P.cols, c = rem - r * P.cols;
+    const InT v = __ldg(base + t * P.stride_t + r * P.stride_r + c * P.stride_c);
+    const double d = (double)v;
+    if (d != d) continue;
+    const int fb = FloatBits<InT>::fracbits(v);
+    if (fb > maxfb) rnd = 1;
+    if (!(d < 0.0 && -d >= sat)) f = fb > f ? fb : f;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    f = max(f, __shfl_xor_sync(0xffffffffu, f, o));
+    rnd |= __shfl_xor_sync(0xffffffffu, rnd, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&P.slice_f[s], f);
+    if (rnd) atomicOr(&P.slice_round[s], 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Per-slice finalisation (one CTA per slice) for a two-level superchunk: subsidelen^2 slots, in-bounds
+// slots have a unit.  Phase 1 aggregates the slice-level suggestion; phase 2 assigns per-unit bits,
+// fills the (instant-major, slot-minor) fixed-point min/max tables, elision flags and work lists.
+struct SliceDesc {
+  i64 t0;
+  int instants;
+  u32 unit_base;   // first unit of the slice
+  u32 n_units;
+  u64 table_base;  // offset of this slice's tables in tbl_min / tbl_max (instants * n_slots entries)
+};
+struct SliceState {
+  int bits;        // parent fractional bits (after compute_fractional_bits, if requested)
+  int need_exact;  // phase 1 -> exact pass
+  int maxfb;
+  int f_exact, round_exact;
+  int sug_round, sug_bits;  // raw slice-level suggest_fraction result (valid when !need_exact)
+  u32 err;         // EF_*
+  u32 n_elided, n_stored;
+};
+struct FinalizeParams {
+  const SliceDesc* slices;
+  SliceState* state;
+  const EncUnit* units_in;
+  EncUnit* units;          // bits / flags written here
+  const UnitStats* ustats;
+  const InstStats* istats;
+  u32 t_max;
+  u32 n_slots;             // subsidelen^2
+  int encoding;            // DCDF_ENC_*
+  int req_bits, round, compute_bits;
+  int plain;               // 1 = plain Chunk::build units: caller's bits, no tables, no elision
+  i64* tbl_min;
+  i64* tbl_max;
+  u32* order_narrow;
+  u32* order_wide;
+  u32* order_counts;       // [0] narrow, [1] wide
+  u8* stored;              // [n_units_total] 1 = Chunk is built and stored (not elided)
+  u32* err;
+};
+
+__global__ void k_finalize_phase1(const FinalizeParams P, u32 n_slices) {
+  const u32 s = blockIdx.x;
+  if (s >= n_slices) return;
+  const SliceDesc sd = P.slices[s];
+  __shared__ double s_vmax[8], s_vneg[8];
+  __shared__ int s_f[8][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double vmax = -INFINITY, vneg = 0.0;
+  int has = 0, fnn = 0, fng = 0;
+  for (u32 i = tid; i < sd.n_units; i += blockDim.x) {
+    const UnitStats us = P.ustats[sd.unit_base + i];
+    if (us.has_value) { has = 1; vmax = fmax(vmax, us.vmax); }
+    vneg = fmin(vneg, us.vneg);
+    fnn = max(fnn, us.frac_nonneg);
+    fng = max(fng, us.frac_neg);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    vneg = fmin(vneg, __shfl_xor_sync(0xffffffffu, vneg, o));
+    has |= __shfl_xor_sync(0xffffffffu, has, o);
+    fnn = max(fnn, __shfl_xor_sync(0xffffffffu, fnn, o));
+    fng = max(fng, __shfl_xor_sync(0xffffffffu, fng, o));
+  }
+  if (lane == 0) { s_vmax[warp] = vmax; s_vneg[warp] = vneg; s_f[warp][0] = has; s_f[warp][1] = fnn; s_f[warp][2] = fng; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
+      vmax = fmax(vmax, s_vmax[w]); vneg = fmin(vneg, s_vneg[w]);
+      has |= s_f[w][0]; fnn = max(fnn, s_f[w][1]); fng = max(fng, s_f[w][2]);
+    }
+    SliceState st;
+    st.bits = P.req_bits; st.need_exact = 0; st.maxfb = 0; st.f_exact = 0; st.round_exact = 0; st.err = 0;
+    st.n_elided = 0; st.n_stored = 0; st.sug_round = 0; st.sug_bits = 0;
+    const bool is_float = P.encoding == 32 || P.encoding == 64;
+    if (is_float && P.compute_bits) {
+      int rnd, bits, e;
+      if (suggest_from_summary(has, vmax, vneg, fnn, fng, rnd, bits, e)) {
+        st.err |= (u32)e;
+        st.sug_round = rnd; st.sug_bits = bits;
+        if (P.round) st.bits = min(bits, P.req_bits);       // mmbuffer.rs:602-603
+        else { if (rnd) st.err |= EF_PRECISION; st.bits = bits; }  // mmbuffer.rs:605-609
+      } else {
+        st.need_exact = 1;
+        st.maxfb = 62 - whole_bits_of(vmax);
+      }
+    }
+    if (!is_float) st.bits = 0;
+    P.state[s] = st;
+  }
+}
+
+template <typename F>
+DCDF_DEVINL i64 fixed_of_raw(u64 raw, int bits, bool round, u32& err) {
+  return to_fixed_dev<F>((F)__longlong_as_double((long long)raw), bits, round, err);
+}
+
+__global__ void k_finalize_phase2(const FinalizeParams P, u32 n_slices) {
+  const u32 s = blockIdx.x;
+  if (s >= n_slices) return;
+  const SliceDesc sd = P.slices[s];
+  const int tid = threadIdx.x;
+  __shared__ int s_bits;
+  __shared__ u32 s_err;
+  const bool is_float = P.encoding == 32 || P.encoding == 64;
+  if (tid == 0) {
+    SliceState st = P.state[s];
+    if (st.need_exact) {
+      const int rnd = st.round_exact, bits = rnd ? st.maxfb : st.f_exact;
+      if (P.round) st.bits = min(bits, P.req_bits);
+      else { if (rnd) st.err |= EF_PRECISION; st.bits = bits; }
+      P.state[s].bits = st.bits;
+    }
+    s_bits = st.bits;
+    s_err = st.err;
+  }
+  __syncthreads();
+  const int pbits = s_bits;
+  const bool round = P.round != 0;
+  u32 err = 0;
+  // tables default to (0,0): out-of-bounds slots are Elided with (0,0) per instant (superchunk.rs:134-139)
+  i64* tmin = P.plain ? nullptr : P.tbl_min + sd.table_base;
+  i64* tmax = P.plain ? nullptr : P.tbl_max + sd.table_base;
+  const u64 n_tbl = P.plain ? 0 : (u64)sd.instants * P.n_slots;
+  for (u64 i = tid; i < n_tbl; i += blockDim.x) { tmin[i] = 0; tmax[i] = 0; }
+  __syncthreads();
+  u32 n_el = 0, n_st = 0;
+  for (u32 i = tid; i < sd.n_units; i += blockDim.x) {
+    const u32 u = sd.unit_base + i;
+    EncUnit unit = P.units_in[u];
+    const UnitStats us = P.ustats[u];
+    bool can_elide = !P.plain;
+    for (int t = 0; t < sd.instants && !P.plain; t++) {
+      const InstStats is = P.istats[(size_t)u * P.t_max + t];
+      i64 fmn, fmx;
+      if (P.encoding == 32) {
+        // min_max_float NaN quirk: min becomes NaN (-> fixed 0) when a NaN follows the first non-NaN
+        fmn = (is.flags() & 3u) ? 0 : fixed_of_raw<float>(is.mn, pbits, round, err);
+        fmx = (is.flags() & 1u) ? 0 : fixed_of_raw<float>(is.mx, pbits, round, err);
+      } else if (P.encoding == 64) {
+        fmn = (is.flags() & 3u) ? 0 : fixed_of_raw<double>(is.mn, pbits, round, err);
+        fmx = (is.flags() & 1u) ? 0 : fixed_of_raw<double>(is.mx, pbits, round, err);
+      } else {
+        fmn = (i64)is.mn; fmx = (i64)is.mx;
+      }
+      tmin[(u64)t * P.n_slots + unit.slot] = fmn;
+      tmax[(u64)t * P.n_slots + unit.slot] = fmx;
+      can_elide = can_elide && fmn == fmx;  // superchunk.rs:145-147
+    }
+    int flags = P.round ? UF_ROUND : 0;
+    int bits = 0;
+    bool narrow = false;
+    if (can_elide) {
+      flags |= UF_SKIP;
+      n_el++;
+    } else {
+      n_st++;
+      if (is_float) {
+        // sub_buffer.compute_fractional_bits() with the parent's bits as the request (superchunk.rs:167)
+        if (us.nonfinite) err |= EF_NONFINITE;
+        if (P.plain) {
+          bits = pbits;  // Chunk::build uses the buffer's bits as they are (chunk.rs:50,84)
+        } else {
+          err |= (u32)us.sug_err;
+          if (P.round) bits = min(us.sug_bits, pbits);
+          else { if (us.sug_round) err |= EF_PRECISION; bits = us.sug_bits; }
+        }
+        if (us.has_value) {
+          const double lim = ldexp(1.0, 29 - bits);  // |fixed| = 2|v| 2^bits + 1 < 2^30
+          narrow = fabs(us.vmax) < lim && fabs(us.vneg) < lim;
+        } else narrow = true;
+      } else {
+        narrow = us.imax < (i64)0x3fffffff && us.imin > -(i64)0x3fffffff;
+      }
+      if (narrow) flags |= UF_NARROW;
+    }
+    unit.bits = bits;
+    unit.flags = flags;
+    P.units[u] = unit;
+    P.stored[u] = can_elide ? 0 : 1;
+    if (!can_elide) {
+      if (narrow) P.order_narrow[atomicAdd(&P.order_counts[0], 1u)] = u;
+      else P.order_wide[atomicAdd(&P.order_counts[1], 1u)] = u;
+    }
+  }
+  if (n_el) atomicAdd(&P.state[s].n_elided, n_el);
+  if (n_st) atomicAdd(&P.state[s].n_stored, n_st);
+  if (err) atomicOr(&s_err, err);
+  __syncthreads();
+  if (tid == 0 && s_err) { P.state[s].err = s_err; atomicOr(P.err, s_err); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MMBuffer3::min_max over a whole region tiled into units (mmbuffer.rs:366-395): one thread per instant
+// combines the per-tile extrema; the NaN quirk is decided on region row-major positions.
+struct RegionMinMaxParams {
+  const EncUnit* units;
+  u32 n_units;
+  const InstStats* istats;
+  u32 t_max;
+  i64 region_cols;
+  int encoding, bits, round;
+  int instants;
+  i64* out_min;
+  i64* out_max;
+  u32* err;
+};
+__global__ void k_region_minmax(const RegionMinMaxParams P) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.instants) return;
+  const bool is_float = P.encoding == 32 || P.encoding == 64;
+  double mn = INFINITY, mx = -INFINITY;
+  i64 imn = INT64_MAX, imx = INT64_MIN;
+  u64 first = ~0ull, last = 0;
+  for (u32 u = 0; u < P.n_units; u++) {
+    const EncUnit unit = P.units[u];
+    const InstStats is = P.istats[(size_t)u * P.t_max + t];
+    if (is_float) {
+      if (is.first != 0xffffffffu) {
+        mn = fmin(mn, __longlong_as_double((long long)is.mn));
+        mx = fmax(mx, __longlong_as_double((long long)is.mx));
+        const u64 r = is.first / (u32)unit.cols, c = is.first % (u32)unit.cols;
+        const u64 key = ((u64)unit.row0 + r) * (u64)P.region_cols + (u64)unit.col0 + c;
+        first = key < first ? key : first;
+      }
+      if (is.last) {
+        const u32 idx = is.last - 1u;
+        const u64 r = idx / (u32)unit.cols, c = idx % (u32)unit.cols;
+        const u64 key = ((u64)unit.row0 + r) * (u64)P.region_cols + (u64)unit.col0 + c + 1ull;
+        last = key > last ? key : last;
+      }
+    } else {
+      imn = (i64)is.mn < imn ? (i64)is.mn : imn;
+      imx = (i64)is.mx > imx ? (i64)is.mx : imx;
+    }
+  }
+  u32 err = 0;
+  i64 fmn, fmx;
+  if (is_float) {
+    const bool all_nan = first == ~0ull;
+    const bool quirk = !all_nan && last > first;
+    if (P.encoding == 32) {
+      fmn = (all_nan || quirk) ? 0 : to_fixed_dev<float>((float)mn, P.bits, P.round != 0, err);
+      fmx = all_nan ? 0 : to_fixed_dev<float>((float)mx, P.bits, P.round != 0, err);
+    } else {
+      fmn = (all_nan || quirk) ? 0 : to_fixed_dev<double>(mn, P.bits, P.round != 0, err);
+      fmx = all_nan ? 0 : to_fixed_dev<double>(mx, P.bits, P.round != 0, err);
+    }
+  } else {
+    fmn = imn; fmx = imx;
+  }
+  P.out_min[t] = fmn;
+  P.out_max[t] = fmx;
+  if (err) atomicOr(P.err, err);
+}
+
+}  // namespace dcdf
