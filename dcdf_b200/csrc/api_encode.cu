@@ -2,7 +2,9 @@
 // Superchunk::build).  Host logic only orchestrates: every data pass is a kernel in encode_tile.cuh,
 // stats.cuh, gather.cuh.  No CPU fallback exists: without a device every call returns DCDF_ERR_CUDA.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 
 #include "gather.cuh"
 #include "host.hpp"
@@ -136,9 +138,25 @@ void time_collect(dcdf_ctx* ctx, int which) {
   else cudaGetLastError();
 }
 
+// DCDF_TRACE=1 prints host-side phase times of run_encode to stderr (adds stream syncs).
+struct Tracer {
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0;
+  Tracer(cudaStream_t s) : on(getenv("DCDF_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[dcdf trace] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 // The whole encode pipeline for a list of <=64x64 units grouped in slices.
 void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces) {
   cudaStream_t st = ctx->stream;
+  Tracer tr(st);
   const u32 n_units = (u32)job.units.size();
   const u32 n_slices = (u32)job.slices.size();
   if (n_units == 0) api_fail(DCDF_ERR_BAD_ARG, "nothing to encode");
@@ -192,6 +210,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   const u64* d_table_base = reinterpret_cast<const u64*>(ctx->slices.as<SliceDesc>() + n_slices);
   const u64* d_table_len = d_table_base + n_slices;
 
+  tr.mark("scratch + uploads");
   // ---- K1: per-unit statistics
   StatParams SP;
   SP.data = job.dev_data;
@@ -209,6 +228,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     default: launch_stats<i64, false>(ctx, SP); break;
   }
   time_end(ctx, KT_STATS);
+  tr.mark("k_unit_stats");
 
   // ---- K1b: slice finalisation
   FinalizeParams FP;
@@ -284,6 +304,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   CK(cudaGetLastError());
   ctx->launches++;
 
+  tr.mark("finalize");
   // ---- K_enc (+ table DACs), with arena growth on overflow
   if (ctx->arena_hint == 0) ctx->arena_hint = std::max<size_t>(job.input_bytes / 2 + (8u << 20), 16u << 20);
   std::vector<uint8_t> head_buf(64);
@@ -321,6 +342,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
       }
     }
     time_end(ctx, KT_ENCODE);
+    tr.mark("k_encode_tiles");
     if (!job.plain) {
       TableDacParams TP;
       TP.tbl_min = d_tbl_min; TP.tbl_max = d_tbl_max;
@@ -333,6 +355,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
       CK(cudaGetLastError());
       ctx->launches++;
     }
+    tr.mark("k_table_dac");
     k_scan_units<<<1, 1024, 0, st>>>(ctx->results.as<UnitResult>(), ctx->stored.as<u8>(), n_units, ctx->chunk_off.as<u64>());
     CK(cudaGetLastError());
     ctx->launches++;
@@ -361,6 +384,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   }
   time_collect(ctx, KT_STATS);
   time_collect(ctx, KT_ENCODE);
+  tr.mark("scan + flags readback");
 
   // ---- read back the small per-unit tables
   out.units.resize(n_units);
@@ -383,6 +407,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   }
   CK(cudaStreamSynchronize(st));
 
+  tr.mark("tables readback");
   // ---- final blobs
   out.blob_size = out.chunk_off[n_units];
   CK(cudaMalloc(&out.blob, out.blob_size + 16));  // +16: decoders read aligned words past the last byte
@@ -399,6 +424,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   GP.encoding = job.encoding;
   GP.n_units = n_units;
   GP.err = d_err;
+  tr.mark("blob alloc");
   time_begin(ctx, KT_GATHER);
   k_gather_chunks<<<n_units, 256, 0, st>>>(GP);
   CK(cudaGetLastError());
@@ -424,6 +450,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   CK(cudaMemcpyAsync(head_buf.data(), ctx->small.p, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   time_collect(ctx, KT_GATHER);
+  tr.mark("gather");
   u32 flags;
   memcpy(&flags, head_buf.data(), 4);
   std::string msg;
@@ -785,7 +812,6 @@ int32_t dcdf_superchunk_build(dcdf_ctx* ctx, const dcdf_array3* a, const uint32_
     job.n_slots = n_slots;
     job.t_max = (uint32_t)std::min<int64_t>(cs, T);
     job.input_bytes = (size_t)T * rows * cols * elem_size(a->encoding);
-    const int lo = 6 - (int)levels[1];
     std::vector<int32_t> slot_unit((size_t)n_slices * n_slots, -1);
     for (uint32_t s = 0; s < n_slices; s++) {
       const int64_t t0 = (int64_t)s * cs, t1 = std::min<int64_t>(t0 + cs, T);
@@ -804,7 +830,8 @@ int32_t dcdf_superchunk_build(dcdf_ctx* ctx, const dcdf_array3* a, const uint32_
           memset(&u, 0, sizeof u);
           u.base = t0 * a->strides[0] + top * a->strides[1] + left * a->strides[2];
           u.rows = (int)(bottom - top); u.cols = (int)(right - left); u.instants = sd.instants;
-          u.lo = lo;
+          // each sub-array is built by Chunk::build from its OWN (clipped) shape: snapshot.rs:118-119
+          u.lo = 6 - (int)levels_for(std::max<int64_t>(u.rows, u.cols), 2);
           u.slot = (uint32_t)(r * subsidelen + c);
           u.row0 = (int)top; u.col0 = (int)left;
           slot_unit[(size_t)s * n_slots + u.slot] = (int32_t)job.units.size();
