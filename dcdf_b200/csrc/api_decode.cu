@@ -66,7 +66,7 @@ MetaBlock* make_meta(dcdf_ctx* ctx, const u8* blob, std::vector<UnitMeta>& units
   try {
     const size_t ub = sizeof(UnitMeta) * units.size(), sb = sizeof(SliceMeta) * slices.size(), mbytes = sizeof(int32_t) * slot_unit.size();
     u8* raw = nullptr;
-    CK(cudaMalloc(&raw, ub + sb + mbytes + 64));
+    raw = static_cast<u8*>(pool_alloc(ub + sb + mbytes + 64, st));
     mb->d.units = reinterpret_cast<UnitMeta*>(raw);
     mb->d.slices = reinterpret_cast<SliceMeta*>(raw + ub);
     mb->d.slot_unit = reinterpret_cast<int32_t*>(raw + ub + sb);
@@ -97,7 +97,7 @@ MetaBlock* make_meta(dcdf_ctx* ctx, const u8* blob, std::vector<UnitMeta>& units
     u64 n_dir = 0;
     for (auto& u : units) if (u.stored) n_dir = std::max<u64>(n_dir, (u64)u.dir_base + (u64)u.instants);
     InstDir* dir = nullptr;
-    CK(cudaMalloc(&dir, sizeof(InstDir) * std::max<u64>(n_dir, 1)));
+    dir = static_cast<InstDir*>(pool_alloc(sizeof(InstDir) * std::max<u64>(n_dir, 1), st));
     *dir_out = dir;
     DP.dir = dir;
     DP.count_only = 0;
@@ -124,7 +124,7 @@ MetaBlock* make_meta(dcdf_ctx* ctx, const u8* blob, std::vector<UnitMeta>& units
     for (int i = 0; i < 3; i++) Q.shape[i] = shape[i];
     return mb;
   } catch (...) {
-    if (mb->d.units) cudaFree(mb->d.units);
+    pool_free(mb->d.units);
     delete mb;
     throw;
   }
@@ -192,8 +192,8 @@ MetaBlock* super_meta(dcdf_ctx* ctx, const dcdf_superchunk* scc) {
 void free_meta(void* p, bool free_dir) {
   MetaBlock* mb = static_cast<MetaBlock*>(p);
   if (!mb) return;
-  if (free_dir && mb->Q.dir) cudaFree(const_cast<InstDir*>(mb->Q.dir));
-  if (mb->d.units) cudaFree(mb->d.units);
+  if (free_dir && mb->Q.dir) pool_free(const_cast<InstDir*>(mb->Q.dir));
+  pool_free(mb->d.units);
   delete mb;
 }
 
@@ -435,7 +435,7 @@ int32_t dcdf_chunk_open(dcdf_ctx* ctx, const uint8_t* bytes, uint64_t len, int32
     dcdf_chunk* c = new dcdf_chunk();
     c->device = ctx->device;
     try {
-      CK(cudaMalloc(&c->bytes, len + 16));
+      c->bytes = static_cast<uint8_t*>(pool_alloc(len + 16, ctx->stream));
       CK(cudaMemsetAsync(c->bytes + len, 0, 16, ctx->stream));
       CK(cudaMemcpyAsync(c->bytes, bytes, len, mem == DCDF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
       c->size = len;
@@ -456,7 +456,7 @@ int32_t dcdf_chunk_open(dcdf_ctx* ctx, const uint8_t* bytes, uint64_t len, int32
     } catch (...) {
       if (c->dir) free_chunk_meta(c->dir);
       c->dir = nullptr;
-      if (c->bytes) cudaFree(c->bytes);
+      pool_free(c->bytes);
       delete c;
       throw;
     }

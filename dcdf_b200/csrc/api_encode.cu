@@ -113,14 +113,24 @@ struct EncodeOut {
   uint64_t tbl_total = 0;
 };
 
-template <typename InT, typename V>
-void launch_encode(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
-  if (grid == 0) return;
+template <typename InT, typename V, bool FULL, int MINB>
+void launch_encode_one(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   const size_t smem = sizeof(EncSmem<V>);
-  CK(cudaFuncSetAttribute(k_encode_tiles<InT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_encode_tiles<InT, V><<<grid, ENC_THREADS, smem, ctx->stream>>>(P);
+  CK(cudaFuncSetAttribute(k_encode_tiles<InT, V, FULL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_encode_tiles<InT, V, FULL, MINB><<<grid, ENC_THREADS, smem, ctx->stream>>>(P);
   CK(cudaGetLastError());
   ctx->launches++;
+}
+// list = wide * 2 + clipped  (narrow kernels are compiled for two resident CTAs per SM)
+template <typename InT>
+void launch_encode(dcdf_ctx* ctx, const EncParams& P, u32 grid, int list) {
+  if (grid == 0) return;
+  switch (list) {
+    case 0: launch_encode_one<InT, int32_t, true, 2>(ctx, P, grid); break;
+    case 1: launch_encode_one<InT, int32_t, false, 2>(ctx, P, grid); break;
+    case 2: launch_encode_one<InT, i64, true, 1>(ctx, P, grid); break;
+    default: launch_encode_one<InT, i64, false, 1>(ctx, P, grid); break;
+  }
 }
 
 template <typename InT, bool IS_FLOAT>
@@ -177,7 +187,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   ctx->istats.reserve(sizeof(InstStats) * (size_t)n_units * job.t_max);
   ctx->slices.reserve(sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_slices);
   ctx->sstate.reserve(sizeof(SliceState) * n_slices);
-  ctx->order.reserve(sizeof(u32) * (2 * (size_t)n_units + 8));
+  ctx->order.reserve(sizeof(u32) * (4 * (size_t)n_units + 8));
   ctx->pieces.reserve(sizeof(Piece) * (n_pieces + 2 * (size_t)n_slices));
   ctx->results.reserve(sizeof(UnitResult) * n_units);
   ctx->stored.reserve(n_units);
@@ -186,14 +196,14 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   if (!job.plain) ctx->tbl_scratch.reserve(sizeof(u64) * 2 * tbl_total);
   int64_t *d_tbl_max = nullptr, *d_tbl_min = nullptr;
   if (!job.plain && tbl_total) {
-    CK(cudaMalloc(&d_tbl_max, sizeof(i64) * tbl_total));
-    CK(cudaMalloc(&d_tbl_min, sizeof(i64) * tbl_total));
+    d_tbl_max = static_cast<int64_t*>(pool_alloc(sizeof(i64) * tbl_total, st));
+    d_tbl_min = static_cast<int64_t*>(pool_alloc(sizeof(i64) * tbl_total, st));
   }
   out.tbl_max = d_tbl_max;
   out.tbl_min = d_tbl_min;
   out.tbl_total = tbl_total;
 
-  // small: [0] err (u32) | [8] arena_head (u64) | [16] order counts (2 x u32)
+  // small: [0] err (u32) | [8] arena_head (u64) | [16] order counts (4 x u32)
   u32* d_err = ctx->small.as<u32>();
   unsigned long long* d_head = reinterpret_cast<unsigned long long*>(ctx->small.as<u8>() + 8);
   u32* d_counts = reinterpret_cast<u32*>(ctx->small.as<u8>() + 16);
@@ -243,8 +253,8 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   FP.encoding = job.encoding;
   FP.req_bits = job.req_bits; FP.round = job.round; FP.compute_bits = job.compute_bits; FP.plain = job.plain;
   FP.tbl_min = d_tbl_min; FP.tbl_max = d_tbl_max;
-  FP.order_narrow = ctx->order.as<u32>();
-  FP.order_wide = ctx->order.as<u32>() + n_units;
+  FP.order = ctx->order.as<u32>();
+  FP.order_pitch = n_units;
   FP.order_counts = d_counts;
   FP.stored = ctx->stored.as<u8>();
   FP.err = d_err;
@@ -323,22 +333,14 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     EP.arena_head = d_head;
     EP.err = d_err;
     time_begin(ctx, KT_ENCODE);
-    for (int wide = 0; wide < 2; wide++) {
-      EP.order = wide ? FP.order_wide : FP.order_narrow;
-      EP.order_count = d_counts + wide;
+    for (int list = 0; list < 4; list++) {
+      EP.order = FP.order + (size_t)list * n_units;
+      EP.order_count = d_counts + list;
       switch (job.encoding) {
-        case DCDF_ENC_F32:
-          if (wide) launch_encode<float, i64>(ctx, EP, n_units); else launch_encode<float, int32_t>(ctx, EP, n_units);
-          break;
-        case DCDF_ENC_F64:
-          if (wide) launch_encode<double, i64>(ctx, EP, n_units); else launch_encode<double, int32_t>(ctx, EP, n_units);
-          break;
-        case DCDF_ENC_I32:
-          if (wide) launch_encode<int32_t, i64>(ctx, EP, n_units); else launch_encode<int32_t, int32_t>(ctx, EP, n_units);
-          break;
-        default:
-          if (wide) launch_encode<i64, i64>(ctx, EP, n_units); else launch_encode<i64, int32_t>(ctx, EP, n_units);
-          break;
+        case DCDF_ENC_F32: launch_encode<float>(ctx, EP, n_units, list); break;
+        case DCDF_ENC_F64: launch_encode<double>(ctx, EP, n_units, list); break;
+        case DCDF_ENC_I32: launch_encode<int32_t>(ctx, EP, n_units, list); break;
+        default: launch_encode<i64>(ctx, EP, n_units, list); break;
       }
     }
     time_end(ctx, KT_ENCODE);
@@ -375,8 +377,8 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     std::string msg;
     int32_t code = status_from_flags(flags, msg);
     if (code != DCDF_OK) {
-      if (d_tbl_max) cudaFree(d_tbl_max);
-      if (d_tbl_min) cudaFree(d_tbl_min);
+      pool_free(d_tbl_max);
+      pool_free(d_tbl_min);
       out.tbl_max = out.tbl_min = nullptr;
       throw ApiFail{code, msg};
     }
@@ -410,7 +412,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   tr.mark("tables readback");
   // ---- final blobs
   out.blob_size = out.chunk_off[n_units];
-  CK(cudaMalloc(&out.blob, out.blob_size + 16));  // +16: decoders read aligned words past the last byte
+  out.blob = static_cast<uint8_t*>(pool_alloc(out.blob_size + 16, st));  // +16: decoders read aligned words past the last byte
   CK(cudaMemsetAsync(out.blob + out.blob_size, 0, 16, st));
   GatherParams GP;
   GP.units = ctx->units.as<EncUnit>();
@@ -434,7 +436,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     u64 off = 0;
     for (u32 i = 0; i < 2 * n_slices; i++) { out.dac_off[i] = off; off += out.dac_pieces[i].size; }
     out.dac_blob_size = off;
-    CK(cudaMalloc(&out.dac_blob, off + 16));
+    out.dac_blob = static_cast<uint8_t*>(pool_alloc(off + 16, st));
     ctx->query_aux.reserve(sizeof(u64) * 2 * n_slices);
     CK(cudaMemcpyAsync(ctx->query_aux.p, out.dac_off.data(), sizeof(u64) * 2 * n_slices, cudaMemcpyHostToDevice, st));
     GatherDacParams DP;
@@ -492,6 +494,10 @@ int32_t dcdf_ctx_create(int32_t device, dcdf_ctx** out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;  // keep freed result buffers cached in the pool
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   } catch (const CudaFail&) {
     delete ctx;
     cudaGetLastError();
@@ -738,7 +744,7 @@ int32_t dcdf_chunk_free(dcdf_chunk* c) {
   if (!c) return DCDF_OK;
   cudaSetDevice(c->device);
   if (c->dir) free_chunk_meta(c->dir);
-  if (c->owner && c->bytes) cudaFree(c->bytes);
+  if (c->owner && c->bytes) pool_free(c->bytes);
   delete c;
   return DCDF_OK;
 }
@@ -900,12 +906,12 @@ int32_t dcdf_superchunk_build(dcdf_ctx* ctx, const dcdf_array3* a, const uint32_
 int32_t dcdf_superchunk_free(dcdf_superchunk* sc) {
   if (!sc) return DCDF_OK;
   cudaSetDevice(sc->device);
-  if (sc->chunk_blob) cudaFree(sc->chunk_blob);
-  if (sc->dac_blob) cudaFree(sc->dac_blob);
-  if (sc->tbl_max) cudaFree(sc->tbl_max);
-  if (sc->tbl_min) cudaFree(sc->tbl_min);
+  pool_free(sc->chunk_blob);
+  pool_free(sc->dac_blob);
+  pool_free(sc->tbl_max);
+  pool_free(sc->tbl_min);
   if (sc->dev_meta) free_super_meta(sc->dev_meta);
-  if (sc->dir) cudaFree(sc->dir);
+  pool_free(sc->dir);
   delete sc;
   return DCDF_OK;
 }

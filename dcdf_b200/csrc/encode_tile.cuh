@@ -44,7 +44,7 @@ struct EncUnit {
   u32 slot;         // caller-defined (subchunk slot inside its slice)
   int row0, col0;   // origin of the tile inside its region (row-major order of the NaN quirk)
 };
-enum : int { UF_ROUND = 1, UF_NARROW = 2, UF_SKIP = 4 };
+enum : int { UF_ROUND = 1, UF_NARROW = 2, UF_SKIP = 4, UF_FULL = 8 /* 64x64, all in bounds */ };
 
 struct Piece {
   u64 off;   // byte offset in the arena (16-byte aligned)
@@ -62,7 +62,7 @@ struct EncParams {
   const void* data;
   i64 stride_t, stride_r, stride_c;  // element strides
   const EncUnit* units;
-  const u32* order;       // unit indices to process (narrow or wide list)
+  const u32* order;       // unit indices to process (one of the four narrow/wide x full/clipped lists)
   const u32* order_count; // number of valid entries in `order` (device scalar)
   Piece* pieces;
   UnitResult* results;
@@ -117,11 +117,16 @@ struct EncSmem {
   UpNode<V> l1[4];
   UpNode<V> l0;
   V s_l1max[4], s_l1min[4], s_l0max, s_l0min;  // cached snapshot upper levels (per-thread regs hold l3,l2)
-  u32 cnt[24];                             // block-reduced counters
+  u32 cntF[2][2][8];                       // fast pass : [candidate 0=snapshot,1=log][0=max,1=min][len > j]
+  u32 cntX[2][2][8];                       // exact pass
+  u32 strF[2][2];                          // fast pass : [candidate][0 = internal nodes on levels <= 4, 1 = internal quads]
+  u32 strX[2][2];
+  u32 bigF;                                // fast pass : some quad / leaf entry of the log needs more than 2 bytes
+  u32 sel_max[8], sel_min[8];              // histogram of the winner (DAC layout)
+  u32 my_size, as_snapshot, go_slow;
   u32 wtot[6][ENC_WARPS];                  // per-warp internal-node counts per level (scan input)
   u32 scan[ENC_WARPS];                     // scratch for the DAC compaction scan
   u32 scan2[ENC_WARPS];
-  int decision;                            // 1 = snapshot
   u64 piece_off;
   __align__(16) u8 stage[STAGE_BYTES];
 };
@@ -268,50 +273,99 @@ struct Hist<i64> {
   DCDF_DEVINL u32 field(int j) const { return (u32)(h >> (8 * j)) & 0xffu; }
 };
 
-// Block-reduce a histogram into smem counters cnt[base .. base+MAXLEN) (two 16-bit fields per redux).
+// Block-reduce a histogram into smem counters cnt[0 .. MAXLEN) (two 16-bit fields per redux).
 template <typename V>
-DCDF_DEVINL void reduce_hist(const Hist<V>& h, u32* cnt, int base) {
+DCDF_DEVINL void reduce_hist(const Hist<V>& h, u32* cnt) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int j = 0; j < VT<V>::MAXLEN; j += 2) {
     u32 packed = h.field(j) | (h.field(j + 1) << 16);
     u32 r = __reduce_add_sync(0xffffffffu, packed);
     if (lane == 0 && r) {
-      if (r & 0xffffu) atomicAdd(&cnt[base + j], r & 0xffffu);
-      if (r >> 16) atomicAdd(&cnt[base + j + 1], r >> 16);
+      if (r & 0xffffu) atomicAdd(&cnt[j], r & 0xffffu);
+      if (r >> 16) atomicAdd(&cnt[j + 1], r >> 16);
     }
   }
 }
 
-// Counter slots in EncSmem::cnt
-enum { C_SMAX = 0, C_SMIN = 8, C_LMAX = 16 /* ..23 */ };
-// log min histogram + lengths live in a second array to keep indices simple
-enum { C2_LMIN = 0, C2_SNM = 8, C2_LNM = 9, C2_N = 10 };
+// Cheap exact accounting for entries known to be short: with m = v ^ (v >> sign) the zigzag code is 2m or
+// 2m+1, so the code needs more than one byte iff m >= 128 and more than two iff m >= 32768.
+template <typename V>
+struct FastAcc {
+  typedef typename VT<V>::U U;
+  u32 c1 = 0;  // entries longer than one byte
+  U big = 0;   // OR of all m (>= 32768 <=> some entry is longer than two bytes)
+  DCDF_DEVINL void add(V v) {
+    const U m = (U)(v ^ (v >> (8 * (int)sizeof(V) - 1)));
+    c1 += m > (U)127 ? 1u : 0u;
+    big |= m;
+  }
+};
+
+// Snapshot / Log serialization from the staged smem arrays into `out` (smem stage or arena); block-wide.
+template <typename V>
+__device__ __forceinline__ u32 serialize_structure(EncSmem<V>& S, u8* out, const EncUnit& unit, int lo, bool as_snapshot,
+                                                   u32 nm_len, u32 n_min) {
+  typedef typename VT<V>::U U;
+  if (threadIdx.x == 0) {
+    out[0] = 2;  // k
+    store_be32(out + 1, (u32)unit.rows);
+    store_be32(out + 5, (u32)unit.cols);
+    store_be32(out + 9, 64u >> lo);  // sidelen
+  }
+  u32 off = 13;
+  off += block_bitmap_emit(S.nm, nm_len, out + off);
+  if (!as_snapshot) off += block_bitmap_emit(S.eqw, nm_len - n_min, out + off);
+  off += block_dac_emit<U, VT<V>::MAXLEN>(S.A, S.sel_max[0], S.sel_max, out + off, S.scan, S.scan2);
+  off += block_dac_emit<U, VT<V>::MAXLEN>(S.B, S.sel_min[0], S.sel_min, out + off, S.scan, S.scan2);
+  return off;
+}
+
+// Conversion of one input cell to the kernel's value type.  The narrow (int32) path is only selected when
+// the stats pass proved |fixed| < 2^30 and the unit has no +-inf, so range checks are dropped there.
+template <typename InT, typename V>
+struct CellConv {
+  static DCDF_DEVINL V get(InT v, int bits, bool round, u32& err) { return (V)Conv<InT>::get(v, bits, round, err); }
+};
+template <>
+struct CellConv<float, int32_t> {
+  static DCDF_DEVINL int32_t get(float n, int bits, bool round, u32& err) {
+    float shifted = n * (float)((i64)1 << bits);
+    const float tr = truncf(shifted);
+    if (shifted - tr > 0.0f) {  // fixed.rs:47
+      if (round) shifted = roundf(shifted);
+      else err |= EF_PRECISION;
+    }
+    const int32_t f = __float2int_rz(shifted * 2.0f) + 1;
+    return n != n ? 0 : f;  // NaN -> 0 (fixed.rs:35-37)
+  }
+};
 
 // ---------------------------------------------------------------------------------------------------
-template <typename InT, typename V>
-__global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P) {
+// MINB: min resident CTAs per SM the register allocator must allow.
+template <typename InT, typename V, bool FULL, int MINB>
+__global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tiles(const EncParams P) {
   typedef typename VT<V>::U U;
   constexpr int MAXLEN = VT<V>::MAXLEN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EncSmem<V>& S = *reinterpret_cast<EncSmem<V>*>(smem_raw);
-  __shared__ u32 cnt2[C2_N];
 
   if (blockIdx.x >= *P.order_count) return;
   const u32 unit_idx = P.order[blockIdx.x];
   const EncUnit unit = P.units[unit_idx];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int lo = unit.lo;
+  const int lo = FULL ? 0 : unit.lo;
   const bool do_round = unit.flags & UF_ROUND;
   const int r0 = 4 * (int)morton_row(tid), c0 = 4 * (int)morton_col(tid);
   const InT* base = static_cast<const InT*>(P.data) + unit.base;
 
   // tree membership of this thread's frame nodes (tree root = frame node (lo, 0))
-  const bool intree4 = lo <= 4 ? ((tid >> (8 - 2 * lo)) == 0) : (tid == 0);
-  const u32 quad_mask = lo <= 4 ? 0xfu : 0x1u;  // lo == 5: only quad 0 of thread 0 is in the tree
+  const bool intree4 = FULL ? true : (lo <= 4 ? ((tid >> (8 - 2 * lo)) == 0) : (tid == 0));
+  const u32 quad_mask = (FULL || lo <= 4) ? 0xfu : 0x1u;  // lo == 5: only quad 0 of thread 0 is in the tree
+  const bool owner[5] = {tid == 0, (tid & 63) == 0, (tid & 15) == 0, (tid & 3) == 0, true};
 
   u32 err = 0;
-  // cached snapshot (reference instant of the current block): leaves + own ancestors
+  // cached snapshot (reference instant of the current block): leaves + own level-3 / level-2 ancestors
   V sv[16];
 #pragma unroll
   for (int m = 0; m < 16; m++) sv[m] = 0;
@@ -327,15 +381,12 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
     // ---------------- convert (a3) and prefetch the next instant
     V tv[16];
 #pragma unroll
-    for (int m = 0; m < 16; m++) {
-      i64 f = Conv<InT>::get(raw[m], unit.bits, do_round, err);
-      tv[m] = (V)f;
-      if (sizeof(V) == 4 && ((inb >> m) & 1u) && (f > (i64)0x3fffffff || f < -(i64)0x3fffffff)) err |= EF_BAD_FORMAT;  // narrow path mis-selected
-    }
-    const u32 cur_inb = inb;
+    for (int m = 0; m < 16; m++) tv[m] = CellConv<InT, V>::get(raw[m], unit.bits, do_round, err);
+    const u32 cur_inb = FULL ? 0xffffu : inb;
     if (inst + 1 < unit.instants)
       load_block<InT>(base + (i64)(inst + 1) * P.stride_t, P.stride_r, P.stride_c, unit.rows, unit.cols, r0, c0, raw, inb);
     const bool first = inst == 0;
+#define CELL_IN(m) (FULL || ((cur_inb >> (m)) & 1u))
 
     // ---------------- bottom-up pyramid inside the thread: levels 6 -> 5 -> 4
     V t5max[4], t5min[4];
@@ -348,7 +399,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         const int m = 4 * q + c;
-        const bool in = (cur_inb >> m) & 1u;
+        const bool in = CELL_IN(m);
         if (in) { mx = vmax(mx, tv[m]); mn = vmin(mn, tv[m]); }
         dq[c] = (in && !first) ? (V)(tv[m] - sv[m]) : (V)0;  // OOB diff = 0 (log.rs:751)
       }
@@ -356,8 +407,8 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
       d0[q] = dq[0];
       if (dq[1] == dq[0] && dq[2] == dq[0] && dq[3] == dq[0]) eq5 |= 1u << q;
     }
-    V t4max = vmax(vmax(t5max[0], t5max[1]), vmax(t5max[2], t5max[3]));
-    V t4min = vmin(vmin(t5min[0], t5min[1]), vmin(t5min[2], t5min[3]));
+    const V t4max = vmax(vmax(t5max[0], t5max[1]), vmax(t5max[2], t5max[3]));
+    const V t4min = vmin(vmin(t5min[0], t5min[1]), vmin(t5min[2], t5min[3]));
     const V diff4 = d0[0];
     const bool eq4 = eq5 == 0xfu && d0[1] == d0[0] && d0[2] == d0[0] && d0[3] == d0[0];
 
@@ -373,17 +424,19 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
     const u32 ok2 = __ballot_sync(0xffffffffu, eq3 && diff3 == diff2);
     const bool eq2 = ((ok2 >> (lane & ~15)) & 0xffffu) == 0xffffu;
 
-    // ---------------- levels 1 and 0 through smem
+    // ---------------- levels 1 and 0 through smem; counters and bit staging are reset meanwhile
     if ((lane & 15) == 0) {
       UpNode<V> n;
       n.tmax = t2max; n.tmin = t2min; n.diff = diff2; n.eq = eq2;
       S.l2[tid >> 4] = n;
     }
-    if (tid < 24) S.cnt[tid] = 0;
-    if (tid < C2_N) cnt2[tid] = 0;
+    if (tid < 32) { (&S.cntF[0][0][0])[tid] = 0; (&S.cntX[0][0][0])[tid] = 0; }
+    if (tid < 4) { (&S.strF[0][0])[tid] = 0; (&S.strX[0][0])[tid] = 0; }
+    if (tid == 0) S.bigF = 0;
+    for (int w = tid; w < NM_WORDS; w += ENC_THREADS) { S.nm[w] = 0; S.eqw[w] = 0; }
     __syncthreads();
     if (tid < 4) {
-      UpNode<V> a = S.l2[4 * tid], b = S.l2[4 * tid + 1], c = S.l2[4 * tid + 2], d = S.l2[4 * tid + 3];
+      const UpNode<V> a = S.l2[4 * tid], b = S.l2[4 * tid + 1], c = S.l2[4 * tid + 2], d = S.l2[4 * tid + 3];
       UpNode<V> n;
       n.tmax = vmax(vmax(a.tmax, b.tmax), vmax(c.tmax, d.tmax));
       n.tmin = vmin(vmin(a.tmin, b.tmin), vmin(c.tmin, d.tmin));
@@ -393,7 +446,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
     }
     __syncthreads();
     if (tid == 0) {
-      UpNode<V> a = S.l1[0], b = S.l1[1], c = S.l1[2], d = S.l1[3];
+      const UpNode<V> a = S.l1[0], b = S.l1[1], c = S.l1[2], d = S.l1[3];
       UpNode<V> n;
       n.tmax = vmax(vmax(a.tmax, b.tmax), vmax(c.tmax, d.tmax));
       n.tmin = vmin(vmin(a.tmin, b.tmin), vmin(c.tmin, d.tmin));
@@ -419,13 +472,9 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
     const bool si[5] = {!u0, !u1, !u2, !u3, !u4};
     const bool li[5] = {!u0 && !N0.eq, !u1 && !N1.eq, !u2 && !eq2, !u3 && !eq3, !u4 && !eq4};
     const u32 si5 = ~u5 & 0xfu, li5 = ~u5 & ~eq5 & 0xfu;
-    // values of the chain, "or 0" for None
     auto or0 = [](V v, V none) { return v == none ? (V)0 : v; };
     const V cmax[5] = {N0.tmax, N1.tmax, t2max, t3max, t4max};
     const V cmin[5] = {N0.tmin, N1.tmin, t2min, t3min, t4min};
-    const V csmax[5] = {s0max, s1max, s2max, s3max, (V)0};  // level 4/5 snapshot values recomputed from sv below
-    const V csmin[5] = {s0min, s1min, s2min, s3min, (V)0};
-    const bool owner[5] = {tid == 0, (tid & 63) == 0, (tid & 15) == 0, (tid & 3) == 0, true};
 
     // snapshot pyramid levels 5/4 of the reference instant, recomputed from the cached leaves
     V s5max[4], s5min[4];
@@ -434,164 +483,231 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
       V mx = VT<V>::NONE_MAX, mn = VT<V>::NONE_MIN;
 #pragma unroll
       for (int c = 0; c < 4; c++)
-        if ((cur_inb >> (4 * q + c)) & 1u) { mx = vmax(mx, sv[4 * q + c]); mn = vmin(mn, sv[4 * q + c]); }
+        if (CELL_IN(4 * q + c)) { mx = vmax(mx, sv[4 * q + c]); mn = vmin(mn, sv[4 * q + c]); }
       s5max[q] = mx; s5min[q] = mn;
     }
     const V s4max = vmax(vmax(s5max[0], s5max[1]), vmax(s5max[2], s5max[3]));
     const V s4min = vmin(vmin(s5min[0], s5min[1]), vmin(s5min[2], s5min[3]));
+    const V csmax[5] = {s0max, s1max, s2max, s3max, s4max};
+    const V csmin[5] = {s0min, s1min, s2min, s3min, s4min};
 
-    // ---------------- histograms of both candidates (a5/a7 entry values, a9 byte lengths)
-    Hist<V> hsmax, hsmin, hlmax, hlmin;
-    u32 snm = 0, lnm = 0;  // nodemap lengths contributed by this thread
+    // alive chains: al_s[l] / al_l[l] = this thread's level-l frame node exists in the snapshot / log tree
+    bool al_s[6], al_l[6];
     {
-      bool sal = intree4 || lo == 5, lal = sal;  // alive flags entering level lo (virtual above)
-      // virtual levels above the root always pass; only the Morton-0 path is in the tree
+      bool a = intree4 || lo == 5, b = a;
 #pragma unroll
       for (int l = 0; l < 5; l++) {
-        if (l < lo) continue;
-        const bool mine = owner[l] && intree4;
-        const V tm = or0(cmax[l], VT<V>::NONE_MAX);
-        const V pmax = cmax[l > 0 ? l - 1 : 0], pmin = cmin[l > 0 ? l - 1 : 0];  // parent (unused at the root)
-        if (sal && mine) {
-          const V e = l == lo ? tm : (V)(pmax - tm);
-          hsmax.add(VT<V>::zz(e));
-          snm++;
-          if (si[l]) hsmin.add(VT<V>::zz(l == lo ? cmin[l] : (V)(cmin[l] - pmin)));
-        }
-        if (!first && lal && mine) {
-          const V smx = l == 4 ? s4max : csmax[l], smn = l == 4 ? s4min : csmin[l];
-          hlmax.add(VT<V>::zz((V)(tm - or0(smx, VT<V>::NONE_MAX))));
-          lnm++;
-          if (li[l]) hlmin.add(VT<V>::zz((V)(cmin[l] - smn)));
-        }
-        sal = sal && si[l];
-        lal = lal && li[l];
+        al_s[l] = l >= lo && a && intree4;
+        al_l[l] = l >= lo && b && intree4;
+        if (l >= lo) { a = a && si[l]; b = b && li[l]; }
       }
-      // level 5 quads and level 6 leaves
-      const bool s4alive = lo == 5 ? (tid == 0) : sal, l4alive = lo == 5 ? (tid == 0) : lal;
+      al_s[5] = (!FULL && lo == 5) ? (tid == 0) : a;
+      al_l[5] = (!FULL && lo == 5) ? (tid == 0) : b;
+    }
+    // structure counts: internal nodes owned on levels <= 4, internal quads
+    u32 sup = 0, lup = 0;
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        if (!((quad_mask >> q) & 1u)) continue;
-        const V tm = or0(t5max[q], VT<V>::NONE_MAX);
-        if (s4alive) {
-          hsmax.add(VT<V>::zz(lo == 5 ? tm : (V)(t4max - tm)));
-          snm++;
-          if ((si5 >> q) & 1u) {
-            hsmin.add(VT<V>::zz(lo == 5 ? t5min[q] : (V)(t5min[q] - t4min)));
+    for (int l = 0; l < 5; l++) {
+      sup += (owner[l] && al_s[l] && si[l]) ? 1u : 0u;
+      lup += (owner[l] && al_l[l] && li[l]) ? 1u : 0u;
+    }
+    const u32 s5c = al_s[5] ? __popc(si5 & quad_mask) : 0u, l5c = al_l[5] ? __popc(li5 & quad_mask) : 0u;
+
+    // ---------------- FAST pass: exact size of the Log, lower bound of the Snapshot (chunk.rs:62)
+    bool slow = first || n_logs == 254u;
+    if (!slow) {
+      Hist<V> hmax, hmin;        // chain entries (levels lo..4): exact
+      FastAcc<V> fmax, fmin;     // quads and leaves: short-entry accounting
+#pragma unroll
+      for (int l = 0; l < 5; l++) {
+        if (l < lo || !(owner[l] && al_l[l])) continue;
+        hmax.add(VT<V>::zz((V)(or0(cmax[l], VT<V>::NONE_MAX) - or0(csmax[l], VT<V>::NONE_MAX))));
+        if (li[l]) hmin.add(VT<V>::zz((V)(cmin[l] - csmin[l])));
+      }
+      if (al_l[5]) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (!FULL && !((quad_mask >> q) & 1u)) continue;
+          fmax.add((V)(or0(t5max[q], VT<V>::NONE_MAX) - or0(s5max[q], VT<V>::NONE_MAX)));
+          if ((li5 >> q) & 1u) {
+            fmin.add((V)(t5min[q] - s5min[q]));
 #pragma unroll
             for (int c = 0; c < 4; c++) {
               const int m = 4 * q + c;
-              const V leaf = ((cur_inb >> m) & 1u) ? tv[m] : (V)0;
-              hsmax.add(VT<V>::zz((V)(t5max[q] - leaf)));
+              fmax.add(CELL_IN(m) ? (V)(tv[m] - sv[m]) : (V)0);
             }
           }
         }
-        if (!first && l4alive) {
+      }
+      // block reduction (16-bit fields; per-warp sums stay far below 65536)
+      {
+        u32 r = __reduce_add_sync(0xffffffffu, fmax.c1 | (fmin.c1 << 16));
+        if (lane == 0 && r) {
+          if (r & 0xffffu) atomicAdd(&S.cntF[1][0][1], r & 0xffffu);
+          if (r >> 16) atomicAdd(&S.cntF[1][1][1], r >> 16);
+        }
+        r = __reduce_add_sync(0xffffffffu, lup | (l5c << 8) | (sup << 16) | (s5c << 24));  // <= 5 / 4 per thread
+        if (lane == 0 && r) {
+          atomicAdd(&S.strF[1][0], r & 0xffu);
+          atomicAdd(&S.strF[1][1], (r >> 8) & 0xffu);
+          atomicAdd(&S.strF[0][0], (r >> 16) & 0xffu);
+          atomicAdd(&S.strF[0][1], r >> 24);
+        }
+        const u32 big = __reduce_or_sync(0xffffffffu, (u32)(((fmax.big | fmin.big) >> 15) != 0));
+        if (lane == 0 && big) S.bigF = 1;
+        if (__any_sync(0xffffffffu, (hmax.h | hmin.h) != 0)) {  // only owner lanes carry chain entries
+          reduce_hist<V>(hmax, S.cntF[1][0]);
+          reduce_hist<V>(hmin, S.cntF[1][1]);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        // n_min = internal nodes, nm_len = 1 + 4 * internal(levels <= 4), n_max = 1 + 4 * internal(all)
+        const u32 l_int = S.strF[1][0] + S.strF[1][1], s_int = S.strF[0][0] + S.strF[0][1];
+        const u32 l_nm = 1u + 4u * S.strF[1][0], s_nm = 1u + 4u * S.strF[0][0];
+        const u32 l_nmax = 1u + 4u * l_int, s_nmax = 1u + 4u * s_int;
+        u32 cm[8], cn[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { cm[j] = S.cntF[1][0][j]; cn[j] = S.cntF[1][1][j]; }
+        cm[0] = l_nmax; cn[0] = l_int;
+        const u32 log_size = 13u + bitmap_size(l_nm) + bitmap_size(l_nm - l_int) + dac_size_from_counts(cm, 8) + dac_size_from_counts(cn, 8);
+        // every snapshot entry takes at least one byte
+        const u32 snap_lb = 13u + bitmap_size(s_nm) + 1u + bitmap_size(s_nmax) + s_nmax + (s_int ? 1u + bitmap_size(s_int) + s_int : 1u);
+        const bool go_slow = S.bigF || snap_lb <= log_size;
+        S.go_slow = go_slow;
+        if (!go_slow) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) { S.sel_max[j] = cm[j]; S.sel_min[j] = cn[j]; }
+          S.my_size = log_size;
+          S.as_snapshot = 0;
+          const u64 need = ((u64)log_size + 15ull) & ~15ull;
+          const u64 off = atomicAdd(P.arena_head, (unsigned long long)need);
+          S.piece_off = off;
+          Piece pc;
+          pc.off = off; pc.size = log_size; pc.kind = 0u;
+          P.pieces[unit.piece_base + inst] = pc;
+        }
+      }
+      __syncthreads();
+      slow = S.go_slow;
+    }
+
+    // ---------------- EXACT pass (first instant, 254-log cap, near ties, long entries): both candidates
+    if (slow) {
+      Hist<V> hsmax, hsmin, hlmax, hlmin;
+#pragma unroll
+      for (int l = 0; l < 5; l++) {
+        if (l < lo || !owner[l]) continue;
+        const V tm = or0(cmax[l], VT<V>::NONE_MAX);
+        const V pmax = cmax[l > 0 ? l - 1 : 0], pmin = cmin[l > 0 ? l - 1 : 0];  // parent (unused at the root)
+        if (al_s[l]) {
+          hsmax.add(VT<V>::zz(l == lo ? tm : (V)(pmax - tm)));
+          if (si[l]) hsmin.add(VT<V>::zz(l == lo ? cmin[l] : (V)(cmin[l] - pmin)));
+        }
+        if (!first && al_l[l]) {
+          hlmax.add(VT<V>::zz((V)(tm - or0(csmax[l], VT<V>::NONE_MAX))));
+          if (li[l]) hlmin.add(VT<V>::zz((V)(cmin[l] - csmin[l])));
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (!FULL && !((quad_mask >> q) & 1u)) continue;
+        const V tm = or0(t5max[q], VT<V>::NONE_MAX);
+        if (al_s[5]) {
+          hsmax.add(VT<V>::zz((!FULL && lo == 5) ? tm : (V)(t4max - tm)));
+          if ((si5 >> q) & 1u) {
+            hsmin.add(VT<V>::zz((!FULL && lo == 5) ? t5min[q] : (V)(t5min[q] - t4min)));
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              const int m = 4 * q + c;
+              hsmax.add(VT<V>::zz((V)(t5max[q] - (CELL_IN(m) ? tv[m] : (V)0))));
+            }
+          }
+        }
+        if (!first && al_l[5]) {
           hlmax.add(VT<V>::zz((V)(tm - or0(s5max[q], VT<V>::NONE_MAX))));
-          lnm++;
           if ((li5 >> q) & 1u) {
             hlmin.add(VT<V>::zz((V)(t5min[q] - s5min[q])));
 #pragma unroll
             for (int c = 0; c < 4; c++) {
               const int m = 4 * q + c;
-              const bool in = (cur_inb >> m) & 1u;
-              hlmax.add(VT<V>::zz(in ? (V)(tv[m] - sv[m]) : (V)0));
+              hlmax.add(VT<V>::zz(CELL_IN(m) ? (V)(tv[m] - sv[m]) : (V)0));
             }
           }
         }
       }
-    }
-    reduce_hist<V>(hsmax, S.cnt, C_SMAX);
-    reduce_hist<V>(hsmin, S.cnt, C_SMIN);
-    if (!first) {
-      reduce_hist<V>(hlmax, S.cnt, C_LMAX);
-      reduce_hist<V>(hlmin, cnt2, C2_LMIN);
-    }
-    {
-      u32 r = __reduce_add_sync(0xffffffffu, snm | (lnm << 16));
-      if (lane == 0) {
-        atomicAdd(&cnt2[C2_SNM], r & 0xffffu);
-        atomicAdd(&cnt2[C2_LNM], r >> 16);
+      reduce_hist<V>(hsmax, S.cntX[0][0]);
+      reduce_hist<V>(hsmin, S.cntX[0][1]);
+      if (!first) {
+        reduce_hist<V>(hlmax, S.cntX[1][0]);
+        reduce_hist<V>(hlmin, S.cntX[1][1]);
       }
-    }
-    __syncthreads();
-
-    // ---------------- sizes and the heuristic (chunk.rs:62)
-    u32 smaxc[8], sminc[8], lmaxc[8], lminc[8];
+      {
+        const u32 r = __reduce_add_sync(0xffffffffu, lup | (sup << 16));
+        if (lane == 0 && r) {
+          atomicAdd(&S.strX[1][0], r & 0xffffu);
+          atomicAdd(&S.strX[0][0], r >> 16);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        u32 sm[8], sn[8], lm[8], ln[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      smaxc[j] = j < MAXLEN ? S.cnt[C_SMAX + j] : 0u;
-      sminc[j] = j < MAXLEN ? S.cnt[C_SMIN + j] : 0u;
-      lmaxc[j] = j < MAXLEN ? S.cnt[C_LMAX + j] : 0u;
-      lminc[j] = j < MAXLEN ? cnt2[C2_LMIN + j] : 0u;
+        for (int j = 0; j < 8; j++) { sm[j] = S.cntX[0][0][j]; sn[j] = S.cntX[0][1][j]; lm[j] = S.cntX[1][0][j]; ln[j] = S.cntX[1][1][j]; }
+        const u32 s_nm = 1u + 4u * S.strX[0][0], l_nm = 1u + 4u * S.strX[1][0];
+        const u32 snap_size = 13u + bitmap_size(s_nm) + dac_size_from_counts(sm, 8) + dac_size_from_counts(sn, 8);
+        const u32 log_size = 13u + bitmap_size(l_nm) + bitmap_size(l_nm - ln[0]) + dac_size_from_counts(lm, 8) + dac_size_from_counts(ln, 8);
+        const bool snap = first || n_logs == 254u || snap_size <= log_size;  // chunk.rs:62
+        const u32 size = snap ? snap_size : log_size;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { S.sel_max[j] = snap ? sm[j] : lm[j]; S.sel_min[j] = snap ? sn[j] : ln[j]; }
+        S.my_size = size;
+        S.as_snapshot = snap;
+        const u64 need = ((u64)size + 15ull) & ~15ull;
+        const u64 off = atomicAdd(P.arena_head, (unsigned long long)need);
+        S.piece_off = off;
+        Piece pc;
+        pc.off = off; pc.size = size; pc.kind = snap ? 1u : 0u;
+        P.pieces[unit.piece_base + inst] = pc;
+      }
+      __syncthreads();
     }
-    const u32 snm_len = cnt2[C2_SNM], lnm_len = cnt2[C2_LNM];
-    const u32 leq_len = lnm_len - lminc[0];  // one equal bit per nodemap-0 node (log.rs:137-146)
-    const u32 snap_size = 13u + bitmap_size(snm_len) + dac_size_from_counts(smaxc, 8) + dac_size_from_counts(sminc, 8);
-    const u32 log_size = 13u + bitmap_size(lnm_len) + bitmap_size(leq_len) + dac_size_from_counts(lmaxc, 8) + dac_size_from_counts(lminc, 8);
-    const bool as_snapshot = first || n_logs == 254u || snap_size <= log_size;
-    const u32 my_size = as_snapshot ? snap_size : log_size;
-
-    // ---------------- arena allocation for the winner
-    if (tid == 0) {
-      const u64 need = ((u64)my_size + 15ull) & ~15ull;
-      const u64 off = atomicAdd(P.arena_head, (unsigned long long)need);
-      S.piece_off = off;
-      Piece pc;
-      pc.off = off; pc.size = my_size; pc.kind = as_snapshot ? 1u : 0u;
-      P.pieces[unit.piece_base + inst] = pc;
-    }
-    for (int w = tid; w < NM_WORDS; w += ENC_THREADS) { S.nm[w] = 0; S.eqw[w] = 0; }
-    __syncthreads();
+    const bool as_snapshot = S.as_snapshot != 0;
+    const u32 my_size = S.my_size;
     const u64 piece_off = S.piece_off;
     const bool fits = piece_off + (((u64)my_size + 15ull) & ~15ull) <= P.arena_cap;
     if (!fits) err |= EF_ARENA_FULL;
 
     // ---------------- BFS positions of the winner: per-level ranks of internal nodes
-    bool in_[5];
+    bool in_[5], al[6];
 #pragma unroll
-    for (int l = 0; l < 5; l++) in_[l] = as_snapshot ? si[l] : li[l];
+    for (int l = 0; l < 5; l++) { in_[l] = as_snapshot ? si[l] : li[l]; al[l] = as_snapshot ? al_s[l] : al_l[l]; }
+    al[5] = as_snapshot ? al_s[5] : al_l[5];
     const u32 in5 = as_snapshot ? si5 : li5;
-    bool al[6];  // al[l]: this thread's level-l frame node exists in the tree (l = 0..4), al[5] = quads exist
-    {
-      bool a = intree4 || lo == 5;
-#pragma unroll
-      for (int l = 0; l < 5; l++) {
-        al[l] = l >= lo && a && intree4;
-        if (l >= lo) a = a && in_[l];
-      }
-      al[5] = lo == 5 ? (tid == 0) : a;
-    }
-    // flags of internal nodes owned by this thread, per level
     u32 rank_in_warp[5];
-    {
+    rank_in_warp[0] = 0;
 #pragma unroll
-      for (int l = 1; l < 5; l++) {
-        const bool f = owner[l] && al[l] && in_[l];
-        const u32 b = __ballot_sync(0xffffffffu, f);
-        rank_in_warp[l] = __popc(b & lanemask_lt());
-        if (lane == 0) S.wtot[l][warp] = __popc(b);
-      }
-      rank_in_warp[0] = 0;
+    for (int l = 1; l < 5; l++) {
+      const bool f = owner[l] && al[l] && in_[l];
+      const u32 b = __ballot_sync(0xffffffffu, f);
+      rank_in_warp[l] = __popc(b & lanemask_lt());
+      if (lane == 0) S.wtot[l][warp] = __popc(b);
     }
-    // level 5: quads
-    u32 q_before = 0, q_count = 0;
+    u32 q_before = 0;
     {
       const u32 mine = al[5] ? (in5 & quad_mask) : 0u;
-      u32 before = 0, tot = 0;
+      u32 tot = 0;
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const u32 b = __ballot_sync(0xffffffffu, (mine >> q) & 1u);
-        before += __popc(b & lanemask_lt());
+        q_before += __popc(b & lanemask_lt());
         tot += __popc(b);
       }
-      q_before = before;
-      q_count = __popc(mine);
       if (lane == 0) S.wtot[5][warp] = tot;
     }
     __syncthreads();
     u32 I[6], Rbase[6];  // I[l]: internal nodes at level l; Rbase[l]: internal nodes at level l in earlier warps
-    I[0] = (lo == 0 && in_[0]) ? 1u : 0u;  // root flag is uniform across the CTA
+    I[0] = (lo == 0 && in_[0]) ? 1u : 0u;  // the root flag is uniform across the CTA
     Rbase[0] = 0;
 #pragma unroll
     for (int l = 1; l < 6; l++) {
@@ -604,7 +720,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
       }
       I[l] = tot; Rbase[l] = bs;
     }
-    // P[l]: BFS index of the first level-l node; M[l]: internal nodes on levels above l
+    // Pn[l]: BFS index of the first level-l node; Mn[l]: internal nodes on levels above l
     u32 Pn[8], Mn[8];
     {
       u32 p = 0, mm = 0, e = 1;  // e = nodes on the current level
@@ -619,23 +735,16 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
       }
       Pn[7] = p; Mn[7] = mm;
     }
-    const u32 n_max = Pn[7], n_min = Mn[6], nm_len = Pn[6];
+    const u32 n_min = Mn[6], nm_len = Pn[6];
     // rank (among internal nodes of its level) of each chain node, as seen by this thread
     u32 R[5];
     R[0] = 0;
-    R[1] = 0;
     {
-      // level 1: four nodes, flags known to everyone through smem-resident N1 of each... recompute from wtot:
-      // owners of level-1 nodes are threads 0,64,128,192 = lane 0 of warps 0,2,4,6
-      u32 r1 = 0;
+      u32 r1 = 0;  // level-1 owners are lane 0 of warps 0, 2, 4, 6
       for (int w = 0; w < (tid >> 6) * 2; w++) r1 += S.wtot[1][w];
       R[1] = r1;
-    }
-    {
-      const u32 r2own = Rbase[2] + rank_in_warp[2];
-      R[2] = shfl(r2own, lane & ~15);
-      const u32 r3own = Rbase[3] + rank_in_warp[3];
-      R[3] = shfl(r3own, lane & ~3);
+      R[2] = shfl(Rbase[2] + rank_in_warp[2], lane & ~15);
+      R[3] = shfl(Rbase[3] + rank_in_warp[3], lane & ~3);
       R[4] = Rbase[4] + rank_in_warp[4];
     }
     const u32 R5 = Rbase[5] + q_before;  // rank of this thread's first internal quad
@@ -651,14 +760,14 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
       const V pmax = cmax[l > 0 ? l - 1 : 0], pmin = cmin[l > 0 ? l - 1 : 0];
       V e;
       if (as_snapshot) e = l == lo ? tm : (V)(pmax - tm);
-      else e = (V)(tm - or0(l == 4 ? s4max : csmax[l], VT<V>::NONE_MAX));
+      else e = (V)(tm - or0(csmax[l], VT<V>::NONE_MAX));
       S.A[pos] = VT<V>::zz(e);
       const u32 ones_before = Mn[l] + R[l];
       if (in_[l]) {
         set_bit(S.nm, pos);
         V mv;
         if (as_snapshot) mv = l == lo ? cmin[l] : (V)(cmin[l] - pmin);
-        else mv = (V)(cmin[l] - (l == 4 ? s4min : csmin[l]));
+        else mv = (V)(cmin[l] - csmin[l]);
         S.B[ones_before] = VT<V>::zz(mv);
       } else if (!as_snapshot) {
         const bool eqf = l == 0 ? (bool)N0.eq : l == 1 ? (bool)N1.eq : l == 2 ? eq2 : l == 3 ? eq3 : eq4;
@@ -670,25 +779,26 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
       u32 r5 = R5;
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        if (!((quad_mask >> q) & 1u)) continue;
-        const u32 pos = lo == 5 ? 0u : Pn[5] + 4u * R[4] + (u32)q;
+        if (!FULL && !((quad_mask >> q) & 1u)) continue;
+        const bool root5 = !FULL && lo == 5;
+        const u32 pos = root5 ? 0u : Pn[5] + 4u * R[4] + (u32)q;
         const V tm = or0(t5max[q], VT<V>::NONE_MAX);
         V e;
-        if (as_snapshot) e = lo == 5 ? tm : (V)(t4max - tm);
+        if (as_snapshot) e = root5 ? tm : (V)(t4max - tm);
         else e = (V)(tm - or0(s5max[q], VT<V>::NONE_MAX));
         S.A[pos] = VT<V>::zz(e);
         const u32 ones_before = Mn[5] + r5;
         if ((in5 >> q) & 1u) {
           set_bit(S.nm, pos);
           V mv;
-          if (as_snapshot) mv = lo == 5 ? t5min[q] : (V)(t5min[q] - t4min);
+          if (as_snapshot) mv = root5 ? t5min[q] : (V)(t5min[q] - t4min);
           else mv = (V)(t5min[q] - s5min[q]);
           S.B[ones_before] = VT<V>::zz(mv);
           const u32 lpos = Pn[6] + 4u * r5;
 #pragma unroll
           for (int c = 0; c < 4; c++) {
             const int m = 4 * q + c;
-            const bool in = (cur_inb >> m) & 1u;
+            const bool in = CELL_IN(m);
             V le;
             if (as_snapshot) le = (V)(t5max[q] - (in ? tv[m] : (V)0));
             else le = in ? (V)(tv[m] - sv[m]) : (V)0;
@@ -700,29 +810,15 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
         }
       }
     }
-    (void)q_count;
     __syncthreads();
 
     // ---------------- serialize (snapshot.rs:48-58 / log.rs:53-64)
     {
       const bool staged = my_size <= (u32)STAGE_BYTES;
-      u8* out = staged ? S.stage : (fits ? P.arena + piece_off : nullptr);
-      if (out != nullptr) {
-        const u32 sidelen = 64u >> lo;
-        if (tid == 0) {
-          out[0] = 2;  // k
-          store_be32(out + 1, (u32)unit.rows);
-          store_be32(out + 5, (u32)unit.cols);
-          store_be32(out + 9, sidelen);
-        }
-        u32 off = 13;
-        off += block_bitmap_emit(S.nm, nm_len, out + off);
-        if (!as_snapshot) off += block_bitmap_emit(S.eqw, nm_len - n_min, out + off);
-        const u32* cmaxc = as_snapshot ? smaxc : lmaxc;
-        const u32* cminc = as_snapshot ? sminc : lminc;
-        (void)n_max;
-        off += block_dac_emit<U, MAXLEN>(S.A, cmaxc[0], cmaxc, out + off, S.scan, S.scan2);
-        off += block_dac_emit<U, MAXLEN>(S.B, cminc[0], cminc, out + off, S.scan, S.scan2);
+      if (staged || fits) {
+        u32 off;
+        if (staged) off = serialize_structure<V>(S, S.stage, unit, lo, as_snapshot, nm_len, n_min);
+        else off = serialize_structure<V>(S, P.arena + piece_off, unit, lo, as_snapshot, nm_len, n_min);
         if (off != my_size) err |= EF_BAD_FORMAT;  // internal consistency: emitted bytes == predicted size
         __syncthreads();
         if (staged && fits) {
@@ -749,6 +845,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
     }
     total_bytes += my_size;
     __syncthreads();
+#undef CELL_IN
   }
 
   if (tid == 0) {
@@ -758,8 +855,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncParams P)
     r.logs = n_log_total;
     P.results[unit_idx] = r;
   }
-  // one atomic per warp for the error bits
-  err = __reduce_or_sync(0xffffffffu, err);
+  err = __reduce_or_sync(0xffffffffu, err);  // one atomic per warp for the error bits
   if (lane == 0 && err) atomicOr(P.err, err);
 }
 

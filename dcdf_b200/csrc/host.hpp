@@ -83,6 +83,17 @@ struct PinBuf {
   T* as() const { return static_cast<T*>(p); }
 };
 
+// Result buffers come from the device's stream-ordered pool (cudaMallocAsync) with an unlimited release
+// threshold: cudaMalloc / cudaFree of multi-GB blobs cost hundreds of milliseconds per call on B200.
+inline void* pool_alloc(size_t bytes, cudaStream_t st) {
+  void* p = nullptr;
+  CK(cudaMallocAsync(&p, bytes ? bytes : 16, st));
+  return p;
+}
+inline void pool_free(void* p) {
+  if (p) cudaFreeAsync(p, 0);  // callers have synchronized every stream that used p
+}
+
 enum { KT_ENCODE = 0, KT_STATS = 1, KT_GATHER = 2, KT_WINDOW = 3, KT_CELL = 4, KT_SEARCH = 5, KT_COUNT = 6 };
 
 }  // namespace dcdf

@@ -344,9 +344,9 @@ struct FinalizeParams {
   int plain;               // 1 = plain Chunk::build units: caller's bits, no tables, no elision
   i64* tbl_min;
   i64* tbl_max;
-  u32* order_narrow;
-  u32* order_wide;
-  u32* order_counts;       // [0] narrow, [1] wide
+  u32* order;              // four work lists of n_units_total entries each: index = wide * 2 + clipped
+  u32 order_pitch;
+  u32* order_counts;       // [4]
   u8* stored;              // [n_units_total] 1 = Chunk is built and stored (not elided)
   u32* err;
 };
@@ -486,13 +486,15 @@ __global__ void k_finalize_phase2(const FinalizeParams P, u32 n_slices) {
       }
       if (narrow) flags |= UF_NARROW;
     }
+    if (unit.rows == 64 && unit.cols == 64 && unit.lo == 0) flags |= UF_FULL;
     unit.bits = bits;
     unit.flags = flags;
     P.units[u] = unit;
     P.stored[u] = can_elide ? 0 : 1;
     if (!can_elide) {
-      if (narrow) P.order_narrow[atomicAdd(&P.order_counts[0], 1u)] = u;
-      else P.order_wide[atomicAdd(&P.order_counts[1], 1u)] = u;
+      const bool full = unit.rows == 64 && unit.cols == 64 && unit.lo == 0;
+      const u32 list = (narrow ? 0u : 2u) + (full ? 0u : 1u);
+      P.order[(size_t)list * P.order_pitch + atomicAdd(&P.order_counts[list], 1u)] = u;
     }
   }
   if (n_el) atomicAdd(&P.state[s].n_elided, n_el);
