@@ -1,8 +1,10 @@
 // api_decode.cu -- C-ABI entry points for the query half of the path (Chunk::read_from, get / fill_cell /
 // fill_window / iter_search at chunk and superchunk level, flat to_fixed / from_fixed).
 #include <algorithm>
+#include <cstdlib>
 
 #include "decode.cuh"
+#include "decode_tile.cuh"
 #include "host.hpp"
 
 using namespace dcdf;
@@ -45,6 +47,7 @@ struct MetaBlock {
   DevMeta d;
   QuerySet Q;
   u64 n_dir = 0;
+  int max_sidelen = 0;  // tiles up to 64x64 take the level-synchronous window decoder
 };
 
 void check_err_word(dcdf_ctx* ctx, u32* d_err, const char* what) {
@@ -108,6 +111,7 @@ MetaBlock* make_meta(dcdf_ctx* ctx, const u8* blob, std::vector<UnitMeta>& units
     CK(cudaMemcpyAsync(units.data(), mb->d.units, ub, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     mb->n_dir = n_dir;
+    for (auto& u : units) if (u.stored) mb->max_sidelen = std::max(mb->max_sidelen, u.sidelen);
     QuerySet& Q = mb->Q;
     Q.blob = blob;
     Q.units = mb->d.units;
@@ -151,6 +155,10 @@ MetaBlock* chunk_meta(dcdf_ctx* ctx, const dcdf_chunk* cc) {
     c->encoding = units[0].enc;
     mb->Q.encoding = c->encoding;
     for (int i = 0; i < 3; i++) mb->Q.shape[i] = c->shape[i];
+    slices[0].instants = (int)c->shape[0];  // now known: refresh the device copy
+    slices[0].bits = c->fractional_bits;
+    CK(cudaMemcpyAsync(mb->d.slices, slices.data(), sizeof(SliceMeta), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
   }
   mb->Q.chunk_size = std::max<i64>(c->shape[0], 1);
   c->dir = mb;
@@ -329,6 +337,40 @@ void do_window_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
   CK(cudaMemcpyAsync(d_c, cubes.data(), sizeof(CubeDev) * n, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_off, out_off, sizeof(u64) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
   OutTarget ot = out_begin(ctx, out, os.esize * total, mem);
+  const bool tiles = mb->max_sidelen <= 64 && getenv("DCDF_WINDOW_CELLS") == nullptr;
+  if (tiles) {
+    // one CTA per (window, slice, subchunk)
+    std::vector<u64> job_base(n + 1);
+    u64 n_jobs = 0;
+    const i64 cs = mb->Q.chunks_sidelen;
+    for (uint64_t i = 0; i < n; i++) {
+      const CubeDev& c = cubes[i];
+      job_base[i] = n_jobs;
+      if (c.end > c.start && c.bottom > c.top && c.right > c.left) {
+        const u64 nsub = (u64)((c.bottom - 1) / cs - c.top / cs + 1) * (u64)((c.right - 1) / cs - c.left / cs + 1);
+        const u64 nsl = (u64)((c.end - 1) / mb->Q.chunk_size - c.start / mb->Q.chunk_size + 1);
+        n_jobs += nsub * nsl;
+      }
+    }
+    job_base[n] = n_jobs;
+    ctx->query_aux.reserve(sizeof(u64) * (n + 1));
+    CK(cudaMemcpyAsync(ctx->query_aux.p, job_base.data(), sizeof(u64) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    TileWindowParams TP;
+    TP.Q = mb->Q; TP.cubes = d_c; TP.out_off = d_off; TP.job_base = ctx->query_aux.as<u64>();
+    TP.n_queries = n; TP.n_jobs = n_jobs; TP.out = ot.dev; TP.raw = os.raw;
+    CK(cudaFuncSetAttribute(k_window_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    tbegin(ctx, KT_WINDOW);
+    if (n_jobs) {
+      const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
+      k_window_tiles<<<grid, DT_THREADS, sizeof(TileSmem), ctx->stream>>>(TP);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+    tend(ctx, KT_WINDOW);
+    out_end(ctx, ot);  // job_base stays alive until here
+    tcollect(ctx, KT_WINDOW);
+    return;
+  }
   const unsigned gy = (unsigned)std::min<uint64_t>(n, 65535);
   const unsigned gx = (unsigned)std::max<i64>(1, std::min<i64>((biggest + 255) / 256, std::max<i64>(1, (i64)ctx->sm_count * 16 / gy)));
   tbegin(ctx, KT_WINDOW);

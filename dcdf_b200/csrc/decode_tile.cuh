@@ -1,0 +1,227 @@
+// decode_tile.cuh -- window decode by level-synchronous expansion of whole <=64x64 tiles.
+//
+// Replaces the per-cell recursion of Snapshot::fill_window (snapshot.rs:204-301) and Log::fill_window
+// (log.rs:311-508) for batched windows: one CTA per (window, time slice, subchunk) walks the requested
+// instants of that chunk in order.  For a Snapshot the k^2 tree is expanded top-down into a dense
+// max-value pyramid in shared memory (every level, Morton order): positions whose parent is an internal
+// node read their own DAC entry (value = parent - max[idx], snapshot.rs:179), all others inherit the
+// parent's value.  BFS indices of children come from a per-level ballot/popc scan of the internal flags,
+// i.e. the same arithmetic as `1 + rank(index) * k^2` (snapshot.rs:177) without touching the rank
+// directory.  A Log is expanded the same way against its block's snapshot pyramid (log.rs:207-293):
+// a log node that stops with equal = 0 is uniform (max_t + max_s of that node), one that stops with
+// equal = 1 adds its offset to the snapshot's cells below it.
+#pragma once
+#include "decode.cuh"
+
+namespace dcdf {
+
+constexpr int DT_THREADS = 256;
+constexpr int DT_WARPS = DT_THREADS / 32;
+constexpr int DT_NODES = 5461;
+constexpr int DT_UPPER = 1365;
+
+struct TileSmem {
+  i64 sval[DT_NODES];   // snapshot max pyramid: level k at offset (4^k - 1) / 3, Morton order inside a level
+  i64 lpay[DT_NODES];   // log expansion payload
+  unsigned short scb[DT_UPPER + 3];  // snapshot: BFS index of the first child (0xffff: not an internal node)
+  unsigned short lcb[DT_UPPER + 3];  // log: same
+  u8 lmode[DT_NODES + 3];            // 0 internal, 1 uniform (value = payload), 2 equal (value = payload + snapshot cell)
+  u32 wtot[DT_WARPS];
+  u32 run;
+};
+
+DCDF_DEVINL u32 lvl_off(int k) { return ((1u << (2 * k)) - 1u) / 3u; }
+
+// Block-wide: turn the "internal" markers of level k into child BFS bases; returns the number of internal nodes.
+DCDF_DEVINL u32 assign_child_bases(unsigned short* cb, int k, u32 p_next, TileSmem& S) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 n = 1u << (2 * k), off = lvl_off(k);
+  u32 running = 0;
+  for (u32 base = 0; base < n; base += DT_THREADS) {
+    const u32 p = base + tid;
+    const bool f = p < n && cb[off + p] != 0xffffu;
+    const u32 b = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) S.wtot[warp] = __popc(b);
+    __syncthreads();
+    u32 before = running, total = 0;
+#pragma unroll
+    for (int w = 0; w < DT_WARPS; w++) {
+      const u32 x = S.wtot[w];
+      if (w < warp) before += x;
+      total += x;
+    }
+    if (f) cb[off + p] = (unsigned short)(p_next + 4u * (before + __popc(b & lanemask_lt())));
+    running += total;
+    __syncthreads();
+  }
+  return running;
+}
+
+// Expand a Snapshot into S.sval / S.scb (L = tree levels, 1..6).
+DCDF_DEVINL void expand_snapshot(const ChunkView& cv, const InstDir& s, int L, TileSmem& S) {
+  const int tid = threadIdx.x;
+  BitMapRef nm{cv.chunk, s.nm_len, s.nm_base};
+  DacRef mx{cv.chunk, &s.max};
+  if (tid == 0) {
+    S.sval[0] = mx.get(0);
+    S.scb[0] = nm.get(0) ? 1 : 0xffff;
+  }
+  __syncthreads();
+  u32 p_next = 1;
+  for (int k = 0; k < L; k++) {
+    const u32 internal = assign_child_bases(S.scb, k, p_next, S);
+    const u32 n1 = 1u << (2 * (k + 1)), o0 = lvl_off(k), o1 = lvl_off(k + 1);
+    const bool has_bits = k + 1 < L;
+    for (u32 p1 = tid; p1 < n1; p1 += DT_THREADS) {
+      const u32 p = p1 >> 2;
+      const u32 cb = S.scb[o0 + p];
+      i64 v = S.sval[o0 + p];
+      bool in = false;
+      if (cb != 0xffffu) {
+        const u32 idx = cb + (p1 & 3u);
+        v -= mx.get(idx);
+        in = has_bits && idx < s.nm_len && nm.get(idx);
+      }
+      S.sval[o1 + p1] = v;
+      if (has_bits) S.scb[o1 + p1] = in ? 1 : 0xffff;
+    }
+    p_next += 4u * internal;
+    __syncthreads();
+  }
+}
+
+// Expand a Log against the snapshot pyramid already in S.sval; cell values end up as (lmode, lpay) of level L.
+DCDF_DEVINL void expand_log(const ChunkView& cv, const InstDir& l, const InstDir& s, int L, TileSmem& S) {
+  const int tid = threadIdx.x;
+  BitMapRef nm{cv.chunk, l.nm_len, l.nm_base}, eq{cv.chunk, l.eq_len, l.eq_base};
+  DacRef mx{cv.chunk, &l.max};
+  if (tid == 0) {
+    const i64 d0 = mx.get(0);
+    const bool single_t = !nm.get(0);
+    if (!single_t) {
+      S.lmode[0] = 0; S.lpay[0] = d0; S.lcb[0] = 1;
+    } else {
+      // log.rs:180-186: a single-node log is uniform unless its equal bit says "snapshot + constant"
+      BitMapRef nm_s{cv.chunk, s.nm_len, s.nm_base};
+      const bool snap_single = !nm_s.get(0);
+      const bool uniform = snap_single || !eq.get(0);
+      S.lmode[0] = uniform ? 1 : 2;
+      S.lpay[0] = uniform ? d0 + S.sval[0] : d0;
+      S.lcb[0] = 0xffff;
+    }
+  }
+  __syncthreads();
+  u32 p_next = 1;
+  for (int k = 0; k < L; k++) {
+    const u32 internal = assign_child_bases(S.lcb, k, p_next, S);
+    const u32 n1 = 1u << (2 * (k + 1)), o0 = lvl_off(k), o1 = lvl_off(k + 1);
+    const bool has_bits = k + 1 < L;
+    for (u32 p1 = tid; p1 < n1; p1 += DT_THREADS) {
+      const u32 p = p1 >> 2;
+      u8 mode = S.lmode[o0 + p];
+      i64 pay = S.lpay[o0 + p];
+      bool in = false;
+      if (mode == 0) {
+        const u32 idx = S.lcb[o0 + p] + (p1 & 3u);
+        const i64 d = mx.get(idx);  // max_t is replaced, not accumulated (log.rs:233)
+        in = has_bits && idx < l.nm_len && nm.get(idx);
+        if (in) {
+          mode = 0; pay = d;
+        } else if (!has_bits) {
+          mode = 2; pay = d;  // bottom level: value = max_t + snapshot cell
+        } else {
+          const bool e = eq.get(idx - nm.rank(idx));  // rank0(idx + 1) - 1 (log.rs:265)
+          mode = e ? 2 : 1;
+          pay = e ? d : d + S.sval[o1 + p1];  // uniform: max_t + max_s of this node (log.rs:266-268)
+        }
+      }
+      S.lmode[o1 + p1] = mode;
+      S.lpay[o1 + p1] = pay;
+      if (has_bits) S.lcb[o1 + p1] = in ? 1 : 0xffff;
+    }
+    p_next += 4u * internal;
+    __syncthreads();
+  }
+}
+
+struct TileWindowParams {
+  QuerySet Q;
+  const CubeDev* cubes;   // validated, ordered
+  const u64* out_off;     // [n] element offsets
+  const u64* job_base;    // [n + 1] prefix of (slices x subchunks) per window
+  u64 n_queries, n_jobs;
+  void* out;
+  int raw;
+};
+
+__global__ void __launch_bounds__(DT_THREADS) k_window_tiles(const TileWindowParams P) {
+  extern __shared__ __align__(16) unsigned char dt_smem_raw[];
+  TileSmem& S = *reinterpret_cast<TileSmem*>(dt_smem_raw);
+  const QuerySet& Q = P.Q;
+  const int tid = threadIdx.x;
+  for (u64 ji = blockIdx.x; ji < P.n_jobs; ji += gridDim.x) {
+    u64 lo_q = 0, hi_q = P.n_queries;
+    while (hi_q - lo_q > 1) {
+      const u64 mid = (lo_q + hi_q) >> 1;
+      if (P.job_base[mid] <= ji) lo_q = mid; else hi_q = mid;
+    }
+    const u64 q = lo_q;
+    const CubeDev c = P.cubes[q];
+    const u64 local = ji - P.job_base[q];
+    const i64 cs = Q.chunks_sidelen;
+    const i64 cr0 = c.top / cs, cc0 = c.left / cs;
+    const i64 ncr = (c.bottom - 1) / cs - cr0 + 1, ncc = (c.right - 1) / cs - cc0 + 1;
+    const u64 nsub = (u64)(ncr * ncc);
+    const u32 s = (u32)(c.start / Q.chunk_size) + (u32)(local / nsub);
+    const u64 sub = local % nsub;
+    const i64 cr = cr0 + (i64)(sub / (u64)ncc), cc = cc0 + (i64)(sub % (u64)ncc);
+    const SliceMeta sm = Q.slices[s];
+    const i64 t_lo = max(c.start, sm.t0), t_hi = min(c.end, sm.t0 + (i64)sm.instants);
+    const i64 chunk_top = cr * cs, chunk_left = cc * cs;
+    const int top = (int)(max(chunk_top, c.top) - chunk_top), bottom = (int)(min(chunk_top + cs, c.bottom) - chunk_top);
+    const int left = (int)(max(chunk_left, c.left) - chunk_left), right = (int)(min(chunk_left + cs, c.right) - chunk_left);
+    const int wr = bottom - top, wc = right - left;
+    const i64 W_rows = c.bottom - c.top, W_cols = c.right - c.left;
+    const u64 obase = P.out_off[q];
+    const u32 slot = (u32)(cr * Q.subsidelen + cc);
+    const int32_t u = Q.slot_unit[sm.slot_base + slot];
+    const UnitMeta m = u >= 0 ? Q.units[u] : UnitMeta{};
+    const bool stored = u >= 0 && m.stored;
+    auto out_index = [&](i64 t, int r, int col) {
+      return obase + (u64)(((t - c.start) * W_rows + (chunk_top + r - c.top)) * W_cols + (chunk_left + col - c.left));
+    };
+    if (!stored) {
+      // Elided: one value per instant from the max table, parent's fractional bits (superchunk.rs:426-433)
+      for (i64 t = t_lo; t < t_hi; t++) {
+        const i64 v = Q.tbl_max[sm.table_base + (u64)(t - sm.t0) * Q.n_slots + slot];
+        for (int i = tid; i < wr * wc; i += DT_THREADS) emit(Q, P.out, out_index(t, top + i / wc, left + i % wc), v, sm.bits, P.raw);
+      }
+      continue;
+    }
+    ChunkView cv{Q.blob + m.blob_off, Q.dir + m.dir_base, m.sidelen};
+    const int L = 31 - __clz(m.sidelen);
+    const u32 oL = lvl_off(L);
+    u32 cur_snap = 0xffffffffu;
+    for (i64 t = t_lo; t < t_hi; t++) {
+      const u32 ti = (u32)(t - sm.t0);
+      const InstDir& d = cv.dir[ti];
+      if (d.snap != cur_snap) {
+        __syncthreads();
+        expand_snapshot(cv, cv.dir[d.snap], L, S);
+        cur_snap = d.snap;
+      }
+      const bool is_log = d.snap != ti;
+      if (is_log) expand_log(cv, d, cv.dir[d.snap], L, S);
+      for (int i = tid; i < wr * wc; i += DT_THREADS) {
+        const int r = top + i / wc, col = left + i % wc;
+        const u32 mo = oL + morton_encode((u32)r, (u32)col);
+        i64 v = S.sval[mo];
+        if (is_log) v = S.lmode[mo] == 1 ? S.lpay[mo] : S.lpay[mo] + v;
+        emit(Q, P.out, out_index(t, r, col), v, m.bits, P.raw);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace dcdf

@@ -114,6 +114,44 @@ struct StatParams {
   InstStats* istats;  // [n_units][t_max]
 };
 
+// warp-wide min / max: one redux for 32-bit types (floats through an order-preserving key), shuffles otherwise
+DCDF_DEVINL u32 fkey(float f) { const u32 b = __float_as_uint(f); return b ^ ((u32)((int32_t)b >> 31) | 0x80000000u); }
+DCDF_DEVINL float funkey(u32 k) { return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu)); }
+DCDF_DEVINL float warp_min(float v) { return funkey(__reduce_min_sync(0xffffffffu, fkey(v))); }
+DCDF_DEVINL float warp_max(float v) { return funkey(__reduce_max_sync(0xffffffffu, fkey(v))); }
+DCDF_DEVINL int32_t warp_min(int32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+DCDF_DEVINL int32_t warp_max(int32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+DCDF_DEVINL u32 warp_min(u32 v) { return __reduce_min_sync(0xffffffffu, v); }
+DCDF_DEVINL u32 warp_max(u32 v) { return __reduce_max_sync(0xffffffffu, v); }
+DCDF_DEVINL double warp_min(double v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+DCDF_DEVINL double warp_max(double v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+DCDF_DEVINL i64 warp_min(i64 v) {
+  for (int o = 16; o > 0; o >>= 1) { const i64 x = __shfl_xor_sync(0xffffffffu, v, o); v = x < v ? x : v; }
+  return v;
+}
+DCDF_DEVINL i64 warp_max(i64 v) {
+  for (int o = 16; o > 0; o >>= 1) { const i64 x = __shfl_xor_sync(0xffffffffu, v, o); v = x > v ? x : v; }
+  return v;
+}
+template <typename T> struct Lim;
+template <> struct Lim<float> { static DCDF_DEVINL float hi() { return INFINITY; } static DCDF_DEVINL float lo() { return -INFINITY; } };
+template <> struct Lim<double> { static DCDF_DEVINL double hi() { return INFINITY; } static DCDF_DEVINL double lo() { return -INFINITY; } };
+template <> struct Lim<int32_t> { static DCDF_DEVINL int32_t hi() { return INT32_MAX; } static DCDF_DEVINL int32_t lo() { return INT32_MIN; } };
+template <> struct Lim<i64> { static DCDF_DEVINL i64 hi() { return INT64_MAX; } static DCDF_DEVINL i64 lo() { return INT64_MIN; } };
+template <typename T> DCDF_DEVINL u64 raw64(T v);
+template <> DCDF_DEVINL u64 raw64<float>(float v) { return (u64)__double_as_longlong((double)v); }
+template <> DCDF_DEVINL u64 raw64<double>(double v) { return (u64)__double_as_longlong(v); }
+template <> DCDF_DEVINL u64 raw64<int32_t>(int32_t v) { return (u64)(i64)v; }
+template <> DCDF_DEVINL u64 raw64<i64>(i64 v) { return (u64)v; }
+
+constexpr int STAT_BATCH = 32;  // instants whose per-warp partials are kept in smem before one finalisation
+
 template <typename InT, bool IS_FLOAT>
 __global__ void __launch_bounds__(STAT_THREADS) k_unit_stats(const StatParams P) {
   const u32 u = blockIdx.x;
@@ -121,107 +159,106 @@ __global__ void __launch_bounds__(STAT_THREADS) k_unit_stats(const StatParams P)
   const EncUnit unit = P.units[u];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const InT* base = static_cast<const InT*>(P.data) + unit.base;
-  const int rows = unit.rows, cols = unit.cols;
-  const int cells = rows * cols;
-  __shared__ double s_mn[8], s_mx[8];
-  __shared__ i64 s_imn[8], s_imx[8];
-  __shared__ u32 s_first[8], s_last[8];
+  const int cols = unit.cols;
+  const int cells = unit.rows * cols;
+  __shared__ InT p_mn[STAT_BATCH][8], p_mx[STAT_BATCH][8];
+  __shared__ u32 p_first[STAT_BATCH][8], p_last[STAT_BATCH][8];
+  __shared__ double s_d[8][2];
+  __shared__ i64 s_l[8][2];
   __shared__ int s_i[8][4];
   __shared__ int s_redo, s_maxfb;
 
-  double vmax = -INFINITY, vneg = 0.0;
-  i64 imax = INT64_MIN, imin = INT64_MAX;
+  // row-major walk without divisions: thread t visits cells t, t + 256, ...
+  const int r_init = tid / cols, c_init = tid - r_init * cols;
+  const int step_r = STAT_THREADS / cols, step_c = STAT_THREADS - step_r * cols;
+
+  InT umax = Lim<InT>::lo(), umin = Lim<InT>::hi();  // unit extrema over non-NaN values
+  InT uneg = (InT)0;                                 // most negative value
   int has = 0, fnn = 0, fng = 0, nonfinite = 0;
 
-  for (int inst = 0; inst < unit.instants; inst++) {
-    const InT* p = base + (i64)inst * P.stride_t;
-    double mn = INFINITY, mx = -INFINITY;
-    i64 lmn = INT64_MAX, lmx = INT64_MIN;
-    u32 first = 0xffffffffu, last = 0;  // row-major position (+1 for last) of first non-NaN / last NaN
-    bool any_nan = false;
-    for (int idx = tid; idx < cells; idx += STAT_THREADS) {
-      const int r = idx / cols, c = idx - r * cols;
-      const InT v = __ldg(p + (i64)r * P.stride_r + (i64)c * P.stride_c);
-      if (IS_FLOAT) {
-        const double d = (double)v;
-        if (d != d) {
-          any_nan = true;
-          last = (u32)idx + 1u;  // idx ascends within a thread
+  for (int i0 = 0; i0 < unit.instants; i0 += STAT_BATCH) {
+    const int nb = min(STAT_BATCH, unit.instants - i0);
+    for (int bi = 0; bi < nb; bi++) {
+      const InT* p = base + (i64)(i0 + bi) * P.stride_t;
+      InT mn = Lim<InT>::hi(), mx = Lim<InT>::lo();
+      u32 first = 0xffffffffu, last = 0;  // row-major position (+1 for last) of first non-NaN / last NaN
+      int r = r_init, c = c_init;
+#pragma unroll 4
+      for (int idx = tid; idx < cells; idx += STAT_THREADS) {
+        const InT v = __ldg(p + (i64)r * P.stride_r + (i64)c * P.stride_c);
+        if (IS_FLOAT) {
+          if (v != v) {
+            last = (u32)idx + 1u;  // idx ascends within a thread
+          } else {
+            first = min(first, (u32)idx);
+            mn = v < mn ? v : mn;
+            mx = v > mx ? v : mx;
+            const int fb = FloatBits<InT>::fracbits(v);
+            if (v < (InT)0) { fng = fb > fng ? fb : fng; uneg = v < uneg ? v : uneg; }
+            else fnn = fb > fnn ? fb : fnn;
+          }
         } else {
-          if (fabs(d) == INFINITY) nonfinite = 1;
-          if (first == 0xffffffffu) first = (u32)idx;
-          mn = fmin(mn, d);
-          mx = fmax(mx, d);
-          const int fb = FloatBits<InT>::fracbits(v);
-          if (d < 0.0) { fng = fb > fng ? fb : fng; vneg = fmin(vneg, d); }
-          else fnn = fb > fnn ? fb : fnn;
+          mn = v < mn ? v : mn;
+          mx = v > mx ? v : mx;
         }
-      } else {
-        const i64 x = (i64)v;
-        lmn = x < lmn ? x : lmn;
-        lmx = x > lmx ? x : lmx;
+        c += step_c; r += step_r;
+        if (c >= cols) { c -= cols; r++; }
       }
-    }
-    (void)any_nan;
-    // warp reduce
-    for (int o = 16; o > 0; o >>= 1) {
-      if (IS_FLOAT) {
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-      } else {
-        i64 a = __shfl_xor_sync(0xffffffffu, lmn, o), b = __shfl_xor_sync(0xffffffffu, lmx, o);
-        lmn = a < lmn ? a : lmn;
-        lmx = b > lmx ? b : lmx;
-      }
-    }
-    if (lane == 0) {
-      s_mn[warp] = mn; s_mx[warp] = mx; s_first[warp] = first; s_last[warp] = last;
-      s_imn[warp] = lmn; s_imx[warp] = lmx;
+      mn = warp_min(mn); mx = warp_max(mx);
+      if (IS_FLOAT) { first = warp_min(first); last = warp_max(last); }
+      if (lane == 0) { p_mn[bi][warp] = mn; p_mx[bi][warp] = mx; p_first[bi][warp] = first; p_last[bi][warp] = last; }
     }
     __syncthreads();
-    if (tid == 0) {
-      InstStats st;
-      if (IS_FLOAT) {
-        for (int w = 1; w < 8; w++) {
-          mn = fmin(mn, s_mn[w]); mx = fmax(mx, s_mx[w]);
-          first = min(first, s_first[w]); last = max(last, s_last[w]);
-        }
-        const bool all_nan = first == 0xffffffffu;
-        st.first = first; st.last = last;
-        st.mn = (u64)__double_as_longlong(mn);
-        st.mx = (u64)__double_as_longlong(mx);
-        if (!all_nan) { has = 1; vmax = fmax(vmax, mx); }
-      } else {
-        for (int w = 1; w < 8; w++) {
-          lmn = s_imn[w] < lmn ? s_imn[w] : lmn;
-          lmx = s_imx[w] > lmx ? s_imx[w] : lmx;
-        }
-        st.first = 0; st.last = 0;
-        st.mn = (u64)lmn; st.mx = (u64)lmx;
-        imin = lmn < imin ? lmn : imin;
-        imax = lmx > imax ? lmx : imax;
-        has = 1;
+    if (tid < nb) {
+      InT mn = p_mn[tid][0], mx = p_mx[tid][0];
+      u32 first = p_first[tid][0], last = p_last[tid][0];
+      for (int w = 1; w < 8; w++) {
+        mn = p_mn[tid][w] < mn ? p_mn[tid][w] : mn;
+        mx = p_mx[tid][w] > mx ? p_mx[tid][w] : mx;
+        first = min(first, p_first[tid][w]); last = max(last, p_last[tid][w]);
       }
-      P.istats[(size_t)u * P.t_max + inst] = st;
+      InstStats st;
+      st.mn = raw64<InT>(mn); st.mx = raw64<InT>(mx);
+      if (IS_FLOAT) {
+        st.first = first; st.last = last;
+        if (first != 0xffffffffu) {
+          has = 1;
+          umax = mx > umax ? mx : umax;
+          if (mx - mx != (InT)0 || mn - mn != (InT)0) nonfinite = 1;  // +-inf among the extrema
+        }
+      } else {
+        st.first = 0; st.last = 0;
+        has = 1;
+        umax = mx > umax ? mx : umax;
+        umin = mn < umin ? mn : umin;
+      }
+      P.istats[(size_t)u * P.t_max + i0 + tid] = st;
     }
     __syncthreads();
   }
 
   // unit-level reductions of the thread-local accumulators
+  umax = warp_max(umax); umin = warp_min(umin); uneg = warp_min(uneg);
   for (int o = 16; o > 0; o >>= 1) {
     fnn = max(fnn, __shfl_xor_sync(0xffffffffu, fnn, o));
     fng = max(fng, __shfl_xor_sync(0xffffffffu, fng, o));
     nonfinite |= __shfl_xor_sync(0xffffffffu, nonfinite, o);
-    vneg = fmin(vneg, __shfl_xor_sync(0xffffffffu, vneg, o));
+    has |= __shfl_xor_sync(0xffffffffu, has, o);
   }
-  if (lane == 0) { s_i[warp][0] = fnn; s_i[warp][1] = fng; s_i[warp][2] = nonfinite; s_mn[warp] = vneg; }
+  if (lane == 0) {
+    s_i[warp][0] = fnn; s_i[warp][1] = fng; s_i[warp][2] = nonfinite; s_i[warp][3] = has;
+    if (IS_FLOAT) { s_d[warp][0] = (double)umax; s_d[warp][1] = (double)uneg; }
+    else { s_l[warp][0] = (i64)umax; s_l[warp][1] = (i64)umin; }
+  }
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < 8; w++) {
-      fnn = max(fnn, s_i[w][0]); fng = max(fng, s_i[w][1]); nonfinite |= s_i[w][2];
-      vneg = fmin(vneg, s_mn[w]);
+    double vmax = -INFINITY, vneg = 0.0;
+    i64 imax = INT64_MIN, imin = INT64_MAX;
+    fnn = 0; fng = 0; nonfinite = 0; has = 0;
+    for (int w = 0; w < 8; w++) {
+      fnn = max(fnn, s_i[w][0]); fng = max(fng, s_i[w][1]); nonfinite |= s_i[w][2]; has |= s_i[w][3];
+      if (IS_FLOAT) { vmax = fmax(vmax, s_d[w][0]); vneg = fmin(vneg, s_d[w][1]); }
+      else { imax = s_l[w][0] > imax ? s_l[w][0] : imax; imin = s_l[w][1] < imin ? s_l[w][1] : imin; }
     }
     UnitStats us;
     us.vmax = vmax; us.vneg = vneg; us.imax = imax; us.imin = imin;
