@@ -193,7 +193,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   ctx->stored.reserve(n_units);
   ctx->chunk_off.reserve(sizeof(u64) * ((size_t)n_units + 1));
   ctx->small.reserve(256);
-  if (!job.plain) ctx->tbl_scratch.reserve(sizeof(u64) * 2 * tbl_total);
+  if (!job.plain) ctx->tbl_scratch.reserve(sizeof(u64) * 4 * tbl_total);
   int64_t *d_tbl_max = nullptr, *d_tbl_min = nullptr;
   if (!job.plain && tbl_total) {
     d_tbl_max = static_cast<int64_t*>(pool_alloc(sizeof(i64) * tbl_total, st));

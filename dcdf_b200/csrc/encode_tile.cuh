@@ -109,10 +109,15 @@ struct UpNode {
 // Shared-memory plan of the encode CTA.
 template <typename V>
 struct EncSmem {
-  typename VT<V>::U A[MAX_NODES + 3];      // zigzag codes of `max` in BFS order
+  // zigzag codes of `max` in BFS order live at A_raw + 3: BFS indices of sibling groups are 1 (mod 4), so every
+  // group of four starts on a 16-byte boundary and is staged with one vector store
+  __align__(16) typename VT<V>::U A_raw[MAX_NODES + 7];
+  __align__(16) typename VT<V>::U C[MAX_NODES + 7];   // DAC compaction ping-pong partner of A / B
   typename VT<V>::U B[MAX_INTERNAL + 3];   // zigzag codes of `min`
-  u32 nm[NM_WORDS];                        // nodemap bits, MSB first
-  u32 eqw[NM_WORDS];                       // equal bits (logs)
+  u8 nmf[MAX_INTERNAL + 3];                // nodemap flags (one byte per node above the leaf level)
+  u8 eqf[MAX_INTERNAL + 3];                // equal flags (logs)
+  u32 nm[NM_WORDS];                        // packed words, MSB first
+  u32 eqw[NM_WORDS];
   UpNode<V> l2[16];
   UpNode<V> l1[4];
   UpNode<V> l0;
@@ -126,18 +131,19 @@ struct EncSmem {
   u32 my_size, as_snapshot, go_slow;
   u32 wtot[6][ENC_WARPS];                  // per-warp internal-node counts per level (scan input)
   u32 scan[ENC_WARPS];                     // scratch for the DAC compaction scan
-  u32 scan2[ENC_WARPS];
   u64 piece_off;
   __align__(16) u8 stage[STAGE_BYTES];
 };
 
 // ---------------------------------------------------------------------------------------------------
 // DAC emission (dac.rs:96-132 + dac.rs:37-44 + bitmap.rs:66-113,128-138), block-wide.
-// `a` holds n zigzag codes (shared memory), n_j = cntgt[j] = number of codes longer than j bytes.
-// Level j is dense: byte = code & 0xff, continuation bit = (code >> 8) != 0; survivors are compacted in
-// place (order preserved) to form level j+1.  Returns bytes written.  All threads must call.
+// `src` holds n zigzag codes (shared memory), n_j = cntgt[j] = number of codes longer than j bytes.
+// Level j is dense: byte = code & 0xff, continuation bit = (code >> 8) != 0.  Each warp owns a contiguous
+// run of the level (a multiple of 32 entries): pass 1 counts its survivors, one barrier turns the counts
+// into offsets, pass 2 writes bytes / bitmap words / rank directory and compacts the survivors (order
+// preserved) into `dst`, which becomes the next level.  Returns bytes written.  All threads must call.
 template <typename U, int MAXLEN>
-__device__ u32 block_dac_emit(U* a, u32 n, const u32* cntgt, u8* out, u32* scan_a, u32* scan_b) {
+__device__ u32 block_dac_emit(U* src, U* dst, const u32* cntgt, u8* out, u32* scan) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int n_levels = 0;
   for (int j = 0; j < MAXLEN; j++)
@@ -155,47 +161,34 @@ __device__ u32 block_dac_emit(U* a, u32 n, const u32* cntgt, u8* out, u32* scan_
       store_be32(p_len, nj);
       store_be32(p_len + 4, 4u);  // k = 4 (bitmap.rs:69)
     }
-    // chunks of 1024 entries: warp w owns [128w, 128w+128) of the chunk, 4 ballots of 32
-    u32 running = 0;  // survivors before this chunk
-    for (u32 c0 = 0; c0 < nj; c0 += 1024u) {
-      U v[4];
-      u32 bal[4];
-      u32 wcount = 0;
-#pragma unroll
-      for (int s = 0; s < 4; s++) {
-        u32 i = c0 + warp * 128u + s * 32u + lane;
-        v[s] = i < nj ? a[i] : (U)0;
-        bool more = i < nj && (v[s] >> 8) != 0;
-        bal[s] = __ballot_sync(0xffffffffu, more);
-        wcount += __popc(bal[s]);
-      }
-      u32* sc = ((c0 >> 10) & 1) ? scan_b : scan_a;
-      if (lane == 0) sc[warp] = wcount;
-      __syncthreads();  // also: every read of this chunk happened before any compacting write
-      u32 wbase = running, total = 0;
-#pragma unroll
-      for (int w = 0; w < ENC_WARPS; w++) {
-        u32 x = sc[w];
-        if (w < warp) wbase += x;
-        total += x;
-      }
-      u32 pre = wbase;
-#pragma unroll
-      for (int s = 0; s < 4; s++) {
-        u32 i0 = c0 + warp * 128u + s * 32u;  // first entry of this ballot
-        u32 i = i0 + lane;
-        if (i < nj) {
-          p_bytes[i] = (u8)(v[s] & 0xff);
-          if ((bal[s] >> lane) & 1u) a[pre + __popc(bal[s] & lanemask_lt())] = (U)(v[s] >> 8);
-        }
-        if (lane == 0 && i0 < nj) store_be32(p_words + 4 * (i0 >> 5), __brev(bal[s]));
-        // rank directory: index[b] = ones in bits [0, 128(b+1))  (bitmap.rs:97-104)
-        if (lane == 0 && s == 3 && (i0 + 32u) <= nj) store_be32(p_index + 4 * ((i0 + 32u) / 128u - 1u), pre + __popc(bal[s]));
-        pre += __popc(bal[s]);
-      }
-      running += total;
+    const u32 seg = ((nj + 32u * ENC_WARPS - 1u) / (32u * ENC_WARPS)) * 32u;
+    const u32 i_lo = min(nj, warp * seg), i_hi = min(nj, i_lo + seg);
+    u32 cnt = 0;
+    for (u32 i0 = i_lo; i0 < i_hi; i0 += 32u) {
+      const u32 i = i0 + lane;
+      cnt += __popc(__ballot_sync(0xffffffffu, i < nj && (src[i] >> 8) != 0));
     }
-    __syncthreads();  // compacted level j+1 complete before it is read
+    if (lane == 0) scan[warp] = cnt;
+    __syncthreads();
+    u32 pre = 0;
+#pragma unroll
+    for (int w = 0; w < ENC_WARPS; w++) pre += w < warp ? scan[w] : 0u;
+    for (u32 i0 = i_lo; i0 < i_hi; i0 += 32u) {
+      const u32 i = i0 + lane;
+      const U v = i < nj ? src[i] : (U)0;
+      const bool more = (v >> 8) != 0;
+      const u32 bal = __ballot_sync(0xffffffffu, more);
+      if (i < nj) p_bytes[i] = (u8)(v & 0xff);
+      if (more) dst[pre + __popc(bal & lanemask_lt())] = (U)(v >> 8);
+      pre += __popc(bal);
+      if (lane == 0) {
+        store_be32(p_words + 4 * (i0 >> 5), __brev(bal));
+        // rank directory: index[b] = ones in bits [0, 128(b+1))  (bitmap.rs:97-104)
+        if (((i0 + 32u) & 127u) == 0 && (i0 + 32u) <= nj) store_be32(p_index + 4 * ((i0 + 32u) / 128u - 1u), pre);
+      }
+    }
+    __syncthreads();  // next level complete in dst; scan[] reusable
+    U* t = src; src = dst; dst = t;
     off += 8 + 4 * blocks + 4 * words + nj;
   }
   return off;
@@ -208,20 +201,32 @@ __host__ __device__ inline u32 dac_size_from_counts(const u32* cntgt, int maxlen
   return s;
 }
 
-// BitMap serialization from MSB-first words held in smem (bitmap.rs:128-138); block-wide.
-__device__ inline u32 block_bitmap_emit(const u32* words_smem, u32 length, u8* out) {
-  const int tid = threadIdx.x;
+// BitMap serialization (bitmap.rs:66-113,128-138) from one flag byte per bit; block-wide.  `words_smem`
+// receives the MSB-first words (ballot + brev), from which the rank directory is summed.
+__device__ inline u32 block_bitmap_emit(const u8* flags, u32* words_smem, u32 length, u8* out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 blocks = length / 128u, words = (length + 31u) / 32u;
+  for (u32 w = warp; w < words; w += ENC_WARPS) {
+    const u32 i = 32u * w + lane;
+    const u32 bal = __ballot_sync(0xffffffffu, i < length && flags[i] != 0);
+    if (lane == 0) {
+      const u32 word = __brev(bal);
+      words_smem[w] = word;
+      store_be32(out + 8 + 4 * blocks + 4 * w, word);
+    }
+  }
   if (tid == 0) {
     store_be32(out, length);
     store_be32(out + 4, 4u);
   }
-  for (u32 b = tid; b < blocks; b += ENC_THREADS) {
-    u32 c = 0;
-    for (u32 w = 0; w < 4 * (b + 1); w++) c += __popc(words_smem[w]);
-    store_be32(out + 8 + 4 * b, c);
+  if (blocks) {
+    __syncthreads();
+    for (u32 b = tid; b < blocks; b += ENC_THREADS) {
+      u32 c = 0;
+      for (u32 w = 0; w < 4 * (b + 1); w++) c += __popc(words_smem[w]);
+      store_be32(out + 8 + 4 * b, c);
+    }
   }
-  for (u32 w = tid; w < words; w += ENC_THREADS) store_be32(out + 8 + 4 * blocks + 4 * w, words_smem[w]);
   return 8 + 4 * blocks + 4 * words;
 }
 
@@ -314,10 +319,11 @@ __device__ __forceinline__ u32 serialize_structure(EncSmem<V>& S, u8* out, const
     store_be32(out + 9, 64u >> lo);  // sidelen
   }
   u32 off = 13;
-  off += block_bitmap_emit(S.nm, nm_len, out + off);
-  if (!as_snapshot) off += block_bitmap_emit(S.eqw, nm_len - n_min, out + off);
-  off += block_dac_emit<U, VT<V>::MAXLEN>(S.A, S.sel_max[0], S.sel_max, out + off, S.scan, S.scan2);
-  off += block_dac_emit<U, VT<V>::MAXLEN>(S.B, S.sel_min[0], S.sel_min, out + off, S.scan, S.scan2);
+  off += block_bitmap_emit(S.nmf, S.nm, nm_len, out + off);
+  if (!as_snapshot) off += block_bitmap_emit(S.eqf, S.eqw, nm_len - n_min, out + off);
+  off += block_dac_emit<U, VT<V>::MAXLEN>(S.A_raw + 3, S.C, S.sel_max, out + off, S.scan);
+  __syncthreads();  // C is reused by the min DAC
+  off += block_dac_emit<U, VT<V>::MAXLEN>(S.B, S.C, S.sel_min, out + off, S.scan);
   return off;
 }
 
@@ -433,7 +439,6 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tiles(const EncPar
     if (tid < 32) { (&S.cntF[0][0][0])[tid] = 0; (&S.cntX[0][0][0])[tid] = 0; }
     if (tid < 4) { (&S.strF[0][0])[tid] = 0; (&S.strX[0][0])[tid] = 0; }
     if (tid == 0) S.bigF = 0;
-    for (int w = tid; w < NM_WORDS; w += ENC_THREADS) { S.nm[w] = 0; S.eqw[w] = 0; }
     __syncthreads();
     if (tid < 4) {
       const UpNode<V> a = S.l2[4 * tid], b = S.l2[4 * tid + 1], c = S.l2[4 * tid + 2], d = S.l2[4 * tid + 3];
@@ -750,7 +755,7 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tiles(const EncPar
     const u32 R5 = Rbase[5] + q_before;  // rank of this thread's first internal quad
 
     // ---------------- stage values / bits in BFS order
-    auto set_bit = [](u32* words, u32 pos) { atomicOr(&words[pos >> 5], 0x80000000u >> (pos & 31u)); };
+    U* const A = S.A_raw + 3;
 #pragma unroll
     for (int l = 0; l < 5; l++) {
       if (l < lo || !(owner[l] && al[l])) continue;
@@ -761,10 +766,10 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tiles(const EncPar
       V e;
       if (as_snapshot) e = l == lo ? tm : (V)(pmax - tm);
       else e = (V)(tm - or0(csmax[l], VT<V>::NONE_MAX));
-      S.A[pos] = VT<V>::zz(e);
+      A[pos] = VT<V>::zz(e);
       const u32 ones_before = Mn[l] + R[l];
+      S.nmf[pos] = in_[l] ? 1 : 0;
       if (in_[l]) {
-        set_bit(S.nm, pos);
         V mv;
         if (as_snapshot) mv = l == lo ? cmin[l] : (V)(cmin[l] - pmin);
         else mv = (V)(cmin[l] - csmin[l]);
@@ -772,41 +777,56 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tiles(const EncPar
       } else if (!as_snapshot) {
         const bool eqf = l == 0 ? (bool)N0.eq : l == 1 ? (bool)N1.eq : l == 2 ? eq2 : l == 3 ? eq3 : eq4;
         const bool un = l == 0 ? u0 : l == 1 ? u1 : l == 2 ? u2 : l == 3 ? u3 : u4;
-        if (!un && eqf) set_bit(S.eqw, pos - ones_before);
+        S.eqf[pos - ones_before] = (!un && eqf) ? 1 : 0;
       }
     }
     if (al[5]) {
       u32 r5 = R5;
+      const bool root5 = !FULL && lo == 5;
+      U qe[4];  // the four level-5 entries of this thread (one sibling group)
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        if (!FULL && !((quad_mask >> q) & 1u)) continue;
-        const bool root5 = !FULL && lo == 5;
-        const u32 pos = root5 ? 0u : Pn[5] + 4u * R[4] + (u32)q;
         const V tm = or0(t5max[q], VT<V>::NONE_MAX);
         V e;
         if (as_snapshot) e = root5 ? tm : (V)(t4max - tm);
         else e = (V)(tm - or0(s5max[q], VT<V>::NONE_MAX));
-        S.A[pos] = VT<V>::zz(e);
+        qe[q] = VT<V>::zz(e);
+      }
+      const u32 qpos = root5 ? 0u : Pn[5] + 4u * R[4];
+      if (!root5) {
+        if (sizeof(U) == 4) *reinterpret_cast<uint4*>(&A[qpos]) = make_uint4((u32)qe[0], (u32)qe[1], (u32)qe[2], (u32)qe[3]);
+        else { A[qpos] = qe[0]; A[qpos + 1] = qe[1]; A[qpos + 2] = qe[2]; A[qpos + 3] = qe[3]; }
+      } else {
+        A[0] = qe[0];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (!FULL && !((quad_mask >> q) & 1u)) continue;
+        const u32 pos = qpos + (u32)q;
         const u32 ones_before = Mn[5] + r5;
-        if ((in5 >> q) & 1u) {
-          set_bit(S.nm, pos);
+        const bool inq = (in5 >> q) & 1u;
+        S.nmf[pos] = inq ? 1 : 0;
+        if (inq) {
           V mv;
           if (as_snapshot) mv = root5 ? t5min[q] : (V)(t5min[q] - t4min);
           else mv = (V)(t5min[q] - s5min[q]);
           S.B[ones_before] = VT<V>::zz(mv);
           const u32 lpos = Pn[6] + 4u * r5;
+          U le[4];
 #pragma unroll
           for (int c = 0; c < 4; c++) {
             const int m = 4 * q + c;
             const bool in = CELL_IN(m);
-            V le;
-            if (as_snapshot) le = (V)(t5max[q] - (in ? tv[m] : (V)0));
-            else le = in ? (V)(tv[m] - sv[m]) : (V)0;
-            S.A[lpos + c] = VT<V>::zz(le);
+            V x;
+            if (as_snapshot) x = (V)(t5max[q] - (in ? tv[m] : (V)0));
+            else x = in ? (V)(tv[m] - sv[m]) : (V)0;
+            le[c] = VT<V>::zz(x);
           }
+          if (sizeof(U) == 4) *reinterpret_cast<uint4*>(&A[lpos]) = make_uint4((u32)le[0], (u32)le[1], (u32)le[2], (u32)le[3]);
+          else { A[lpos] = le[0]; A[lpos + 1] = le[1]; A[lpos + 2] = le[2]; A[lpos + 3] = le[3]; }
           r5++;
         } else if (!as_snapshot) {
-          if (!((u5 >> q) & 1u) && ((eq5 >> q) & 1u)) set_bit(S.eqw, pos - ones_before);
+          S.eqf[pos - ones_before] = (!((u5 >> q) & 1u) && ((eq5 >> q) & 1u)) ? 1 : 0;
         }
       }
     }

@@ -16,7 +16,7 @@ struct TableDacParams {
   const i64* tbl_max;
   const u64* table_base;  // [n_slices]
   const u64* table_len;   // [n_slices] instants * n_slots
-  u64* scratch;           // zigzag codes, same indexing as the tables; [2][total]
+  u64* scratch;           // zigzag codes + compaction partners, same indexing as the tables; [4][total]
   u64 total;              // sum of table_len
   Piece* pieces;          // [n_slices][2]  (0 = max, 1 = min)
   u8* arena;
@@ -31,9 +31,10 @@ __global__ void __launch_bounds__(ENC_THREADS) k_table_dac(const TableDacParams 
   const int tid = threadIdx.x, lane = tid & 31;
   const i64* src = (which == 0 ? P.tbl_max : P.tbl_min) + P.table_base[s];
   u64* a = P.scratch + (u64)which * P.total + P.table_base[s];
+  u64* a2 = P.scratch + (u64)(2 + which) * P.total + P.table_base[s];  // compaction partner
   const u32 n = (u32)P.table_len[s];
   __shared__ u32 cnt[8];
-  __shared__ u32 scan_a[ENC_WARPS], scan_b[ENC_WARPS];
+  __shared__ u32 scan_a[ENC_WARPS];
   __shared__ u64 s_off;
   if (tid < 8) cnt[tid] = 0;
   __syncthreads();
@@ -70,7 +71,10 @@ __global__ void __launch_bounds__(ENC_THREADS) k_table_dac(const TableDacParams 
     if (tid == 0) atomicOr(P.err, (u32)EF_ARENA_FULL);
     return;
   }
-  const u32 wrote = block_dac_emit<u64, 8>(a, n, c, P.arena + off, scan_a, scan_b);
+  __shared__ u32 c_s[8];
+  if (tid < 8) c_s[tid] = c[tid];
+  __syncthreads();
+  const u32 wrote = block_dac_emit<u64, 8>(a, a2, c_s, P.arena + off, scan_a);
   if (tid == 0 && wrote != size) atomicOr(P.err, (u32)EF_BAD_FORMAT);
 }
 

@@ -42,14 +42,24 @@ template <typename T>
 struct FloatBits;
 template <>
 struct FloatBits<int32_t> {
+  static DCDF_DEVINL int fast(int32_t) { return 0; }
   static DCDF_DEVINL int fracbits(int32_t) { return 0; }
 };
 template <>
 struct FloatBits<i64> {
+  static DCDF_DEVINL int fast(i64) { return 0; }
   static DCDF_DEVINL int fracbits(i64) { return 0; }
 };
 template <>
 struct FloatBits<float> {
+  // branch-free: NaN / inf give 0 (E = 255), zero gives 0
+  static DCDF_DEVINL int fast(float v) {
+    const u32 b = __float_as_uint(v);
+    const int E = (b >> 23) & 0xff;
+    const u32 M = (b & 0x7fffffu) | (E ? 0x800000u : 0u);
+    const int fb = 150 - (E ? E : 1) - (__ffs((int)M) - 1);
+    return (M != 0 && fb > 0) ? fb : 0;
+  }
   static DCDF_DEVINL int fracbits(float v) {
     u32 b = __float_as_uint(v);
     int E = (b >> 23) & 0xff;
@@ -66,6 +76,13 @@ struct FloatBits<float> {
 };
 template <>
 struct FloatBits<double> {
+  static DCDF_DEVINL int fast(double v) {
+    const u64 b = (u64)__double_as_longlong(v);
+    const int E = (int)((b >> 52) & 0x7ff);
+    const u64 M = (b & 0xfffffffffffffull) | (E ? (1ull << 52) : 0ull);
+    const int fb = 1075 - (E ? E : 1) - (__ffsll((long long)M) - 1);
+    return (M != 0 && fb > 0) ? fb : 0;
+  }
   static DCDF_DEVINL int fracbits(double v) {
     u64 b = (u64)__double_as_longlong(v);
     int E = (int)((b >> 52) & 0x7ff);
@@ -171,6 +188,8 @@ __global__ void __launch_bounds__(STAT_THREADS) k_unit_stats(const StatParams P)
   // row-major walk without divisions: thread t visits cells t, t + 256, ...
   const int r_init = tid / cols, c_init = tid - r_init * cols;
   const int step_r = STAT_THREADS / cols, step_c = STAT_THREADS - step_r * cols;
+  const i64 q_step = (i64)step_r * P.stride_r + (i64)step_c * P.stride_c;  // pointer step for 256 cells ahead
+  const i64 q_wrap = P.stride_r - (i64)cols * P.stride_c;                  // extra step when the column wraps
 
   InT umax = Lim<InT>::lo(), umin = Lim<InT>::hi();  // unit extrema over non-NaN values
   InT uneg = (InT)0;                                 // most negative value
@@ -182,27 +201,41 @@ __global__ void __launch_bounds__(STAT_THREADS) k_unit_stats(const StatParams P)
       const InT* p = base + (i64)(i0 + bi) * P.stride_t;
       InT mn = Lim<InT>::hi(), mx = Lim<InT>::lo();
       u32 first = 0xffffffffu, last = 0;  // row-major position (+1 for last) of first non-NaN / last NaN
-      int r = r_init, c = c_init;
-#pragma unroll 4
-      for (int idx = tid; idx < cells; idx += STAT_THREADS) {
-        const InT v = __ldg(p + (i64)r * P.stride_r + (i64)c * P.stride_c);
-        if (IS_FLOAT) {
-          if (v != v) {
-            last = (u32)idx + 1u;  // idx ascends within a thread
+      // all loads of the instant are issued before any value is consumed (16 per thread for a full tile);
+      // the pointer walks the tile row-major without divisions
+      const InT* q = p + (i64)r_init * P.stride_r + (i64)c_init * P.stride_c;
+      int c = c_init;
+      for (int idx0 = tid; idx0 < cells; idx0 += 16 * STAT_THREADS) {
+        InT vals[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const int idx = idx0 + j * STAT_THREADS;
+          vals[j] = idx < cells ? __ldg(q) : (InT)0;
+          c += step_c;
+          q += q_step;
+          if (c >= cols) { c -= cols; q += q_wrap; }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const int idx = idx0 + j * STAT_THREADS;
+          if (idx >= cells) break;
+          const InT v = vals[j];
+          if (IS_FLOAT) {
+            const bool isn = v != v;
+            last = isn ? (u32)idx + 1u : last;           // idx ascends within a thread
+            first = min(first, isn ? 0xffffffffu : (u32)idx);
+            mn = (isn || v > mn) ? mn : v;
+            mx = (isn || v < mx) ? mx : v;
+            uneg = (isn || v > uneg) ? uneg : v;
+            const int fb = FloatBits<InT>::fast(v);
+            const bool neg = v < (InT)0;
+            fng = max(fng, neg ? fb : 0);
+            fnn = max(fnn, neg ? 0 : fb);
           } else {
-            first = min(first, (u32)idx);
             mn = v < mn ? v : mn;
             mx = v > mx ? v : mx;
-            const int fb = FloatBits<InT>::fracbits(v);
-            if (v < (InT)0) { fng = fb > fng ? fb : fng; uneg = v < uneg ? v : uneg; }
-            else fnn = fb > fnn ? fb : fnn;
           }
-        } else {
-          mn = v < mn ? v : mn;
-          mx = v > mx ? v : mx;
         }
-        c += step_c; r += step_r;
-        if (c >= cols) { c -= cols; r++; }
       }
       mn = warp_min(mn); mx = warp_max(mx);
       if (IS_FLOAT) { first = warp_min(first); last = warp_max(last); }
