@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 
+#include "encode_big.cuh"
 #include "gather.cuh"
 #include "host.hpp"
 #include "stats.cuh"
@@ -460,6 +461,229 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   if (code != DCDF_OK) throw ApiFail{code, msg};
 }
 
+
+// ===================================================================================== big Chunk::build
+// Chunk::build for padded sides above 64 (encode_big.cuh).  Host-driven: one small counter readback per
+// instant for the Snapshot-vs-Log decision (chunk.rs:62); every data pass is a kernel.
+struct BigResult {
+  uint8_t* blob = nullptr;
+  uint64_t size = 0;
+  uint32_t snapshots = 0, logs = 0;
+  std::vector<uint32_t> block_instants;
+};
+
+struct BigScratch {
+  dcdf_ctx* ctx;
+  u8* base = nullptr;
+  size_t used = 0, cap = 0;
+  template <typename T>
+  T* take(size_t n) {
+    used = (used + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + used);
+    used += n * sizeof(T);
+    return p;
+  }
+};
+
+unsigned big_grid(dcdf_ctx* ctx, u64 n, int block = 256) {
+  return (unsigned)std::max<u64>(1, std::min<u64>((n + block - 1) / block, (u64)ctx->sm_count * 16));
+}
+
+// out[i] = exclusive prefix of in[0..n)
+void big_scan(dcdf_ctx* ctx, const u64* in, u64 n, u64* out, u64* block_sums) {
+  if (n == 0) return;
+  const unsigned nb = (unsigned)((n + SCAN_ITEMS - 1) / SCAN_ITEMS);
+  kb_scan_blocks<<<nb, 1024, 0, ctx->stream>>>(in, n, out, block_sums);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (nb > 1) {
+    kb_scan_top<<<1, 1024, 0, ctx->stream>>>(block_sums, nb);
+    kb_scan_add<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(out, n, block_sums);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+  }
+}
+
+u32 host_dac_size(const unsigned long long* h) {
+  u32 c[8];
+  for (int j = 0; j < 8; j++) c[j] = (u32)h[j];
+  return dac_size_from_counts(c, 8);
+}
+
+template <typename InT>
+void big_chunk_encode(dcdf_ctx* ctx, const void* dev_data, const int64_t* strides, int encoding, int64_t T, int64_t rows,
+                      int64_t cols, int bits, int round, BigResult& R) {
+  cudaStream_t st = ctx->stream;
+  const int L = (int)levels_for(std::max(rows, cols), 2);
+  if (L > 12) api_fail(DCDF_ERR_BAD_ARG, "rasters larger than 4096 x 4096 must be split into a superchunk");
+  const u64 side = 1ull << L, N = (u64)big_lvl_off(L + 1), n_upper = (u64)big_lvl_off(L);
+  const u64 n_blocks_scan = (N + SCAN_ITEMS - 1) / SCAN_ITEMS + 1;
+  // ---- scratch
+  size_t need = 5 * N * 8 + N + 5 * N * 8 + 2 * (n_upper + 64) + 2 * (N / 32 + 64) * 8 + n_blocks_scan * 8 + sizeof(BigCounts) + 64 * 1024;
+  ctx->tbl_scratch.reserve(need);
+  BigScratch S{ctx, ctx->tbl_scratch.as<u8>(), 0, ctx->tbl_scratch.cap};
+  BigPyr P;
+  P.tmax = S.take<i64>(N); P.tmin = S.take<i64>(N); P.smax = S.take<i64>(N); P.smin = S.take<i64>(N); P.diff = S.take<i64>(N);
+  P.fl = S.take<u8>(N);
+  P.L = L; P.N = N;
+  u64* scan = S.take<u64>(N);
+  u64* A = S.take<u64>(N);
+  u64* B = S.take<u64>(N);
+  u64* Cb = S.take<u64>(N);
+  u64* more = S.take<u64>(N);
+  u8* nmf = S.take<u8>(n_upper + 64);
+  u8* eqf = S.take<u8>(n_upper + 64);
+  u64* popc = S.take<u64>(N / 32 + 64);
+  u64* popc_scan = S.take<u64>(N / 32 + 64);
+  u64* block_sums = S.take<u64>(n_blocks_scan);
+  BigCounts* d_counts = S.take<BigCounts>(1);
+  ctx->small.reserve(256);
+  u32* d_err = ctx->small.as<u32>();
+  CK(cudaMemsetAsync(d_err, 0, 64, st));
+  CK(cudaMemsetAsync(P.smax, 0, N * 8, st));
+  // ---- arena (host-side bump allocation; grown by copy when it fills up)
+  if (ctx->arena.cap < (64u << 20)) ctx->arena.reserve(64u << 20);
+  u64 head = 0;
+  std::vector<Piece> pieces((size_t)T);
+  const InT* data = static_cast<const InT*>(dev_data);
+  uint32_t n_logs = 0, run = 0;
+  u64 total_bytes = 6;
+  for (int64_t inst = 0; inst < T; inst++) {
+    const bool first = inst == 0;
+    kb_leaves<InT><<<big_grid(ctx, side * side), 256, 0, st>>>(data + inst * strides[0], strides[1], strides[2], (int)rows, (int)cols, bits,
+                                                              round, P, d_err);
+    for (int l = L - 1; l >= 0; l--) kb_reduce<<<big_grid(ctx, 1ull << (2 * l)), 256, 0, st>>>(P, l);
+    CK(cudaMemsetAsync(d_counts, 0, sizeof(BigCounts), st));
+    kb_classify<<<big_grid(ctx, N), 256, 0, st>>>(P, first ? 1 : 0, d_counts);
+    CK(cudaGetLastError());
+    ctx->launches += 2 + L;
+    BigCounts hc;
+    CK(cudaMemcpyAsync(&hc, d_counts, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // sizes (snapshot.rs:84-93, log.rs:92-98) and the heuristic (chunk.rs:62)
+    const u32 snap_size = 13u + bitmap_size((u32)hc.n_upper[0]) + host_dac_size(hc.h[0][0]) + host_dac_size(hc.h[0][1]);
+    const u32 log_size = 13u + bitmap_size((u32)hc.n_upper[1]) + bitmap_size((u32)(hc.n_upper[1] - hc.n_int[1])) +
+                         host_dac_size(hc.h[1][0]) + host_dac_size(hc.h[1][1]);
+    const bool snap = first || n_logs == 254u || snap_size <= log_size;
+    const int cand = snap ? 0 : 1;
+    const u32 size = snap ? snap_size : log_size;
+    const u64 need_bytes = ((u64)size + 15ull) & ~15ull;
+    if (head + need_bytes > ctx->arena.cap) {  // grow, keeping what was already emitted
+      DevBuf bigger;
+      bigger.reserve((size_t)std::max<u64>(2 * ctx->arena.cap, head + need_bytes + (64u << 20)));
+      CK(cudaMemcpyAsync(bigger.p, ctx->arena.p, head, cudaMemcpyDeviceToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      ctx->arena.release();
+      ctx->arena = bigger;
+    }
+    u8* out = ctx->arena.as<u8>() + head;
+    pieces[(size_t)inst] = Piece{head, size, snap ? 1u : 0u};
+    head += need_bytes;
+    // ---- emit the winner
+    const u64 nm_len = hc.n_upper[cand], n_int = hc.n_int[cand];
+    kb_scan_input<<<big_grid(ctx, N), 256, 0, st>>>(P, cand, more);
+    big_scan(ctx, more, N, scan, block_sums);
+    kb_scatter<<<big_grid(ctx, N), 256, 0, st>>>(P, cand, scan, A, B, nmf, eqf);
+    kb_header<<<1, 1, 0, st>>>(out, (int)rows, (int)cols, (int)side);
+    ctx->launches += 3;
+    u64 off = 13;
+    auto emit_bitmap = [&](const u8* flags, u64 length) {
+      const u64 words = (length + 31) / 32, blocks = length / 128;
+      kb_bitmap_words<<<(unsigned)std::max<u64>(1, (words * 32 + 255) / 256), 256, 0, st>>>(flags, length, out + off + 8 + 4 * blocks, popc);
+      big_scan(ctx, popc, words, popc_scan, block_sums);
+      kb_bitmap_index<<<(unsigned)std::max<u64>(1, (blocks + 255) / 256), 256, 0, st>>>(popc_scan, popc, length, out + off);
+      ctx->launches += 2;
+      off += 8 + 4 * blocks + 4 * words;
+    };
+    emit_bitmap(nmf, nm_len);
+    if (!snap) emit_bitmap(eqf, nm_len - n_int);
+    auto emit_dac = [&](u64* X, const unsigned long long* h) {
+      int n_levels = 0;
+      for (int j = 0; j < 8; j++) if (h[j] > 0) n_levels = j + 1;
+      kb_byte<<<1, 1, 0, st>>>(out + off, (u8)n_levels);
+      ctx->launches++;
+      off += 1;
+      u64* Y = Cb;
+      for (int j = 0; j < n_levels; j++) {
+        const u64 nj = h[j];
+        const unsigned g = (unsigned)((nj + 255) / 256);
+        kb_dac_more<<<g, 256, 0, st>>>(X, nj, more);
+        big_scan(ctx, more, nj, scan, block_sums);
+        kb_dac_level<<<g, 256, 0, st>>>(X, nj, scan, out + off, Y);
+        ctx->launches += 2;
+        off += 8 + 4 * (nj / 128) + 4 * ((nj + 31) / 32) + nj;
+        std::swap(X, Y);
+      }
+    };
+    emit_dac(A, hc.h[cand][0]);
+    emit_dac(B, hc.h[cand][1]);
+    CK(cudaGetLastError());
+    if (off != size) api_fail(DCDF_ERR_BAD_FORMAT, "big chunk: emitted %llu bytes, predicted %u", (unsigned long long)off, size);
+    if (snap) {
+      kb_copy_ts<<<big_grid(ctx, N), 256, 0, st>>>(P);
+      ctx->launches++;
+      if (!first) R.block_instants.push_back(run);
+      run = 0;
+      R.snapshots++;
+      n_logs = 0;
+      total_bytes += 1;
+    } else {
+      n_logs++;
+      R.logs++;
+    }
+    run++;
+    total_bytes += size;
+  }
+  R.block_instants.push_back(run);
+  u32 flags = 0;
+  CK(cudaMemcpyAsync(&flags, d_err, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::string msg;
+  int32_t code = status_from_flags(flags, msg);
+  if (code != DCDF_OK) throw ApiFail{code, msg};
+  // ---- frame the pieces as Chunk bytes (chunk.rs:235-243, block.rs:88-95)
+  if ((u64)T > 0xfffffff0ull) api_fail(DCDF_ERR_BAD_ARG, "too many instants");
+  ctx->pieces.reserve(sizeof(Piece) * (size_t)T);
+  ctx->units.reserve(sizeof(EncUnit));
+  ctx->results.reserve(sizeof(UnitResult));
+  ctx->stored.reserve(16);
+  ctx->chunk_off.reserve(16);
+  EncUnit eu;
+  memset(&eu, 0, sizeof eu);
+  eu.rows = (int)rows; eu.cols = (int)cols; eu.instants = (int)T; eu.bits = bits; eu.piece_base = 0;
+  UnitResult ur;
+  ur.bytes = total_bytes; ur.snapshots = R.snapshots; ur.logs = R.logs;
+  const u8 one = 1;
+  const u64 zero = 0;
+  CK(cudaMemcpyAsync(ctx->pieces.p, pieces.data(), sizeof(Piece) * (size_t)T, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->units.p, &eu, sizeof eu, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->results.p, &ur, sizeof ur, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->stored.p, &one, 1, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->chunk_off.p, &zero, 8, cudaMemcpyHostToDevice, st));
+  R.size = total_bytes;
+  R.blob = static_cast<uint8_t*>(pool_alloc(total_bytes + 16, st));
+  CK(cudaMemsetAsync(R.blob + total_bytes, 0, 16, st));
+  GatherParams GP;
+  GP.units = ctx->units.as<EncUnit>();
+  GP.results = ctx->results.as<UnitResult>();
+  GP.stored = ctx->stored.as<u8>();
+  GP.pieces = ctx->pieces.as<Piece>();
+  GP.chunk_off = ctx->chunk_off.as<u64>();
+  GP.arena = ctx->arena.as<u8>();
+  GP.out = R.blob;
+  GP.out_cap = total_bytes;
+  GP.encoding = encoding;
+  GP.n_units = 1;
+  GP.err = d_err;
+  k_gather_chunks<<<1, 256, 0, st>>>(GP);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaMemcpyAsync(&flags, d_err, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  code = status_from_flags(flags, msg);
+  if (code != DCDF_OK) { pool_free(R.blob); R.blob = nullptr; throw ApiFail{code, msg}; }
+}
+
 void copy_out(dcdf_ctx* ctx, const uint8_t* dev_src, uint64_t n, uint8_t* dst, uint64_t cap, int32_t mem) {
   if (!dst) api_fail(DCDF_ERR_BAD_ARG, "null destination");
   if (cap < n) api_fail(DCDF_ERR_BAD_ARG, "destination too small: need %llu bytes", (unsigned long long)n);
@@ -692,7 +916,33 @@ int32_t dcdf_chunk_build(dcdf_ctx* ctx, const dcdf_array3* a, int32_t k, int32_t
     const int64_t longest = std::max(rows, cols);
     if (longest < 2) api_fail(DCDF_ERR_BAD_ARG, "1x1 rasters have an empty nodemap (snapshot.rs:166)");
     const uint32_t L = levels_for(longest, 2);
-    if (L > 6) api_fail(DCDF_ERR_BAD_ARG, "Chunk::build on the GPU handles sides up to 64; use dcdf_superchunk_build for larger rasters");
+    if (L > 6) {
+      // multi-level path: dense pyramid in global memory + device-wide scans (encode_big.cuh)
+      const void* dev = stage_input(ctx, a);
+      const bool is_float = a->encoding == DCDF_ENC_F32 || a->encoding == DCDF_ENC_F64;
+      const int bits = is_float ? fractional_bits : 0;
+      BigResult R;
+      switch (a->encoding) {
+        case DCDF_ENC_F32: big_chunk_encode<float>(ctx, dev, a->strides, a->encoding, a->shape[0], rows, cols, bits, round ? 1 : 0, R); break;
+        case DCDF_ENC_F64: big_chunk_encode<double>(ctx, dev, a->strides, a->encoding, a->shape[0], rows, cols, bits, round ? 1 : 0, R); break;
+        case DCDF_ENC_I32: big_chunk_encode<int32_t>(ctx, dev, a->strides, a->encoding, a->shape[0], rows, cols, bits, 0, R); break;
+        default: big_chunk_encode<i64>(ctx, dev, a->strides, a->encoding, a->shape[0], rows, cols, bits, 0, R); break;
+      }
+      dcdf_chunk* c = new dcdf_chunk();
+      c->device = ctx->device;
+      c->bytes = R.blob; c->size = R.size; c->owner = true;
+      for (int i = 0; i < 3; i++) c->shape[i] = a->shape[i];
+      c->encoding = a->encoding;
+      c->fractional_bits = bits;
+      c->n_blocks = R.snapshots;
+      c->block_instants = R.block_instants;
+      if (stats) {
+        stats->size = R.size; stats->elided = stats->local = stats->external = 0;
+        stats->snapshots = R.snapshots; stats->logs = R.logs;
+      }
+      *out = c;
+      return;
+    }
     EncodeJob job;
     job.dev_data = stage_input(ctx, a);
     job.encoding = a->encoding;

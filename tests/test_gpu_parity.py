@@ -122,6 +122,40 @@ def test_chunk_build_strided_view_and_device_input(ctx):
     _diff(got.write_to(), ref.serialize(), "strided device view")
 
 
+@pytest.mark.parametrize("shape", [(5, 65, 65), (4, 70, 130), (3, 200, 300), (6, 128, 128), (3, 1, 100)])
+def test_big_chunk_build_multi_level(ctx, shape):
+    """Chunk::build for padded sides above 64 (dense pyramid + device-wide scans path)."""
+    rng = np.random.default_rng(shape[1])
+    base = rng.integers(0, 30, shape[1:])
+    frames = []
+    for i in range(shape[0]):
+        f = base.copy()
+        m = rng.random(shape[1:]) < 0.02 * i
+        f[m] += rng.integers(-300, 300, m.sum())
+        frames.append(f if i != 2 else rng.integers(-10 ** 6, 10 ** 6, shape[1:]))
+    data = np.stack(frames).astype(np.int64)
+    got, ref = _check_chunk(ctx, data)
+    f32 = (data / 16.0).astype(np.float32)
+    f32[rng.random(f32.shape) < 0.1] = np.nan
+    got, ref = _check_chunk(ctx, f32, fractional_bits=4)
+    T, R, Cc = shape
+    g = got.search(0, T, R // 3, R, 0, Cc // 2 + 1, -100, 100)
+    o = ref.search(0, T, R // 3, R, 0, Cc // 2 + 1, -100, 100)
+    assert np.array_equal(g, o)
+
+
+def test_c1_config_chunk_build_and_get_window(ctx):
+    """BASELINE configs[0]: synthetic 256x256x100 f32 raster, Chunk build (Snapshot + Log) then get_window."""
+    from dcdf_b200 import synth
+    data = synth.raster_slice(0, 100, 256, 256).numpy()
+    got, ref = _check_chunk(ctx, data, fractional_bits=4)
+    assert len(got.block_instants()) > 1 and max(got.block_instants()) > 1    # both snapshots and logs
+    w = got.window(10, 90, 17, 250, 3, 256)
+    assert np.array_equal(w, data[10:90, 17:250, 3:256])
+    series = got.cell(0, 100, 255, 0)
+    assert np.array_equal(series, data[:, 255, 0])
+
+
 @pytest.mark.parametrize("bad,code", [("precision", 2), ("inf", 1), ("overflow", 3)])
 def test_chunk_build_data_errors(ctx, bad, code):
     from dcdf_b200 import Chunk, DcdfError
