@@ -92,6 +92,10 @@ def _declare(lib):
         "dcdf_superchunk_free": (i32, [vp]),
         "dcdf_superchunk_count": (i32, [vp, _P(u32)]),
         "dcdf_superchunk_get_info": (i32, [vp, u32, _P(SuperchunkInfo)]),
+        "dcdf_superchunk_node_count": (i32, [vp, _P(u32)]),
+        "dcdf_superchunk_node_info": (i32, [vp, u32, u32, _P(SuperchunkInfo)]),
+        "dcdf_superchunk_node_refs": (i32, [vp, vp, u32, u32, vp, vp, vp, vp, vp]),
+        "dcdf_superchunk_node_bytes": (i32, [vp, vp, u32, u32, i32, vp, u64, i32]),
         "dcdf_superchunk_refs": (i32, [vp, vp, u32, vp, vp, vp, vp]),
         "dcdf_superchunk_bytes": (i32, [vp, vp, u32, i32, vp, u64, i32]),
         "dcdf_superchunk_total_bytes": (i32, [vp, _P(u64)]),

@@ -268,32 +268,47 @@ class Superchunk(_Queryable):
                                                  int(compute_bits), int(chunk_size or 0), C.byref(h)))
         return cls(ctx, h, d.encoding, tuple(d.shape))
 
-    def info(self, slice_=0):
+    def node_count(self):
+        n = C.c_uint32()
+        self.ctx.check(self.ctx._lib.dcdf_superchunk_node_count(self._h, C.byref(n)))
+        return n.value
+
+    def info(self, slice_=0, node=0):
         info = SuperchunkInfo()
-        self.ctx.check(self.ctx._lib.dcdf_superchunk_get_info(self._h, slice_, C.byref(info)))
+        self.ctx.check(self.ctx._lib.dcdf_superchunk_node_info(self._h, slice_, node, C.byref(info)))
         return info
 
-    def refs(self, slice_=0):
-        n = self.info(slice_).n_refs
+    def refs(self, slice_=0, node=0, with_children=False):
+        """Reference kinds of a node's subchunk slots (row-major), offsets / sizes / bits of stored Chunks and,
+        with_children, the node index of nested superchunk references (-1 otherwise)."""
+        n = self.info(slice_, node).n_refs
         kinds = np.zeros(n, np.int32)
+        child = np.zeros(n, np.int32)
         off = np.zeros(n, np.uint64)
         size = np.zeros(n, np.uint64)
         bits = np.zeros(n, np.int32)
-        self.ctx.check(self.ctx._lib.dcdf_superchunk_refs(self.ctx._h, self._h, slice_, _ptr(kinds), _ptr(off), _ptr(size), _ptr(bits)))
-        return kinds, off, size, bits
+        self.ctx.check(self.ctx._lib.dcdf_superchunk_node_refs(self.ctx._h, self._h, slice_, node, _ptr(kinds), _ptr(child),
+                                                               _ptr(off), _ptr(size), _ptr(bits)))
+        return (kinds, off, size, bits, child) if with_children else (kinds, off, size, bits)
 
-    def bytes(self, slice_=0, which=0):
-        info = self.info(slice_)
-        n = [info.chunk_bytes, info.max_dac_bytes, info.min_dac_bytes][which]
+    def bytes(self, slice_=0, which=0, node=0):
+        """which 0: every stored Chunk of the slice back to back; 1 / 2: max / min Dac of `node`."""
+        if which == 0:
+            n = self.info(slice_, 0).chunk_bytes
+            buf = np.empty(max(n, 1), np.uint8)
+            self.ctx.check(self.ctx._lib.dcdf_superchunk_bytes(self.ctx._h, self._h, slice_, 0, _ptr(buf), n, MEM_HOST))
+            return buf[:n].tobytes()
+        info = self.info(slice_, node)
+        n = info.max_dac_bytes if which == 1 else info.min_dac_bytes
         buf = np.empty(max(n, 1), np.uint8)
-        self.ctx.check(self.ctx._lib.dcdf_superchunk_bytes(self.ctx._h, self._h, slice_, which, _ptr(buf), n, MEM_HOST))
+        self.ctx.check(self.ctx._lib.dcdf_superchunk_node_bytes(self.ctx._h, self._h, slice_, node, which, _ptr(buf), n, MEM_HOST))
         return buf[:n].tobytes()
 
-    def chunk_bytes(self, slice_=0):
-        """-> list (one per subchunk slot, row-major) of Chunk bytes or None for Elided."""
-        kinds, off, size, _ = self.refs(slice_)
-        blob = self.bytes(slice_, 0)
-        return [blob[int(o):int(o + s)] if k == _ffi.REF_EXTERNAL else None for k, o, s in zip(kinds, off, size)]
+    def chunk_bytes(self, slice_=0, node=0, blob=None):
+        """-> list (one per subchunk slot of `node`, row-major) of Chunk bytes, or None for Elided / nested slots."""
+        kinds, off, size, _ = self.refs(slice_, node)
+        blob = self.bytes(slice_, 0) if blob is None else blob
+        return [blob[int(o):int(o + s)] if (k == _ffi.REF_EXTERNAL and s > 0) else None for k, o, s in zip(kinds, off, size)]
 
     def total_bytes(self):
         n = C.c_uint64()

@@ -39,6 +39,7 @@ struct DevMeta {
   UnitMeta* units = nullptr;
   SliceMeta* slices = nullptr;
   int32_t* slot_unit = nullptr;
+  SlotDesc* slot_desc = nullptr;
   u32* err = nullptr;
 };
 
@@ -62,22 +63,25 @@ void check_err_word(dcdf_ctx* ctx, u32* d_err, const char* what) {
 }
 
 MetaBlock* make_meta(dcdf_ctx* ctx, const u8* blob, std::vector<UnitMeta>& units, const std::vector<SliceMeta>& slices,
-                     const std::vector<int32_t>& slot_unit, u32 n_slots, i64 chunk_size, int chunks_sidelen, int subsidelen,
+                     const std::vector<int32_t>& slot_unit, const std::vector<SlotDesc>& slot_desc, u32 n_slots, i64 chunk_size, int chunks_sidelen, int subsidelen,
                      int encoding, const i64* shape, const i64* tbl_max, void** dir_out, bool count_first) {
   cudaStream_t st = ctx->stream;
   MetaBlock* mb = new MetaBlock();
   try {
-    const size_t ub = sizeof(UnitMeta) * units.size(), sb = sizeof(SliceMeta) * slices.size(), mbytes = sizeof(int32_t) * slot_unit.size();
+    const size_t ub = sizeof(UnitMeta) * units.size(), sb = sizeof(SliceMeta) * slices.size(),
+                 mbytes = (sizeof(int32_t) * slot_unit.size() + 15) & ~size_t(15), db = sizeof(SlotDesc) * slot_desc.size();
     u8* raw = nullptr;
-    raw = static_cast<u8*>(pool_alloc(ub + sb + mbytes + 64, st));
+    raw = static_cast<u8*>(pool_alloc(ub + sb + mbytes + db + 64, st));
     mb->d.units = reinterpret_cast<UnitMeta*>(raw);
     mb->d.slices = reinterpret_cast<SliceMeta*>(raw + ub);
     mb->d.slot_unit = reinterpret_cast<int32_t*>(raw + ub + sb);
-    mb->d.err = reinterpret_cast<u32*>(raw + ub + sb + ((mbytes + 15) & ~size_t(15)));
+    mb->d.slot_desc = reinterpret_cast<SlotDesc*>(raw + ub + sb + mbytes);
+    mb->d.err = reinterpret_cast<u32*>(raw + ub + sb + mbytes + ((db + 15) & ~size_t(15)));
+    CK(cudaMemcpyAsync(mb->d.slot_desc, slot_desc.data(), db, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(mb->d.err, 0, 16, st));
     CK(cudaMemcpyAsync(mb->d.units, units.data(), ub, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(mb->d.slices, slices.data(), sb, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(mb->d.slot_unit, slot_unit.data(), mbytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(mb->d.slot_unit, slot_unit.data(), sizeof(int32_t) * slot_unit.size(), cudaMemcpyHostToDevice, st));
     DirParams DP;
     DP.blob = blob;
     DP.units = mb->d.units;
@@ -118,6 +122,7 @@ MetaBlock* make_meta(dcdf_ctx* ctx, const u8* blob, std::vector<UnitMeta>& units
     Q.dir = dir;
     Q.slices = mb->d.slices;
     Q.slot_unit = mb->d.slot_unit;
+    Q.slot_desc = mb->d.slot_desc;
     Q.tbl_max = tbl_max;
     Q.n_slices = (u32)slices.size();
     Q.n_slots = n_slots;
@@ -146,9 +151,10 @@ MetaBlock* chunk_meta(dcdf_ctx* ctx, const dcdf_chunk* cc) {
   memset(&slices[0], 0, sizeof(SliceMeta));
   slices[0].t0 = 0; slices[0].instants = (int)c->shape[0]; slices[0].bits = c->fractional_bits;
   std::vector<int32_t> slot_unit(1, 0);
+  std::vector<SlotDesc> slot_desc(1, SlotDesc{0, 0, 0});
   void* dir = nullptr;
   const bool count_first = c->shape[0] == 0;
-  MetaBlock* mb = make_meta(ctx, c->bytes, units, slices, slot_unit, 1, 0, 1 << 30, 1, c->encoding, c->shape, nullptr, &dir, count_first);
+  MetaBlock* mb = make_meta(ctx, c->bytes, units, slices, slot_unit, slot_desc, 1, 0, 1 << 30, 1, c->encoding, c->shape, nullptr, &dir, count_first);
   if (count_first) {
     c->shape[0] = units[0].instants; c->shape[1] = units[0].rows; c->shape[2] = units[0].cols;
     c->fractional_bits = units[0].bits;
@@ -178,20 +184,45 @@ MetaBlock* super_meta(dcdf_ctx* ctx, const dcdf_superchunk* scc) {
     m.dir_base = sc->units[u].piece_base;
     m.instants = sc->units[u].instants;
   }
+  const uint32_t n_nodes = (uint32_t)sc->nodes.size();
   std::vector<SliceMeta> slices(sc->slices.size());
+  std::vector<SlotDesc> slot_desc(sc->slot_unit.size(), SlotDesc{0, 0, 0});
   for (size_t s = 0; s < slices.size(); s++) {
     SliceMeta& m = slices[s];
     memset(&m, 0, sizeof m);
     m.t0 = sc->slices[s].t0;
     m.instants = (int)sc->slices[s].info.shape[0];
-    m.bits = sc->slices[s].info.fractional_bits;
+    m.bits = sc->nstate[s * n_nodes].bits;
     m.table_base = sc->slices[s].table_base;
     m.slot_base = (u32)(s * sc->n_slots);
+    // flatten the node tree: every in-bounds leaf slot either has a stored chunk or inherits the table entry of
+    // the shallowest node that elided one of its ancestors (superchunk.rs:325-330 applied along the recursion)
+    for (int gr = 0; gr < sc->leaf_rows; gr++)
+      for (int gc = 0; gc < sc->leaf_cols; gc++) {
+        const size_t slot = s * sc->n_slots + (size_t)gr * sc->leaf_grid + gc;
+        const int64_t row = (int64_t)gr * sc->leaf_side, col = (int64_t)gc * sc->leaf_side;
+        uint32_t node = 0;
+        for (;;) {
+          const TreeNode& nd = sc->nodes[node];
+          const auto& g = sc->geom[node];
+          const int64_t cr = (row - g.top) / g.chunks_sidelen, cc = (col - g.left) / g.chunks_sidelen;
+          const u32 c = (u32)(cr * g.subsidelen + cc);
+          const TreeChild& ch = sc->children[nd.first_child + c];
+          bool descend = false;
+          if (ch.kind == 2 && sc->nstate[s * n_nodes + ch.index].alive) { node = (uint32_t)ch.index; descend = true; }
+          if (descend) continue;
+          SlotDesc d;
+          d.tbl0 = sc->slices[s].table_base + (u64)nd.tbl_off * (u64)m.instants + c;
+          d.stride = nd.n_children;
+          d.bits = sc->nstate[s * n_nodes + node].bits;
+          slot_desc[slot] = d;
+          break;
+        }
+      }
   }
   void* dir = nullptr;
-  const auto& i0 = sc->slices[0].info;
-  MetaBlock* mb = make_meta(ctx, sc->chunk_blob, units, slices, sc->slot_unit, sc->n_slots, sc->chunk_size, (int)i0.chunks_sidelen,
-                            (int)i0.subsidelen, sc->encoding, sc->shape, sc->tbl_max, &dir, false);
+  MetaBlock* mb = make_meta(ctx, sc->chunk_blob, units, slices, sc->slot_unit, slot_desc, sc->n_slots, sc->chunk_size, sc->leaf_side,
+                            (int)sc->leaf_grid, sc->encoding, sc->shape, sc->tbl_max, &dir, false);
   sc->dir = dir;
   sc->dev_meta = mb;
   return mb;

@@ -24,6 +24,8 @@ int32_t status_from_flags(u32 f, std::string& msg) {
   if (f & EF_NONFINITE) { msg = "cannot convert a non-finite value to fixed point (fixed.rs:39-41)"; return DCDF_ERR_NONFINITE; }
   if (f & EF_OVERFLOW) { msg = "overflow converting to fixed point (fixed.rs:66-69)"; return DCDF_ERR_OVERFLOW; }
   if (f & EF_PRECISION) { msg = "loss of precision converting to fixed point (fixed.rs:51-57)"; return DCDF_ERR_PRECISION_LOSS; }
+  if (f & EF_BAD_LEVELS) { msg = "tree levels passed in do not match the levels a nested sub-array needs (superchunk.rs:105-110)"; return DCDF_ERR_BAD_LEVELS; }
+  if (f & EF_REGION_EXACT) { msg = "nested region with negatives far below its positive range needs the exact fraction pass, which is not built for nested superchunks yet"; return DCDF_ERR_BAD_ARG; }
   if (f & EF_BAD_FORMAT) { msg = "internal consistency check failed in the encoder"; return DCDF_ERR_BAD_FORMAT; }
   if (f & EF_OUT_CAP) { msg = "output buffer too small"; return DCDF_ERR_BAD_ARG; }
   return DCDF_OK;
@@ -82,6 +84,83 @@ const void* stage_input(dcdf_ctx* ctx, const dcdf_array3* a) {
   return ctx->input_copy.p;
 }
 
+struct TreeGeo {
+  std::vector<TreeNode> nodes;
+  std::vector<TreeChild> children;
+  std::vector<dcdf_superchunk::NodeGeom> geom;
+  std::vector<int32_t> leaf_unit;
+  int leaf_rows = 0, leaf_cols = 0, leaf_side = 1;
+  int64_t leaf_grid = 1;
+  uint64_t tbl_per_instant = 0;
+};
+
+// Static node tree of Superchunk::build's recursion (superchunk.rs:88-181) for a rows x cols raster.
+void build_tree(TreeGeo& G, int64_t rows, int64_t cols, const uint32_t* levels, uint32_t n_levels) {
+  const int D = (int)n_levels - 1;
+  std::vector<uint32_t> suffix(n_levels + 1, 0);  // suffix[d] = sum of levels[d..]
+  for (int d = (int)n_levels - 1; d >= 0; d--) suffix[d] = suffix[d + 1] + levels[d];
+  const int ls = 1 << levels[n_levels - 1];
+  G.leaf_side = ls;
+  G.leaf_rows = (int)((rows + ls - 1) / ls);
+  G.leaf_cols = (int)((cols + ls - 1) / ls);
+  G.leaf_grid = ((int64_t)1 << suffix[0]) / ls;
+  G.leaf_unit.assign((size_t)G.leaf_rows * G.leaf_cols, -1);
+  for (int i = 0; i < G.leaf_rows * G.leaf_cols; i++) G.leaf_unit[i] = i;
+  struct Pending { int depth; int64_t top, left; int parent; u32 child_slot; };
+  std::vector<Pending> queue;
+  queue.push_back({0, 0, 0, -1, 0});
+  for (size_t qi = 0; qi < queue.size(); qi++) {
+    const Pending pd = queue[qi];
+    const int d = pd.depth;
+    const int64_t side = (int64_t)1 << suffix[d];
+    const int64_t nrows = std::min(side, rows - pd.top), ncols = std::min(side, cols - pd.left);
+    TreeNode nd;
+    nd.parent = pd.parent; nd.depth = d;
+    nd.first_child = (u32)G.children.size();
+    const int64_t sub = (int64_t)1 << levels[d];
+    nd.n_children = (u32)(sub * sub);
+    nd.tbl_off = (u32)G.tbl_per_instant;
+    nd.levels_ok = levels_for(std::max(nrows, ncols), 2) == suffix[d] ? 1 : 0;
+    G.tbl_per_instant += nd.n_children;
+    const int id = (int)G.nodes.size();
+    if (pd.parent >= 0) G.children[G.nodes[pd.parent].first_child + pd.child_slot].index = id;
+    G.nodes.push_back(nd);
+    const int64_t cs = side / sub;
+    G.geom.push_back({pd.top, pd.left, nrows, ncols, side, cs, sub, levels[d]});
+    G.children.resize(G.children.size() + nd.n_children);
+    for (int64_t r = 0; r < sub; r++)
+      for (int64_t c = 0; c < sub; c++) {
+        TreeChild ch;
+        memset(&ch, 0, sizeof ch);
+        const int64_t ctop = pd.top + r * cs, cleft = pd.left + c * cs;
+        const u32 slot = (u32)(r * sub + c);
+        if (ctop >= rows || cleft >= cols) {
+          ch.kind = 0;
+        } else {
+          const int64_t cr = std::min(cs, rows - ctop), cc = std::min(cs, cols - cleft);
+          ch.gr0 = (int)(ctop / ls); ch.gc0 = (int)(cleft / ls);
+          ch.gr1 = (int)((ctop + cr + ls - 1) / ls); ch.gc1 = (int)((cleft + cc + ls - 1) / ls);
+          const bool at_bottom = d == D - 1;
+          bool as_chunk = at_bottom;
+          if (!at_bottom && levels_for(std::max(cr, cc), 2) <= levels[d + 1]) {  // superchunk.rs:153-163
+            if (cr > ls || cc > ls)
+              api_fail(DCDF_ERR_BAD_ARG, "a clipped region is demoted to a Chunk larger than the leaf subchunks; not built on the GPU yet");
+            as_chunk = true;
+          }
+          if (as_chunk) {
+            ch.kind = 1;
+            ch.index = ch.gr0 * G.leaf_cols + ch.gc0;
+          } else {
+            ch.kind = 2;
+            ch.index = -1;
+            queue.push_back({d + 1, ctop, cleft, id, slot});
+          }
+        }
+        G.children[nd.first_child + slot] = ch;
+      }
+  }
+}
+
 struct EncodeJob {
   const void* dev_data = nullptr;
   int encoding = 0;
@@ -94,6 +173,7 @@ struct EncodeJob {
   int plain = 0, req_bits = 0, round = 0, compute_bits = 0;
   int64_t rows = 0, cols = 0;  // full raster (exact pass)
   size_t input_bytes = 0;
+  TreeGeo* tree = nullptr;     // node tree for superchunk builds (null: plain Chunk::build units)
 };
 
 struct EncodeOut {
@@ -108,7 +188,8 @@ struct EncodeOut {
   uint64_t blob_size = 0;
   uint8_t* dac_blob = nullptr;
   uint64_t dac_blob_size = 0;
-  std::vector<uint64_t> dac_off;  // [n_slices][2]
+  std::vector<uint64_t> dac_off;  // [n_slices][n_nodes][2]
+  std::vector<NodeState> nstate;  // [n_slices][n_nodes]
   int64_t* tbl_max = nullptr;
   int64_t* tbl_min = nullptr;
   uint64_t tbl_total = 0;
@@ -118,7 +199,7 @@ template <typename InT, typename V, bool FULL, int MINB>
 void launch_encode_one(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   const size_t smem = sizeof(EncSmem<V>);
   CK(cudaFuncSetAttribute(k_encode_tiles<InT, V, FULL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_encode_tiles<InT, V, FULL, MINB><<<grid, ENC_THREADS, smem, ctx->stream>>>(P);
+  k_encode_tiles<InT, V, FULL, MINB><<<grid, ENC_THREADS, smem, FULL ? ctx->stream : ctx->aux_stream>>>(P);
   CK(cudaGetLastError());
   ctx->launches++;
 }
@@ -175,10 +256,16 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   for (auto& u : job.units) { u.piece_base = (u32)n_pieces; n_pieces += (u64)u.instants; }
   if (n_pieces > 0xfffffff0ull) api_fail(DCDF_ERR_BAD_ARG, "too many (unit, instant) pairs for one call");
   u64 tbl_total = 0;
-  std::vector<uint64_t> table_base(n_slices);
+  const u32 n_nodes = job.tree ? (u32)job.tree->nodes.size() : 1u;
+  const u32 n_tables = n_slices * n_nodes;
+  std::vector<uint64_t> table_base(n_tables), table_len(n_tables);
   for (u32 s = 0; s < n_slices; s++) {
-    table_base[s] = tbl_total;
     job.slices[s].table_base = tbl_total;
+    for (u32 n = 0; n < n_nodes; n++) {
+      const u64 off = job.tree ? (u64)job.tree->nodes[n].tbl_off : 0, nch = job.tree ? (u64)job.tree->nodes[n].n_children : 0;
+      table_base[(size_t)s * n_nodes + n] = tbl_total + off * (u64)job.slices[s].instants;
+      table_len[(size_t)s * n_nodes + n] = job.plain ? 0 : nch * (u64)job.slices[s].instants;
+    }
     tbl_total += job.plain ? 0 : job.table_len[s];
   }
 
@@ -186,10 +273,10 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   ctx->units.reserve(sizeof(EncUnit) * n_units);
   ctx->ustats.reserve(sizeof(UnitStats) * n_units);
   ctx->istats.reserve(sizeof(InstStats) * (size_t)n_units * job.t_max);
-  ctx->slices.reserve(sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_slices);
+  ctx->slices.reserve(sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_tables);
   ctx->sstate.reserve(sizeof(SliceState) * n_slices);
   ctx->order.reserve(sizeof(u32) * (4 * (size_t)n_units + 8));
-  ctx->pieces.reserve(sizeof(Piece) * (n_pieces + 2 * (size_t)n_slices));
+  ctx->pieces.reserve(sizeof(Piece) * (n_pieces + 2 * (size_t)n_tables));
   ctx->results.reserve(sizeof(UnitResult) * n_units);
   ctx->stored.reserve(n_units);
   ctx->chunk_off.reserve(sizeof(u64) * ((size_t)n_units + 1));
@@ -209,17 +296,36 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   unsigned long long* d_head = reinterpret_cast<unsigned long long*>(ctx->small.as<u8>() + 8);
   u32* d_counts = reinterpret_cast<u32*>(ctx->small.as<u8>() + 16);
 
-  ctx->pin.reserve(sizeof(EncUnit) * n_units + sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_slices + 64);
+  ctx->pin.reserve(sizeof(EncUnit) * n_units + sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_tables + 64);
   EncUnit* h_units = ctx->pin.as<EncUnit>();
   memcpy(h_units, job.units.data(), sizeof(EncUnit) * n_units);
   SliceDesc* h_slices = reinterpret_cast<SliceDesc*>(h_units + n_units);
   memcpy(h_slices, job.slices.data(), sizeof(SliceDesc) * n_slices);
   u64* h_tb = reinterpret_cast<u64*>(h_slices + n_slices);
-  for (u32 s = 0; s < n_slices; s++) { h_tb[s] = table_base[s]; h_tb[n_slices + s] = job.plain ? 0 : job.table_len[s]; }
+  for (u32 i = 0; i < n_tables; i++) { h_tb[i] = table_base[i]; h_tb[n_tables + i] = table_len[i]; }
   CK(cudaMemcpyAsync(ctx->units.p, h_units, sizeof(EncUnit) * n_units, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->slices.p, h_slices, sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_slices, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->slices.p, h_slices, sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_tables, cudaMemcpyHostToDevice, st));
   const u64* d_table_base = reinterpret_cast<const u64*>(ctx->slices.as<SliceDesc>() + n_slices);
-  const u64* d_table_len = d_table_base + n_slices;
+  const u64* d_table_len = d_table_base + n_tables;
+  // static node tree + per-(slice, node) state
+  TreeNode* d_nodes = nullptr;
+  TreeChild* d_children = nullptr;
+  int32_t* d_leaf_unit = nullptr;
+  NodeState* d_nstate = nullptr;
+  if (job.tree) {
+    const TreeGeo& G = *job.tree;
+    const size_t b0 = sizeof(TreeNode) * G.nodes.size(), b1 = sizeof(TreeChild) * G.children.size(),
+                 b2 = sizeof(int32_t) * G.leaf_unit.size(), b3 = sizeof(NodeState) * (size_t)n_tables;
+    ctx->tree_buf.reserve(b0 + b1 + b2 + b3 + 1024);
+    u8* tb = ctx->tree_buf.as<u8>();
+    d_nodes = reinterpret_cast<TreeNode*>(tb);
+    d_children = reinterpret_cast<TreeChild*>(tb + ((b0 + 255) & ~size_t(255)));
+    d_leaf_unit = reinterpret_cast<int32_t*>(reinterpret_cast<u8*>(d_children) + ((b1 + 255) & ~size_t(255)));
+    d_nstate = reinterpret_cast<NodeState*>(reinterpret_cast<u8*>(d_leaf_unit) + ((b2 + 255) & ~size_t(255)));
+    CK(cudaMemcpyAsync(d_nodes, G.nodes.data(), b0, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_children, G.children.data(), b1, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_leaf_unit, G.leaf_unit.data(), b2, cudaMemcpyHostToDevice, st));
+  }
 
   tr.mark("scratch + uploads");
   // ---- K1: per-unit statistics
@@ -311,7 +417,24 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
       CK(cudaStreamSynchronize(st));
     }
   }
-  k_finalize_phase2<<<n_slices, 256, 0, st>>>(FP, n_slices);
+  if (job.tree) {
+    const TreeGeo& G = *job.tree;
+    TreeParams TP;
+    TP.slices = FP.slices; TP.state = FP.state;
+    TP.nodes = d_nodes; TP.children = d_children; TP.n_nodes = n_nodes;
+    TP.leaf_unit = d_leaf_unit; TP.leaf_cols = G.leaf_cols; TP.leaf_side = G.leaf_side;
+    TP.tbl_per_instant = G.tbl_per_instant;
+    TP.nstate = d_nstate;
+    TP.units = ctx->units.as<EncUnit>();
+    TP.ustats = SP.ustats; TP.istats = SP.istats; TP.t_max = job.t_max;
+    TP.encoding = job.encoding; TP.round = job.round;
+    TP.tbl_min = d_tbl_min; TP.tbl_max = d_tbl_max;
+    TP.order = FP.order; TP.order_pitch = FP.order_pitch; TP.order_counts = FP.order_counts;
+    TP.stored = FP.stored; TP.err = d_err;
+    k_finalize_tree<<<n_slices, 256, 0, st>>>(TP, n_slices);
+  } else {
+    k_finalize_phase2<<<n_slices, 256, 0, st>>>(FP, n_slices);
+  }
   CK(cudaGetLastError());
   ctx->launches++;
 
@@ -334,6 +457,8 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     EP.arena_head = d_head;
     EP.err = d_err;
     time_begin(ctx, KT_ENCODE);
+    CK(cudaEventRecord(ctx->fork_ev, st));  // clipped-tile lists run on the auxiliary stream beside the full-tile lists
+    CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));
     for (int list = 0; list < 4; list++) {
       EP.order = FP.order + (size_t)list * n_units;
       EP.order_count = d_counts + list;
@@ -344,17 +469,20 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
         default: launch_encode<i64>(ctx, EP, n_units, list); break;
       }
     }
+    CK(cudaEventRecord(ctx->join_ev, ctx->aux_stream));
+    CK(cudaStreamWaitEvent(st, ctx->join_ev, 0));
     time_end(ctx, KT_ENCODE);
     tr.mark("k_encode_tiles");
     if (!job.plain) {
       TableDacParams TP;
       TP.tbl_min = d_tbl_min; TP.tbl_max = d_tbl_max;
       TP.table_base = d_table_base; TP.table_len = d_table_len;
+      TP.alive = reinterpret_cast<const int*>(d_nstate);
       TP.scratch = ctx->tbl_scratch.as<u64>();
       TP.total = tbl_total;
       TP.pieces = ctx->pieces.as<Piece>() + n_pieces;
       TP.arena = ctx->arena.as<u8>(); TP.arena_cap = arena_cap; TP.arena_head = d_head; TP.err = d_err;
-      k_table_dac<<<dim3(n_slices, 2), ENC_THREADS, 0, st>>>(TP);
+      k_table_dac<<<dim3(n_tables, 2), ENC_THREADS, 0, st>>>(TP);
       CK(cudaGetLastError());
       ctx->launches++;
     }
@@ -401,8 +529,10 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   CK(cudaMemcpyAsync(out.chunk_off.data(), ctx->chunk_off.p, sizeof(u64) * ((size_t)n_units + 1), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(out.states.data(), ctx->sstate.p, sizeof(SliceState) * n_slices, cudaMemcpyDeviceToHost, st));
   if (!job.plain) {
-    out.dac_pieces.resize(2 * (size_t)n_slices);
-    CK(cudaMemcpyAsync(out.dac_pieces.data(), ctx->pieces.as<Piece>() + n_pieces, sizeof(Piece) * 2 * n_slices, cudaMemcpyDeviceToHost, st));
+    out.dac_pieces.resize(2 * (size_t)n_tables);
+    CK(cudaMemcpyAsync(out.dac_pieces.data(), ctx->pieces.as<Piece>() + n_pieces, sizeof(Piece) * 2 * n_tables, cudaMemcpyDeviceToHost, st));
+    out.nstate.resize(n_tables);
+    CK(cudaMemcpyAsync(out.nstate.data(), d_nstate, sizeof(NodeState) * n_tables, cudaMemcpyDeviceToHost, st));
   }
   if (want_pieces) {
     out.pieces.resize(n_pieces);
@@ -433,19 +563,19 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   CK(cudaGetLastError());
   ctx->launches++;
   if (!job.plain) {
-    out.dac_off.resize(2 * (size_t)n_slices);
+    out.dac_off.resize(2 * (size_t)n_tables);
     u64 off = 0;
-    for (u32 i = 0; i < 2 * n_slices; i++) { out.dac_off[i] = off; off += out.dac_pieces[i].size; }
+    for (u32 i = 0; i < 2 * n_tables; i++) { out.dac_off[i] = off; off += out.dac_pieces[i].size; }
     out.dac_blob_size = off;
     out.dac_blob = static_cast<uint8_t*>(pool_alloc(off + 16, st));
-    ctx->query_aux.reserve(sizeof(u64) * 2 * n_slices);
-    CK(cudaMemcpyAsync(ctx->query_aux.p, out.dac_off.data(), sizeof(u64) * 2 * n_slices, cudaMemcpyHostToDevice, st));
+    ctx->query_aux.reserve(sizeof(u64) * 2 * n_tables);
+    CK(cudaMemcpyAsync(ctx->query_aux.p, out.dac_off.data(), sizeof(u64) * 2 * n_tables, cudaMemcpyHostToDevice, st));
     GatherDacParams DP;
     DP.pieces = ctx->pieces.as<Piece>() + n_pieces;
     DP.dst_off = ctx->query_aux.as<u64>();
     DP.arena = ctx->arena.as<u8>();
     DP.out = out.dac_blob;
-    k_gather_dacs<<<2 * n_slices, 256, 0, st>>>(DP);
+    k_gather_dacs<<<2 * n_tables, 256, 0, st>>>(DP);
     CK(cudaGetLastError());
     ctx->launches++;
   }
@@ -715,6 +845,9 @@ int32_t dcdf_ctx_create(int32_t device, dcdf_ctx** out) {
     CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     for (auto& ev : ctx->ev) CK(cudaEventCreate(&ev));
+    CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
@@ -737,11 +870,14 @@ int32_t dcdf_ctx_destroy(dcdf_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->input_copy, &ctx->units, &ctx->ustats, &ctx->istats, &ctx->slices, &ctx->sstate, &ctx->tbl_scratch,
                     &ctx->order, &ctx->pieces, &ctx->results, &ctx->stored, &ctx->chunk_off, &ctx->arena, &ctx->small,
-                    &ctx->exact, &ctx->query_in, &ctx->query_out, &ctx->query_aux};
+                    &ctx->exact, &ctx->query_in, &ctx->query_out, &ctx->query_aux, &ctx->tree_buf};
   for (auto* b : bufs) b->release();
   ctx->pin.release();
   ctx->pin2.release();
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return DCDF_OK;
@@ -1046,15 +1182,18 @@ int32_t dcdf_superchunk_build(dcdf_ctx* ctx, const dcdf_array3* a, const uint32_
     for (uint32_t i = 0; i < n_levels; i++) user_levels += levels[i];
     if (user_levels != total_levels)
       api_fail(DCDF_ERR_BAD_LEVELS, "Need %u tree levels to encode array, but %u levels passed in (superchunk.rs:105-110)", total_levels, user_levels);
-    if (n_levels != 2) api_fail(DCDF_ERR_BAD_ARG, "nested superchunks (more than two k2_levels entries) are not built on the GPU yet");
-    if (levels[1] > 6) api_fail(DCDF_ERR_BAD_ARG, "leaf subchunks larger than 64x64 are not built on the GPU yet");
+    if (levels[n_levels - 1] > 6) api_fail(DCDF_ERR_BAD_ARG, "leaf subchunks larger than 64x64 are not built on the GPU yet");
+    if (total_levels > 16) api_fail(DCDF_ERR_BAD_ARG, "raster side too large");
     const int64_t sidelen = (int64_t)1 << total_levels;
-    const int64_t subsidelen = (int64_t)1 << levels[0];
-    const int64_t chunks_sidelen = sidelen / subsidelen;
-    if (chunks_sidelen < 2 && false) api_fail(DCDF_ERR_BAD_ARG, "unreachable");
     const int64_t cs = chunk_size > 0 ? chunk_size : T;
     const uint32_t n_slices = (uint32_t)((T + cs - 1) / cs);
-    const uint32_t n_slots = (uint32_t)(subsidelen * subsidelen);
+
+    TreeGeo G;
+    build_tree(G, rows, cols, levels, n_levels);
+    const uint32_t n_nodes = (uint32_t)G.nodes.size();
+    const int ls = G.leaf_side;
+    const uint32_t n_slots = (uint32_t)(G.leaf_grid * G.leaf_grid);
+    const uint32_t units_per_slice = (uint32_t)(G.leaf_rows * G.leaf_cols);
 
     EncodeJob job;
     job.dev_data = stage_input(ctx, a);
@@ -1068,37 +1207,33 @@ int32_t dcdf_superchunk_build(dcdf_ctx* ctx, const dcdf_array3* a, const uint32_
     job.n_slots = n_slots;
     job.t_max = (uint32_t)std::min<int64_t>(cs, T);
     job.input_bytes = (size_t)T * rows * cols * elem_size(a->encoding);
+    job.tree = &G;
     std::vector<int32_t> slot_unit((size_t)n_slices * n_slots, -1);
     for (uint32_t s = 0; s < n_slices; s++) {
       const int64_t t0 = (int64_t)s * cs, t1 = std::min<int64_t>(t0 + cs, T);
       SliceDesc sd;
       memset(&sd, 0, sizeof sd);
       sd.t0 = t0; sd.instants = (int)(t1 - t0); sd.unit_base = (uint32_t)job.units.size();
-      for (int64_t r = 0; r < subsidelen; r++) {
-        const int64_t top = r * chunks_sidelen;
-        if (top >= rows) break;
-        const int64_t bottom = std::min(top + chunks_sidelen, rows);
-        for (int64_t c = 0; c < subsidelen; c++) {
-          const int64_t left = c * chunks_sidelen;
-          if (left >= cols) break;
-          const int64_t right = std::min(left + chunks_sidelen, cols);
+      for (int gr = 0; gr < G.leaf_rows; gr++)
+        for (int gc = 0; gc < G.leaf_cols; gc++) {
+          const int64_t top = (int64_t)gr * ls, left = (int64_t)gc * ls;
           EncUnit u;
           memset(&u, 0, sizeof u);
           u.base = t0 * a->strides[0] + top * a->strides[1] + left * a->strides[2];
-          u.rows = (int)(bottom - top); u.cols = (int)(right - left); u.instants = sd.instants;
+          u.rows = (int)std::min<int64_t>(ls, rows - top); u.cols = (int)std::min<int64_t>(ls, cols - left);
+          u.instants = sd.instants;
           // each sub-array is built by Chunk::build from its OWN (clipped) shape: snapshot.rs:118-119
           u.lo = 6 - (int)levels_for(std::max<int64_t>(u.rows, u.cols), 2);
-          u.slot = (uint32_t)(r * subsidelen + c);
+          u.slot = (uint32_t)((int64_t)gr * G.leaf_grid + gc);
           u.row0 = (int)top; u.col0 = (int)left;
           slot_unit[(size_t)s * n_slots + u.slot] = (int32_t)job.units.size();
           job.units.push_back(u);
         }
-      }
       sd.n_units = (uint32_t)job.units.size() - sd.unit_base;
       job.slices.push_back(sd);
-      job.table_len.push_back((uint64_t)sd.instants * n_slots);
+      job.table_len.push_back((uint64_t)sd.instants * G.tbl_per_instant);
     }
-    // a 1x1 leaf subchunk cannot be a Chunk (snapshot.rs:166); it can only appear elided
+    (void)units_per_slice;
     EncodeOut eo;
     run_encode(ctx, job, eo, false);
 
@@ -1116,42 +1251,78 @@ int32_t dcdf_superchunk_build(dcdf_ctx* ctx, const dcdf_array3* a, const uint32_
     sc->chunk_blob = eo.blob; sc->chunk_blob_size = eo.blob_size;
     sc->dac_blob = eo.dac_blob; sc->dac_blob_size = eo.dac_blob_size;
     sc->tbl_max = eo.tbl_max; sc->tbl_min = eo.tbl_min; sc->tbl_len = eo.tbl_total;
-    const bool is_float = a->encoding == DCDF_ENC_F32 || a->encoding == DCDF_ENC_F64;
+    sc->nodes = G.nodes; sc->children = G.children; sc->geom = G.geom; sc->leaf_unit = G.leaf_unit;
+    sc->leaf_rows = G.leaf_rows; sc->leaf_cols = G.leaf_cols; sc->leaf_side = G.leaf_side; sc->leaf_grid = G.leaf_grid;
+    sc->tbl_per_instant = G.tbl_per_instant;
+    sc->nstate = std::move(eo.nstate);
+    sc->node_dac_off.resize((size_t)n_slices * n_nodes * 2);
+    sc->node_dac_size.resize((size_t)n_slices * n_nodes * 2);
+    for (size_t i = 0; i < sc->node_dac_off.size(); i++) { sc->node_dac_off[i] = eo.dac_off[i]; sc->node_dac_size[i] = eo.dac_pieces[i].size; }
     for (uint32_t s = 0; s < n_slices; s++) {
       dcdf_superchunk::Slice sl;
       memset(&sl.info, 0, sizeof sl.info);
       const SliceDesc& sd = job.slices[s];
       sl.t0 = sd.t0; sl.unit_base = sd.unit_base; sl.n_units = sd.n_units;
       sl.table_base = sd.table_base;
-      sl.info.shape[0] = sd.instants; sl.info.shape[1] = rows; sl.info.shape[2] = cols;
-      sl.info.sidelen = sidelen; sl.info.chunks_sidelen = chunks_sidelen; sl.info.subsidelen = subsidelen;
-      sl.info.levels = levels[0];
-      sl.info.encoding = a->encoding;
-      sl.info.fractional_bits = is_float ? eo.states[s].bits : 0;
-      sl.info.n_refs = n_slots;
-      sl.dac_off[0] = eo.dac_off[2 * s]; sl.dac_off[1] = eo.dac_off[2 * s + 1];
-      sl.dac_size[0] = eo.dac_pieces[2 * s].size; sl.dac_size[1] = eo.dac_pieces[2 * s + 1].size;
-      sl.info.max_dac_bytes = sl.dac_size[0]; sl.info.min_dac_bytes = sl.dac_size[1];
       sl.chunk_blob_off = sc->chunk_off[sd.unit_base];
+      sl.info.shape[0] = sd.instants;
       sl.info.chunk_bytes = sc->chunk_off[sd.unit_base + sd.n_units] - sc->chunk_off[sd.unit_base];
-      dcdf_build_stats& bs = sl.info.stats;
-      uint32_t stored = 0;
-      for (uint32_t i = 0; i < sd.n_units; i++) {
-        const uint32_t u = sd.unit_base + i;
-        if (!sc->stored[u]) continue;
-        stored++;
-        bs.snapshots += sc->results[u].snapshots;
-        bs.logs += sc->results[u].logs;
-      }
-      bs.external = stored;
-      bs.local = 0;
-      bs.elided = n_slots - stored;
-      bs.size = sl.info.chunk_bytes + sl.dac_size[0] + sl.dac_size[1];
       sc->slices.push_back(sl);
     }
+    (void)sidelen;
     *out = sc;
   });
 }
+
+namespace {
+// MMStruct3Build counters of one node (recursive, superchunk.rs:200-269)
+void node_stats(const dcdf_superchunk* sc, uint32_t slice, uint32_t node, dcdf_build_stats& bs, uint64_t& chunk_bytes) {
+  const uint32_t n_nodes = (uint32_t)sc->nodes.size();
+  const TreeNode& nd = sc->nodes[node];
+  const auto& sl = sc->slices[slice];
+  memset(&bs, 0, sizeof bs);
+  chunk_bytes = 0;
+  for (u32 c = 0; c < nd.n_children; c++) {
+    const TreeChild& ch = sc->children[nd.first_child + c];
+    if (ch.kind == 1) {
+      const uint32_t u = sl.unit_base + (uint32_t)ch.index;
+      if (sc->stored[u]) {
+        bs.external++; bs.snapshots += sc->results[u].snapshots; bs.logs += sc->results[u].logs;
+        chunk_bytes += sc->results[u].bytes;
+        continue;
+      }
+    } else if (ch.kind == 2 && sc->nstate[(size_t)slice * n_nodes + ch.index].alive) {
+      dcdf_build_stats cb;
+      uint64_t cbytes;
+      node_stats(sc, slice, (uint32_t)ch.index, cb, cbytes);
+      bs.external++; bs.snapshots += cb.snapshots; bs.logs += cb.logs;
+      bs.size += cb.size;
+      continue;
+    }
+    bs.elided++;
+  }
+  const size_t di = ((size_t)slice * n_nodes + node) * 2;
+  bs.size += chunk_bytes + sc->node_dac_size[di] + sc->node_dac_size[di + 1];
+}
+
+void fill_node_info(const dcdf_superchunk* sc, uint32_t slice, uint32_t node, dcdf_superchunk_info* info) {
+  const uint32_t n_nodes = (uint32_t)sc->nodes.size();
+  memset(info, 0, sizeof *info);
+  const auto& g = sc->geom[node];
+  const NodeState& st = sc->nstate[(size_t)slice * n_nodes + node];
+  const bool is_float = sc->encoding == DCDF_ENC_F32 || sc->encoding == DCDF_ENC_F64;
+  info->shape[0] = sc->slices[slice].info.shape[0]; info->shape[1] = g.rows; info->shape[2] = g.cols;
+  info->sidelen = g.sidelen; info->chunks_sidelen = g.chunks_sidelen; info->subsidelen = g.subsidelen;
+  info->levels = g.levels;
+  info->encoding = sc->encoding;
+  info->fractional_bits = is_float ? st.bits : 0;
+  info->n_refs = st.alive ? sc->nodes[node].n_children : 0;
+  const size_t di = ((size_t)slice * n_nodes + node) * 2;
+  info->max_dac_bytes = sc->node_dac_size[di]; info->min_dac_bytes = sc->node_dac_size[di + 1];
+  if (st.alive) node_stats(sc, slice, node, info->stats, info->chunk_bytes);
+  if (node == 0) info->chunk_bytes = sc->slices[slice].info.chunk_bytes;  // the slice's whole chunk blob
+}
+}  // namespace
 
 int32_t dcdf_superchunk_free(dcdf_superchunk* sc) {
   if (!sc) return DCDF_OK;
@@ -1172,36 +1343,74 @@ int32_t dcdf_superchunk_count(const dcdf_superchunk* sc, uint32_t* n) {
   return DCDF_OK;
 }
 
+int32_t dcdf_superchunk_node_count(const dcdf_superchunk* sc, uint32_t* n) {
+  if (!sc || !n) return DCDF_ERR_BAD_ARG;
+  *n = (uint32_t)sc->nodes.size();
+  return DCDF_OK;
+}
+
 int32_t dcdf_superchunk_get_info(const dcdf_superchunk* sc, uint32_t slice, dcdf_superchunk_info* info) {
   if (!sc || !info || slice >= sc->slices.size()) return DCDF_ERR_BAD_ARG;
-  *info = sc->slices[slice].info;
+  fill_node_info(sc, slice, 0, info);
   return DCDF_OK;
+}
+
+int32_t dcdf_superchunk_node_info(const dcdf_superchunk* sc, uint32_t slice, uint32_t node, dcdf_superchunk_info* info) {
+  if (!sc || !info || slice >= sc->slices.size() || node >= sc->nodes.size()) return DCDF_ERR_BAD_ARG;
+  fill_node_info(sc, slice, node, info);
+  return DCDF_OK;
+}
+
+int32_t dcdf_superchunk_node_refs(dcdf_ctx* ctx, const dcdf_superchunk* sc, uint32_t slice, uint32_t node, int32_t* kinds,
+                                  int32_t* child_node, uint64_t* chunk_off, uint64_t* chunk_size, int32_t* chunk_bits) {
+  return guarded(ctx, [&] {
+    if (!sc || slice >= sc->slices.size() || node >= sc->nodes.size()) api_fail(DCDF_ERR_BAD_ARG, "bad slice / node");
+    const uint32_t n_nodes = (uint32_t)sc->nodes.size();
+    const auto& sl = sc->slices[slice];
+    const TreeNode& nd = sc->nodes[node];
+    if (!sc->nstate[(size_t)slice * n_nodes + node].alive) api_fail(DCDF_ERR_BAD_ARG, "node %u is not built in slice %u (elided)", node, slice);
+    for (u32 c = 0; c < nd.n_children; c++) {
+      const TreeChild& ch = sc->children[nd.first_child + c];
+      int32_t kind = DCDF_REF_ELIDED, cn = -1, bits = 0;
+      uint64_t off = 0, size = 0;
+      if (ch.kind == 1) {
+        const uint32_t u = sl.unit_base + (uint32_t)ch.index;
+        if (sc->stored[u]) { kind = DCDF_REF_EXTERNAL; off = sc->chunk_off[u] - sl.chunk_blob_off; size = sc->results[u].bytes; bits = sc->units[u].bits; }
+      } else if (ch.kind == 2 && sc->nstate[(size_t)slice * n_nodes + ch.index].alive) {
+        kind = DCDF_REF_EXTERNAL; cn = ch.index;
+      }
+      if (kinds) kinds[c] = kind;
+      if (child_node) child_node[c] = cn;
+      if (chunk_off) chunk_off[c] = off;
+      if (chunk_size) chunk_size[c] = size;
+      if (chunk_bits) chunk_bits[c] = bits;
+    }
+  });
 }
 
 int32_t dcdf_superchunk_refs(dcdf_ctx* ctx, const dcdf_superchunk* sc, uint32_t slice, int32_t* kinds, uint64_t* chunk_off,
                              uint64_t* chunk_size, int32_t* chunk_bits) {
+  return dcdf_superchunk_node_refs(ctx, sc, slice, 0, kinds, nullptr, chunk_off, chunk_size, chunk_bits);
+}
+
+int32_t dcdf_superchunk_node_bytes(dcdf_ctx* ctx, const dcdf_superchunk* sc, uint32_t slice, uint32_t node, int32_t which,
+                                   uint8_t* dst, uint64_t cap, int32_t mem) {
   return guarded(ctx, [&] {
-    if (!sc || slice >= sc->slices.size()) api_fail(DCDF_ERR_BAD_ARG, "bad slice");
-    const auto& sl = sc->slices[slice];
-    for (uint32_t i = 0; i < sc->n_slots; i++) {
-      const int32_t u = sc->slot_unit[(size_t)slice * sc->n_slots + i];
-      const bool st = u >= 0 && sc->stored[u];
-      if (kinds) kinds[i] = st ? DCDF_REF_EXTERNAL : DCDF_REF_ELIDED;
-      if (chunk_off) chunk_off[i] = st ? sc->chunk_off[u] - sl.chunk_blob_off : 0;
-      if (chunk_size) chunk_size[i] = st ? sc->results[u].bytes : 0;
-      if (chunk_bits) chunk_bits[i] = st ? sc->units[u].bits : 0;
-    }
+    if (!sc || slice >= sc->slices.size() || node >= sc->nodes.size() || which < 1 || which > 2) api_fail(DCDF_ERR_BAD_ARG, "bad slice / node / which");
+    const size_t di = ((size_t)slice * sc->nodes.size() + node) * 2 + (size_t)(which - 1);
+    copy_out(ctx, sc->dac_blob + sc->node_dac_off[di], sc->node_dac_size[di], dst, cap, mem);
   });
 }
 
 int32_t dcdf_superchunk_bytes(dcdf_ctx* ctx, const dcdf_superchunk* sc, uint32_t slice, int32_t which, uint8_t* dst,
                               uint64_t cap, int32_t mem) {
-  return guarded(ctx, [&] {
-    if (!sc || slice >= sc->slices.size() || which < 0 || which > 2) api_fail(DCDF_ERR_BAD_ARG, "bad slice / which");
-    const auto& sl = sc->slices[slice];
-    if (which == 0) copy_out(ctx, sc->chunk_blob + sl.chunk_blob_off, sl.info.chunk_bytes, dst, cap, mem);
-    else copy_out(ctx, sc->dac_blob + sl.dac_off[which - 1], sl.dac_size[which - 1], dst, cap, mem);
-  });
+  if (which == 0)
+    return guarded(ctx, [&] {
+      if (!sc || slice >= sc->slices.size()) api_fail(DCDF_ERR_BAD_ARG, "bad slice");
+      const auto& sl = sc->slices[slice];
+      copy_out(ctx, sc->chunk_blob + sl.chunk_blob_off, sl.info.chunk_bytes, dst, cap, mem);
+    });
+  return dcdf_superchunk_node_bytes(ctx, sc, slice, 0, which, dst, cap, mem);
 }
 
 int32_t dcdf_superchunk_total_bytes(const dcdf_superchunk* sc, uint64_t* n) {

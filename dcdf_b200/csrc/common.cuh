@@ -20,6 +20,8 @@ enum : u32 {
   EF_ARENA_FULL = 1u << 3,
   EF_BAD_FORMAT = 1u << 4,
   EF_OUT_CAP = 1u << 5,
+  EF_BAD_LEVELS = 1u << 6,    // superchunk.rs:105-110 inside a recursion
+  EF_REGION_EXACT = 1u << 7,  // nested region needs the exact saturating-cast pass (not built yet)
 };
 
 #define DCDF_DEVINL __device__ __forceinline__

@@ -44,12 +44,20 @@ struct SliceMeta {
   u32 slot_base;    // first entry of this slice in slot_unit
   u32 pad;
 };
+// Where the value of a cell of an Elided subchunk comes from: entry (instant * stride) of the max table of the
+// superchunk node that elided it, decoded with that node's fractional bits (superchunk.rs:325-330).
+struct SlotDesc {
+  u64 tbl0;
+  u32 stride;
+  int bits;
+};
 struct QuerySet {
   const u8* blob;
   const UnitMeta* units;
   const InstDir* dir;
   const SliceMeta* slices;
   const int32_t* slot_unit;  // [n_slices][n_slots] unit index or -1
+  const SlotDesc* slot_desc; // [n_slices][n_slots] source of elided values
   const i64* tbl_max;
   u32 n_slices, n_slots;
   i64 chunk_size;            // instants per slice
@@ -289,8 +297,9 @@ DCDF_DEVINL i64 set_get(const QuerySet& Q, i64 instant, i64 row, i64 col, int& b
       return chunk_get(cv, ti, (u32)(row % Q.chunks_sidelen), (u32)(col % Q.chunks_sidelen));
     }
   }
-  bits = sm.bits;
-  return Q.tbl_max[sm.table_base + (u64)ti * Q.n_slots + slot];  // Elided: superchunk.rs:325-330
+  const SlotDesc sdsc = Q.slot_desc[sm.slot_base + slot];
+  bits = sdsc.bits;
+  return Q.tbl_max[sdsc.tbl0 + (u64)ti * sdsc.stride];  // Elided: superchunk.rs:325-330
 }
 
 template <typename OutT>
@@ -579,7 +588,8 @@ __global__ void k_search(const SearchParams P, int write) {
   }
   if (!done) {
     // Elided subchunk: one value per instant from the max table (superchunk.rs:541-559)
-    const i64 v = Q.tbl_max[sm.table_base + (u64)ti * Q.n_slots + slot];
+    const SlotDesc sdsc = Q.slot_desc[sm.slot_base + slot];
+    const i64 v = Q.tbl_max[sdsc.tbl0 + (u64)ti * sdsc.stride];
     if (lower <= v && v <= upper) sink.push_rect(top, bottom, left, right, 0, 0);
   }
   if (!write) P.counts[ji] = sink.n;

@@ -192,9 +192,10 @@ __global__ void __launch_bounds__(DT_THREADS) k_window_tiles(const TileWindowPar
     };
     if (!stored) {
       // Elided: one value per instant from the max table, parent's fractional bits (superchunk.rs:426-433)
+      const SlotDesc sdsc = Q.slot_desc[sm.slot_base + slot];
       for (i64 t = t_lo; t < t_hi; t++) {
-        const i64 v = Q.tbl_max[sm.table_base + (u64)(t - sm.t0) * Q.n_slots + slot];
-        for (int i = tid; i < wr * wc; i += DT_THREADS) emit(Q, P.out, out_index(t, top + i / wc, left + i % wc), v, sm.bits, P.raw);
+        const i64 v = Q.tbl_max[sdsc.tbl0 + (u64)(t - sm.t0) * sdsc.stride];
+        for (int i = tid; i < wr * wc; i += DT_THREADS) emit(Q, P.out, out_index(t, top + i / wc, left + i % wc), v, sdsc.bits, P.raw);
       }
       continue;
     }

@@ -14,11 +14,12 @@ namespace dcdf {
 struct TableDacParams {
   const i64* tbl_min;
   const i64* tbl_max;
-  const u64* table_base;  // [n_slices]
-  const u64* table_len;   // [n_slices] instants * n_slots
+  const u64* table_base;  // [n_tables]
+  const u64* table_len;   // [n_tables] instants * n_children
+  const int* alive;       // [n_tables] stride 2 ints (NodeState): tables of nodes that are not built are skipped
   u64* scratch;           // zigzag codes + compaction partners, same indexing as the tables; [4][total]
   u64 total;              // sum of table_len
-  Piece* pieces;          // [n_slices][2]  (0 = max, 1 = min)
+  Piece* pieces;          // [n_tables][2]  (0 = max, 1 = min)
   u8* arena;
   u64 arena_cap;
   unsigned long long* arena_head;
@@ -29,6 +30,10 @@ struct TableDacParams {
 __global__ void __launch_bounds__(ENC_THREADS) k_table_dac(const TableDacParams P) {
   const u32 s = blockIdx.x, which = blockIdx.y;  // which: 0 = max, 1 = min
   const int tid = threadIdx.x, lane = tid & 31;
+  if (P.alive && !P.alive[2 * s]) {
+    if (tid == 0) { Piece pc; pc.off = 0; pc.size = 0; pc.kind = 2u + which; P.pieces[2 * s + which] = pc; }
+    return;
+  }
   const i64* src = (which == 0 ? P.tbl_max : P.tbl_min) + P.table_base[s];
   u64* a = P.scratch + (u64)which * P.total + P.table_base[s];
   u64* a2 = P.scratch + (u64)(2 + which) * P.total + P.table_base[s];  // compaction partner

@@ -11,6 +11,7 @@
 #include "../../include/dcdf_cuda.h"
 #include "common.cuh"
 #include "encode_tile.cuh"
+#include "tree_types.hpp"
 
 namespace dcdf {
 
@@ -102,6 +103,8 @@ struct dcdf_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux_stream = nullptr;  // clipped-tile encode list runs beside the full-tile list
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
   std::string last_error;
   uint64_t launches = 0;
   float kernel_ms[dcdf::KT_COUNT] = {0, 0, 0, 0, 0, 0};
@@ -109,7 +112,7 @@ struct dcdf_ctx {
   int sm_count = 148;
   // scratch
   dcdf::DevBuf input_copy, units, ustats, istats, slices, sstate, tbl_scratch, order, pieces, results, stored, chunk_off,
-      arena, small, exact, query_in, query_out, query_aux;
+      arena, small, exact, query_in, query_out, query_aux, tree_buf;
   dcdf::PinBuf pin, pin2;
   size_t arena_hint = 0;
 };
@@ -147,7 +150,18 @@ struct dcdf_superchunk {
   std::vector<uint8_t> stored;
   std::vector<uint64_t> chunk_off;  // [n_units + 1] into chunk_blob
   std::vector<dcdf::UnitResult> results;
-  std::vector<int32_t> slot_unit;   // [n_slices][n_slots] -> unit index or -1
+  std::vector<int32_t> slot_unit;   // [n_slices][n_slots] -> unit index or -1 (n_slots = padded leaf grid)
+  // static node tree (same geometry for every slice) and per-slice node results
+  struct NodeGeom { int64_t top, left, rows, cols, sidelen, chunks_sidelen, subsidelen; uint32_t levels; };
+  std::vector<dcdf::TreeNode> nodes;
+  std::vector<dcdf::TreeChild> children;
+  std::vector<NodeGeom> geom;
+  std::vector<dcdf::NodeState> nstate;           // [n_slices][n_nodes]
+  std::vector<uint64_t> node_dac_off, node_dac_size;  // [n_slices][n_nodes][2] into dac_blob
+  std::vector<int32_t> leaf_unit;                // [leaf_rows][leaf_cols] unit index inside a slice
+  int leaf_rows = 0, leaf_cols = 0, leaf_side = 0;
+  int64_t leaf_grid = 0;                         // padded leaf tiles per side
+  uint64_t tbl_per_instant = 0;
   // device blobs
   uint8_t* chunk_blob = nullptr;
   uint64_t chunk_blob_size = 0;

@@ -7,6 +7,7 @@
 #pragma once
 #include "common.cuh"
 #include "encode_tile.cuh"
+#include "tree_types.hpp"
 
 namespace dcdf {
 
@@ -636,6 +637,199 @@ __global__ void k_region_minmax(const RegionMinMaxParams P) {
   P.out_min[t] = fmn;
   P.out_max[t] = fmx;
   if (err) atomicOr(P.err, err);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-level Superchunk::build finalisation (superchunk.rs:88-270 including its recursion :171).
+// The node tree is static geometry (same for every slice): node 0 is the root superchunk, further nodes are
+// the in-bounds regions that recurse.  Every child of a node is out of bounds, a leaf unit (Chunk) or
+// another node; its statistics are the combination of the leaf tiles it covers.
+struct TreeParams {
+  const SliceDesc* slices;
+  SliceState* state;         // root bits come from phase 1
+  const TreeNode* nodes;
+  const TreeChild* children;
+  u32 n_nodes;
+  const int32_t* leaf_unit;  // [leaf_rows * leaf_cols] unit index inside the slice or -1
+  int leaf_cols;             // leaf tiles per row of the in-bounds leaf grid
+  int leaf_side;
+  u64 tbl_per_instant;       // sum of n_children over all nodes
+  NodeState* nstate;         // [n_slices][n_nodes]
+  EncUnit* units;
+  const UnitStats* ustats;
+  const InstStats* istats;
+  u32 t_max;
+  int encoding, round;
+  i64* tbl_min;
+  i64* tbl_max;
+  u32* order;
+  u32 order_pitch;
+  u32* order_counts;
+  u8* stored;
+  u32* err;
+};
+
+// one CTA per slice; nodes in index order (parents first); one thread per child of the current node
+__global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n_slices) {
+  const u32 s = blockIdx.x;
+  if (s >= n_slices) return;
+  const SliceDesc sd = P.slices[s];
+  const int tid = threadIdx.x;
+  const bool is_float = P.encoding == 32 || P.encoding == 64;
+  const bool round = P.round != 0;
+  NodeState* ns = P.nstate + (size_t)s * P.n_nodes;
+  u32 err = 0;
+  u32 n_el = 0, n_st = 0;
+  if (tid == 0) {
+    ns[0].alive = 1;
+    ns[0].bits = P.state[s].bits;
+    for (u32 n = 1; n < P.n_nodes; n++) { ns[n].alive = 0; ns[n].bits = 0; }
+  }
+  __syncthreads();
+  for (u32 n = 0; n < P.n_nodes; n++) {
+    const TreeNode nd = P.nodes[n];
+    const bool alive = ns[n].alive != 0;
+    const int nbits = ns[n].bits;
+    i64* tmin = P.tbl_min + sd.table_base + (u64)nd.tbl_off * (u64)sd.instants;
+    i64* tmax = P.tbl_max + sd.table_base + (u64)nd.tbl_off * (u64)sd.instants;
+    if (alive && !nd.levels_ok) err |= EF_BAD_LEVELS;
+    for (u32 c = tid; c < nd.n_children; c += blockDim.x) {
+      const TreeChild ch = P.children[nd.first_child + c];
+      if (!alive) {
+        if (ch.kind == 1) {
+          const u32 u = sd.unit_base + (u32)ch.index;
+          EncUnit unit = P.units[u];
+          unit.flags |= UF_SKIP;
+          P.units[u] = unit;
+          P.stored[u] = 0;
+        }
+        continue;
+      }
+      if (ch.kind == 0) {  // entirely outside the raster: Elided with (0,0) per instant (superchunk.rs:134-139)
+        for (int t = 0; t < sd.instants; t++) { tmin[(u64)t * nd.n_children + c] = 0; tmax[(u64)t * nd.n_children + c] = 0; }
+        continue;
+      }
+      // region statistics: combine the leaf tiles the child covers
+      bool has = false, nonfinite = false;
+      double vmax = -INFINITY, vneg = 0.0;
+      int fnn = 0, fng = 0;
+      i64 imax = INT64_MIN, imin = INT64_MAX;
+      bool can_elide = true;
+      const i64 region_cols = (i64)(ch.gc1 - ch.gc0) * P.leaf_side;
+      for (int t = 0; t < sd.instants; t++) {
+        double mn = INFINITY, mx = -INFINITY;
+        i64 lmn = INT64_MAX, lmx = INT64_MIN;
+        u64 first = ~0ull, last = 0;
+        for (int gr = ch.gr0; gr < ch.gr1; gr++)
+          for (int gc = ch.gc0; gc < ch.gc1; gc++) {
+            const int32_t lu = P.leaf_unit[gr * P.leaf_cols + gc];
+            if (lu < 0) continue;
+            const u32 u = sd.unit_base + (u32)lu;
+            const InstStats is = P.istats[(size_t)u * P.t_max + t];
+            if (is_float) {
+              const int ucols = P.units[u].cols;
+              const u64 r_off = (u64)(gr - ch.gr0) * P.leaf_side, c_off = (u64)(gc - ch.gc0) * P.leaf_side;
+              if (is.first != 0xffffffffu) {
+                mn = fmin(mn, __longlong_as_double((long long)is.mn));
+                mx = fmax(mx, __longlong_as_double((long long)is.mx));
+                const u64 key = (r_off + is.first / (u32)ucols) * (u64)region_cols + c_off + is.first % (u32)ucols;
+                first = key < first ? key : first;
+              }
+              if (is.last) {
+                const u32 idx = is.last - 1u;
+                const u64 key = (r_off + idx / (u32)ucols) * (u64)region_cols + c_off + idx % (u32)ucols + 1ull;
+                last = key > last ? key : last;
+              }
+            } else {
+              lmn = (i64)is.mn < lmn ? (i64)is.mn : lmn;
+              lmx = (i64)is.mx > lmx ? (i64)is.mx : lmx;
+            }
+          }
+        i64 fmn, fmx;
+        if (is_float) {
+          const bool all_nan = first == ~0ull;
+          const bool quirk = !all_nan && last > first;  // mmbuffer.rs:485-487
+          if (P.encoding == 32) {
+            fmn = (all_nan || quirk) ? 0 : to_fixed_dev<float>((float)mn, nbits, round, err);
+            fmx = all_nan ? 0 : to_fixed_dev<float>((float)mx, nbits, round, err);
+          } else {
+            fmn = (all_nan || quirk) ? 0 : to_fixed_dev<double>(mn, nbits, round, err);
+            fmx = all_nan ? 0 : to_fixed_dev<double>(mx, nbits, round, err);
+          }
+        } else {
+          fmn = lmn; fmx = lmx;
+        }
+        tmin[(u64)t * nd.n_children + c] = fmn;
+        tmax[(u64)t * nd.n_children + c] = fmx;
+        can_elide = can_elide && fmn == fmx;  // superchunk.rs:145-147
+      }
+      // unit-level summaries over the covered tiles (for compute_fractional_bits of the child, :167)
+      for (int gr = ch.gr0; gr < ch.gr1; gr++)
+        for (int gc = ch.gc0; gc < ch.gc1; gc++) {
+          const int32_t lu = P.leaf_unit[gr * P.leaf_cols + gc];
+          if (lu < 0) continue;
+          const UnitStats us = P.ustats[sd.unit_base + (u32)lu];
+          if (us.has_value) { has = true; vmax = fmax(vmax, us.vmax); }
+          vneg = fmin(vneg, us.vneg);
+          fnn = max(fnn, us.frac_nonneg); fng = max(fng, us.frac_neg);
+          nonfinite = nonfinite || us.nonfinite;
+          imax = us.imax > imax ? us.imax : imax;
+          imin = us.imin < imin ? us.imin : imin;
+        }
+      int cbits = 0;
+      if (!can_elide && is_float) {
+        int sug_round = 0, sug_bits = 0, sug_err = 0;
+        if (ch.kind == 1) {
+          const UnitStats us = P.ustats[sd.unit_base + (u32)ch.index];
+          sug_round = us.sug_round; sug_bits = us.sug_bits; sug_err = us.sug_err;  // exact (second pass inside k_unit_stats)
+        } else if (!suggest_from_summary(has, vmax, vneg, fnn, fng, sug_round, sug_bits, sug_err)) {
+          err |= EF_REGION_EXACT;
+        }
+        err |= (u32)sug_err;
+        if (nonfinite) err |= EF_NONFINITE;
+        if (round) cbits = min(sug_bits, nbits);               // mmbuffer.rs:602-603
+        else { if (sug_round) err |= EF_PRECISION; cbits = sug_bits; }
+      }
+      if (ch.kind == 2) {
+        ns[ch.index].alive = can_elide ? 0 : 1;
+        ns[ch.index].bits = cbits;
+      } else {
+        const u32 u = sd.unit_base + (u32)ch.index;
+        EncUnit unit = P.units[u];
+        int flags = round ? UF_ROUND : 0;
+        bool narrow = false;
+        if (can_elide) {
+          flags |= UF_SKIP;
+          n_el++;
+        } else {
+          n_st++;
+          if (is_float) {
+            if (has) {
+              const double lim = ldexp(1.0, 29 - cbits);  // |fixed| = 2|v| 2^bits + 1 < 2^30
+              narrow = fabs(vmax) < lim && fabs(vneg) < lim;
+            } else narrow = true;
+          } else {
+            narrow = imax < (i64)0x3fffffff && imin > -(i64)0x3fffffff;
+          }
+          if (narrow) flags |= UF_NARROW;
+        }
+        const bool full = unit.rows == 64 && unit.cols == 64 && unit.lo == 0;
+        if (full) flags |= UF_FULL;
+        unit.bits = cbits;
+        unit.flags = flags;
+        P.units[u] = unit;
+        P.stored[u] = can_elide ? 0 : 1;
+        if (!can_elide) {
+          const u32 list = (narrow ? 0u : 2u) + (full ? 0u : 1u);
+          P.order[(size_t)list * P.order_pitch + atomicAdd(&P.order_counts[list], 1u)] = u;
+        }
+      }
+    }
+    __syncthreads();  // node states written by this node's children are read by later nodes
+  }
+  if (n_el) atomicAdd(&P.state[s].n_elided, n_el);
+  if (n_st) atomicAdd(&P.state[s].n_stored, n_st);
+  if (err) { atomicOr(&P.state[s].err, err); atomicOr(P.err, err); }
 }
 
 }  // namespace dcdf

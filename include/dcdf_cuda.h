@@ -166,6 +166,18 @@ typedef struct dcdf_superchunk_info {
   dcdf_build_stats stats;
 } dcdf_superchunk_info;
 int32_t dcdf_superchunk_count(const dcdf_superchunk* sc, uint32_t* n_slices);
+/* Nested superchunks (more than two k2_levels entries, superchunk.rs:171): the recursion's node tree is static
+ * geometry shared by all slices.  Node 0 is the root; dcdf_superchunk_get_info / _refs / _bytes address node 0.
+ * A node that is Elided in a slice has n_refs == 0 there. */
+int32_t dcdf_superchunk_node_count(const dcdf_superchunk* sc, uint32_t* n_nodes);
+int32_t dcdf_superchunk_node_info(const dcdf_superchunk* sc, uint32_t slice, uint32_t node, dcdf_superchunk_info* info);
+/* As dcdf_superchunk_refs for any node; child_node[i] is the node index of a nested superchunk reference, -1 for
+ * Chunk references and Elided slots. */
+int32_t dcdf_superchunk_node_refs(dcdf_ctx* ctx, const dcdf_superchunk* sc, uint32_t slice, uint32_t node, int32_t* kinds,
+                                  int32_t* child_node, uint64_t* chunk_off, uint64_t* chunk_size, int32_t* chunk_bits);
+/* which 1 = max Dac, 2 = min Dac of the node. */
+int32_t dcdf_superchunk_node_bytes(dcdf_ctx* ctx, const dcdf_superchunk* sc, uint32_t slice, uint32_t node, int32_t which,
+                                   uint8_t* dst, uint64_t cap, int32_t mem);
 int32_t dcdf_superchunk_get_info(const dcdf_superchunk* sc, uint32_t slice, dcdf_superchunk_info* info);
 /* Reference kinds (DCDF_REF_*) per subchunk, row-major (superchunk.rs:127-181, 206-240) and, for
  * stored subchunks, [offset, offset+size) of its Chunk bytes inside the slice's chunk-byte blob and its

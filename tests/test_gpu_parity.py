@@ -266,6 +266,33 @@ def test_log_search_reference_bug_parity(ctx):
 
 
 # ----------------------------------------------------------------------------- Superchunk
+def _cmp_node(got, s, gnode, ref, rnode, blob, path="root"):
+    """Walk the GPU node tree and the oracle's tree in lock step."""
+    rinfo, ginfo = ref.node_info(rnode), got.info(s, gnode)
+    for f in ("sidelen", "chunks_sidelen", "subsidelen", "levels", "fractional_bits", "encoding", "n_refs"):
+        assert getattr(ginfo, f) == getattr(rinfo, f), (path, f, getattr(ginfo, f), getattr(rinfo, f))
+    assert tuple(ginfo.shape) == tuple(rinfo.shape), path
+    rk, rchild = ref.node_refs(rnode)
+    gk, goff, gsize, gbits, gchild = got.refs(s, gnode, with_children=True)
+    assert gk.tolist() == rk.tolist(), f"{path}: Elided / External pattern differs"
+    chunks = got.chunk_bytes(s, gnode, blob)
+    for slot, (k, child) in enumerate(zip(rk, rchild)):
+        if k == 0:
+            assert chunks[slot] is None and gchild[slot] == -1
+            continue
+        cinfo = ref.node_info(int(child))
+        if cinfo.kind == 1:
+            _diff(chunks[slot], ref.node_bytes(int(child)), f"slice {s} {path} slot {slot}")
+            assert gbits[slot] == cinfo.fractional_bits and gchild[slot] == -1
+        else:
+            assert gchild[slot] >= 0
+            _cmp_node(got, s, int(gchild[slot]), ref, int(child), blob, f"{path}/{slot}")
+    _diff(got.bytes(s, 1, gnode), ref.node_bytes(rnode, 1), f"slice {s} {path} max DAC")
+    _diff(got.bytes(s, 2, gnode), ref.node_bytes(rnode, 2), f"slice {s} {path} min DAC")
+    st, rs = ginfo.stats, rinfo.stats
+    assert (st.elided, st.external, st.snapshots, st.logs, st.size) == (rs.elided, rs.external, rs.snapshots, rs.logs, rs.size), path
+
+
 def _check_superchunk(ctx, data, levels, chunk_size=0, fractional_bits=0, round_=False, compute_bits=True):
     from dcdf_b200 import Superchunk
     got = Superchunk.build(ctx, data, levels, fractional_bits=fractional_bits, round=round_, compute_bits=compute_bits, chunk_size=chunk_size)
@@ -275,24 +302,7 @@ def _check_superchunk(ctx, data, levels, chunk_size=0, fractional_bits=0, round_
     for s in range(got.n_slices):
         sub = data[s * cs:(s + 1) * cs]
         ref = orc.superchunk_build(sub, levels, fractional_bits=fractional_bits, round_=round_, compute_bits=compute_bits)
-        rinfo, ginfo = ref.node_info(0), got.info(s)
-        for f in ("sidelen", "chunks_sidelen", "subsidelen", "levels", "fractional_bits", "encoding", "n_refs"):
-            assert getattr(ginfo, f) == getattr(rinfo, f), f
-        assert tuple(ginfo.shape) == tuple(rinfo.shape)
-        rk, rchild = ref.node_refs(0)
-        gk, goff, gsize, gbits = got.refs(s)
-        assert gk.tolist() == rk.tolist(), "Elided / External pattern differs"
-        chunks = got.chunk_bytes(s)
-        for slot, (k, child) in enumerate(zip(rk, rchild)):
-            if k == 0:
-                assert chunks[slot] is None
-                continue
-            _diff(chunks[slot], ref.node_bytes(int(child)), f"slice {s} slot {slot}")
-            assert gbits[slot] == ref.node_info(int(child)).fractional_bits
-        _diff(got.bytes(s, 1), ref.node_bytes(0, 1), f"slice {s} max DAC")
-        _diff(got.bytes(s, 2), ref.node_bytes(0, 2), f"slice {s} min DAC")
-        st, rs = ginfo.stats, rinfo.stats
-        assert (st.elided, st.external, st.snapshots, st.logs, st.size) == (rs.elided, rs.external, rs.snapshots, rs.logs, rs.size)
+        _cmp_node(got, s, 0, ref, 0, got.bytes(s, 0))
     return got
 
 
@@ -304,6 +314,38 @@ def test_superchunk_reference_structures(ctx):
     _check_superchunk(ctx, fx.farray(32, 13), [2, 3], chunk_size=5)
     _check_superchunk(ctx, fx.farray(16, 9, np.float64), [1, 3], chunk_size=4)
     _check_superchunk(ctx, fx.array(40, 6, np.int32), [3, 3])
+
+
+def test_nested_superchunks(ctx):
+    """Superchunk::build recursion (superchunk.rs:171): more than two k2_levels entries."""
+    from dcdf_b200 import synth
+    _check_superchunk(ctx, fx.farray(32, 9), [1, 2, 2])                       # superchunk.rs:1177-1196
+    data = synth.raster_slice(0, 11, 150, 200).numpy()
+    got = _check_superchunk(ctx, data, [1, 1, 6], chunk_size=4)
+    assert got.node_count() == 5
+    assert np.array_equal(got.window(1, 10, 5, 150, 60, 200), data[1:10, 5:150, 60:200])
+    assert np.array_equal(got.cell(0, 11, 140, 190), data[:, 140, 190])
+    _check_superchunk(ctx, fx.array(64, 5), [1, 2, 3])
+    # a clipped corner region small enough to be demoted to a plain Chunk (superchunk.rs:153-163)
+    d2 = synth.raster_slice(0, 5, 130, 130).numpy()
+    got = _check_superchunk(ctx, d2, [1, 1, 6])
+    assert np.array_equal(got.window(0, 5, 0, 130, 0, 130), d2)
+    # regions elided at the upper level: values must come from the upper node's table
+    d3 = np.full((6, 200, 200), 7.5, np.float32)
+    d3[:, :100, :100] = synth.raster_slice(0, 6, 100, 100).numpy()
+    got = _check_superchunk(ctx, d3, [1, 1, 6])
+    assert np.array_equal(got.window(0, 6, 0, 200, 0, 200), d3)
+    assert got.get(3, 199, 199) == 7.5
+
+
+def test_nested_bad_levels_inside_recursion(ctx):
+    from dcdf_b200 import DcdfError, Superchunk
+    data = fx.array(84, 4)       # region (1,1) is 20x20: needs 5 levels, neither <= 2 (demotion) nor == 2 + 4
+    with pytest.raises(orc.OracleError) as eo:
+        orc.superchunk_build(data, [1, 2, 4])
+    with pytest.raises(DcdfError) as eg:
+        Superchunk.build(ctx, data, [1, 2, 4])
+    assert eg.value.code == eo.value.code == 4
 
 
 def test_superchunk_bad_levels(ctx):
@@ -381,3 +423,30 @@ def test_c2_shaped_slice_round_trip(ctx):
         kind, bits = orc.suggest_fraction(tile)
         ref = orc.chunk_build(tile, fractional_bits=bits)
         _diff(chunks[r * 32 + c], ref.serialize(), f"subchunk ({r},{c})")
+
+
+def test_c5_shaped_nested_round_trip(ctx):
+    """0.1-degree global grid (1801 x 3600), k2_levels [2,4,6] as in examples/example.py:201: 16 nested
+    superchunks over 29 x 57 leaf subchunks.  Encode -> decode == input; three subchunks vs the oracle."""
+    import torch
+    from dcdf_b200 import Superchunk, synth
+    dev = synth.raster_slice(0, 8, 1801, 3600, device="cuda")
+    sc = Superchunk.build(ctx, dev, [2, 4, 6])
+    assert sc.node_count() == 1 + 8                      # 2 x 4 in-bounds 1024-side regions of the 4 x 4 root grid
+    info = sc.info(0)
+    assert (info.sidelen, info.chunks_sidelen, info.subsidelen) == (4096, 1024, 4)
+    out = torch.empty_like(dev)
+    sc.window(0, 8, 0, 1801, 0, 3600, out=out)
+    assert torch.equal(out, dev)
+    host = dev.cpu().numpy()
+    kinds, off, size, bits, child = sc.refs(0, 0, with_children=True)
+    assert kinds.tolist()[:4] == [2, 2, 2, 2] and kinds.tolist()[8:] == [0] * 8
+    blob = sc.bytes(0, 0)
+    node = int(child[5])                                 # region row 1, col 1: rows 1024..1801, cols 1024..2048
+    ninfo = sc.info(0, node)
+    assert tuple(ninfo.shape) == (8, 777, 1024) and ninfo.subsidelen == 16
+    chunks = sc.chunk_bytes(0, node, blob)
+    for (r, c) in ((0, 0), (12, 15), (7, 3)):
+        tile = np.ascontiguousarray(host[:, 1024 + r * 64:1024 + (r + 1) * 64, 1024 + c * 64:1024 + (c + 1) * 64])
+        kind, b = orc.suggest_fraction(tile)
+        _diff(chunks[r * 16 + c], orc.chunk_build(tile, fractional_bits=b).serialize(), f"nested subchunk ({r},{c})")
