@@ -508,8 +508,8 @@ int32_t dcdf_chunk_open(dcdf_ctx* ctx, const uint8_t* bytes, uint64_t len, int32
     dcdf_chunk* c = new dcdf_chunk();
     c->device = ctx->device;
     try {
-      c->bytes = static_cast<uint8_t*>(pool_alloc(len + 16, ctx->stream));
-      CK(cudaMemsetAsync(c->bytes + len, 0, 16, ctx->stream));
+      c->bytes = static_cast<uint8_t*>(pool_alloc(len + 64, ctx->stream));
+      CK(cudaMemsetAsync(c->bytes + len, 0, 64, ctx->stream));
       CK(cudaMemcpyAsync(c->bytes, bytes, len, mem == DCDF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
       c->size = len;
       c->owner = true;

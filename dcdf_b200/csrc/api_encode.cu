@@ -543,8 +543,8 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   tr.mark("tables readback");
   // ---- final blobs
   out.blob_size = out.chunk_off[n_units];
-  out.blob = static_cast<uint8_t*>(pool_alloc(out.blob_size + 16, st));  // +16: decoders read aligned words past the last byte
-  CK(cudaMemsetAsync(out.blob + out.blob_size, 0, 16, st));
+  out.blob = static_cast<uint8_t*>(pool_alloc(out.blob_size + 64, st));  // padding: decoders read aligned 16-byte blocks past the last byte
+  CK(cudaMemsetAsync(out.blob + out.blob_size, 0, 64, st));
   GatherParams GP;
   GP.units = ctx->units.as<EncUnit>();
   GP.results = ctx->results.as<UnitResult>();
@@ -791,8 +791,8 @@ void big_chunk_encode(dcdf_ctx* ctx, const void* dev_data, const int64_t* stride
   CK(cudaMemcpyAsync(ctx->stored.p, &one, 1, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->chunk_off.p, &zero, 8, cudaMemcpyHostToDevice, st));
   R.size = total_bytes;
-  R.blob = static_cast<uint8_t*>(pool_alloc(total_bytes + 16, st));
-  CK(cudaMemsetAsync(R.blob + total_bytes, 0, 16, st));
+  R.blob = static_cast<uint8_t*>(pool_alloc(total_bytes + 64, st));
+  CK(cudaMemsetAsync(R.blob + total_bytes, 0, 64, st));
   GatherParams GP;
   GP.units = ctx->units.as<EncUnit>();
   GP.results = ctx->results.as<UnitResult>();

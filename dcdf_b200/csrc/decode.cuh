@@ -21,6 +21,7 @@ struct DacDir {
 };
 struct InstDir {
   u32 off;      // structure start (from chunk start)
+  u32 size;     // serialized bytes of the structure
   u32 snap;     // directory index (within the chunk) of the block's Snapshot; == own index for snapshots
   u32 nm_len, nm_base;
   u32 eq_len, eq_base;  // logs only (eq_base == 0 for snapshots)
@@ -72,8 +73,8 @@ DCDF_DEVINL u32 be32_at(const u8* base, u32 off) {
   const uintptr_t a = (uintptr_t)(base + off);
   const u32* w = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
   const u32 sh = (u32)(a & 3) * 8u;
-  const u32 lo = __ldg(w);
-  const u32 le = sh ? __funnelshift_r(lo, __ldg(w + 1), sh) : lo;
+  const u32 lo = w[0];  // plain loads: `base` may point to a shared-memory copy of the structure
+  const u32 le = sh ? __funnelshift_r(lo, w[1], sh) : lo;
   return __byte_perm(le, 0, 0x0123);
 }
 
@@ -109,7 +110,7 @@ struct DacRef {
       if (index >= len) break;  // malformed input guard
       const u32 words = base + 8u + 4u * (len / 128u);
       const u32 bytes = words + 4u * ((len + 31u) / 32u);
-      n |= (u64)__ldg(chunk + bytes + index) << (8u * j);
+      n |= (u64)chunk[bytes + index] << (8u * j);
       BitMapRef bm{chunk, len, base};
       if (bm.get(index)) index = bm.rank(index);
       else break;
@@ -117,6 +118,29 @@ struct DacRef {
     return unzigzag64(n);
   }
 };
+
+// Fast accessors for dense expansion: the MSB-first word stream of a BitMap is a plain MSB-first byte stream,
+// so a bit test is one byte load; most DAC entries are one byte long (no continuation bit).
+struct BitsFast {
+  const u8* bits;  // first byte of the bitmap words
+  DCDF_DEVINL bool get(u32 i) const { return (bits[i >> 3] >> (7u - (i & 7u))) & 1u; }
+};
+DCDF_DEVINL BitsFast bits_fast(const u8* chunk, u32 len, u32 base) { return BitsFast{chunk + base + 8u + 4u * (len / 128u)}; }
+struct DacFast {
+  const u8* bytes0;
+  BitsFast more0;
+  DacRef slow;
+  DCDF_DEVINL i64 get(u32 index) const {
+    if (slow.d->n_levels == 0) return 0;
+    if (!more0.get(index)) return unzigzag64((u64)bytes0[index]);
+    return slow.get(index);
+  }
+};
+DCDF_DEVINL DacFast dac_fast(const u8* chunk, const DacDir* d) {
+  const u32 len = d->len[0], base = d->base[0];
+  const u32 words = base + 8u + 4u * (len / 128u);
+  return DacFast{chunk + words + 4u * ((len + 31u) / 32u), BitsFast{chunk + words}, DacRef{chunk, d}};
+}
 
 // ------------------------------------------------------------------ directory builder (Chunk::read_from)
 struct DirParams {
@@ -196,6 +220,7 @@ __global__ void k_build_dir(const DirParams P) {
       if (i > 0) parse_bitmap(c, d.eq_len, d.eq_base);
       parse_dac(c, d.max);
       parse_dac(c, d.min);
+      d.size = (u32)c.pos - d.off;
       if (c.ok && d.nm_len == 0) c.ok = false;
       if (c.ok && !P.count_only) {
         if (inst >= (u32)m.instants) c.ok = false;

@@ -19,49 +19,81 @@ constexpr int DT_THREADS = 256;
 constexpr int DT_WARPS = DT_THREADS / 32;
 constexpr int DT_NODES = 5461;
 constexpr int DT_UPPER = 1365;
+constexpr int DT_STAGE_S = 12 * 1024;   // shared-memory copy of the block's Snapshot bytes (when it fits)
+constexpr int DT_STAGE_L = 8 * 1024;   // ... and of the current Log
 
 struct TileSmem {
   i64 sval[DT_NODES];   // snapshot max pyramid: level k at offset (4^k - 1) / 3, Morton order inside a level
-  i64 lpay[DT_NODES];   // log expansion payload
+  i64 lpay[DT_UPPER + 3];   // log expansion payload (levels above the cells)
   unsigned short scb[DT_UPPER + 3];  // snapshot: BFS index of the first child (0xffff: not an internal node)
   unsigned short lcb[DT_UPPER + 3];  // log: same
-  u8 lmode[DT_NODES + 3];            // 0 internal, 1 uniform (value = payload), 2 equal (value = payload + snapshot cell)
+  u8 lmode[DT_UPPER + 3];            // 0 internal, 1 uniform (value = payload), 2 equal (value = payload + snapshot cell)
   u32 wtot[DT_WARPS];
   u32 run;
+  InstDir dir_s, dir_l;              // directory entries of the structures being expanded
+  __align__(16) u8 stage_s[DT_STAGE_S + 32];
+  __align__(16) u8 stage_l[DT_STAGE_L + 32];
 };
 
-DCDF_DEVINL u32 lvl_off(int k) { return ((1u << (2 * k)) - 1u) / 3u; }
+DCDF_DEVINL u32 lvl_off(int k) { return (0x55555555u >> (32 - 2 * k)) & (k ? 0xffffffffu : 0u); }  // (4^k - 1) / 3
 
-// Block-wide: turn the "internal" markers of level k into child BFS bases; returns the number of internal nodes.
+// Copy `size` bytes starting at global address `src` into `stage` keeping the address modulo 16, and return
+// the pointer that corresponds to `src`.  Falls back to `src` itself when the structure does not fit.
+DCDF_DEVINL const u8* stage_bytes(const u8* src, u32 size, u8* stage, u32 cap) {
+  const u32 mis = (u32)((uintptr_t)src & 15u);
+  if (size + mis + 4u > cap) return src;
+  const uint4* g = reinterpret_cast<const uint4*>(src - mis);
+  uint4* d = reinterpret_cast<uint4*>(stage);
+  const u32 n16 = (size + mis + 4u + 15u) / 16u;  // +4: be32_at reads one aligned word past the last byte
+  for (u32 i = threadIdx.x; i < n16; i += DT_THREADS) d[i] = g[i];
+  return stage + mis;
+}
+
+// Block-wide: turn the "internal" markers of level k (k <= 5, at most 1024 positions) into child BFS bases;
+// returns the number of internal nodes.  Each warp owns a contiguous run of positions (ballots stay in
+// registers), one barrier turns the per-warp counts into offsets.
 DCDF_DEVINL u32 assign_child_bases(unsigned short* cb, int k, u32 p_next, TileSmem& S) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 n = 1u << (2 * k), off = lvl_off(k);
-  u32 running = 0;
-  for (u32 base = 0; base < n; base += DT_THREADS) {
-    const u32 p = base + tid;
-    const bool f = p < n && cb[off + p] != 0xffffu;
-    const u32 b = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) S.wtot[warp] = __popc(b);
-    __syncthreads();
-    u32 before = running, total = 0;
+  const u32 seg = n > 32u * DT_WARPS ? n / DT_WARPS : 32u;  // 32 or 128
+  u32 bal[4], cnt = 0;
 #pragma unroll
-    for (int w = 0; w < DT_WARPS; w++) {
-      const u32 x = S.wtot[w];
-      if (w < warp) before += x;
-      total += x;
-    }
-    if (f) cb[off + p] = (unsigned short)(p_next + 4u * (before + __popc(b & lanemask_lt())));
-    running += total;
-    __syncthreads();
+  for (int s = 0; s < 4; s++) {
+    const u32 p = warp * seg + s * 32u + lane;
+    const bool f = s * 32u < seg && p < n && cb[off + p] != 0xffffu;
+    bal[s] = __ballot_sync(0xffffffffu, f);
+    cnt += __popc(bal[s]);
   }
-  return running;
+  if (lane == 0) S.wtot[warp] = cnt;
+  __syncthreads();
+  u32 before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < DT_WARPS; w++) {
+    const u32 x = S.wtot[w];
+    if (w < warp) before += x;
+    total += x;
+  }
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const u32 p = warp * seg + s * 32u + lane;
+    if ((bal[s] >> lane) & 1u) cb[off + p] = (unsigned short)(p_next + 4u * (before + __popc(bal[s] & lanemask_lt())));
+    before += __popc(bal[s]);
+  }
+  __syncthreads();
+  return total;
+}
+
+// Level L (the cells) is stored row-major with pitch 2^L so that the output loop reads consecutive addresses;
+// the levels above stay in Morton order.
+DCDF_DEVINL u32 cell_index(u32 p1, int L, bool last) {
+  return last ? (morton_row(p1) << L) + morton_col(p1) : p1;
 }
 
 // Expand a Snapshot into S.sval / S.scb (L = tree levels, 1..6).
 DCDF_DEVINL void expand_snapshot(const ChunkView& cv, const InstDir& s, int L, TileSmem& S) {
   const int tid = threadIdx.x;
-  BitMapRef nm{cv.chunk, s.nm_len, s.nm_base};
-  DacRef mx{cv.chunk, &s.max};
+  const BitsFast nm = bits_fast(cv.chunk, s.nm_len, s.nm_base);
+  const DacFast mx = dac_fast(cv.chunk, &s.max);
   if (tid == 0) {
     S.sval[0] = mx.get(0);
     S.scb[0] = nm.get(0) ? 1 : 0xffff;
@@ -82,7 +114,7 @@ DCDF_DEVINL void expand_snapshot(const ChunkView& cv, const InstDir& s, int L, T
         v -= mx.get(idx);
         in = has_bits && idx < s.nm_len && nm.get(idx);
       }
-      S.sval[o1 + p1] = v;
+      S.sval[o1 + cell_index(p1, L, !has_bits)] = v;
       if (has_bits) S.scb[o1 + p1] = in ? 1 : 0xffff;
     }
     p_next += 4u * internal;
@@ -90,11 +122,13 @@ DCDF_DEVINL void expand_snapshot(const ChunkView& cv, const InstDir& s, int L, T
   }
 }
 
-// Expand a Log against the snapshot pyramid already in S.sval; cell values end up as (lmode, lpay) of level L.
-DCDF_DEVINL void expand_log(const ChunkView& cv, const InstDir& l, const InstDir& s, int L, TileSmem& S) {
+// Expand a Log against the snapshot pyramid already in S.sval down to level L - 1 (the 2x2 quads); the cells are
+// produced by the caller's fused output pass.
+DCDF_DEVINL void expand_log(const ChunkView& cv, const ChunkView& cv_snap, const InstDir& l, const InstDir& s, int L, TileSmem& S) {
   const int tid = threadIdx.x;
-  BitMapRef nm{cv.chunk, l.nm_len, l.nm_base}, eq{cv.chunk, l.eq_len, l.eq_base};
-  DacRef mx{cv.chunk, &l.max};
+  const BitsFast nm = bits_fast(cv.chunk, l.nm_len, l.nm_base);
+  const BitMapRef nm_rank{cv.chunk, l.nm_len, l.nm_base}, eq{cv.chunk, l.eq_len, l.eq_base};
+  const DacFast mx = dac_fast(cv.chunk, &l.max);
   if (tid == 0) {
     const i64 d0 = mx.get(0);
     const bool single_t = !nm.get(0);
@@ -102,7 +136,7 @@ DCDF_DEVINL void expand_log(const ChunkView& cv, const InstDir& l, const InstDir
       S.lmode[0] = 0; S.lpay[0] = d0; S.lcb[0] = 1;
     } else {
       // log.rs:180-186: a single-node log is uniform unless its equal bit says "snapshot + constant"
-      BitMapRef nm_s{cv.chunk, s.nm_len, s.nm_base};
+      BitMapRef nm_s{cv_snap.chunk, s.nm_len, s.nm_base};
       const bool snap_single = !nm_s.get(0);
       const bool uniform = snap_single || !eq.get(0);
       S.lmode[0] = uniform ? 1 : 2;
@@ -114,8 +148,9 @@ DCDF_DEVINL void expand_log(const ChunkView& cv, const InstDir& l, const InstDir
   u32 p_next = 1;
   for (int k = 0; k < L; k++) {
     const u32 internal = assign_child_bases(S.lcb, k, p_next, S);
+    if (k == L - 1) break;  // child bases of the quads are all the fused cell pass needs
     const u32 n1 = 1u << (2 * (k + 1)), o0 = lvl_off(k), o1 = lvl_off(k + 1);
-    const bool has_bits = k + 1 < L;
+    const bool has_bits = true;
     for (u32 p1 = tid; p1 < n1; p1 += DT_THREADS) {
       const u32 p = p1 >> 2;
       u8 mode = S.lmode[o0 + p];
@@ -130,14 +165,14 @@ DCDF_DEVINL void expand_log(const ChunkView& cv, const InstDir& l, const InstDir
         } else if (!has_bits) {
           mode = 2; pay = d;  // bottom level: value = max_t + snapshot cell
         } else {
-          const bool e = eq.get(idx - nm.rank(idx));  // rank0(idx + 1) - 1 (log.rs:265)
+          const bool e = eq.get(idx - nm_rank.rank(idx));  // rank0(idx + 1) - 1 (log.rs:265)
           mode = e ? 2 : 1;
           pay = e ? d : d + S.sval[o1 + p1];  // uniform: max_t + max_s of this node (log.rs:266-268)
         }
       }
       S.lmode[o1 + p1] = mode;
       S.lpay[o1 + p1] = pay;
-      if (has_bits) S.lcb[o1 + p1] = in ? 1 : 0xffff;
+      S.lcb[o1 + p1] = in ? 1 : 0xffff;
     }
     p_next += 4u * internal;
     __syncthreads();
@@ -199,29 +234,69 @@ __global__ void __launch_bounds__(DT_THREADS) k_window_tiles(const TileWindowPar
       }
       continue;
     }
-    ChunkView cv{Q.blob + m.blob_off, Q.dir + m.dir_base, m.sidelen};
+    const u8* chunk = Q.blob + m.blob_off;
+    const InstDir* dir = Q.dir + m.dir_base;
     const int L = 31 - __clz(m.sidelen);
     const u32 oL = lvl_off(L);
     u32 cur_snap = 0xffffffffu;
+    ChunkView cv_s{chunk, dir, m.sidelen};
+    const u8* cv_l_chunk = chunk;
     for (i64 t = t_lo; t < t_hi; t++) {
       const u32 ti = (u32)(t - sm.t0);
-      const InstDir& d = cv.dir[ti];
-      if (d.snap != cur_snap) {
-        __syncthreads();
-        expand_snapshot(cv, cv.dir[d.snap], L, S);
-        cur_snap = d.snap;
-      }
-      const bool is_log = d.snap != ti;
-      if (is_log) expand_log(cv, d, cv.dir[d.snap], L, S);
-      for (int i = tid; i < wr * wc; i += DT_THREADS) {
-        const int r = top + i / wc, col = left + i % wc;
-        const u32 mo = oL + morton_encode((u32)r, (u32)col);
-        i64 v = S.sval[mo];
-        if (is_log) v = S.lmode[mo] == 1 ? S.lpay[mo] : S.lpay[mo] + v;
-        emit(Q, P.out, out_index(t, r, col), v, m.bits, P.raw);
-      }
+      const u32 snap = dir[ti].snap;
       __syncthreads();
+      if (snap != cur_snap) {
+        if (tid == 0) S.dir_s = dir[snap];
+        const u32 off = dir[snap].off;
+        cv_s.chunk = stage_bytes(chunk + off, dir[snap].size, S.stage_s, DT_STAGE_S + 32) - off;
+        __syncthreads();
+        expand_snapshot(cv_s, S.dir_s, L, S);
+        cur_snap = snap;
+      }
+      const bool is_log = snap != ti;
+      if (is_log) {
+        if (tid == 0) S.dir_l = dir[ti];
+        const u32 off = dir[ti].off;
+        cv_l_chunk = stage_bytes(chunk + off, dir[ti].size, S.stage_l, DT_STAGE_L + 32) - off;
+        ChunkView cv_l{cv_l_chunk, dir, m.sidelen};
+        __syncthreads();
+        expand_log(cv_l, cv_s, S.dir_l, S.dir_s, L, S);
+      }
+      if (!is_log) {
+        // rows of the window inside this tile; consecutive threads write consecutive columns
+        for (int r = top + (tid / 64); r < bottom; r += DT_THREADS / 64) {
+          const int col = left + (tid & 63);
+          if (col < right) emit(Q, P.out, out_index(t, r, col), S.sval[oL + ((u32)r << L) + (u32)col], m.bits, P.raw);
+        }
+      } else {
+        // fused cell pass: one thread per 2x2 quad (row-major over quads so that a warp writes whole row segments);
+        // value = payload (uniform), payload + snapshot cell (equal), or the cell's own log entry + snapshot cell
+        const DacFast mxl = dac_fast(cv_l_chunk, &S.dir_l.max);
+        const int half = 1 << (L - 1);
+        const u32 oQ = lvl_off(L - 1);
+        for (int qi = tid; qi < half * half; qi += DT_THREADS) {
+          const int qr = qi >> (L - 1), qc = qi & (half - 1);
+          const int r0q = 2 * qr, c0q = 2 * qc;
+          if (r0q + 1 < top || r0q >= bottom || c0q + 1 < left || c0q >= right) continue;
+          const u32 q = L > 1 ? morton_encode((u32)qr, (u32)qc) : 0u;
+          const u8 mode = S.lmode[oQ + q];
+          const i64 pay = S.lpay[oQ + q];
+          const u32 cb = S.lcb[oQ + q];
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const int r = r0q + (c >> 1), col = c0q + (c & 1);
+            if (r < top || r >= bottom || col < left || col >= right) continue;
+            const i64 sc = S.sval[oL + ((u32)r << L) + (u32)col];
+            i64 v;
+            if (mode == 1) v = pay;
+            else if (mode == 2) v = pay + sc;
+            else v = mxl.get(cb + (u32)c) + sc;
+            emit(Q, P.out, out_index(t, r, col), v, m.bits, P.raw);
+          }
+        }
+      }
     }
+    __syncthreads();
   }
 }
 
