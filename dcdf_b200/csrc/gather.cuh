@@ -137,6 +137,24 @@ struct GatherParams {
 
 constexpr int GATHER_MAX_T = 1024;
 
+// Warp-cooperative copy of n bytes from a 4-byte aligned source to an arbitrarily aligned destination:
+// destination-aligned 32-bit stores, each built from two aligned source words with a funnel shift.
+DCDF_DEVINL void warp_copy_bytes(u8* dst, const u8* src, u32 n, int lane) {
+  const u32 head = min(n, (u32)((4u - ((uintptr_t)dst & 3u)) & 3u));
+  if ((u32)lane < head) dst[lane] = src[lane];
+  const u32 body = (n - head) >> 2;
+  u32* d4 = reinterpret_cast<u32*>(dst + head);
+  const u8* s0 = src + head;
+  const u32 sh = (u32)((uintptr_t)s0 & 3u) * 8u;
+  const u32* s4 = reinterpret_cast<const u32*>((uintptr_t)s0 & ~(uintptr_t)3);
+  for (u32 w = lane; w < body; w += 32) {
+    const u32 lo = s4[w];
+    d4[w] = sh ? __funnelshift_r(lo, s4[w + 1], sh) : lo;
+  }
+  const u32 done = head + 4u * body;
+  if (done + (u32)lane < n) dst[done + lane] = src[done + lane];
+}
+
 __global__ void __launch_bounds__(256) k_gather_chunks(const GatherParams P) {
   const u32 u = blockIdx.x;
   if (u >= P.n_units || !P.stored[u]) return;
@@ -184,7 +202,7 @@ __global__ void __launch_bounds__(256) k_gather_chunks(const GatherParams P) {
       const Piece pc = pieces[t0 + i];
       const u8* src = P.arena + pc.off;
       u8* dst = out + dst_off[i];
-      for (u32 b = lane; b < pc.size; b += 32) dst[b] = src[b];
+      warp_copy_bytes(dst, src, pc.size, lane);
     }
     __syncthreads();
   }

@@ -191,6 +191,8 @@ __global__ void __launch_bounds__(STAT_THREADS) k_unit_stats(const StatParams P)
   const int step_r = STAT_THREADS / cols, step_c = STAT_THREADS - step_r * cols;
   const i64 q_step = (i64)step_r * P.stride_r + (i64)step_c * P.stride_c;  // pointer step for 256 cells ahead
   const i64 q_wrap = P.stride_r - (i64)cols * P.stride_c;                  // extra step when the column wraps
+  const bool vec4 = sizeof(InT) == 4 && cols == 64 && P.stride_c == 1 && ((P.stride_r * 4) & 15) == 0 && ((P.stride_t * 4) & 15) == 0 &&
+                    (((uintptr_t)base) & 15) == 0;
 
   InT umax = Lim<InT>::lo(), umin = Lim<InT>::hi();  // unit extrema over non-NaN values
   InT uneg = (InT)0;                                 // most negative value
@@ -202,39 +204,75 @@ __global__ void __launch_bounds__(STAT_THREADS) k_unit_stats(const StatParams P)
       const InT* p = base + (i64)(i0 + bi) * P.stride_t;
       InT mn = Lim<InT>::hi(), mx = Lim<InT>::lo();
       u32 first = 0xffffffffu, last = 0;  // row-major position (+1 for last) of first non-NaN / last NaN
-      // all loads of the instant are issued before any value is consumed (16 per thread for a full tile);
-      // the pointer walks the tile row-major without divisions
-      const InT* q = p + (i64)r_init * P.stride_r + (i64)c_init * P.stride_c;
-      int c = c_init;
-      for (int idx0 = tid; idx0 < cells; idx0 += 16 * STAT_THREADS) {
-        InT vals[16];
+      if (vec4) {
+        // full 64-column tile with 16-byte aligned rows: four 128-bit loads per thread and instant
+        uint4 qv[4];
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          const int idx = idx0 + j * STAT_THREADS;
-          vals[j] = idx < cells ? __ldg(q) : (InT)0;
-          c += step_c;
-          q += q_step;
-          if (c >= cols) { c -= cols; q += q_wrap; }
+        for (int j = 0; j < 4; j++) {
+          const int row = (tid >> 4) + 16 * j;
+          qv[j] = row < unit.rows ? __ldg(reinterpret_cast<const uint4*>(p + (i64)row * P.stride_r + 4 * (tid & 15))) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          const int idx = idx0 + j * STAT_THREADS;
-          if (idx >= cells) break;
-          const InT v = vals[j];
-          if (IS_FLOAT) {
-            const bool isn = v != v;
-            last = isn ? (u32)idx + 1u : last;           // idx ascends within a thread
-            first = min(first, isn ? 0xffffffffu : (u32)idx);
-            mn = (isn || v > mn) ? mn : v;
-            mx = (isn || v < mx) ? mx : v;
-            uneg = (isn || v > uneg) ? uneg : v;
-            const int fb = FloatBits<InT>::fast(v);
-            const bool neg = v < (InT)0;
-            fng = max(fng, neg ? fb : 0);
-            fnn = max(fnn, neg ? 0 : fb);
-          } else {
-            mn = v < mn ? v : mn;
-            mx = v > mx ? v : mx;
+        for (int j = 0; j < 4; j++) {
+          const int row = (tid >> 4) + 16 * j;
+          if (row >= unit.rows) break;
+          const u32 wv[4] = {qv[j].x, qv[j].y, qv[j].z, qv[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int idx = row * 64 + 4 * (tid & 15) + e;
+            const InT v = *reinterpret_cast<const InT*>(&wv[e]);
+            if (IS_FLOAT) {
+              const bool isn = v != v;
+              last = isn ? (u32)idx + 1u : last;
+              first = min(first, isn ? 0xffffffffu : (u32)idx);
+              mn = (isn || v > mn) ? mn : v;
+              mx = (isn || v < mx) ? mx : v;
+              uneg = (isn || v > uneg) ? uneg : v;
+              const int fb = FloatBits<InT>::fast(v);
+              const bool neg = v < (InT)0;
+              fng = max(fng, neg ? fb : 0);
+              fnn = max(fnn, neg ? 0 : fb);
+            } else {
+              mn = v < mn ? v : mn;
+              mx = v > mx ? v : mx;
+            }
+          }
+        }
+      } else {
+      // all loads of the instant are issued before any value is consumed (16 per thread for a full tile);
+        // the pointer walks the tile row-major without divisions
+        const InT* q = p + (i64)r_init * P.stride_r + (i64)c_init * P.stride_c;
+        int c = c_init;
+        for (int idx0 = tid; idx0 < cells; idx0 += 16 * STAT_THREADS) {
+          InT vals[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const int idx = idx0 + j * STAT_THREADS;
+            vals[j] = idx < cells ? __ldg(q) : (InT)0;
+            c += step_c;
+            q += q_step;
+            if (c >= cols) { c -= cols; q += q_wrap; }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const int idx = idx0 + j * STAT_THREADS;
+            if (idx >= cells) break;
+            const InT v = vals[j];
+            if (IS_FLOAT) {
+              const bool isn = v != v;
+              last = isn ? (u32)idx + 1u : last;           // idx ascends within a thread
+              first = min(first, isn ? 0xffffffffu : (u32)idx);
+              mn = (isn || v > mn) ? mn : v;
+              mx = (isn || v < mx) ? mx : v;
+              uneg = (isn || v > uneg) ? uneg : v;
+              const int fb = FloatBits<InT>::fast(v);
+              const bool neg = v < (InT)0;
+              fng = max(fng, neg ? fb : 0);
+              fnn = max(fnn, neg ? 0 : fb);
+            } else {
+              mn = v < mn ? v : mn;
+              mx = v > mx ? v : mx;
+            }
           }
         }
       }
