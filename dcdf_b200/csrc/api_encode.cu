@@ -7,6 +7,7 @@
 #include <cstdlib>
 
 #include "encode_big.cuh"
+#include "encode_v4.cuh"
 #include "gather.cuh"
 #include "host.hpp"
 #include "stats.cuh"
@@ -203,10 +204,29 @@ void launch_encode_one(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   CK(cudaGetLastError());
   ctx->launches++;
 }
+// Full 64x64 tiles with 31-bit values: 64-thread CTAs, 64 cells per thread (encode_v4.cuh).
+// Enabled with DCDF_ENCODE_V4=1 while it is being tuned; DCDF_STAGE_LIMIT=<bytes> lowers the size above
+// which a structure is emitted straight into the arena (tests use it to cover that path).
+template <typename InT>
+void launch_encode_v4(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
+  constexpr int MINB = 5;
+  static const u32 stage_limit = [] {
+    const char* e = getenv("DCDF_STAGE_LIMIT");
+    const long v = e ? atol(e) : (long)E4_POOL;
+    return (u32)std::min<long>(std::max<long>(v, 0), (long)E4_POOL);
+  }();
+  const size_t smem = sizeof(E4Smem);
+  CK(cudaFuncSetAttribute(k_encode_v4<InT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_encode_v4<InT, MINB><<<grid, E4_THREADS, smem, ctx->stream>>>(P, stage_limit);
+  CK(cudaGetLastError());
+  ctx->launches++;
+}
 // list = wide * 2 + clipped  (narrow kernels are compiled for two resident CTAs per SM)
 template <typename InT>
 void launch_encode(dcdf_ctx* ctx, const EncParams& P, u32 grid, int list) {
   if (grid == 0) return;
+  static const bool use_v4 = getenv("DCDF_ENCODE_V4") != nullptr;  // TODO flip once it beats k_encode_tiles
+  if (list == 0 && use_v4) { launch_encode_v4<InT>(ctx, P, grid); return; }
   switch (list) {
     case 0: launch_encode_one<InT, int32_t, true, 2>(ctx, P, grid); break;
     case 1: launch_encode_one<InT, int32_t, false, 2>(ctx, P, grid); break;
