@@ -205,7 +205,7 @@ void launch_encode_one(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   ctx->launches++;
 }
 // Full 64x64 tiles with 31-bit values: 64-thread CTAs, 64 cells per thread (encode_v4.cuh).
-// Enabled with DCDF_ENCODE_V4=1 while it is being tuned; DCDF_STAGE_LIMIT=<bytes> lowers the size above
+// DCDF_ENCODE_V2=1 routes them through k_encode_tiles instead; DCDF_STAGE_LIMIT=<bytes> lowers the size above
 // which a structure is emitted straight into the arena (tests use it to cover that path).
 template <typename InT>
 void launch_encode_v4(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
@@ -225,8 +225,8 @@ void launch_encode_v4(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
 template <typename InT>
 void launch_encode(dcdf_ctx* ctx, const EncParams& P, u32 grid, int list) {
   if (grid == 0) return;
-  static const bool use_v4 = getenv("DCDF_ENCODE_V4") != nullptr;  // TODO flip once it beats k_encode_tiles
-  if (list == 0 && use_v4) { launch_encode_v4<InT>(ctx, P, grid); return; }
+  static const bool force_v2 = getenv("DCDF_ENCODE_V2") != nullptr;
+  if (list == 0 && !force_v2) { launch_encode_v4<InT>(ctx, P, grid); return; }
   switch (list) {
     case 0: launch_encode_one<InT, int32_t, true, 2>(ctx, P, grid); break;
     case 1: launch_encode_one<InT, int32_t, false, 2>(ctx, P, grid); break;

@@ -3,9 +3,11 @@
 //
 // Same reference functions as encode_tile.cuh (chunk.rs:42-96, snapshot.rs:108-156 + 439-500, log.rs:112-165 +
 // 725-817, bitmap.rs:66-113, dac.rs:96-132 and the serializers), different mapping:
-//   * thread t owns the level-3 node with Morton index t: 8x8 cells in registers (Morton order), the snapshot
-//     they are compared with in 64 more registers.  Levels 6..3 of the min/max/equal pyramid never leave the
-//     thread, levels 2 and 1 take two shuffle rounds, the root one 4-record exchange through shared memory.
+//   * thread t owns the level-3 node with Morton index t: 8x8 cells, kept as fixed-point quads in shared memory
+//     (one image for the instant, one for the snapshot of the current block; a new snapshot just swaps the two)
+//     and walked by short rolled loops -- the fully unrolled register version ran out of instruction cache.
+//     Levels 6..3 of the min/max/equal pyramid never leave the thread, levels 2 and 1 take two shuffle rounds,
+//     the root one 4-record exchange through shared memory.
 //   * every DAC entry is classified by length ONCE into bit masks (entry longer than 1 / 2 / 3 bytes); the sizes
 //     of both candidate encodings, the BFS layout and every output position follow from popcounts of those
 //     masks, one packed warp scan and one cross-warp exchange.
@@ -34,7 +36,8 @@ DCDF_DEVINL u32 e4_fsum(u32 x) { return e4_f2(x) + e4_f3(x) + e4_f4(x) + e4_f5(x
 
 struct E4Smem {
   __align__(16) u8 pool[E4_POOL];
-  int4 svs[16][E4_THREADS];  // snapshot of the current block: quad q of thread t (four cells, Morton order)
+  int4 cell[2][16][E4_THREADS];  // fixed-point cells of the instant and of the block's snapshot: [image][quad q][thread t]
+  int2 l4[2][4][E4_THREADS];     // (max, min) of the four level-4 nodes of each image
   int4 rec1[4];       // level-1 nodes: tmax, tmin, first-cell diff, equal
   int2 ent1[4];       // level-1 log entries: tmax - smax, tmin - smin
   u32 wt[2][2][10];   // [warp][0 = snapshot, 1 = log][STRUCT, a1, b1, c1, a2, b2, c2, a3, b3, c3]
@@ -144,24 +147,29 @@ struct E4Cand {
 
 // Snapshot entry masks for length class J (snapshot.rs:122-147: parent_max - child_max, child_min - parent_min).
 template <int J>
-DCDF_DEVINL void e4_snap_masks(const int (&tv)[64], const int (&t4max)[4], const int (&t4min)[4], int t3max, int t3min, int t2max,
-                               int t2min, int t1max, int t1min, u64& ml, u32& mq, u32& mu) {
+DCDF_DEVINL void e4_snap_masks(const E4Smem& S, int cur, int tid, int t3max, int t3min, int t2max, int t2min, int t1max, int t1min,
+                               u64& ml, u32& mq, u32& mu) {
   ml = 0; mq = 0; mu = 0;
-#pragma unroll
+#pragma unroll 1
   for (int a = 0; a < 4; a++) {
+    const int2 n4 = S.l4[cur][a][tid];
+    u32 leaf16 = 0, qx = 0, qn = 0;
 #pragma unroll
     for (int b = 0; b < 4; b++) {
-      const int m0 = 16 * a + 4 * b, q = 4 * a + b;
-      const int qmax = max(max(tv[m0], tv[m0 + 1]), max(tv[m0 + 2], tv[m0 + 3]));
-      const int qmin = min(min(tv[m0], tv[m0 + 1]), min(tv[m0 + 2], tv[m0 + 3]));
-#pragma unroll
-      for (int c = 0; c < 4; c++)
-        if (e4_longer<J>(qmax - tv[m0 + c])) ml |= 1ull << (63 - (m0 + c));
-      if (e4_longer<J>(t4max[a] - qmax)) mq |= 1u << (15 - q);
-      if (e4_longer<J>(qmin - t4min[a])) mq |= 1u << (31 - q);
+      const int4 t = S.cell[cur][4 * a + b][tid];
+      const int qmax = max(max(t.x, t.y), max(t.z, t.w));
+      const int qmin = min(min(t.x, t.y), min(t.z, t.w));
+      if (e4_longer<J>(qmax - t.x)) leaf16 |= 1u << (15 - 4 * b);
+      if (e4_longer<J>(qmax - t.y)) leaf16 |= 1u << (14 - 4 * b);
+      if (e4_longer<J>(qmax - t.z)) leaf16 |= 1u << (13 - 4 * b);
+      if (e4_longer<J>(qmax - t.w)) leaf16 |= 1u << (12 - 4 * b);
+      if (e4_longer<J>(n4.x - qmax)) qx |= 1u << (3 - b);
+      if (e4_longer<J>(qmin - n4.y)) qn |= 1u << (3 - b);
     }
-    if (e4_longer<J>(t3max - t4max[a])) mu |= 1u << (3 - a);
-    if (e4_longer<J>(t4min[a] - t3min)) mu |= 1u << (7 - a);
+    ml |= (u64)leaf16 << (48 - 16 * a);
+    mq |= (qx << (12 - 4 * a)) | (qn << (28 - 4 * a));
+    if (e4_longer<J>(t3max - n4.x)) mu |= 1u << (3 - a);
+    if (e4_longer<J>(n4.y - t3min)) mu |= 1u << (7 - a);
   }
   if (e4_longer<J>(t2max - t3max)) mu |= 1u << 8;
   if (e4_longer<J>(t3min - t2min)) mu |= 1u << 9;
@@ -171,31 +179,29 @@ DCDF_DEVINL void e4_snap_masks(const int (&tv)[64], const int (&t4max)[4], const
 
 // Log entry masks for length class J (log.rs:128-158: max_t - max_s, min_t - min_s per node, t - s per leaf).
 template <int J>
-DCDF_DEVINL void e4_log_masks(const int (&tv)[64], const int4 (*svs)[E4_THREADS], const int (&t4max)[4], const int (&t4min)[4], int t3max,
-                              int t3min, int t2max, int t2min, int s3max, int s3min, int s2max, int s2min, u64& ml, u32& mq,
-                              u32& mu) {
+DCDF_DEVINL void e4_log_masks(const E4Smem& S, int cur, int ref, int tid, int t3max, int t3min, int t2max, int t2min, int s3max,
+                              int s3min, int s2max, int s2min, u64& ml, u32& mq, u32& mu) {
   ml = 0; mq = 0; mu = 0;
-#pragma unroll
+#pragma unroll 1
   for (int a = 0; a < 4; a++) {
-    int s4max = INT32_MIN, s4min = INT32_MAX;
+    const int2 n4 = S.l4[cur][a][tid], s4 = S.l4[ref][a][tid];
+    u32 leaf16 = 0, qx = 0, qn = 0;
 #pragma unroll
     for (int b = 0; b < 4; b++) {
-      const int m0 = 16 * a + 4 * b, q = 4 * a + b;
-      const int4 sq = svs[q][threadIdx.x];
-      const int sv[4] = {sq.x, sq.y, sq.z, sq.w};
-      const int qmax = max(max(tv[m0], tv[m0 + 1]), max(tv[m0 + 2], tv[m0 + 3]));
-      const int qmin = min(min(tv[m0], tv[m0 + 1]), min(tv[m0 + 2], tv[m0 + 3]));
-      const int sqmax = max(max(sv[0], sv[1]), max(sv[2], sv[3]));
-      const int sqmin = min(min(sv[0], sv[1]), min(sv[2], sv[3]));
-      s4max = max(s4max, sqmax); s4min = min(s4min, sqmin);
-#pragma unroll
-      for (int c = 0; c < 4; c++)
-        if (e4_longer<J>(tv[m0 + c] - sv[c])) ml |= 1ull << (63 - (m0 + c));
-      if (e4_longer<J>(qmax - sqmax)) mq |= 1u << (15 - q);
-      if (e4_longer<J>(qmin - sqmin)) mq |= 1u << (31 - q);
+      const int4 t = S.cell[cur][4 * a + b][tid], s = S.cell[ref][4 * a + b][tid];
+      const int qmax = max(max(t.x, t.y), max(t.z, t.w)), qmin = min(min(t.x, t.y), min(t.z, t.w));
+      const int sqmax = max(max(s.x, s.y), max(s.z, s.w)), sqmin = min(min(s.x, s.y), min(s.z, s.w));
+      if (e4_longer<J>(t.x - s.x)) leaf16 |= 1u << (15 - 4 * b);
+      if (e4_longer<J>(t.y - s.y)) leaf16 |= 1u << (14 - 4 * b);
+      if (e4_longer<J>(t.z - s.z)) leaf16 |= 1u << (13 - 4 * b);
+      if (e4_longer<J>(t.w - s.w)) leaf16 |= 1u << (12 - 4 * b);
+      if (e4_longer<J>(qmax - sqmax)) qx |= 1u << (3 - b);
+      if (e4_longer<J>(qmin - sqmin)) qn |= 1u << (3 - b);
     }
-    if (e4_longer<J>(t4max[a] - s4max)) mu |= 1u << (3 - a);
-    if (e4_longer<J>(t4min[a] - s4min)) mu |= 1u << (7 - a);
+    ml |= (u64)leaf16 << (48 - 16 * a);
+    mq |= (qx << (12 - 4 * a)) | (qn << (28 - 4 * a));
+    if (e4_longer<J>(n4.x - s4.x)) mu |= 1u << (3 - a);
+    if (e4_longer<J>(n4.y - s4.y)) mu |= 1u << (7 - a);
   }
   if (e4_longer<J>(t3max - s3max)) mu |= 1u << 8;
   if (e4_longer<J>(t3min - s3min)) mu |= 1u << 9;
@@ -328,27 +334,21 @@ DCDF_DEVINL void e4_top_bits(u8* w0, u8* w1, u8* w2, u32 (&p)[4], int e) {
   if (l3) p[3]++;
 }
 
+// Two rows of the thread's 8x8 block: x[0..7] = row `row`, x[8..15] = row `row + 1`.
 template <typename InT>
-DCDF_DEVINL void e4_load_tile(const InT* p, i64 sr, i64 sc, int r0, int c0, bool vec, int (&tv)[64], int bits, bool do_round, u32& err) {
+DCDF_DEVINL void e4_fetch_pair(const InT* p, i64 sr, i64 sc, int row, int c0, bool vec, InT (&x)[16]) {
 #pragma unroll
-  for (int r = 0; r < 8; r++) {
+  for (int rr = 0; rr < 2; rr++) {
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-      InT x[4];
       if (sizeof(InT) == 4 && vec) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(p + (i64)(r0 + r) * sr + c0 + 4 * h));
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(p + (i64)(row + rr) * sr + c0 + 4 * h));
         const u32 w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int cc = 0; cc < 4; cc++) x[cc] = *reinterpret_cast<const InT*>(&w[cc]);
+        for (int cc = 0; cc < 4; cc++) x[8 * rr + 4 * h + cc] = *reinterpret_cast<const InT*>(&w[cc]);
       } else {
 #pragma unroll
-        for (int cc = 0; cc < 4; cc++) x[cc] = __ldg(p + (i64)(r0 + r) * sr + (i64)(c0 + 4 * h + cc) * sc);
-      }
-#pragma unroll
-      for (int cc = 0; cc < 4; cc++) {
-        const int c = 4 * h + cc;
-        const int m = (((r >> 2) & 1) << 5) | (((c >> 2) & 1) << 4) | (((r >> 1) & 1) << 3) | (((c >> 1) & 1) << 2) | ((r & 1) << 1) | (c & 1);
-        tv[m] = CellConv<InT, int32_t>::get(x[cc], bits, do_round, err);
+        for (int cc = 0; cc < 4; cc++) x[8 * rr + 4 * h + cc] = __ldg(p + (i64)(row + rr) * sr + (i64)(c0 + 4 * h + cc) * sc);
       }
     }
   }
@@ -375,65 +375,87 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
     uint4* z = reinterpret_cast<uint4*>(S.pool);
     for (int i = tid; i < E4_POOL / 16; i += E4_THREADS) z[i] = make_uint4(0, 0, 0, 0);
   }
+#pragma unroll 1
+  for (int q = 0; q < 16; q++) S.cell[1][q][tid] = make_int4(0, 0, 0, 0);
+#pragma unroll 1
+  for (int a = 0; a < 4; a++) S.l4[1][a][tid] = make_int2(0, 0);
 
   u32 err = 0;
-#pragma unroll
-  for (int q = 0; q < 16; q++) S.svs[q][tid] = make_int4(0, 0, 0, 0);
+  int cur = 0, ref = 1;  // images: cells of this instant / of the block's snapshot
   int s3max = 0, s3min = 0, s2max = 0, s2min = 0, s1max = 0, s1min = 0, s0max = 0, s0min = 0;
   u32 n_logs = 0, n_snap = 0, n_log_total = 0;
   u64 total_bytes = 0;
 
   for (int inst = 0; inst < unit.instants; inst++) {
     const bool first = inst == 0;
-    int tv[64];
-    e4_load_tile<InT>(base + (i64)inst * P.stride_t, P.stride_r, P.stride_c, r0, c0, vec, tv, unit.bits, do_round, err);
+    // ---------------- load + convert (a3): two rows at a time, the next pair in flight while this one is converted
+    {
+      const InT* pi = base + (i64)inst * P.stride_t;
+      InT nx[16];
+      e4_fetch_pair<InT>(pi, P.stride_r, P.stride_c, r0, c0, vec, nx);
+#pragma unroll 1
+      for (int rp = 0; rp < 4; rp++) {
+        InT cu[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) cu[i] = nx[i];
+        if (rp < 3) e4_fetch_pair<InT>(pi, P.stride_r, P.stride_c, r0 + 2 * (rp + 1), c0, vec, nx);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          int4 v;
+          v.x = CellConv<InT, int32_t>::get(cu[2 * j], unit.bits, do_round, err);
+          v.y = CellConv<InT, int32_t>::get(cu[2 * j + 1], unit.bits, do_round, err);
+          v.z = CellConv<InT, int32_t>::get(cu[8 + 2 * j], unit.bits, do_round, err);
+          v.w = CellConv<InT, int32_t>::get(cu[8 + 2 * j + 1], unit.bits, do_round, err);
+          S.cell[cur][8 * (rp >> 1) + 4 * (j >> 1) + 2 * (rp & 1) + (j & 1)][tid] = v;
+        }
+      }
+    }
 
     // ---------------- levels 6..3 inside the thread: min/max, uniform and equal flags, log length-1 masks
-    int t4max[4], t4min[4];
     u32 u5 = 0, eq5 = 0, u4 = 0, eq4 = 0;
     E4Cand L;  // log candidate
     L.ml[0] = 0; L.mq[0] = 0; L.mu[0] = 0;
-    int dfirst4[4];
-#pragma unroll
+    int t3max = INT32_MIN, t3min = INT32_MAX, diff3 = 0;
+    bool eq3 = true;
+#pragma unroll 1
     for (int a = 0; a < 4; a++) {
-      int amax = INT32_MIN, amin = INT32_MAX, s4max = INT32_MIN, s4min = INT32_MAX;
-      int dfirst = 0;
+      const int2 s4 = S.l4[ref][a][tid];
+      int amax = INT32_MIN, amin = INT32_MAX, dfirst = 0;
       bool aeq = true;
+      u32 leaf16 = 0, u5n = 0, e5n = 0, qx = 0, qn = 0;
 #pragma unroll
       for (int b = 0; b < 4; b++) {
-        const int m0 = 16 * a + 4 * b, q = 4 * a + b;
-        const int qmax = max(max(tv[m0], tv[m0 + 1]), max(tv[m0 + 2], tv[m0 + 3]));
-        const int qmin = min(min(tv[m0], tv[m0 + 1]), min(tv[m0 + 2], tv[m0 + 3]));
-        const int4 sq = S.svs[q][tid];
-        const int sqmax = max(max(sq.x, sq.y), max(sq.z, sq.w));
-        const int sqmin = min(min(sq.x, sq.y), min(sq.z, sq.w));
-        const int d0 = tv[m0] - sq.x, d1 = tv[m0 + 1] - sq.y, d2 = tv[m0 + 2] - sq.z, d3 = tv[m0 + 3] - sq.w;
+        const int4 t = S.cell[cur][4 * a + b][tid], sq = S.cell[ref][4 * a + b][tid];
+        const int qmax = max(max(t.x, t.y), max(t.z, t.w)), qmin = min(min(t.x, t.y), min(t.z, t.w));
+        const int sqmax = max(max(sq.x, sq.y), max(sq.z, sq.w)), sqmin = min(min(sq.x, sq.y), min(sq.z, sq.w));
+        const int d0 = t.x - sq.x, d1 = t.y - sq.y, d2 = t.z - sq.z, d3 = t.w - sq.w;
         const bool e5 = (((d1 ^ d0) | (d2 ^ d0) | (d3 ^ d0)) == 0);  // all four leaf diffs equal (log.rs:780-806)
-        if (qmax == qmin) u5 |= 1u << (15 - q);
-        if (e5) eq5 |= 1u << (15 - q);
-        if (e4_longer<1>(d0)) L.ml[0] |= 1ull << (63 - m0);
-        if (e4_longer<1>(d1)) L.ml[0] |= 1ull << (62 - m0);
-        if (e4_longer<1>(d2)) L.ml[0] |= 1ull << (61 - m0);
-        if (e4_longer<1>(d3)) L.ml[0] |= 1ull << (60 - m0);
-        if (e4_longer<1>(qmax - sqmax)) L.mq[0] |= 1u << (15 - q);
-        if (e4_longer<1>(qmin - sqmin)) L.mq[0] |= 1u << (31 - q);
+        if (qmax == qmin) u5n |= 1u << (3 - b);
+        if (e5) e5n |= 1u << (3 - b);
+        if (e4_longer<1>(d0)) leaf16 |= 1u << (15 - 4 * b);
+        if (e4_longer<1>(d1)) leaf16 |= 1u << (14 - 4 * b);
+        if (e4_longer<1>(d2)) leaf16 |= 1u << (13 - 4 * b);
+        if (e4_longer<1>(d3)) leaf16 |= 1u << (12 - 4 * b);
+        if (e4_longer<1>(qmax - sqmax)) qx |= 1u << (3 - b);
+        if (e4_longer<1>(qmin - sqmin)) qn |= 1u << (3 - b);
         amax = max(amax, qmax); amin = min(amin, qmin);
-        s4max = max(s4max, sqmax); s4min = min(s4min, sqmin);
         if (b == 0) dfirst = d0;
         aeq = aeq && e5 && d0 == dfirst;
       }
-      t4max[a] = amax; t4min[a] = amin;
-      dfirst4[a] = dfirst;
+      S.l4[cur][a][tid] = make_int2(amax, amin);
+      L.ml[0] |= (u64)leaf16 << (48 - 16 * a);
+      L.mq[0] |= (qx << (12 - 4 * a)) | (qn << (28 - 4 * a));
+      u5 |= u5n << (12 - 4 * a);
+      eq5 |= e5n << (12 - 4 * a);
       if (amax == amin) u4 |= 1u << (3 - a);
       if (aeq) eq4 |= 1u << (3 - a);
-      if (e4_longer<1>(amax - s4max)) L.mu[0] |= 1u << (3 - a);
-      if (e4_longer<1>(amin - s4min)) L.mu[0] |= 1u << (7 - a);
+      if (e4_longer<1>(amax - s4.x)) L.mu[0] |= 1u << (3 - a);
+      if (e4_longer<1>(amin - s4.y)) L.mu[0] |= 1u << (7 - a);
+      t3max = max(t3max, amax); t3min = min(t3min, amin);
+      if (a == 0) diff3 = dfirst;
+      eq3 = eq3 && aeq && dfirst == diff3;
     }
-    const int t3max = max(max(t4max[0], t4max[1]), max(t4max[2], t4max[3]));
-    const int t3min = min(min(t4min[0], t4min[1]), min(t4min[2], t4min[3]));
     const bool u3 = t3max == t3min;
-    const bool eq3 = eq4 == 0xfu && dfirst4[1] == dfirst4[0] && dfirst4[2] == dfirst4[0] && dfirst4[3] == dfirst4[0];
-    const int diff3 = dfirst4[0];
     if (e4_longer<1>(t3max - s3max)) L.mu[0] |= 1u << 8;
     if (e4_longer<1>(t3min - s3min)) L.mu[0] |= 1u << 9;
 
@@ -458,8 +480,8 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
     {
       const bool far = (((u32)(t2min - s2max) + 32768u) | ((u32)(t2max - s2min) + 32768u)) > 65535u;
       if (!first && __any_sync(0xffffffffu, far)) {
-        e4_log_masks<2>(tv, S.svs, t4max, t4min, t3max, t3min, t2max, t2min, s3max, s3min, s2max, s2min, L.ml[1], L.mq[1], L.mu[1]);
-        e4_log_masks<3>(tv, S.svs, t4max, t4min, t3max, t3min, t2max, t2min, s3max, s3min, s2max, s2min, L.ml[2], L.mq[2], L.mu[2]);
+        e4_log_masks<2>(S, cur, ref, tid, t3max, t3min, t2max, t2min, s3max, s3min, s2max, s2min, L.ml[1], L.mq[1], L.mu[1]);
+        e4_log_masks<3>(S, cur, ref, tid, t3max, t3min, t2max, t2min, s3max, s3min, s2max, s2min, L.ml[2], L.mq[2], L.mu[2]);
       }
     }
     // structure flags: snapshot internal = !uniform (snapshot.rs:133); log internal = !uniform && !equal (log.rs:137-152)
@@ -536,12 +558,12 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
     if (slow) {
       // ---------------- exact Snapshot size
       const u32 log_size = my_size;
-      e4_snap_masks<1>(tv, t4max, t4min, t3max, t3min, t2max, t2min, t1max, t1min, C.ml[0], C.mq[0], C.mu[0]);
+      e4_snap_masks<1>(S, cur, tid, t3max, t3min, t2max, t2min, t1max, t1min, C.ml[0], C.mq[0], C.mu[0]);
       const bool far = (u32)(t1max - t1min) > 32767u;
       const bool hi_s = __any_sync(0xffffffffu, far);
       if (hi_s) {
-        e4_snap_masks<2>(tv, t4max, t4min, t3max, t3min, t2max, t2min, t1max, t1min, C.ml[1], C.mq[1], C.mu[1]);
-        e4_snap_masks<3>(tv, t4max, t4min, t3max, t3min, t2max, t2min, t1max, t1min, C.ml[2], C.mq[2], C.mu[2]);
+        e4_snap_masks<2>(S, cur, tid, t3max, t3min, t2max, t2min, t1max, t1min, C.ml[1], C.mq[1], C.mu[1]);
+        e4_snap_masks<3>(S, cur, tid, t3max, t3min, t2max, t2min, t1max, t1min, C.ml[2], C.mq[2], C.mu[2]);
       }
       e4_count(C, owner2, ws);
 #pragma unroll
@@ -653,13 +675,13 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
         u64 accL = 0; int nL = 0;
         u32 accM = 0; int nM = 0;
         u32 accE = 0; int nE = 0;
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-          if ((ai5 >> (15 - q)) & 1u) {
-            accL = (accL << 4) | ((W.ml[0] >> (60 - 4 * q)) & 0xfull); nL += 4;
-            accM = (accM << 1) | ((W.mq[0] >> (31 - q)) & 1u); nM += 1;
-          } else if ((X5 >> (15 - q)) & 1u) {
-            accE = (accE << 1) | ((eqb5 >> (15 - q)) & 1u); nE += 1;
+#pragma unroll 1
+        for (int bit = 15; bit >= 0; bit--) {  // quad q = 15 - bit
+          if ((ai5 >> bit) & 1u) {
+            accL = (accL << 4) | ((W.ml[0] >> (4 * bit)) & 0xfull); nL += 4;
+            accM = (accM << 1) | ((W.mq[0] >> (16 + bit)) & 1u); nM += 1;
+          } else if ((X5 >> bit) & 1u) {
+            accE = (accE << 1) | ((eqb5 >> bit) & 1u); nE += 1;
           }
         }
         if (nL) e4_or_run(xw[0], Pn6 + 4u * R5, accL << (64 - nL));
@@ -773,25 +795,22 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
       // ---- leaves
       rx1 = e4_base_x(T, pre, 1, 6); rx2 = any_hi ? e4_base_x(T, pre, 2, 6) : 0u; rx3 = any_hi ? e4_base_x(T, pre, 3, 6) : 0u;
       {
-        u8* const dst = xb[0] + Pn6 + 4u * R5;
-        u32 r = 0;
-#pragma unroll
+        u8* dst = xb[0] + Pn6 + 4u * R5;
+#pragma unroll 1
         for (int q = 0; q < 16; q++) {
           if ((ai5 >> (15 - q)) & 1u) {
-            const int m0 = 4 * q;
+            const int4 t = S.cell[cur][q][tid];
             u32 z[4];
             if (as_snapshot) {
-              const int qmax = max(max(tv[m0], tv[m0 + 1]), max(tv[m0 + 2], tv[m0 + 3]));
-#pragma unroll
-              for (int c = 0; c < 4; c++) z[c] = zigzag32(qmax - tv[m0 + c]);
+              const int qmax = max(max(t.x, t.y), max(t.z, t.w));
+              z[0] = zigzag32(qmax - t.x); z[1] = zigzag32(qmax - t.y); z[2] = zigzag32(qmax - t.z); z[3] = zigzag32(qmax - t.w);
             } else {
-              const int4 sq = S.svs[q][tid];
-              z[0] = zigzag32(tv[m0] - sq.x); z[1] = zigzag32(tv[m0 + 1] - sq.y);
-              z[2] = zigzag32(tv[m0 + 2] - sq.z); z[3] = zigzag32(tv[m0 + 3] - sq.w);
+              const int4 sq = S.cell[ref][q][tid];
+              z[0] = zigzag32(t.x - sq.x); z[1] = zigzag32(t.y - sq.y); z[2] = zigzag32(t.z - sq.z); z[3] = zigzag32(t.w - sq.w);
             }
-            e4_store4(dst + 4u * r, z[0], z[1], z[2], z[3]);
-            r++;
-            if ((W.ml[0] >> (60 - 4 * q)) & 0xfull) {
+            e4_store4(dst, z[0], z[1], z[2], z[3]);
+            dst += 4;
+            if ((W.ml[0] >> (4 * (15 - q))) & 0xfull) {
 #pragma unroll
               for (int c = 0; c < 4; c++)
                 if (z[c] > 0xffu) e4_emit_hi(xb[1], xb[2], xb[3], z[c], rx1, rx2, rx3);
@@ -799,72 +818,66 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
           }
         }
       }
-      // ---- quads (level 5) and level-4 nodes
+      // ---- quads (level 5)
       rx1 = e4_base_x(T, pre, 1, 5); rx2 = any_hi ? e4_base_x(T, pre, 2, 5) : 0u; rx3 = any_hi ? e4_base_x(T, pre, 3, 5) : 0u;
       rn1 = e4_base_n(T, pre, 1, 5); rn2 = any_hi ? e4_base_n(T, pre, 2, 5) : 0u; rn3 = any_hi ? e4_base_n(T, pre, 3, 5) : 0u;
-      int s4max[4], s4min[4];
       {
-        u8* const dst = xb[0] + Pn5 + 4u * R4;
-        u8* const dmn = nb[0] + Mn5 + R5;
-        u32 r = 0, rm = 0;
-#pragma unroll
+        u8* dst = xb[0] + Pn5 + 4u * R4;
+        u8* dmn = nb[0] + Mn5 + R5;
+#pragma unroll 1
         for (int a = 0; a < 4; a++) {
-          int smax = INT32_MIN, smin = INT32_MAX;
-          u32 zx[4], zn[4];
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            const int m0 = 16 * a + 4 * b;
-            const int qmax = max(max(tv[m0], tv[m0 + 1]), max(tv[m0 + 2], tv[m0 + 3]));
-            const int qmin = min(min(tv[m0], tv[m0 + 1]), min(tv[m0 + 2], tv[m0 + 3]));
-            if (as_snapshot) {
-              zx[b] = zigzag32(t4max[a] - qmax);
-              zn[b] = zigzag32(qmin - t4min[a]);
-            } else {
-              const int4 sq = S.svs[4 * a + b][tid];
-              const int sqmax = max(max(sq.x, sq.y), max(sq.z, sq.w));
-              const int sqmin = min(min(sq.x, sq.y), min(sq.z, sq.w));
-              smax = max(smax, sqmax); smin = min(smin, sqmin);
-              zx[b] = zigzag32(qmax - sqmax);
-              zn[b] = zigzag32(qmin - sqmin);
-            }
-          }
-          s4max[a] = smax; s4min[a] = smin;
           if ((ai4 >> (3 - a)) & 1u) {
-            e4_store4(dst + 4u * r, zx[0], zx[1], zx[2], zx[3]);
-            r++;
+            const int2 n4 = S.l4[cur][a][tid];
+            u32 zx[4], zn[4];
 #pragma unroll
             for (int b = 0; b < 4; b++) {
-              if (zx[b] > 0xffu) e4_emit_hi(xb[1], xb[2], xb[3], zx[b], rx1, rx2, rx3);
+              const int4 t = S.cell[cur][4 * a + b][tid];
+              const int qmax = max(max(t.x, t.y), max(t.z, t.w)), qmin = min(min(t.x, t.y), min(t.z, t.w));
+              if (as_snapshot) {
+                zx[b] = zigzag32(n4.x - qmax);
+                zn[b] = zigzag32(qmin - n4.y);
+              } else {
+                const int4 sq = S.cell[ref][4 * a + b][tid];
+                const int sqmax = max(max(sq.x, sq.y), max(sq.z, sq.w)), sqmin = min(min(sq.x, sq.y), min(sq.z, sq.w));
+                zx[b] = zigzag32(qmax - sqmax);
+                zn[b] = zigzag32(qmin - sqmin);
+              }
             }
+            e4_store4(dst, zx[0], zx[1], zx[2], zx[3]);
+            dst += 4;
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+              if (zx[b] > 0xffu) e4_emit_hi(xb[1], xb[2], xb[3], zx[b], rx1, rx2, rx3);
+            const u32 in5a = W.in5 >> (12 - 4 * a);
 #pragma unroll
             for (int b = 0; b < 4; b++) {
-              if ((W.in5 >> (15 - (4 * a + b))) & 1u) {
-                dmn[rm++] = (u8)zn[b];
+              if ((in5a >> (3 - b)) & 1u) {
+                *dmn++ = (u8)zn[b];
                 if (zn[b] > 0xffu) e4_emit_hi(nb[1], nb[2], nb[3], zn[b], rn1, rn2, rn3);
               }
             }
           }
         }
       }
-      if (x4) {
+      if (x4) {  // ---- level-4 nodes
         rx1 = e4_base_x(T, pre, 1, 4); rx2 = any_hi ? e4_base_x(T, pre, 2, 4) : 0u; rx3 = any_hi ? e4_base_x(T, pre, 3, 4) : 0u;
         rn1 = e4_base_n(T, pre, 1, 4); rn2 = any_hi ? e4_base_n(T, pre, 2, 4) : 0u; rn3 = any_hi ? e4_base_n(T, pre, 3, 4) : 0u;
         u32 zx[4], zn[4];
 #pragma unroll
         for (int a = 0; a < 4; a++) {
-          zx[a] = zigzag32(as_snapshot ? t3max - t4max[a] : t4max[a] - s4max[a]);
-          zn[a] = zigzag32(as_snapshot ? t4min[a] - t3min : t4min[a] - s4min[a]);
+          const int2 n4 = S.l4[cur][a][tid], s4 = S.l4[ref][a][tid];
+          zx[a] = zigzag32(as_snapshot ? t3max - n4.x : n4.x - s4.x);
+          zn[a] = zigzag32(as_snapshot ? n4.y - t3min : n4.y - s4.y);
         }
         e4_store4(xb[0] + Pn4 + 4u * R3, zx[0], zx[1], zx[2], zx[3]);
-        u8* const dmn = nb[0] + Mn4 + R4;
-        u32 rm = 0;
+        u8* dmn = nb[0] + Mn4 + R4;
 #pragma unroll
         for (int a = 0; a < 4; a++)
           if (zx[a] > 0xffu) e4_emit_hi(xb[1], xb[2], xb[3], zx[a], rx1, rx2, rx3);
 #pragma unroll
         for (int a = 0; a < 4; a++) {
           if ((W.in4 >> (3 - a)) & 1u) {
-            dmn[rm++] = (u8)zn[a];
+            *dmn++ = (u8)zn[a];
             if (zn[a] > 0xffu) e4_emit_hi(nb[1], nb[2], nb[3], zn[a], rn1, rn2, rn3);
           }
         }
@@ -989,8 +1002,8 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
 
     // ---------------- bookkeeping: start a new block or extend the current one
     if (as_snapshot) {
-#pragma unroll
-      for (int q = 0; q < 16; q++) S.svs[q][tid] = make_int4(tv[4 * q], tv[4 * q + 1], tv[4 * q + 2], tv[4 * q + 3]);
+      ref = cur;  // the instant's image becomes the block's snapshot; the old snapshot image is overwritten next
+      cur ^= 1;
       s3max = t3max; s3min = t3min; s2max = t2max; s2min = t2min; s1max = t1max; s1min = t1min; s0max = t0max; s0min = t0min;
       n_snap++;
       n_logs = 0;

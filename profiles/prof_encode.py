@@ -4,14 +4,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dcdf_b200 import Context, Superchunk, synth, _ffi
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-data = synth.raster(T, 721, 1440, device="cuda")
+R = int(sys.argv[2]) if len(sys.argv) > 2 else 721
+C = int(sys.argv[3]) if len(sys.argv) > 3 else 1440
+data = synth.raster(T, R, C, device="cuda")
 ctx = Context(0)
 for i in range(2):
     sc = Superchunk.build(ctx, data, [5, 6], compute_bits=True, chunk_size=64)
     print("encode ms", ctx.last_kernel_ms(_ffi.KT_ENCODE), "stats ms", ctx.last_kernel_ms(_ffi.KT_STATS), "bytes", sc.total_bytes())
     if i == 0:
         sc.close()
-out = torch.empty((T, 721, 1440), device="cuda", dtype=torch.float32)
-sc.window(0, T, 0, 721, 0, 1440, out=out)
+out = torch.empty((T, R, C), device="cuda", dtype=torch.float32)
+sc.window(0, T, 0, R, 0, C, out=out)
 torch.cuda.synchronize()
 print("decode ms", ctx.last_kernel_ms(_ffi.KT_WINDOW), "equal", bool(torch.equal(out, data)))
