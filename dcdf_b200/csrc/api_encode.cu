@@ -5,12 +5,14 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
 
 #include "encode_big.cuh"
 #include "encode_v4.cuh"
 #include "gather.cuh"
 #include "host.hpp"
 #include "stats.cuh"
+#include "xfer.cuh"
 
 using namespace dcdf;
 
@@ -81,7 +83,13 @@ const void* stage_input(dcdf_ctx* ctx, const dcdf_array3* a) {
   for (int i = 0; i < 3; i++) span += (size_t)(a->shape[i] - 1) * (size_t)a->strides[i];
   size_t bytes = span * elem_size(a->encoding);
   ctx->input_copy.reserve(bytes);
+  // One host-to-device engine per GPU: uploads of different contexts are queued first come first served and each one
+  // runs at the full link rate, so the kernels and downloads of one context overlap the upload of the next instead of
+  // all contexts uploading (and then computing) in lockstep.
+  static std::mutex upload_mutex[64];
+  std::lock_guard<std::mutex> lock(upload_mutex[ctx->device & 63]);
   CK(cudaMemcpyAsync(ctx->input_copy.p, a->base, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return ctx->input_copy.p;
 }
 
@@ -209,13 +217,14 @@ void launch_encode_one(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
 // which a structure is emitted straight into the arena (tests use it to cover that path).
 template <typename InT>
 void launch_encode_v4(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
-  constexpr int MINB = 5;
+  constexpr int MINB = 4;
   static const u32 stage_limit = [] {
     const char* e = getenv("DCDF_STAGE_LIMIT");
     const long v = e ? atol(e) : (long)E4_POOL;
     return (u32)std::min<long>(std::max<long>(v, 0), (long)E4_POOL);
   }();
-  const size_t smem = sizeof(E4Smem);
+  static const size_t pad = getenv("DCDF_V4_PAD") ? (size_t)atol(getenv("DCDF_V4_PAD")) : 0;  // occupancy experiments
+  const size_t smem = sizeof(E4Smem) + pad;
   CK(cudaFuncSetAttribute(k_encode_v4<InT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_encode_v4<InT, MINB><<<grid, E4_THREADS, smem, ctx->stream>>>(P, stage_limit);
   CK(cudaGetLastError());
@@ -323,8 +332,8 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   memcpy(h_slices, job.slices.data(), sizeof(SliceDesc) * n_slices);
   u64* h_tb = reinterpret_cast<u64*>(h_slices + n_slices);
   for (u32 i = 0; i < n_tables; i++) { h_tb[i] = table_base[i]; h_tb[n_tables + i] = table_len[i]; }
-  CK(cudaMemcpyAsync(ctx->units.p, h_units, sizeof(EncUnit) * n_units, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->slices.p, h_slices, sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_tables, cudaMemcpyHostToDevice, st));
+  copy_by_kernel(ctx, ctx->units.p, h_units, sizeof(EncUnit) * n_units);  // ctx->pin is pinned: read in place
+  copy_by_kernel(ctx, ctx->slices.p, h_slices, sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_tables);
   const u64* d_table_base = reinterpret_cast<const u64*>(ctx->slices.as<SliceDesc>() + n_slices);
   const u64* d_table_len = d_table_base + n_tables;
   // static node tree + per-(slice, node) state
@@ -342,9 +351,9 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     d_children = reinterpret_cast<TreeChild*>(tb + ((b0 + 255) & ~size_t(255)));
     d_leaf_unit = reinterpret_cast<int32_t*>(reinterpret_cast<u8*>(d_children) + ((b1 + 255) & ~size_t(255)));
     d_nstate = reinterpret_cast<NodeState*>(reinterpret_cast<u8*>(d_leaf_unit) + ((b2 + 255) & ~size_t(255)));
-    CK(cudaMemcpyAsync(d_nodes, G.nodes.data(), b0, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_children, G.children.data(), b1, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_leaf_unit, G.leaf_unit.data(), b2, cudaMemcpyHostToDevice, st));
+    upload_small(ctx, d_nodes, G.nodes.data(), b0);
+    upload_small(ctx, d_children, G.children.data(), b1);
+    upload_small(ctx, d_leaf_unit, G.leaf_unit.data(), b2);
   }
 
   tr.mark("scratch + uploads");
@@ -395,8 +404,8 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     // fixed.rs:150 (rare).  The flags are a few bytes per slice, read back once per call.
     SliceState* ss = ctx->sstate.as<SliceState>();
     std::vector<SliceState> hs(n_slices);
-    CK(cudaMemcpyAsync(hs.data(), ss, sizeof(SliceState) * n_slices, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    read_small(ctx, hs.data(), ss, sizeof(SliceState) * n_slices);
+    sync_reads(ctx);
     bool any = false;
     for (auto& s : hs) any = any || s.need_exact;
     if (any) {
@@ -406,8 +415,8 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
       for (u32 s = 0; s < n_slices; s++) { t0[s] = job.slices[s].t0; inst[s] = job.slices[s].instants; }
       i64* d_t0 = ctx->exact.as<i64>();
       int* d_inst = reinterpret_cast<int*>(d_t0 + n_slices);
-      CK(cudaMemcpyAsync(d_t0, t0.data(), sizeof(i64) * n_slices, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(d_inst, inst.data(), sizeof(int) * n_slices, cudaMemcpyHostToDevice, st));
+      upload_small(ctx, d_t0, t0.data(), sizeof(i64) * n_slices);
+      upload_small(ctx, d_inst, inst.data(), sizeof(int) * n_slices);
       ExactParams XP;
       XP.data = job.dev_data;
       XP.stride_t = job.strides[0]; XP.stride_r = job.strides[1]; XP.stride_c = job.strides[2];
@@ -419,8 +428,8 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
       int* d_maxfb = d_need + n_slices;
       int* d_f = d_maxfb + n_slices;
       int* d_round = d_f + n_slices;
-      CK(cudaMemcpyAsync(d_need, need.data(), sizeof(int) * n_slices, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(d_maxfb, maxfb.data(), sizeof(int) * n_slices, cudaMemcpyHostToDevice, st));
+      upload_small(ctx, d_need, need.data(), sizeof(int) * n_slices);
+      upload_small(ctx, d_maxfb, maxfb.data(), sizeof(int) * n_slices);
       CK(cudaMemsetAsync(d_f, 0, 2 * sizeof(int) * n_slices, st));
       XP.slice_need = d_need; XP.slice_maxfb = d_maxfb; XP.slice_f = d_f; XP.slice_round = d_round;
       dim3 grid((unsigned)std::min<int64_t>(4 * ctx->sm_count, 65535), n_slices);
@@ -429,12 +438,11 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
       CK(cudaGetLastError());
       ctx->launches++;
       std::vector<int> f(n_slices), r(n_slices);
-      CK(cudaMemcpyAsync(f.data(), d_f, sizeof(int) * n_slices, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(r.data(), d_round, sizeof(int) * n_slices, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
+      read_small(ctx, f.data(), d_f, sizeof(int) * n_slices);
+      read_small(ctx, r.data(), d_round, sizeof(int) * n_slices);
+      sync_reads(ctx);
       for (u32 s = 0; s < n_slices; s++) { hs[s].f_exact = f[s]; hs[s].round_exact = r[s]; }
-      CK(cudaMemcpyAsync(ss, hs.data(), sizeof(SliceState) * n_slices, cudaMemcpyHostToDevice, st));
-      CK(cudaStreamSynchronize(st));
+      upload_small(ctx, ss, hs.data(), sizeof(SliceState) * n_slices);
     }
   }
   if (job.tree) {
@@ -510,8 +518,8 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     k_scan_units<<<1, 1024, 0, st>>>(ctx->results.as<UnitResult>(), ctx->stored.as<u8>(), n_units, ctx->chunk_off.as<u64>());
     CK(cudaGetLastError());
     ctx->launches++;
-    CK(cudaMemcpyAsync(head_buf.data(), ctx->small.p, 64, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    read_small(ctx, head_buf.data(), ctx->small.p, 64);
+    sync_reads(ctx);
     u32 flags;
     u64 head;
     memcpy(&flags, head_buf.data(), 4);
@@ -543,22 +551,22 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   out.stored.resize(n_units);
   out.chunk_off.resize((size_t)n_units + 1);
   out.states.resize(n_slices);
-  CK(cudaMemcpyAsync(out.units.data(), ctx->units.p, sizeof(EncUnit) * n_units, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(out.results.data(), ctx->results.p, sizeof(UnitResult) * n_units, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(out.stored.data(), ctx->stored.p, n_units, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(out.chunk_off.data(), ctx->chunk_off.p, sizeof(u64) * ((size_t)n_units + 1), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(out.states.data(), ctx->sstate.p, sizeof(SliceState) * n_slices, cudaMemcpyDeviceToHost, st));
+  read_small(ctx, out.units.data(), ctx->units.p, sizeof(EncUnit) * n_units);
+  read_small(ctx, out.results.data(), ctx->results.p, sizeof(UnitResult) * n_units);
+  read_small(ctx, out.stored.data(), ctx->stored.p, n_units);
+  read_small(ctx, out.chunk_off.data(), ctx->chunk_off.p, sizeof(u64) * ((size_t)n_units + 1));
+  read_small(ctx, out.states.data(), ctx->sstate.p, sizeof(SliceState) * n_slices);
   if (!job.plain) {
     out.dac_pieces.resize(2 * (size_t)n_tables);
-    CK(cudaMemcpyAsync(out.dac_pieces.data(), ctx->pieces.as<Piece>() + n_pieces, sizeof(Piece) * 2 * n_tables, cudaMemcpyDeviceToHost, st));
+    read_small(ctx, out.dac_pieces.data(), ctx->pieces.as<Piece>() + n_pieces, sizeof(Piece) * 2 * n_tables);
     out.nstate.resize(n_tables);
-    CK(cudaMemcpyAsync(out.nstate.data(), d_nstate, sizeof(NodeState) * n_tables, cudaMemcpyDeviceToHost, st));
+    read_small(ctx, out.nstate.data(), d_nstate, sizeof(NodeState) * n_tables);
   }
   if (want_pieces) {
     out.pieces.resize(n_pieces);
     CK(cudaMemcpyAsync(out.pieces.data(), ctx->pieces.p, sizeof(Piece) * n_pieces, cudaMemcpyDeviceToHost, st));
   }
-  CK(cudaStreamSynchronize(st));
+  sync_reads(ctx);
 
   tr.mark("tables readback");
   // ---- final blobs
@@ -589,7 +597,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     out.dac_blob_size = off;
     out.dac_blob = static_cast<uint8_t*>(pool_alloc(off + 16, st));
     ctx->query_aux.reserve(sizeof(u64) * 2 * n_tables);
-    CK(cudaMemcpyAsync(ctx->query_aux.p, out.dac_off.data(), sizeof(u64) * 2 * n_tables, cudaMemcpyHostToDevice, st));
+    upload_small(ctx, ctx->query_aux.p, out.dac_off.data(), sizeof(u64) * 2 * n_tables);
     GatherDacParams DP;
     DP.pieces = ctx->pieces.as<Piece>() + n_pieces;
     DP.dst_off = ctx->query_aux.as<u64>();
@@ -600,8 +608,8 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     ctx->launches++;
   }
   time_end(ctx, KT_GATHER);
-  CK(cudaMemcpyAsync(head_buf.data(), ctx->small.p, 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  read_small(ctx, head_buf.data(), ctx->small.p, 4);
+  sync_reads(ctx);
   time_collect(ctx, KT_GATHER);
   tr.mark("gather");
   u32 flags;
@@ -894,6 +902,8 @@ int32_t dcdf_ctx_destroy(dcdf_ctx* ctx) {
   for (auto* b : bufs) b->release();
   ctx->pin.release();
   ctx->pin2.release();
+  ctx->xfer_up.release();
+  ctx->xfer_down.release();
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);

@@ -115,6 +115,11 @@ struct dcdf_ctx {
       arena, small, exact, query_in, query_out, query_aux, tree_buf;
   dcdf::PinBuf pin, pin2;
   size_t arena_hint = 0;
+  // small transfers through mapped pinned memory (xfer.cuh)
+  dcdf::PinBuf xfer_up, xfer_down;
+  size_t up_off = 0, down_off = 0;
+  struct PendingRead { void* dst; size_t off, n; };
+  std::vector<PendingRead> reads;
 };
 
 // One Chunk resident on the device.  `bytes` may point into a superchunk's blob (owner == false).
