@@ -44,7 +44,8 @@ struct EncUnit {
   u32 slot;         // caller-defined (subchunk slot inside its slice)
   int row0, col0;   // origin of the tile inside its region (row-major order of the NaN quirk)
 };
-enum : int { UF_ROUND = 1, UF_NARROW = 2, UF_SKIP = 4, UF_FULL = 8 /* 64x64, all in bounds */ };
+enum : int { UF_ROUND = 1, UF_NARROW = 2, UF_SKIP = 4, UF_FULL = 8 /* 64x64, all in bounds */,
+              UF_EXACT = 16 /* float unit whose values all have <= bits fractional bits and are finite: to_fixed never rounds */ };
 
 struct Piece {
   u64 off;   // byte offset in the arena (16-byte aligned)

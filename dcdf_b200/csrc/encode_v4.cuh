@@ -334,6 +334,21 @@ DCDF_DEVINL void e4_top_bits(u8* w0, u8* w1, u8* w2, u32 (&p)[4], int e) {
   if (l3) p[3]++;
 }
 
+// to_fixed of one cell (a3).  `exact`: the stats pass proved that no value of the unit has more than `bits`
+// fractional bits and none is infinite, so n * 2^(bits+1) is an integer and fixed.rs:47-57 never rounds or fails.
+template <typename InT>
+DCDF_DEVINL int e4_conv(InT x, int bits, bool do_round, bool exact, float scale2, u32& err) {
+  return CellConv<InT, int32_t>::get(x, bits, do_round, err);
+}
+template <>
+DCDF_DEVINL int e4_conv<float>(float x, int bits, bool do_round, bool exact, float scale2, u32& err) {
+  if (exact) {
+    const int f = __float2int_rz(x * scale2) + 1;
+    return x != x ? 0 : f;  // NaN -> 0 (fixed.rs:35-37)
+  }
+  return CellConv<float, int32_t>::get(x, bits, do_round, err);
+}
+
 // Two rows of the thread's 8x8 block: x[0..7] = row `row`, x[8..15] = row `row + 1`.
 template <typename InT>
 DCDF_DEVINL void e4_fetch_pair(const InT* p, i64 sr, i64 sc, int row, int c0, bool vec, InT (&x)[16]) {
@@ -364,6 +379,8 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
   const EncUnit unit = P.units[unit_idx];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool do_round = unit.flags & UF_ROUND;
+  const bool exact = unit.flags & UF_EXACT;
+  const float scale2 = (float)((i64)2 << unit.bits);
   const int r0 = 8 * (int)morton_row(tid), c0 = 8 * (int)morton_col(tid);
   const InT* base = static_cast<const InT*>(P.data) + unit.base;
   const bool vec = sizeof(InT) == 4 && P.stride_c == 1 && ((P.stride_r * 4) & 15) == 0 && ((P.stride_t * 4) & 15) == 0 &&
@@ -402,10 +419,10 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           int4 v;
-          v.x = CellConv<InT, int32_t>::get(cu[2 * j], unit.bits, do_round, err);
-          v.y = CellConv<InT, int32_t>::get(cu[2 * j + 1], unit.bits, do_round, err);
-          v.z = CellConv<InT, int32_t>::get(cu[8 + 2 * j], unit.bits, do_round, err);
-          v.w = CellConv<InT, int32_t>::get(cu[8 + 2 * j + 1], unit.bits, do_round, err);
+          v.x = e4_conv<InT>(cu[2 * j], unit.bits, do_round, exact, scale2, err);
+          v.y = e4_conv<InT>(cu[2 * j + 1], unit.bits, do_round, exact, scale2, err);
+          v.z = e4_conv<InT>(cu[8 + 2 * j], unit.bits, do_round, exact, scale2, err);
+          v.w = e4_conv<InT>(cu[8 + 2 * j + 1], unit.bits, do_round, exact, scale2, err);
           S.cell[cur][8 * (rp >> 1) + 4 * (j >> 1) + 2 * (rp & 1) + (j & 1)][tid] = v;
         }
       }
@@ -675,6 +692,10 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
         u64 accL = 0; int nL = 0;
         u32 accM = 0; int nM = 0;
         u32 accE = 0; int nE = 0;
+        if (ai5 == 0xffffu) {  // every quad is internal: the runs are the masks themselves
+          accL = W.ml[0]; nL = 64;
+          accM = W.mq[0] >> 16; nM = 16;
+        } else
 #pragma unroll 1
         for (int bit = 15; bit >= 0; bit--) {  // quad q = 15 - bit
           if ((ai5 >> bit) & 1u) {

@@ -594,6 +594,7 @@ __global__ void k_finalize_phase2(const FinalizeParams P, u32 n_slices) {
         narrow = us.imax < (i64)0x3fffffff && us.imin > -(i64)0x3fffffff;
       }
       if (narrow) flags |= UF_NARROW;
+      if (is_float && !us.nonfinite && max(us.frac_nonneg, us.frac_neg) <= bits) flags |= UF_EXACT;
     }
     if (unit.rows == 64 && unit.cols == 64 && unit.lo == 0) flags |= UF_FULL;
     unit.bits = bits;
