@@ -147,7 +147,15 @@ DCDF_DEVINL void warp_copy_bytes(u8* dst, const u8* src, u32 n, int lane) {
   const u8* s0 = src + head;
   const u32 sh = (u32)((uintptr_t)s0 & 3u) * 8u;
   const u32* s4 = reinterpret_cast<const u32*>((uintptr_t)s0 & ~(uintptr_t)3);
-  for (u32 w = lane; w < body; w += 32) {
+  u32 w = lane;
+  for (; w + 96 < body; w += 128) {  // four independent word pairs in flight per lane
+    u32 lo[4], hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { lo[j] = s4[w + 32 * j]; hi[j] = sh ? s4[w + 32 * j + 1] : 0u; }
+#pragma unroll
+    for (int j = 0; j < 4; j++) d4[w + 32 * j] = sh ? __funnelshift_r(lo[j], hi[j], sh) : lo[j];
+  }
+  for (; w < body; w += 32) {
     const u32 lo = s4[w];
     d4[w] = sh ? __funnelshift_r(lo, s4[w + 1], sh) : lo;
   }
@@ -168,6 +176,7 @@ __global__ void __launch_bounds__(256) k_gather_chunks(const GatherParams P) {
   }
   u8* out = P.out + base;
   __shared__ u32 dst_off[GATHER_MAX_T];
+  __shared__ Piece pcs[GATHER_MAX_T];  // piece table of the current batch, fetched by all threads at once
   __shared__ u32 carry_off, last_snap_pos, block_count;
   const Piece* pieces = P.pieces + unit.piece_base;
   if (tid == 0) {
@@ -181,10 +190,12 @@ __global__ void __launch_bounds__(256) k_gather_chunks(const GatherParams P) {
   __syncthreads();
   for (int t0 = 0; t0 < unit.instants; t0 += GATHER_MAX_T) {
     const int nt = min(GATHER_MAX_T, unit.instants - t0);
+    for (int i = tid; i < nt; i += 256) pcs[i] = pieces[t0 + i];
+    __syncthreads();
     if (tid == 0) {
       u32 off = carry_off, lsp = last_snap_pos, bc = block_count;
       for (int i = 0; i < nt; i++) {
-        const Piece pc = pieces[t0 + i];
+        const Piece pc = pcs[i];
         if (pc.kind == 1u) {
           if (lsp) out[lsp] = (u8)bc;        // close the previous block: n_instants (block.rs:89)
           lsp = off;
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(256) k_gather_chunks(const GatherParams P) {
     }
     __syncthreads();
     for (int i = warp; i < nt; i += 8) {
-      const Piece pc = pieces[t0 + i];
+      const Piece pc = pcs[i];
       const u8* src = P.arena + pc.off;
       u8* dst = out + dst_off[i];
       warp_copy_bytes(dst, src, pc.size, lane);

@@ -171,7 +171,7 @@ template <> DCDF_DEVINL u64 raw64<i64>(i64 v) { return (u64)v; }
 constexpr int STAT_BATCH = 32;  // instants whose per-warp partials are kept in smem before one finalisation
 
 template <typename InT, bool IS_FLOAT>
-__global__ void __launch_bounds__(STAT_THREADS) k_unit_stats(const StatParams P) {
+__global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams P) {
   const u32 u = blockIdx.x;
   if (u >= P.n_units) return;
   const EncUnit unit = P.units[u];
@@ -851,6 +851,7 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
             narrow = imax < (i64)0x3fffffff && imin > -(i64)0x3fffffff;
           }
           if (narrow) flags |= UF_NARROW;
+          if (is_float && !nonfinite && max(fnn, fng) <= cbits) flags |= UF_EXACT;  // a leaf child covers exactly its own unit
         }
         const bool full = unit.rows == 64 && unit.cols == 64 && unit.lo == 0;
         if (full) flags |= UF_FULL;
