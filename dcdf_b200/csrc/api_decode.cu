@@ -5,6 +5,7 @@
 
 #include "decode.cuh"
 #include "decode_tile.cuh"
+#include "decode_tile2.cuh"
 #include "host.hpp"
 
 using namespace dcdf;
@@ -389,11 +390,18 @@ void do_window_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
     TileWindowParams TP;
     TP.Q = mb->Q; TP.cubes = d_c; TP.out_off = d_off; TP.job_base = ctx->query_aux.as<u64>();
     TP.n_queries = n; TP.n_jobs = n_jobs; TP.out = ot.dev; TP.raw = os.raw;
-    CK(cudaFuncSetAttribute(k_window_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    // default: level-synchronous expansion (decode_tile.cuh); DCDF_WINDOW_WALK=1: per-thread sub-tree walk (decode_tile2.cuh)
+    static const bool walk_v1 = getenv("DCDF_WINDOW_WALK") == nullptr;
+    if (walk_v1) CK(cudaFuncSetAttribute(k_window_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
     tbegin(ctx, KT_WINDOW);
     if (n_jobs) {
-      const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
-      k_window_tiles<<<grid, DT_THREADS, sizeof(TileSmem), ctx->stream>>>(TP);
+      if (walk_v1) {
+        const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
+        k_window_tiles<<<grid, DT_THREADS, sizeof(TileSmem), ctx->stream>>>(TP);
+      } else {
+        const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
+        k_window_tiles2<<<grid, DW_THREADS, 0, ctx->stream>>>(TP);
+      }
       CK(cudaGetLastError());
       ctx->launches++;
     }

@@ -39,13 +39,13 @@ DCDF_DEVINL u32 lvl_off(int k) { return (0x55555555u >> (32 - 2 * k)) & (k ? 0xf
 
 // Copy `size` bytes starting at global address `src` into `stage` keeping the address modulo 16, and return
 // the pointer that corresponds to `src`.  Falls back to `src` itself when the structure does not fit.
-DCDF_DEVINL const u8* stage_bytes(const u8* src, u32 size, u8* stage, u32 cap) {
+DCDF_DEVINL const u8* stage_bytes(const u8* src, u32 size, u8* stage, u32 cap, u32 n_threads = DT_THREADS) {
   const u32 mis = (u32)((uintptr_t)src & 15u);
   if (size + mis + 4u > cap) return src;
   const uint4* g = reinterpret_cast<const uint4*>(src - mis);
   uint4* d = reinterpret_cast<uint4*>(stage);
   const u32 n16 = (size + mis + 4u + 15u) / 16u;  // +4: be32_at reads one aligned word past the last byte
-  for (u32 i = threadIdx.x; i < n16; i += DT_THREADS) d[i] = g[i];
+  for (u32 i = threadIdx.x; i < n16; i += n_threads) d[i] = g[i];
   return stage + mis;
 }
 
@@ -179,6 +179,27 @@ DCDF_DEVINL void expand_log(const ChunkView& cv, const ChunkView& cv_snap, const
   }
 }
 
+// Output of one cell: raw fixed point, or the chunk's own encoding with from_fixed applied to floats (fixed.rs:81-86;
+// the divide by 2^(bits+1) is an exact scaling, done as a multiply by the exact reciprocal).
+struct CellOut {
+  void* out;
+  int kind;  // 0: i64 (raw / ENC_I64), 1: i32, 2: f32, 3: f64
+  float inv32;
+  double inv64;
+  DCDF_DEVINL void init(const QuerySet& Q, void* out_, int raw, int bits) {
+    out = out_;
+    kind = (raw || Q.encoding == 8) ? 0 : Q.encoding == 4 ? 1 : Q.encoding == 32 ? 2 : 3;
+    inv32 = __int_as_float((126 - bits) << 23);                          // 2^-(bits+1)
+    inv64 = __longlong_as_double((long long)(1022 - bits) << 52);
+  }
+  DCDF_DEVINL void put(u64 i, i64 fixed) const {
+    if (kind == 2) static_cast<float*>(out)[i] = fixed == 0 ? __int_as_float(0x7fc00000) : __ll2float_rn(fixed - 1) * inv32;
+    else if (kind == 0) static_cast<i64*>(out)[i] = fixed;
+    else if (kind == 1) static_cast<int32_t*>(out)[i] = (int32_t)fixed;
+    else static_cast<double*>(out)[i] = fixed == 0 ? __longlong_as_double(0x7ff8000000000000ll) : __ll2double_rn(fixed - 1) * inv64;
+  }
+};
+
 struct TileWindowParams {
   QuerySet Q;
   const CubeDev* cubes;   // validated, ordered
@@ -222,9 +243,12 @@ __global__ void __launch_bounds__(DT_THREADS) k_window_tiles(const TileWindowPar
     const int32_t u = Q.slot_unit[sm.slot_base + slot];
     const UnitMeta m = u >= 0 ? Q.units[u] : UnitMeta{};
     const bool stored = u >= 0 && m.stored;
+    const i64 tile_org = (chunk_top - c.top) * W_cols + (chunk_left - c.left);  // element offset of tile cell (0, 0)
     auto out_index = [&](i64 t, int r, int col) {
-      return obase + (u64)(((t - c.start) * W_rows + (chunk_top + r - c.top)) * W_cols + (chunk_left + col - c.left));
+      return obase + (u64)((t - c.start) * W_rows * W_cols + tile_org) + (u64)((i64)r * W_cols + col);
     };
+    CellOut co;
+    co.init(Q, P.out, P.raw, m.bits);
     if (!stored) {
       // Elided: one value per instant from the max table, parent's fractional bits (superchunk.rs:426-433)
       const SlotDesc sdsc = Q.slot_desc[sm.slot_base + slot];
@@ -266,7 +290,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_window_tiles(const TileWindowPar
         // rows of the window inside this tile; consecutive threads write consecutive columns
         for (int r = top + (tid / 64); r < bottom; r += DT_THREADS / 64) {
           const int col = left + (tid & 63);
-          if (col < right) emit(Q, P.out, out_index(t, r, col), S.sval[oL + ((u32)r << L) + (u32)col], m.bits, P.raw);
+          if (col < right) co.put(out_index(t, r, col), S.sval[oL + ((u32)r << L) + (u32)col]);
         }
       } else {
         // fused cell pass: one thread per 2x2 quad (row-major over quads so that a warp writes whole row segments);
@@ -291,7 +315,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_window_tiles(const TileWindowPar
             if (mode == 1) v = pay;
             else if (mode == 2) v = pay + sc;
             else v = mxl.get(cb + (u32)c) + sc;
-            emit(Q, P.out, out_index(t, r, col), v, m.bits, P.raw);
+            co.put(out_index(t, r, col), v);
           }
         }
       }
