@@ -50,6 +50,7 @@ struct MetaBlock {
   QuerySet Q;
   u64 n_dir = 0;
   int max_sidelen = 0;  // tiles up to 64x64 take the level-synchronous window decoder
+  int max_dac_levels = 0;  // <= 3: the window decoder can expand in 32-bit values
 };
 
 void check_err_word(dcdf_ctx* ctx, u32* d_err, const char* what) {
@@ -116,7 +117,7 @@ MetaBlock* make_meta(dcdf_ctx* ctx, const u8* blob, std::vector<UnitMeta>& units
     CK(cudaMemcpyAsync(units.data(), mb->d.units, ub, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     mb->n_dir = n_dir;
-    for (auto& u : units) if (u.stored) mb->max_sidelen = std::max(mb->max_sidelen, u.sidelen);
+    for (auto& u : units) if (u.stored) { mb->max_sidelen = std::max(mb->max_sidelen, u.sidelen); mb->max_dac_levels = std::max(mb->max_dac_levels, u.dac_levels); }
     QuerySet& Q = mb->Q;
     Q.blob = blob;
     Q.units = mb->d.units;
@@ -392,12 +393,17 @@ void do_window_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
     TP.n_queries = n; TP.n_jobs = n_jobs; TP.out = ot.dev; TP.raw = os.raw;
     // default: level-synchronous expansion (decode_tile.cuh); DCDF_WINDOW_WALK=1: per-thread sub-tree walk (decode_tile2.cuh)
     static const bool walk_v1 = getenv("DCDF_WINDOW_WALK") == nullptr;
-    if (walk_v1) CK(cudaFuncSetAttribute(k_window_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    const bool narrow = mb->max_dac_levels <= 3 && getenv("DCDF_WINDOW_WIDE") == nullptr;
+    if (walk_v1) {
+      CK(cudaFuncSetAttribute(k_window_tiles<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<i64>)));
+      CK(cudaFuncSetAttribute(k_window_tiles<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<int32_t>)));
+    }
     tbegin(ctx, KT_WINDOW);
     if (n_jobs) {
       if (walk_v1) {
         const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
-        k_window_tiles<<<grid, DT_THREADS, sizeof(TileSmem), ctx->stream>>>(TP);
+        if (narrow) k_window_tiles<int32_t><<<grid, DT_THREADS, sizeof(TileSmemT<int32_t>), ctx->stream>>>(TP);
+        else k_window_tiles<i64><<<grid, DT_THREADS, sizeof(TileSmemT<i64>), ctx->stream>>>(TP);
       } else {
         const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
         k_window_tiles2<<<grid, DW_THREADS, 0, ctx->stream>>>(TP);

@@ -36,6 +36,8 @@ struct UnitMeta {
   int bits;       // fractional bits of this chunk
   int stored;     // 0 = elided (no bytes)
   int enc;
+  int dac_levels; // most byte levels of any max DAC of the chunk (<= 3: every entry is below 2^23 in magnitude)
+  int pad_;
 };
 struct SliceMeta {
   i64 t0;
@@ -200,7 +202,7 @@ __global__ void k_build_dir(const DirParams P) {
   const u32 fb = c.u8_();
   const u32 n_blocks = c.u32_();
   if (!(enc == 4 || enc == 8 || enc == 32 || enc == 64) || n_blocks == 0) c.ok = false;
-  u32 inst = 0;
+  u32 inst = 0, dac_levels = 0;
   int rows = 0, cols = 0, sidelen = 0;
   for (u32 b = 0; b < n_blocks && c.ok; b++) {
     const u32 n_inst = c.u8_();
@@ -220,6 +222,7 @@ __global__ void k_build_dir(const DirParams P) {
       if (i > 0) parse_bitmap(c, d.eq_len, d.eq_base);
       parse_dac(c, d.max);
       parse_dac(c, d.min);
+      dac_levels = max(dac_levels, d.max.n_levels);
       d.size = (u32)c.pos - d.off;
       if (c.ok && d.nm_len == 0) c.ok = false;
       if (c.ok && !P.count_only) {
@@ -235,7 +238,7 @@ __global__ void k_build_dir(const DirParams P) {
     atomicOr(P.err, (u32)EF_BAD_FORMAT);
     return;
   }
-  m.rows = rows; m.cols = cols; m.sidelen = sidelen; m.bits = (int)fb; m.enc = (int)enc;
+  m.rows = rows; m.cols = cols; m.sidelen = sidelen; m.bits = (int)fb; m.enc = (int)enc; m.dac_levels = (int)dac_levels;
   if (P.count_only) m.instants = (int)inst;
   P.units[u] = m;
   (void)n_blocks;

@@ -22,9 +22,13 @@ constexpr int DT_UPPER = 1365;
 constexpr int DT_STAGE_S = 12 * 1024;   // shared-memory copy of the block's Snapshot bytes (when it fits)
 constexpr int DT_STAGE_L = 8 * 1024;   // ... and of the current Log
 
-struct TileSmem {
-  i64 sval[DT_NODES];   // snapshot max pyramid: level k at offset (4^k - 1) / 3, Morton order inside a level
-  i64 lpay[DT_UPPER + 3];   // log expansion payload (levels above the cells)
+// V = int32_t when every max DAC of the handle has at most three byte levels (entries below 2^23 in magnitude, so no
+// sum along a root-to-cell path of <= 7 nodes leaves 32 bits), i64 otherwise; the narrow layout lets four CTAs share
+// an SM instead of two.
+template <typename V>
+struct TileSmemT {
+  V sval[DT_NODES];   // snapshot max pyramid: level k at offset (4^k - 1) / 3, Morton order inside a level
+  V lpay[DT_UPPER + 3];   // log expansion payload (levels above the cells)
   unsigned short scb[DT_UPPER + 3];  // snapshot: BFS index of the first child (0xffff: not an internal node)
   unsigned short lcb[DT_UPPER + 3];  // log: same
   u8 lmode[DT_UPPER + 3];            // 0 internal, 1 uniform (value = payload), 2 equal (value = payload + snapshot cell)
@@ -34,6 +38,7 @@ struct TileSmem {
   __align__(16) u8 stage_s[DT_STAGE_S + 32];
   __align__(16) u8 stage_l[DT_STAGE_L + 32];
 };
+typedef TileSmemT<i64> TileSmem;
 
 DCDF_DEVINL u32 lvl_off(int k) { return (0x55555555u >> (32 - 2 * k)) & (k ? 0xffffffffu : 0u); }  // (4^k - 1) / 3
 
@@ -52,7 +57,8 @@ DCDF_DEVINL const u8* stage_bytes(const u8* src, u32 size, u8* stage, u32 cap, u
 // Block-wide: turn the "internal" markers of level k (k <= 5, at most 1024 positions) into child BFS bases;
 // returns the number of internal nodes.  Each warp owns a contiguous run of positions (ballots stay in
 // registers), one barrier turns the per-warp counts into offsets.
-DCDF_DEVINL u32 assign_child_bases(unsigned short* cb, int k, u32 p_next, TileSmem& S) {
+template <typename V>
+DCDF_DEVINL u32 assign_child_bases(unsigned short* cb, int k, u32 p_next, TileSmemT<V>& S) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 n = 1u << (2 * k), off = lvl_off(k);
   const u32 seg = n > 32u * DT_WARPS ? n / DT_WARPS : 32u;  // 32 or 128
@@ -90,12 +96,13 @@ DCDF_DEVINL u32 cell_index(u32 p1, int L, bool last) {
 }
 
 // Expand a Snapshot into S.sval / S.scb (L = tree levels, 1..6).
-DCDF_DEVINL void expand_snapshot(const ChunkView& cv, const InstDir& s, int L, TileSmem& S) {
+template <typename V>
+DCDF_DEVINL void expand_snapshot(const ChunkView& cv, const InstDir& s, int L, TileSmemT<V>& S) {
   const int tid = threadIdx.x;
   const BitsFast nm = bits_fast(cv.chunk, s.nm_len, s.nm_base);
   const DacFast mx = dac_fast(cv.chunk, &s.max);
   if (tid == 0) {
-    S.sval[0] = mx.get(0);
+    S.sval[0] = (V)mx.get(0);
     S.scb[0] = nm.get(0) ? 1 : 0xffff;
   }
   __syncthreads();
@@ -107,11 +114,11 @@ DCDF_DEVINL void expand_snapshot(const ChunkView& cv, const InstDir& s, int L, T
     for (u32 p1 = tid; p1 < n1; p1 += DT_THREADS) {
       const u32 p = p1 >> 2;
       const u32 cb = S.scb[o0 + p];
-      i64 v = S.sval[o0 + p];
+      V v = S.sval[o0 + p];
       bool in = false;
       if (cb != 0xffffu) {
         const u32 idx = cb + (p1 & 3u);
-        v -= mx.get(idx);
+        v -= (V)mx.get(idx);
         in = has_bits && idx < s.nm_len && nm.get(idx);
       }
       S.sval[o1 + cell_index(p1, L, !has_bits)] = v;
@@ -124,13 +131,14 @@ DCDF_DEVINL void expand_snapshot(const ChunkView& cv, const InstDir& s, int L, T
 
 // Expand a Log against the snapshot pyramid already in S.sval down to level L - 1 (the 2x2 quads); the cells are
 // produced by the caller's fused output pass.
-DCDF_DEVINL void expand_log(const ChunkView& cv, const ChunkView& cv_snap, const InstDir& l, const InstDir& s, int L, TileSmem& S) {
+template <typename V>
+DCDF_DEVINL void expand_log(const ChunkView& cv, const ChunkView& cv_snap, const InstDir& l, const InstDir& s, int L, TileSmemT<V>& S) {
   const int tid = threadIdx.x;
   const BitsFast nm = bits_fast(cv.chunk, l.nm_len, l.nm_base);
   const BitMapRef nm_rank{cv.chunk, l.nm_len, l.nm_base}, eq{cv.chunk, l.eq_len, l.eq_base};
   const DacFast mx = dac_fast(cv.chunk, &l.max);
   if (tid == 0) {
-    const i64 d0 = mx.get(0);
+    const V d0 = (V)mx.get(0);
     const bool single_t = !nm.get(0);
     if (!single_t) {
       S.lmode[0] = 0; S.lpay[0] = d0; S.lcb[0] = 1;
@@ -154,11 +162,11 @@ DCDF_DEVINL void expand_log(const ChunkView& cv, const ChunkView& cv_snap, const
     for (u32 p1 = tid; p1 < n1; p1 += DT_THREADS) {
       const u32 p = p1 >> 2;
       u8 mode = S.lmode[o0 + p];
-      i64 pay = S.lpay[o0 + p];
+      V pay = S.lpay[o0 + p];
       bool in = false;
       if (mode == 0) {
         const u32 idx = S.lcb[o0 + p] + (p1 & 3u);
-        const i64 d = mx.get(idx);  // max_t is replaced, not accumulated (log.rs:233)
+        const V d = (V)mx.get(idx);  // max_t is replaced, not accumulated (log.rs:233)
         in = has_bits && idx < l.nm_len && nm.get(idx);
         if (in) {
           mode = 0; pay = d;
@@ -210,9 +218,10 @@ struct TileWindowParams {
   int raw;
 };
 
+template <typename V>
 __global__ void __launch_bounds__(DT_THREADS) k_window_tiles(const TileWindowParams P) {
   extern __shared__ __align__(16) unsigned char dt_smem_raw[];
-  TileSmem& S = *reinterpret_cast<TileSmem*>(dt_smem_raw);
+  TileSmemT<V>& S = *reinterpret_cast<TileSmemT<V>*>(dt_smem_raw);
   const QuerySet& Q = P.Q;
   const int tid = threadIdx.x;
   for (u64 ji = blockIdx.x; ji < P.n_jobs; ji += gridDim.x) {
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_window_tiles(const TileWindowPar
         // rows of the window inside this tile; consecutive threads write consecutive columns
         for (int r = top + (tid / 64); r < bottom; r += DT_THREADS / 64) {
           const int col = left + (tid & 63);
-          if (col < right) co.put(out_index(t, r, col), S.sval[oL + ((u32)r << L) + (u32)col]);
+          if (col < right) co.put(out_index(t, r, col), (i64)S.sval[oL + ((u32)r << L) + (u32)col]);
         }
       } else {
         // fused cell pass: one thread per 2x2 quad (row-major over quads so that a warp writes whole row segments);
@@ -304,18 +313,18 @@ __global__ void __launch_bounds__(DT_THREADS) k_window_tiles(const TileWindowPar
           if (r0q + 1 < top || r0q >= bottom || c0q + 1 < left || c0q >= right) continue;
           const u32 q = L > 1 ? morton_encode((u32)qr, (u32)qc) : 0u;
           const u8 mode = S.lmode[oQ + q];
-          const i64 pay = S.lpay[oQ + q];
+          const V pay = S.lpay[oQ + q];
           const u32 cb = S.lcb[oQ + q];
 #pragma unroll
           for (int c = 0; c < 4; c++) {
             const int r = r0q + (c >> 1), col = c0q + (c & 1);
             if (r < top || r >= bottom || col < left || col >= right) continue;
-            const i64 sc = S.sval[oL + ((u32)r << L) + (u32)col];
-            i64 v;
+            const V sc = S.sval[oL + ((u32)r << L) + (u32)col];
+            V v;
             if (mode == 1) v = pay;
             else if (mode == 2) v = pay + sc;
-            else v = mxl.get(cb + (u32)c) + sc;
-            co.put(out_index(t, r, col), v);
+            else v = (V)mxl.get(cb + (u32)c) + sc;
+            co.put(out_index(t, r, col), (i64)v);
           }
         }
       }
