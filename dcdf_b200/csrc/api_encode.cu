@@ -215,7 +215,7 @@ void launch_encode_one(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
 // Full 64x64 tiles with 31-bit values: 64-thread CTAs, 64 cells per thread (encode_v4.cuh).
 // DCDF_ENCODE_V2=1 routes them through k_encode_tiles instead; DCDF_STAGE_LIMIT=<bytes> lowers the size above
 // which a structure is emitted straight into the arena (tests use it to cover that path).
-template <typename InT>
+template <typename InT, bool FULL>
 void launch_encode_v4(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   constexpr int MINB = 4;
   static const u32 stage_limit = [] {
@@ -225,8 +225,8 @@ void launch_encode_v4(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   }();
   static const size_t pad = getenv("DCDF_V4_PAD") ? (size_t)atol(getenv("DCDF_V4_PAD")) : 0;  // occupancy experiments
   const size_t smem = sizeof(E4Smem) + pad;
-  CK(cudaFuncSetAttribute(k_encode_v4<InT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_encode_v4<InT, MINB><<<grid, E4_THREADS, smem, ctx->stream>>>(P, stage_limit);
+  CK(cudaFuncSetAttribute(k_encode_v4<InT, MINB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_encode_v4<InT, MINB, FULL><<<grid, E4_THREADS, smem, FULL ? ctx->stream : ctx->aux_stream>>>(P, stage_limit);
   CK(cudaGetLastError());
   ctx->launches++;
 }
@@ -235,10 +235,11 @@ template <typename InT>
 void launch_encode(dcdf_ctx* ctx, const EncParams& P, u32 grid, int list) {
   if (grid == 0) return;
   static const bool force_v2 = getenv("DCDF_ENCODE_V2") != nullptr;
-  if (list == 0 && !force_v2) { launch_encode_v4<InT>(ctx, P, grid); return; }
+  if (list == 0 && !force_v2) { launch_encode_v4<InT, true>(ctx, P, grid); return; }
+  if (list == 4 && !force_v2) { launch_encode_v4<InT, false>(ctx, P, grid); return; }
   switch (list) {
     case 0: launch_encode_one<InT, int32_t, true, 2>(ctx, P, grid); break;
-    case 1: launch_encode_one<InT, int32_t, false, 2>(ctx, P, grid); break;
+    case 1: case 4: launch_encode_one<InT, int32_t, false, 2>(ctx, P, grid); break;
     case 2: launch_encode_one<InT, i64, true, 1>(ctx, P, grid); break;
     default: launch_encode_one<InT, i64, false, 1>(ctx, P, grid); break;
   }
@@ -304,7 +305,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   ctx->istats.reserve(sizeof(InstStats) * (size_t)n_units * job.t_max);
   ctx->slices.reserve(sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_tables);
   ctx->sstate.reserve(sizeof(SliceState) * n_slices);
-  ctx->order.reserve(sizeof(u32) * (4 * (size_t)n_units + 8));
+  ctx->order.reserve(sizeof(u32) * (5 * (size_t)n_units + 8));
   ctx->pieces.reserve(sizeof(Piece) * (n_pieces + 2 * (size_t)n_tables));
   ctx->results.reserve(sizeof(UnitResult) * n_units);
   ctx->stored.reserve(n_units);
@@ -320,7 +321,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   out.tbl_min = d_tbl_min;
   out.tbl_total = tbl_total;
 
-  // small: [0] err (u32) | [8] arena_head (u64) | [16] order counts (4 x u32)
+  // small: [0] err (u32) | [8] arena_head (u64) | [16] order counts (5 x u32)
   u32* d_err = ctx->small.as<u32>();
   unsigned long long* d_head = reinterpret_cast<unsigned long long*>(ctx->small.as<u8>() + 8);
   u32* d_counts = reinterpret_cast<u32*>(ctx->small.as<u8>() + 16);
@@ -487,7 +488,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     time_begin(ctx, KT_ENCODE);
     CK(cudaEventRecord(ctx->fork_ev, st));  // clipped-tile lists run on the auxiliary stream beside the full-tile lists
     CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));
-    for (int list = 0; list < 4; list++) {
+    for (int list = 0; list < 5; list++) {
       EP.order = FP.order + (size_t)list * n_units;
       EP.order_count = d_counts + list;
       switch (job.encoding) {

@@ -136,6 +136,27 @@ DCDF_DEVINL u32 e4_dac_size(const u32* cnt) {
 }
 DCDF_DEVINL u8* e4_words_of(u8* out, u32 hdr, u32 len) { return out + hdr + 8u + 4u * (len >> 7); }
 
+// Clipped tiles (FULL == false): cells outside the raster are None (snapshot.rs:448-456) -- kept as INT32_MIN in the cell
+// images, nodes without any cell inside as (max, min) = (INT32_MIN, INT32_MAX).  max() / min() then skip them by
+// themselves; every place that turns a max into an entry maps None to 0 (`None => 0`, snapshot.rs:122-130, log.rs:128-135).
+constexpr int E4_NONE = INT32_MIN;
+template <bool FULL>
+DCDF_DEVINL int e4_o0(int v) { return FULL ? v : (v == E4_NONE ? 0 : v); }
+DCDF_DEVINL int e4_sub(int a, int b) { return (int)((u32)a - (u32)b); }  // wraps (operands may be sentinels)
+template <bool FULL>
+DCDF_DEVINL bool e4_unif(int mx, int mn) { return FULL ? mx == mn : (mx == mn || mx == E4_NONE); }  // a None node is uniform
+template <bool FULL>
+DCDF_DEVINL void e4_qmm(const int4& t, int& qmax, int& qmin) {
+  qmax = max(max(t.x, t.y), max(t.z, t.w));
+  if (FULL) {
+    qmin = min(min(t.x, t.y), min(t.z, t.w));
+  } else {
+    const int a = t.x == E4_NONE ? INT32_MAX : t.x, b = t.y == E4_NONE ? INT32_MAX : t.y;
+    const int c = t.z == E4_NONE ? INT32_MAX : t.z, d = t.w == E4_NONE ? INT32_MAX : t.w;
+    qmin = min(min(a, b), min(c, d));
+  }
+}
+
 // The masks that describe one candidate encoding of the current instant, as seen by one thread.
 struct E4Cand {
   u32 in5, in4;       // internal flags: 16 quads (quad q = bit 15-q), 4 level-4 nodes (node a = bit 3-a)
@@ -146,7 +167,7 @@ struct E4Cand {
 };
 
 // Snapshot entry masks for length class J (snapshot.rs:122-147: parent_max - child_max, child_min - parent_min).
-template <int J>
+template <int J, bool FULL>
 DCDF_DEVINL void e4_snap_masks(const E4Smem& S, int cur, int tid, int t3max, int t3min, int t2max, int t2min, int t1max, int t1min,
                                u64& ml, u32& mq, u32& mu) {
   ml = 0; mq = 0; mu = 0;
@@ -157,28 +178,28 @@ DCDF_DEVINL void e4_snap_masks(const E4Smem& S, int cur, int tid, int t3max, int
 #pragma unroll
     for (int b = 0; b < 4; b++) {
       const int4 t = S.cell[cur][4 * a + b][tid];
-      const int qmax = max(max(t.x, t.y), max(t.z, t.w));
-      const int qmin = min(min(t.x, t.y), min(t.z, t.w));
-      if (e4_longer<J>(qmax - t.x)) leaf16 |= 1u << (15 - 4 * b);
-      if (e4_longer<J>(qmax - t.y)) leaf16 |= 1u << (14 - 4 * b);
-      if (e4_longer<J>(qmax - t.z)) leaf16 |= 1u << (13 - 4 * b);
-      if (e4_longer<J>(qmax - t.w)) leaf16 |= 1u << (12 - 4 * b);
-      if (e4_longer<J>(n4.x - qmax)) qx |= 1u << (3 - b);
-      if (e4_longer<J>(qmin - n4.y)) qn |= 1u << (3 - b);
+      int qmax, qmin;
+      e4_qmm<FULL>(t, qmax, qmin);
+      if (e4_longer<J>(e4_sub(qmax, e4_o0<FULL>(t.x)))) leaf16 |= 1u << (15 - 4 * b);  // a cell outside the raster counts as 0
+      if (e4_longer<J>(e4_sub(qmax, e4_o0<FULL>(t.y)))) leaf16 |= 1u << (14 - 4 * b);
+      if (e4_longer<J>(e4_sub(qmax, e4_o0<FULL>(t.z)))) leaf16 |= 1u << (13 - 4 * b);
+      if (e4_longer<J>(e4_sub(qmax, e4_o0<FULL>(t.w)))) leaf16 |= 1u << (12 - 4 * b);
+      if (e4_longer<J>(e4_sub(n4.x, e4_o0<FULL>(qmax)))) qx |= 1u << (3 - b);
+      if (e4_longer<J>(e4_sub(qmin, n4.y))) qn |= 1u << (3 - b);
     }
     ml |= (u64)leaf16 << (48 - 16 * a);
     mq |= (qx << (12 - 4 * a)) | (qn << (28 - 4 * a));
-    if (e4_longer<J>(t3max - n4.x)) mu |= 1u << (3 - a);
-    if (e4_longer<J>(n4.y - t3min)) mu |= 1u << (7 - a);
+    if (e4_longer<J>(e4_sub(t3max, e4_o0<FULL>(n4.x)))) mu |= 1u << (3 - a);
+    if (e4_longer<J>(e4_sub(n4.y, t3min))) mu |= 1u << (7 - a);
   }
-  if (e4_longer<J>(t2max - t3max)) mu |= 1u << 8;
-  if (e4_longer<J>(t3min - t2min)) mu |= 1u << 9;
-  if (e4_longer<J>(t1max - t2max)) mu |= 1u << 10;
-  if (e4_longer<J>(t2min - t1min)) mu |= 1u << 11;
+  if (e4_longer<J>(e4_sub(t2max, e4_o0<FULL>(t3max)))) mu |= 1u << 8;
+  if (e4_longer<J>(e4_sub(t3min, t2min))) mu |= 1u << 9;
+  if (e4_longer<J>(e4_sub(t1max, e4_o0<FULL>(t2max)))) mu |= 1u << 10;
+  if (e4_longer<J>(e4_sub(t2min, t1min))) mu |= 1u << 11;
 }
 
 // Log entry masks for length class J (log.rs:128-158: max_t - max_s, min_t - min_s per node, t - s per leaf).
-template <int J>
+template <int J, bool FULL>
 DCDF_DEVINL void e4_log_masks(const E4Smem& S, int cur, int ref, int tid, int t3max, int t3min, int t2max, int t2min, int s3max,
                               int s3min, int s2max, int s2min, u64& ml, u32& mq, u32& mu) {
   ml = 0; mq = 0; mu = 0;
@@ -189,24 +210,25 @@ DCDF_DEVINL void e4_log_masks(const E4Smem& S, int cur, int ref, int tid, int t3
 #pragma unroll
     for (int b = 0; b < 4; b++) {
       const int4 t = S.cell[cur][4 * a + b][tid], s = S.cell[ref][4 * a + b][tid];
-      const int qmax = max(max(t.x, t.y), max(t.z, t.w)), qmin = min(min(t.x, t.y), min(t.z, t.w));
-      const int sqmax = max(max(s.x, s.y), max(s.z, s.w)), sqmin = min(min(s.x, s.y), min(s.z, s.w));
-      if (e4_longer<J>(t.x - s.x)) leaf16 |= 1u << (15 - 4 * b);
-      if (e4_longer<J>(t.y - s.y)) leaf16 |= 1u << (14 - 4 * b);
-      if (e4_longer<J>(t.z - s.z)) leaf16 |= 1u << (13 - 4 * b);
-      if (e4_longer<J>(t.w - s.w)) leaf16 |= 1u << (12 - 4 * b);
-      if (e4_longer<J>(qmax - sqmax)) qx |= 1u << (3 - b);
-      if (e4_longer<J>(qmin - sqmin)) qn |= 1u << (3 - b);
+      int qmax, qmin, sqmax, sqmin;
+      e4_qmm<FULL>(t, qmax, qmin);
+      e4_qmm<FULL>(s, sqmax, sqmin);
+      if (e4_longer<J>(e4_sub(t.x, s.x))) leaf16 |= 1u << (15 - 4 * b);  // None - None = 0 (log.rs:751)
+      if (e4_longer<J>(e4_sub(t.y, s.y))) leaf16 |= 1u << (14 - 4 * b);
+      if (e4_longer<J>(e4_sub(t.z, s.z))) leaf16 |= 1u << (13 - 4 * b);
+      if (e4_longer<J>(e4_sub(t.w, s.w))) leaf16 |= 1u << (12 - 4 * b);
+      if (e4_longer<J>(e4_sub(e4_o0<FULL>(qmax), e4_o0<FULL>(sqmax)))) qx |= 1u << (3 - b);
+      if (e4_longer<J>(e4_sub(qmin, sqmin))) qn |= 1u << (3 - b);
     }
     ml |= (u64)leaf16 << (48 - 16 * a);
     mq |= (qx << (12 - 4 * a)) | (qn << (28 - 4 * a));
-    if (e4_longer<J>(n4.x - s4.x)) mu |= 1u << (3 - a);
-    if (e4_longer<J>(n4.y - s4.y)) mu |= 1u << (7 - a);
+    if (e4_longer<J>(e4_sub(e4_o0<FULL>(n4.x), e4_o0<FULL>(s4.x)))) mu |= 1u << (3 - a);
+    if (e4_longer<J>(e4_sub(n4.y, s4.y))) mu |= 1u << (7 - a);
   }
-  if (e4_longer<J>(t3max - s3max)) mu |= 1u << 8;
-  if (e4_longer<J>(t3min - s3min)) mu |= 1u << 9;
-  if (e4_longer<J>(t2max - s2max)) mu |= 1u << 10;
-  if (e4_longer<J>(t2min - s2min)) mu |= 1u << 11;
+  if (e4_longer<J>(e4_sub(e4_o0<FULL>(t3max), e4_o0<FULL>(s3max)))) mu |= 1u << 8;
+  if (e4_longer<J>(e4_sub(t3min, s3min))) mu |= 1u << 9;
+  if (e4_longer<J>(e4_sub(e4_o0<FULL>(t2max), e4_o0<FULL>(s2max)))) mu |= 1u << 10;
+  if (e4_longer<J>(e4_sub(t2min, s2min))) mu |= 1u << 11;
 }
 
 // Per-thread packed counters of one candidate (relative to "the root is an internal node").
@@ -349,9 +371,35 @@ DCDF_DEVINL int e4_conv<float>(float x, int bits, bool do_round, bool exact, flo
   return CellConv<float, int32_t>::get(x, bits, do_round, err);
 }
 
-// Two rows of the thread's 8x8 block: x[0..7] = row `row`, x[8..15] = row `row + 1`.
-template <typename InT>
-DCDF_DEVINL void e4_fetch_pair(const InT* p, i64 sr, i64 sc, int row, int c0, bool vec, InT (&x)[16]) {
+// Two rows of the thread's 8x8 block: x[0..7] = row `row`, x[8..15] = row `row + 1`.  Clipped tiles: `inb` gets one
+// bit per cell that lies inside rows x cols (the others are not read).
+template <typename InT, bool FULL>
+DCDF_DEVINL void e4_fetch_pair(const InT* p, i64 sr, i64 sc, int row, int c0, bool vec, int rows, int cols, InT (&x)[16], u32& inb) {
+  inb = 0xffffu;
+  if (!FULL) {
+    inb = 0;
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        if (sizeof(InT) == 4 && vec && row + rr < rows && c0 + 4 * h + 3 < cols) {  // whole group inside: one 128-bit load
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(p + (i64)(row + rr) * sr + c0 + 4 * h));
+          const u32 w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int cc = 0; cc < 4; cc++) x[8 * rr + 4 * h + cc] = *reinterpret_cast<const InT*>(&w[cc]);
+          inb |= 0xfu << (8 * rr + 4 * h);
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < 4; cc++) {
+            const bool in = row + rr < rows && c0 + 4 * h + cc < cols;
+            x[8 * rr + 4 * h + cc] = in ? __ldg(p + (i64)(row + rr) * sr + (i64)(c0 + 4 * h + cc) * sc) : InT(0);
+            inb |= in ? 1u << (8 * rr + 4 * h + cc) : 0u;
+          }
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int rr = 0; rr < 2; rr++) {
 #pragma unroll
@@ -369,7 +417,7 @@ DCDF_DEVINL void e4_fetch_pair(const InT* p, i64 sr, i64 sc, int row, int c0, bo
   }
 }
 
-template <typename InT, int MINB>
+template <typename InT, int MINB, bool FULL>
 __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams P, const u32 stage_limit) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   E4Smem& S = *reinterpret_cast<E4Smem*>(smem_raw);
@@ -409,13 +457,15 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
     {
       const InT* pi = base + (i64)inst * P.stride_t;
       InT nx[16];
-      e4_fetch_pair<InT>(pi, P.stride_r, P.stride_c, r0, c0, vec, nx);
+      u32 nxb;
+      e4_fetch_pair<InT, FULL>(pi, P.stride_r, P.stride_c, r0, c0, vec, unit.rows, unit.cols, nx, nxb);
 #pragma unroll 1
       for (int rp = 0; rp < 4; rp++) {
         InT cu[16];
+        const u32 cub = nxb;
 #pragma unroll
         for (int i = 0; i < 16; i++) cu[i] = nx[i];
-        if (rp < 3) e4_fetch_pair<InT>(pi, P.stride_r, P.stride_c, r0 + 2 * (rp + 1), c0, vec, nx);
+        if (rp < 3) e4_fetch_pair<InT, FULL>(pi, P.stride_r, P.stride_c, r0 + 2 * (rp + 1), c0, vec, unit.rows, unit.cols, nx, nxb);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           int4 v;
@@ -423,6 +473,12 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
           v.y = e4_conv<InT>(cu[2 * j + 1], unit.bits, do_round, exact, scale2, err);
           v.z = e4_conv<InT>(cu[8 + 2 * j], unit.bits, do_round, exact, scale2, err);
           v.w = e4_conv<InT>(cu[8 + 2 * j + 1], unit.bits, do_round, exact, scale2, err);
+          if (!FULL) {
+            if (!((cub >> (2 * j)) & 1u)) v.x = E4_NONE;
+            if (!((cub >> (2 * j + 1)) & 1u)) v.y = E4_NONE;
+            if (!((cub >> (8 + 2 * j)) & 1u)) v.z = E4_NONE;
+            if (!((cub >> (8 + 2 * j + 1)) & 1u)) v.w = E4_NONE;
+          }
           S.cell[cur][8 * (rp >> 1) + 4 * (j >> 1) + 2 * (rp & 1) + (j & 1)][tid] = v;
         }
       }
@@ -443,18 +499,19 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
 #pragma unroll
       for (int b = 0; b < 4; b++) {
         const int4 t = S.cell[cur][4 * a + b][tid], sq = S.cell[ref][4 * a + b][tid];
-        const int qmax = max(max(t.x, t.y), max(t.z, t.w)), qmin = min(min(t.x, t.y), min(t.z, t.w));
-        const int sqmax = max(max(sq.x, sq.y), max(sq.z, sq.w)), sqmin = min(min(sq.x, sq.y), min(sq.z, sq.w));
-        const int d0 = t.x - sq.x, d1 = t.y - sq.y, d2 = t.z - sq.z, d3 = t.w - sq.w;
+        int qmax, qmin, sqmax, sqmin;
+        e4_qmm<FULL>(t, qmax, qmin);
+        e4_qmm<FULL>(sq, sqmax, sqmin);
+        const int d0 = e4_sub(t.x, sq.x), d1 = e4_sub(t.y, sq.y), d2 = e4_sub(t.z, sq.z), d3 = e4_sub(t.w, sq.w);  // None - None = 0
         const bool e5 = (((d1 ^ d0) | (d2 ^ d0) | (d3 ^ d0)) == 0);  // all four leaf diffs equal (log.rs:780-806)
-        if (qmax == qmin) u5n |= 1u << (3 - b);
+        if (e4_unif<FULL>(qmax, qmin)) u5n |= 1u << (3 - b);
         if (e5) e5n |= 1u << (3 - b);
         if (e4_longer<1>(d0)) leaf16 |= 1u << (15 - 4 * b);
         if (e4_longer<1>(d1)) leaf16 |= 1u << (14 - 4 * b);
         if (e4_longer<1>(d2)) leaf16 |= 1u << (13 - 4 * b);
         if (e4_longer<1>(d3)) leaf16 |= 1u << (12 - 4 * b);
-        if (e4_longer<1>(qmax - sqmax)) qx |= 1u << (3 - b);
-        if (e4_longer<1>(qmin - sqmin)) qn |= 1u << (3 - b);
+        if (e4_longer<1>(e4_sub(e4_o0<FULL>(qmax), e4_o0<FULL>(sqmax)))) qx |= 1u << (3 - b);
+        if (e4_longer<1>(e4_sub(qmin, sqmin))) qn |= 1u << (3 - b);
         amax = max(amax, qmax); amin = min(amin, qmin);
         if (b == 0) dfirst = d0;
         aeq = aeq && e5 && d0 == dfirst;
@@ -464,17 +521,17 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
       L.mq[0] |= (qx << (12 - 4 * a)) | (qn << (28 - 4 * a));
       u5 |= u5n << (12 - 4 * a);
       eq5 |= e5n << (12 - 4 * a);
-      if (amax == amin) u4 |= 1u << (3 - a);
+      if (e4_unif<FULL>(amax, amin)) u4 |= 1u << (3 - a);
       if (aeq) eq4 |= 1u << (3 - a);
-      if (e4_longer<1>(amax - s4.x)) L.mu[0] |= 1u << (3 - a);
-      if (e4_longer<1>(amin - s4.y)) L.mu[0] |= 1u << (7 - a);
+      if (e4_longer<1>(e4_sub(e4_o0<FULL>(amax), e4_o0<FULL>(s4.x)))) L.mu[0] |= 1u << (3 - a);
+      if (e4_longer<1>(e4_sub(amin, s4.y))) L.mu[0] |= 1u << (7 - a);
       t3max = max(t3max, amax); t3min = min(t3min, amin);
       if (a == 0) diff3 = dfirst;
       eq3 = eq3 && aeq && dfirst == diff3;
     }
-    const bool u3 = t3max == t3min;
-    if (e4_longer<1>(t3max - s3max)) L.mu[0] |= 1u << 8;
-    if (e4_longer<1>(t3min - s3min)) L.mu[0] |= 1u << 9;
+    const bool u3 = e4_unif<FULL>(t3max, t3min);
+    if (e4_longer<1>(e4_sub(e4_o0<FULL>(t3max), e4_o0<FULL>(s3max)))) L.mu[0] |= 1u << 8;
+    if (e4_longer<1>(e4_sub(t3min, s3min))) L.mu[0] |= 1u << 9;
 
     // ---------------- levels 2 and 1 with shuffles (4 resp. 16 consecutive lanes)
     int t2max = max(t3max, shfl_xor(t3max, 1)); t2max = max(t2max, shfl_xor(t2max, 2));
@@ -482,23 +539,23 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
     const int diff2 = shfl(diff3, lane & ~3);
     const u32 ok3 = __ballot_sync(0xffffffffu, eq3 && diff3 == diff2);
     const bool eq2 = ((ok3 >> (lane & ~3)) & 0xfu) == 0xfu;
-    const bool u2 = t2max == t2min;
+    const bool u2 = e4_unif<FULL>(t2max, t2min);
     int t1max = max(t2max, shfl_xor(t2max, 4)); t1max = max(t1max, shfl_xor(t1max, 8));
     int t1min = min(t2min, shfl_xor(t2min, 4)); t1min = min(t1min, shfl_xor(t1min, 8));
     const int diff1 = shfl(diff2, lane & ~15);
     const u32 ok2 = __ballot_sync(0xffffffffu, eq2 && diff2 == diff1);
     const bool eq1 = ((ok2 >> (lane & ~15)) & 0xffffu) == 0xffffu;
-    const bool u1 = t1max == t1min;
-    if (e4_longer<1>(t2max - s2max)) L.mu[0] |= 1u << 10;
-    if (e4_longer<1>(t2min - s2min)) L.mu[0] |= 1u << 11;
+    const bool u1 = e4_unif<FULL>(t1max, t1min);
+    if (e4_longer<1>(e4_sub(e4_o0<FULL>(t2max), e4_o0<FULL>(s2max)))) L.mu[0] |= 1u << 10;
+    if (e4_longer<1>(e4_sub(t2min, s2min))) L.mu[0] |= 1u << 11;
 
     // log entries longer than two bytes can only exist where the level-2 value ranges are that far apart
     L.ml[1] = L.ml[2] = 0; L.mq[1] = L.mq[2] = 0; L.mu[1] = L.mu[2] = 0;
     {
-      const bool far = (((u32)(t2min - s2max) + 32768u) | ((u32)(t2max - s2min) + 32768u)) > 65535u;
+      const bool far = (((u32)e4_sub(t2min, s2max) + 32768u) | ((u32)e4_sub(t2max, s2min) + 32768u)) > 65535u;
       if (!first && __any_sync(0xffffffffu, far)) {
-        e4_log_masks<2>(S, cur, ref, tid, t3max, t3min, t2max, t2min, s3max, s3min, s2max, s2min, L.ml[1], L.mq[1], L.mu[1]);
-        e4_log_masks<3>(S, cur, ref, tid, t3max, t3min, t2max, t2min, s3max, s3min, s2max, s2min, L.ml[2], L.mq[2], L.mu[2]);
+        e4_log_masks<2, FULL>(S, cur, ref, tid, t3max, t3min, t2max, t2min, s3max, s3min, s2max, s2min, L.ml[1], L.mq[1], L.mu[1]);
+        e4_log_masks<3, FULL>(S, cur, ref, tid, t3max, t3min, t2max, t2min, s3max, s3min, s2max, s2min, L.ml[2], L.mq[2], L.mu[2]);
       }
     }
     // structure flags: snapshot internal = !uniform (snapshot.rs:133); log internal = !uniform && !equal (log.rs:137-152)
@@ -525,7 +582,7 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
     }
     if ((lane & 15) == 0) {
       S.rec1[k1] = make_int4(t1max, t1min, diff1, eq1 ? 1 : 0);
-      S.ent1[k1] = make_int2(t1max - s1max, t1min - s1min);
+      S.ent1[k1] = make_int2(e4_sub(e4_o0<FULL>(t1max), e4_o0<FULL>(s1max)), e4_sub(t1min, s1min));
     }
     __syncthreads();  // B1
 
@@ -544,7 +601,7 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
     u32 l_in1 = 0, s_in1 = 0;  // level-1 internal flags, node k = bit 3-k
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      const bool un = n1max[k] == n1min[k];
+      const bool un = e4_unif<FULL>(n1max[k], n1min[k]);
       if (!un) s_in1 |= 1u << (3 - k);
       if (!un && !n1eq[k]) l_in1 |= 1u << (3 - k);
     }
@@ -571,16 +628,18 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
     }
     int s_e1max[4], s_e1min[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) { s_e1max[k] = t0max - n1max[k]; s_e1min[k] = n1min[k] - t0min; }
+    for (int k = 0; k < 4; k++) { s_e1max[k] = e4_sub(t0max, e4_o0<FULL>(n1max[k])); s_e1min[k] = e4_sub(n1min[k], t0min); }
     if (slow) {
       // ---------------- exact Snapshot size
       const u32 log_size = my_size;
-      e4_snap_masks<1>(S, cur, tid, t3max, t3min, t2max, t2min, t1max, t1min, C.ml[0], C.mq[0], C.mu[0]);
-      const bool far = (u32)(t1max - t1min) > 32767u;
+      e4_snap_masks<1, FULL>(S, cur, tid, t3max, t3min, t2max, t2min, t1max, t1min, C.ml[0], C.mq[0], C.mu[0]);
+      // entries longer than two bytes need a value range that wide -- or, in a clipped tile, a cell outside the raster
+      // next to large values (its entry is the quad's max itself)
+      const bool far = !FULL || (u32)e4_sub(t1max, t1min) > 32767u;
       const bool hi_s = __any_sync(0xffffffffu, far);
       if (hi_s) {
-        e4_snap_masks<2>(S, cur, tid, t3max, t3min, t2max, t2min, t1max, t1min, C.ml[1], C.mq[1], C.mu[1]);
-        e4_snap_masks<3>(S, cur, tid, t3max, t3min, t2max, t2min, t1max, t1min, C.ml[2], C.mq[2], C.mu[2]);
+        e4_snap_masks<2, FULL>(S, cur, tid, t3max, t3min, t2max, t2min, t1max, t1min, C.ml[1], C.mq[1], C.mu[1]);
+        e4_snap_masks<3, FULL>(S, cur, tid, t3max, t3min, t2max, t2min, t1max, t1min, C.ml[2], C.mq[2], C.mu[2]);
       }
       e4_count(C, owner2, ws);
 #pragma unroll
@@ -801,7 +860,7 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
           for (int k = 0; k < 4; k++) {
             const bool ik = (in1m >> (3 - k)) & 1u;
             if (ik) e4_set_bit(nm_words, 1u + (u32)k);
-            else if (!as_snapshot && n1max[k] != n1min[k] && n1eq[k]) e4_set_bit(eq_words, (u32)k - (u32)__popc(in1m >> (4 - k)));
+            else if (!as_snapshot && !e4_unif<FULL>(n1max[k], n1min[k]) && n1eq[k]) e4_set_bit(eq_words, (u32)k - (u32)__popc(in1m >> (4 - k)));
             e4_top_bits(xw[0], xw[1], xw[2], px, e1x[k]);
             if (ik) e4_top_bits(nw[0], nw[1], nw[2], pn, e1n[k]);
           }
@@ -824,10 +883,12 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
             u32 z[4];
             if (as_snapshot) {
               const int qmax = max(max(t.x, t.y), max(t.z, t.w));
-              z[0] = zigzag32(qmax - t.x); z[1] = zigzag32(qmax - t.y); z[2] = zigzag32(qmax - t.z); z[3] = zigzag32(qmax - t.w);
+              z[0] = zigzag32(e4_sub(qmax, e4_o0<FULL>(t.x))); z[1] = zigzag32(e4_sub(qmax, e4_o0<FULL>(t.y)));
+              z[2] = zigzag32(e4_sub(qmax, e4_o0<FULL>(t.z))); z[3] = zigzag32(e4_sub(qmax, e4_o0<FULL>(t.w)));
             } else {
               const int4 sq = S.cell[ref][q][tid];
-              z[0] = zigzag32(t.x - sq.x); z[1] = zigzag32(t.y - sq.y); z[2] = zigzag32(t.z - sq.z); z[3] = zigzag32(t.w - sq.w);
+              z[0] = zigzag32(e4_sub(t.x, sq.x)); z[1] = zigzag32(e4_sub(t.y, sq.y));
+              z[2] = zigzag32(e4_sub(t.z, sq.z)); z[3] = zigzag32(e4_sub(t.w, sq.w));
             }
             e4_store4(dst, z[0], z[1], z[2], z[3]);
             dst += 4;
@@ -853,15 +914,17 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
 #pragma unroll
             for (int b = 0; b < 4; b++) {
               const int4 t = S.cell[cur][4 * a + b][tid];
-              const int qmax = max(max(t.x, t.y), max(t.z, t.w)), qmin = min(min(t.x, t.y), min(t.z, t.w));
+              int qmax, qmin;
+              e4_qmm<FULL>(t, qmax, qmin);
               if (as_snapshot) {
-                zx[b] = zigzag32(n4.x - qmax);
-                zn[b] = zigzag32(qmin - n4.y);
+                zx[b] = zigzag32(e4_sub(n4.x, e4_o0<FULL>(qmax)));
+                zn[b] = zigzag32(e4_sub(qmin, n4.y));
               } else {
                 const int4 sq = S.cell[ref][4 * a + b][tid];
-                const int sqmax = max(max(sq.x, sq.y), max(sq.z, sq.w)), sqmin = min(min(sq.x, sq.y), min(sq.z, sq.w));
-                zx[b] = zigzag32(qmax - sqmax);
-                zn[b] = zigzag32(qmin - sqmin);
+                int sqmax, sqmin;
+                e4_qmm<FULL>(sq, sqmax, sqmin);
+                zx[b] = zigzag32(e4_sub(e4_o0<FULL>(qmax), e4_o0<FULL>(sqmax)));
+                zn[b] = zigzag32(e4_sub(qmin, sqmin));
               }
             }
             e4_store4(dst, zx[0], zx[1], zx[2], zx[3]);
@@ -887,8 +950,8 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
 #pragma unroll
         for (int a = 0; a < 4; a++) {
           const int2 n4 = S.l4[cur][a][tid], s4 = S.l4[ref][a][tid];
-          zx[a] = zigzag32(as_snapshot ? t3max - n4.x : n4.x - s4.x);
-          zn[a] = zigzag32(as_snapshot ? n4.y - t3min : n4.y - s4.y);
+          zx[a] = zigzag32(as_snapshot ? e4_sub(t3max, e4_o0<FULL>(n4.x)) : e4_sub(e4_o0<FULL>(n4.x), e4_o0<FULL>(s4.x)));
+          zn[a] = zigzag32(as_snapshot ? e4_sub(n4.y, t3min) : e4_sub(n4.y, s4.y));
         }
         e4_store4(xb[0] + Pn4 + 4u * R3, zx[0], zx[1], zx[2], zx[3]);
         u8* dmn = nb[0] + Mn4 + R4;
@@ -908,11 +971,11 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
         const u32 bn1 = e4_base_n(T, pre, 1, 3), bn2 = any_hi ? e4_base_n(T, pre, 2, 3) : 0u, bn3 = any_hi ? e4_base_n(T, pre, 3, 3) : 0u;
         if (x3) {
           rx1 = bx1; rx2 = bx2; rx3 = bx3; rn1 = bn1; rn2 = bn2; rn3 = bn3;
-          const u32 zx = zigzag32(as_snapshot ? t2max - t3max : t3max - s3max);
+          const u32 zx = zigzag32(as_snapshot ? e4_sub(t2max, e4_o0<FULL>(t3max)) : e4_sub(e4_o0<FULL>(t3max), e4_o0<FULL>(s3max)));
           xb[0][Pn3 + 4u * R2p + (u32)(tid & 3)] = (u8)zx;
           if (zx > 0xffu) e4_emit_hi(xb[1], xb[2], xb[3], zx, rx1, rx2, rx3);
           if (W.in3) {
-            const u32 zn = zigzag32(as_snapshot ? t3min - t2min : t3min - s3min);
+            const u32 zn = zigzag32(as_snapshot ? e4_sub(t3min, t2min) : e4_sub(t3min, s3min));
             nb[0][Mn3 + R3] = (u8)zn;
             if (zn > 0xffu) e4_emit_hi(nb[1], nb[2], nb[3], zn, rn1, rn2, rn3);
           }
@@ -923,11 +986,11 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
         const u32 bn1 = e4_base_n(T, pre, 1, 2), bn2 = any_hi ? e4_base_n(T, pre, 2, 2) : 0u, bn3 = any_hi ? e4_base_n(T, pre, 3, 2) : 0u;
         if (x2 && owner2) {
           rx1 = bx1; rx2 = bx2; rx3 = bx3; rn1 = bn1; rn2 = bn2; rn3 = bn3;
-          const u32 zx = zigzag32(as_snapshot ? t1max - t2max : t2max - s2max);
+          const u32 zx = zigzag32(as_snapshot ? e4_sub(t1max, e4_o0<FULL>(t2max)) : e4_sub(e4_o0<FULL>(t2max), e4_o0<FULL>(s2max)));
           xb[0][Pn2 + 4u * R1 + (u32)((tid >> 2) & 3)] = (u8)zx;
           if (zx > 0xffu) e4_emit_hi(xb[1], xb[2], xb[3], zx, rx1, rx2, rx3);
           if (W.in2) {
-            const u32 zn = zigzag32(as_snapshot ? t2min - t1min : t2min - s2min);
+            const u32 zn = zigzag32(as_snapshot ? e4_sub(t2min, t1min) : e4_sub(t2min, s2min));
             nb[0][Mn2 + R2own] = (u8)zn;
             if (zn > 0xffu) e4_emit_hi(nb[1], nb[2], nb[3], zn, rn1, rn2, rn3);
           }

@@ -603,7 +603,8 @@ __global__ void k_finalize_phase2(const FinalizeParams P, u32 n_slices) {
     P.stored[u] = can_elide ? 0 : 1;
     if (!can_elide) {
       const bool full = unit.rows == 64 && unit.cols == 64 && unit.lo == 0;
-      const u32 list = (narrow ? 0u : 2u) + (full ? 0u : 1u);
+      u32 list = (narrow ? 0u : 2u) + (full ? 0u : 1u);
+      if (narrow && !full && unit.lo == 0) list = 4u;  // clipped, but still a 64-side tree: k_encode_v4<.., false>
       P.order[(size_t)list * P.order_pitch + atomicAdd(&P.order_counts[list], 1u)] = u;
     }
   }
@@ -860,7 +861,8 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
         P.units[u] = unit;
         P.stored[u] = can_elide ? 0 : 1;
         if (!can_elide) {
-          const u32 list = (narrow ? 0u : 2u) + (full ? 0u : 1u);
+          u32 list = (narrow ? 0u : 2u) + (full ? 0u : 1u);
+          if (narrow && !full && unit.lo == 0) list = 4u;  // clipped, but still a 64-side tree: k_encode_v4<.., false>
           P.order[(size_t)list * P.order_pitch + atomicAdd(&P.order_counts[list], 1u)] = u;
         }
       }
