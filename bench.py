@@ -197,7 +197,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i64", "data": "synthetic",
-        "config": {"workload": "ERA5-shaped 721x1440 f32, 64-instant Superchunk encode [5,6] (bounded sample)", "sample": sample},
+        "config": {"workload": f"ERA5-shaped {GRID[0]}x{GRID[1]} f32, {INSTANTS} hourly instants per GPU, Superchunk encode k2_levels {LEVELS} chunk_size {CHUNK_SIZE} (configs[1])",
+                   "sample": sample, "l2": "n/a (CPU)", "parallelism": f"{workers} host threads, one 64-instant slice each"},
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
