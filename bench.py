@@ -419,7 +419,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": algo / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": algo / (k_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_kind": peak_kind,
                          "frac_of_nominal_8TBps": algo / (k_ms * 1e-3) / 1e9 / 8000.0,
-                         "kernel": "k_encode_v4 (full tiles) with k_encode_tiles (clipped ring) on a second stream; one timed region",
+                         "kernel": "k_encode_v4 (64-side tiles: full on the main stream, clipped on a second stream; k_encode_tiles only for the corner tile with a 32-side tree); one timed region",
                          "traffic_note": "ncu dram bytes of k_encode_v4 per (unit, instant) x full units of this launch (profiles/r1_traffic.json)",
                          "kernel_ms": k_ms, "stats_kernel_ms": sum(stat_ms) / len(stat_ms),
                          "gather_ms": sum(gather_ms) / len(gather_ms), "algorithmic_bytes": int(algo)},

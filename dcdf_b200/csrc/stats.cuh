@@ -198,6 +198,18 @@ __global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams
   InT uneg = (InT)0;                                 // most negative value
   int has = 0, fnn = 0, fng = 0, nonfinite = 0;
 
+  // vec4 path: the next instant's four 128-bit loads are in flight while the current one is reduced
+  uint4 nxt[4];
+  auto fetch4 = [&](int inst) {
+    const InT* p = base + (i64)inst * P.stride_t;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int row = (tid >> 4) + 16 * j;
+      nxt[j] = row < unit.rows ? __ldg(reinterpret_cast<const uint4*>(p + (i64)row * P.stride_r + 4 * (tid & 15))) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  if (vec4) fetch4(0);
+
   for (int i0 = 0; i0 < unit.instants; i0 += STAT_BATCH) {
     const int nb = min(STAT_BATCH, unit.instants - i0);
     for (int bi = 0; bi < nb; bi++) {
@@ -208,10 +220,8 @@ __global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams
         // full 64-column tile with 16-byte aligned rows: four 128-bit loads per thread and instant
         uint4 qv[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int row = (tid >> 4) + 16 * j;
-          qv[j] = row < unit.rows ? __ldg(reinterpret_cast<const uint4*>(p + (i64)row * P.stride_r + 4 * (tid & 15))) : make_uint4(0, 0, 0, 0);
-        }
+        for (int j = 0; j < 4; j++) qv[j] = nxt[j];
+        if (i0 + bi + 1 < unit.instants) fetch4(i0 + bi + 1);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int row = (tid >> 4) + 16 * j;

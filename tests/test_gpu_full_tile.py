@@ -84,6 +84,31 @@ def test_full_tile_int(ctx, kind):
     _check(ctx, data.astype(np.int32))
 
 
+@pytest.mark.parametrize("rows,cols", [(64, 40), (40, 64), (33, 64), (64, 33), (50, 50), (63, 63), (37, 64)])
+def test_clipped_tile_with_64_side_tree(ctx, rows, cols):
+    """Clipped tiles that keep a 64-side tree go through the full-tile encoder with None cells; large values make the
+    entries of cells outside the raster (quad max - 0) two to four bytes long."""
+    rng = np.random.default_rng(rows * 64 + cols)
+    for scale, span in ((1, 50), (3000, 2000), (200_000, 100_000), (2 ** 27, 2 ** 26)):
+        base = scale + rng.integers(0, span, (rows, cols))
+        frames = [base]
+        for i in range(1, 9):
+            f = frames[-1].copy()
+            if i % 4 == 0:
+                f = scale + rng.integers(0, span, (rows, cols))
+            elif i % 4 == 1:
+                f = f + 5
+            else:
+                m = rng.random((rows, cols)) < 0.2
+                f[m] += rng.integers(-span // 4 - 1, span // 4 + 1, m.sum())
+            frames.append(f)
+        data = np.stack(frames).astype(np.int64)
+        _check(ctx, data)
+    f32 = (np.stack(frames) % 4096 / 8.0).astype(np.float32)
+    f32[rng.random(f32.shape) < 0.1] = np.nan
+    _check(ctx, f32, fractional_bits=3)
+
+
 def test_full_tile_uniform_levels(ctx):
     """Uniform and equal sub-trees at every level of the quadtree, including the root."""
     rng = np.random.default_rng(11)
