@@ -170,6 +170,16 @@ template <> DCDF_DEVINL u64 raw64<i64>(i64 v) { return (u64)v; }
 
 constexpr int STAT_BATCH = 32;  // instants whose per-warp partials are kept in smem before one finalisation
 
+// min / max that ignore NaN operands (IEEE minNum / maxNum); integer overloads only keep the templates well formed
+DCDF_DEVINL float stat_fmin(float a, float b) { return fminf(a, b); }
+DCDF_DEVINL float stat_fmax(float a, float b) { return fmaxf(a, b); }
+DCDF_DEVINL double stat_fmin(double a, double b) { return fmin(a, b); }
+DCDF_DEVINL double stat_fmax(double a, double b) { return fmax(a, b); }
+DCDF_DEVINL int32_t stat_fmin(int32_t a, int32_t b) { return a < b ? a : b; }
+DCDF_DEVINL int32_t stat_fmax(int32_t a, int32_t b) { return a > b ? a : b; }
+DCDF_DEVINL i64 stat_fmin(i64 a, i64 b) { return a < b ? a : b; }
+DCDF_DEVINL i64 stat_fmax(i64 a, i64 b) { return a > b ? a : b; }
+
 template <typename InT, bool IS_FLOAT>
 __global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams P) {
   const u32 u = blockIdx.x;
@@ -222,6 +232,7 @@ __global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams
 #pragma unroll
         for (int j = 0; j < 4; j++) qv[j] = nxt[j];
         if (i0 + bi + 1 < unit.instants) fetch4(i0 + bi + 1);
+        bool anynan = false;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int row = (tid >> 4) + 16 * j;
@@ -229,15 +240,14 @@ __global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams
           const u32 wv[4] = {qv[j].x, qv[j].y, qv[j].z, qv[j].w};
 #pragma unroll
           for (int e = 0; e < 4; e++) {
-            const int idx = row * 64 + 4 * (tid & 15) + e;
             const InT v = *reinterpret_cast<const InT*>(&wv[e]);
             if (IS_FLOAT) {
-              const bool isn = v != v;
-              last = isn ? (u32)idx + 1u : last;
-              first = min(first, isn ? 0xffffffffu : (u32)idx);
-              mn = (isn || v > mn) ? mn : v;
-              mx = (isn || v < mx) ? mx : v;
-              uneg = (isn || v > uneg) ? uneg : v;
+              // fmin / fmax skip NaN operands, which is what the reference's comparisons do (mmbuffer.rs:465-499);
+              // the NaN positions are only worked out (below) for warps that saw one
+              anynan = anynan || v != v;
+              mn = stat_fmin(mn, v);
+              mx = stat_fmax(mx, v);
+              uneg = stat_fmin(uneg, v);
               const int fb = FloatBits<InT>::fast(v);
               const bool neg = v < (InT)0;
               fng = max(fng, neg ? fb : 0);
@@ -246,6 +256,26 @@ __global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams
               mn = v < mn ? v : mn;
               mx = v > mx ? v : mx;
             }
+          }
+        }
+        if (IS_FLOAT) {
+          if (__any_sync(0xffffffffu, anynan)) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int row = (tid >> 4) + 16 * j;
+              if (row >= unit.rows) break;
+              const u32 wv[4] = {qv[j].x, qv[j].y, qv[j].z, qv[j].w};
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                const int idx = row * 64 + 4 * (tid & 15) + e;
+                const InT v = *reinterpret_cast<const InT*>(&wv[e]);
+                const bool isn = v != v;
+                last = isn ? (u32)idx + 1u : last;
+                first = min(first, isn ? 0xffffffffu : (u32)idx);
+              }
+            }
+          } else if ((tid >> 4) < unit.rows) {
+            first = (u32)((tid >> 4) * 64 + 4 * (tid & 15));  // no NaN in this warp: the thread's first cell
           }
         }
       } else {
