@@ -41,6 +41,7 @@ struct E4Smem {
   int4 rec1[4];       // level-1 nodes: tmax, tmin, first-cell diff, equal
   int2 ent1[4];       // level-1 log entries: tmax - smax, tmin - smin
   u32 wt[2][2][10];   // [warp][0 = snapshot, 1 = log][STRUCT, a1, b1, c1, a2, b2, c2, a3, b3, c3]
+  u32 hi[2][2];       // [warp][candidate]: words 4..9 are valid (some entry below the level-1 nodes is longer than two bytes)
   u32 bm_off[12], bm_len[12];
   u32 n_bm;
   unsigned long long piece_off;
@@ -69,6 +70,13 @@ DCDF_DEVINL u64 e4_expand16(u32 x) { return ((u64)e4_expand8(x >> 8) << 32) | (u
 
 DCDF_DEVINL u32 e4_bswap(u32 x) { return __byte_perm(x, 0u, 0x0123u); }
 
+// OR without a return value; the staged image lives in shared memory, where the generic atomic is several times slower
+// than the shared-space reduction.
+DCDF_DEVINL void e4_red_or(u32* p, u32 v) {
+  if (__isShared(p)) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+  else atomicOr(p, v);
+}
+
 // OR a run of up to 64 bits (left-aligned in V: the first stream bit is bit 63) into the bit stream that starts
 // at byte `bytes` (any alignment), at stream bit `bitpos`.  Works on the aligned 32-bit containers.
 DCDF_DEVINL void e4_or_run(u8* bytes, u32 bitpos, u64 V) {
@@ -82,9 +90,9 @@ DCDF_DEVINL void e4_or_run(u8* bytes, u32 bitpos, u64 V) {
   const u32 w0 = hi >> s;
   const u32 w1 = __funnelshift_r(lo, hi, s);
   const u32 w2 = __funnelshift_r(0u, lo, s);
-  if (w0) atomicOr(w, e4_bswap(w0));
-  if (w1) atomicOr(w + 1, e4_bswap(w1));
-  if (w2) atomicOr(w + 2, e4_bswap(w2));
+  if (w0) e4_red_or(w, e4_bswap(w0));
+  if (w1) e4_red_or(w + 1, e4_bswap(w1));
+  if (w2) e4_red_or(w + 2, e4_bswap(w2));
 }
 DCDF_DEVINL void e4_or_bits(u8* bytes, u32 bitpos, u32 bits, int n) {  // n <= 32 bits, right-aligned in `bits`
   if (n > 0 && bits) e4_or_run(bytes, bitpos, (u64)bits << (64 - n));
@@ -290,8 +298,15 @@ struct E4Tot {
 };
 DCDF_DEVINL void e4_totals(E4Tot& T, const E4Smem& S, int cand, bool in0, u32 in1m, const int (&e1max)[4], const int (&e1min)[4],
                            int e0max, int e0min) {
+  const bool hi = in0 && (S.hi[0][cand] | S.hi[1][cand]) != 0;
 #pragma unroll
-  for (int i = 0; i < 10; i++) T.tot[i] = in0 ? S.wt[0][cand][i] + S.wt[1][cand][i] : 0u;
+  for (int i = 0; i < 4; i++) T.tot[i] = in0 ? S.wt[0][cand][i] + S.wt[1][cand][i] : 0u;
+#pragma unroll
+  for (int i = 4; i < 10; i++) T.tot[i] = 0u;
+  if (hi) {
+#pragma unroll
+    for (int i = 4; i < 10; i++) T.tot[i] = (S.hi[0][cand] ? S.wt[0][cand][i] : 0u) + (S.hi[1][cand] ? S.wt[1][cand][i] : 0u);
+  }
   T.I0 = in0 ? 1u : 0u;
   T.I1 = in0 ? (u32)__popc(in1m) : 0u;
   const u32 upper = T.I0 + T.I1 + e4_f2(T.tot[0]) + e4_f3(T.tot[0]) + e4_f4(T.tot[0]);
@@ -299,15 +314,22 @@ DCDF_DEVINL void e4_totals(E4Tot& T, const E4Smem& S, int cand, bool in0, u32 in
   T.nm_len = 1u + 4u * upper;
   T.cmax[0] = 1u + 4u * T.n_int;
   T.cmin[0] = T.n_int;
+  // entries of the root and the level-1 nodes
+  bool top_hi = e4_longer<2>(e0max) || e4_longer<2>(e0min);
+#pragma unroll
+  for (int k = 0; k < 4; k++) top_hi = top_hi || e4_longer<2>(e1max[k]) || e4_longer<2>(e1min[k]);
 #pragma unroll
   for (int j = 1; j < 4; j++) {
-    u32 tm = e4_longer_j(e0max, j) ? 1u : 0u, tn = 0;
-    if (in0) {
-      tn = e4_longer_j(e0min, j) ? 1u : 0u;
+    u32 tm = 0, tn = 0;
+    if (j == 1 || hi || top_hi) {
+      tm = e4_longer_j(e0max, j) ? 1u : 0u;
+      if (in0) {
+        tn = e4_longer_j(e0min, j) ? 1u : 0u;
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        tm += e4_longer_j(e1max[k], j) ? 1u : 0u;
-        tn += (((in1m >> (3 - k)) & 1u) && e4_longer_j(e1min[k], j)) ? 1u : 0u;
+        for (int k = 0; k < 4; k++) {
+          tm += e4_longer_j(e1max[k], j) ? 1u : 0u;
+          tn += (((in1m >> (3 - k)) & 1u) && e4_longer_j(e1min[k], j)) ? 1u : 0u;
+        }
       }
     }
     T.cmax[j] = tm + e4_fsum(T.tot[3 * j - 2]) + T.tot[3 * j - 1];
@@ -451,21 +473,24 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
   u32 n_logs = 0, n_snap = 0, n_log_total = 0;
   u64 total_bytes = 0;
 
+  InT nx[16];  // two rows of the block, loaded ahead of their use
+  u32 nxb;
+  e4_fetch_pair<InT, FULL>(base, P.stride_r, P.stride_c, r0, c0, vec, unit.rows, unit.cols, nx, nxb);
+
   for (int inst = 0; inst < unit.instants; inst++) {
     const bool first = inst == 0;
     // ---------------- load + convert (a3): two rows at a time, the next pair in flight while this one is converted
     {
       const InT* pi = base + (i64)inst * P.stride_t;
-      InT nx[16];
-      u32 nxb;
-      e4_fetch_pair<InT, FULL>(pi, P.stride_r, P.stride_c, r0, c0, vec, unit.rows, unit.cols, nx, nxb);
 #pragma unroll 1
       for (int rp = 0; rp < 4; rp++) {
         InT cu[16];
         const u32 cub = nxb;
 #pragma unroll
         for (int i = 0; i < 16; i++) cu[i] = nx[i];
+        // next pair of this instant, or the first pair of the next instant (in flight during the rest of this one)
         if (rp < 3) e4_fetch_pair<InT, FULL>(pi, P.stride_r, P.stride_c, r0 + 2 * (rp + 1), c0, vec, unit.rows, unit.cols, nx, nxb);
+        else if (inst + 1 < unit.instants) e4_fetch_pair<InT, FULL>(pi + P.stride_t, P.stride_r, P.stride_c, r0, c0, vec, unit.rows, unit.cols, nx, nxb);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           int4 v;
@@ -575,10 +600,12 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
       if (lane == 0) S.wt[warp][0][0] = r;
 #pragma unroll
       for (int i = 0; i < 10; i++) {
-        if (i < 4 || hi_l) r = __reduce_add_sync(0xffffffffu, wl[i]);
-        else r = 0;
-        if (lane == 0) S.wt[warp][1][i] = r;
+        if (i < 4 || hi_l) {
+          r = __reduce_add_sync(0xffffffffu, wl[i]);
+          if (lane == 0) S.wt[warp][1][i] = r;
+        }
       }
+      if (lane == 0) S.hi[warp][1] = hi_l ? 1u : 0u;
     }
     if ((lane & 15) == 0) {
       S.rec1[k1] = make_int4(t1max, t1min, diff1, eq1 ? 1 : 0);
@@ -644,10 +671,12 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
       e4_count(C, owner2, ws);
 #pragma unroll
       for (int i = 0; i < 10; i++) {
-        u32 r = 0;
-        if (i < 4 || hi_s) r = __reduce_add_sync(0xffffffffu, ws[i]);
-        if (lane == 0) S.wt[warp][0][i] = r;
+        if (i < 4 || hi_s) {
+          const u32 r = __reduce_add_sync(0xffffffffu, ws[i]);
+          if (lane == 0) S.wt[warp][0][i] = r;
+        }
       }
+      if (lane == 0) S.hi[warp][0] = hi_s ? 1u : 0u;
       __syncthreads();  // B1'
       e4_totals(T, S, 0, s_in0, s_in1, s_e1max, s_e1min, t0max, t0min);
       const u32 snap_size = 13u + bitmap_size(T.nm_len) + e4_dac_size(T.cmax) + e4_dac_size(T.cmin);
@@ -736,7 +765,7 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
 #pragma unroll
     for (int i = 0; i < 10; i++) {
       pre[i] = 0;
-      if (i < 4 || any_hi) pre[i] = e4_warp_excl(as_snapshot ? ws[i] : wl[i], lane) + ((warp == 1 && in0) ? S.wt[0][cand][i] : 0u);
+      if (i < 4 || any_hi) pre[i] = e4_warp_excl(as_snapshot ? ws[i] : wl[i], lane) + ((warp == 1 && in0 && (i < 4 || S.hi[0][cand])) ? S.wt[0][cand][i] : 0u);
     }
     const u32 R2own = e4_f2(pre[0]);                       // internal level-2 nodes before the own group (valid on owner lanes)
     const u32 R2p = e4_f2(shfl(pre[0], lane & ~3));        // the same, seen by every lane of the group
@@ -872,73 +901,66 @@ __global__ void __launch_bounds__(E4_THREADS, MINB) k_encode_v4(const EncParams 
     if (emit) {
       // ================= phase B: DAC bytes =================
       u32 rx1, rx2, rx3, rn1, rn2, rn3;
-      // ---- leaves
-      rx1 = e4_base_x(T, pre, 1, 6); rx2 = any_hi ? e4_base_x(T, pre, 2, 6) : 0u; rx3 = any_hi ? e4_base_x(T, pre, 3, 6) : 0u;
+      // ---- leaves and quads: one pass over the alive level-4 nodes, their four quads side by side (independent
+      // loads and arithmetic; only the rare multi-byte entries keep running positions)
       {
-        u8* dst = xb[0] + Pn6 + 4u * R5;
-#pragma unroll 1
-        for (int q = 0; q < 16; q++) {
-          if ((ai5 >> (15 - q)) & 1u) {
-            const int4 t = S.cell[cur][q][tid];
-            u32 z[4];
-            if (as_snapshot) {
-              const int qmax = max(max(t.x, t.y), max(t.z, t.w));
-              z[0] = zigzag32(e4_sub(qmax, e4_o0<FULL>(t.x))); z[1] = zigzag32(e4_sub(qmax, e4_o0<FULL>(t.y)));
-              z[2] = zigzag32(e4_sub(qmax, e4_o0<FULL>(t.z))); z[3] = zigzag32(e4_sub(qmax, e4_o0<FULL>(t.w)));
-            } else {
-              const int4 sq = S.cell[ref][q][tid];
-              z[0] = zigzag32(e4_sub(t.x, sq.x)); z[1] = zigzag32(e4_sub(t.y, sq.y));
-              z[2] = zigzag32(e4_sub(t.z, sq.z)); z[3] = zigzag32(e4_sub(t.w, sq.w));
-            }
-            e4_store4(dst, z[0], z[1], z[2], z[3]);
-            dst += 4;
-            if ((W.ml[0] >> (4 * (15 - q))) & 0xfull) {
-#pragma unroll
-              for (int c = 0; c < 4; c++)
-                if (z[c] > 0xffu) e4_emit_hi(xb[1], xb[2], xb[3], z[c], rx1, rx2, rx3);
-            }
-          }
-        }
-      }
-      // ---- quads (level 5)
-      rx1 = e4_base_x(T, pre, 1, 5); rx2 = any_hi ? e4_base_x(T, pre, 2, 5) : 0u; rx3 = any_hi ? e4_base_x(T, pre, 3, 5) : 0u;
-      rn1 = e4_base_n(T, pre, 1, 5); rn2 = any_hi ? e4_base_n(T, pre, 2, 5) : 0u; rn3 = any_hi ? e4_base_n(T, pre, 3, 5) : 0u;
-      {
-        u8* dst = xb[0] + Pn5 + 4u * R4;
+        u32 lx1 = e4_base_x(T, pre, 1, 6), lx2 = any_hi ? e4_base_x(T, pre, 2, 6) : 0u, lx3 = any_hi ? e4_base_x(T, pre, 3, 6) : 0u;
+        rx1 = e4_base_x(T, pre, 1, 5); rx2 = any_hi ? e4_base_x(T, pre, 2, 5) : 0u; rx3 = any_hi ? e4_base_x(T, pre, 3, 5) : 0u;
+        rn1 = e4_base_n(T, pre, 1, 5); rn2 = any_hi ? e4_base_n(T, pre, 2, 5) : 0u; rn3 = any_hi ? e4_base_n(T, pre, 3, 5) : 0u;
+        u8* dst6 = xb[0] + Pn6 + 4u * R5;
+        u8* dst5 = xb[0] + Pn5 + 4u * R4;
         u8* dmn = nb[0] + Mn5 + R5;
 #pragma unroll 1
         for (int a = 0; a < 4; a++) {
-          if ((ai4 >> (3 - a)) & 1u) {
-            const int2 n4 = S.l4[cur][a][tid];
-            u32 zx[4], zn[4];
+          if (!((ai4 >> (3 - a)) & 1u)) continue;
+          const int2 n4 = S.l4[cur][a][tid];
+          const u32 in5a = (W.in5 >> (12 - 4 * a)) & 0xfu;
+          const u32 ml16 = (u32)(W.ml[0] >> (48 - 16 * a)) & 0xffffu;
+          u32 zx[4], zn[4], z[4][4];
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const int4 t = S.cell[cur][4 * a + b][tid];
+            int qmax, qmin;
+            e4_qmm<FULL>(t, qmax, qmin);
+            if (as_snapshot) {
+              zx[b] = zigzag32(e4_sub(n4.x, e4_o0<FULL>(qmax)));
+              zn[b] = zigzag32(e4_sub(qmin, n4.y));
+              z[b][0] = zigzag32(e4_sub(qmax, e4_o0<FULL>(t.x))); z[b][1] = zigzag32(e4_sub(qmax, e4_o0<FULL>(t.y)));
+              z[b][2] = zigzag32(e4_sub(qmax, e4_o0<FULL>(t.z))); z[b][3] = zigzag32(e4_sub(qmax, e4_o0<FULL>(t.w)));
+            } else {
+              const int4 sq = S.cell[ref][4 * a + b][tid];
+              int sqmax, sqmin;
+              e4_qmm<FULL>(sq, sqmax, sqmin);
+              zx[b] = zigzag32(e4_sub(e4_o0<FULL>(qmax), e4_o0<FULL>(sqmax)));
+              zn[b] = zigzag32(e4_sub(qmin, sqmin));
+              z[b][0] = zigzag32(e4_sub(t.x, sq.x)); z[b][1] = zigzag32(e4_sub(t.y, sq.y));
+              z[b][2] = zigzag32(e4_sub(t.z, sq.z)); z[b][3] = zigzag32(e4_sub(t.w, sq.w));
+            }
+          }
+          e4_store4(dst5, zx[0], zx[1], zx[2], zx[3]);
+          dst5 += 4;
+#pragma unroll
+          for (int b = 0; b < 4; b++)
+            if ((in5a >> (3 - b)) & 1u) e4_store4(dst6 + 4u * (u32)__popc(in5a >> (4 - b)), z[b][0], z[b][1], z[b][2], z[b][3]);
+          dst6 += 4u * (u32)__popc(in5a);
+          if (ml16) {
 #pragma unroll
             for (int b = 0; b < 4; b++) {
-              const int4 t = S.cell[cur][4 * a + b][tid];
-              int qmax, qmin;
-              e4_qmm<FULL>(t, qmax, qmin);
-              if (as_snapshot) {
-                zx[b] = zigzag32(e4_sub(n4.x, e4_o0<FULL>(qmax)));
-                zn[b] = zigzag32(e4_sub(qmin, n4.y));
-              } else {
-                const int4 sq = S.cell[ref][4 * a + b][tid];
-                int sqmax, sqmin;
-                e4_qmm<FULL>(sq, sqmax, sqmin);
-                zx[b] = zigzag32(e4_sub(e4_o0<FULL>(qmax), e4_o0<FULL>(sqmax)));
-                zn[b] = zigzag32(e4_sub(qmin, sqmin));
+              if (((in5a >> (3 - b)) & 1u) && ((ml16 >> (12 - 4 * b)) & 0xfu)) {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                  if (z[b][c] > 0xffu) e4_emit_hi(xb[1], xb[2], xb[3], z[b][c], lx1, lx2, lx3);
               }
             }
-            e4_store4(dst, zx[0], zx[1], zx[2], zx[3]);
-            dst += 4;
+          }
 #pragma unroll
-            for (int b = 0; b < 4; b++)
-              if (zx[b] > 0xffu) e4_emit_hi(xb[1], xb[2], xb[3], zx[b], rx1, rx2, rx3);
-            const u32 in5a = W.in5 >> (12 - 4 * a);
+          for (int b = 0; b < 4; b++)
+            if (zx[b] > 0xffu) e4_emit_hi(xb[1], xb[2], xb[3], zx[b], rx1, rx2, rx3);
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-              if ((in5a >> (3 - b)) & 1u) {
-                *dmn++ = (u8)zn[b];
-                if (zn[b] > 0xffu) e4_emit_hi(nb[1], nb[2], nb[3], zn[b], rn1, rn2, rn3);
-              }
+          for (int b = 0; b < 4; b++) {
+            if ((in5a >> (3 - b)) & 1u) {
+              *dmn++ = (u8)zn[b];
+              if (zn[b] > 0xffu) e4_emit_hi(nb[1], nb[2], nb[3], zn[b], rn1, rn2, rn3);
             }
           }
         }
