@@ -132,16 +132,27 @@ struct DacFast {
   const u8* bytes0;
   BitsFast more0;
   DacRef slow;
+  bool empty;  // no levels at all: every lookup yields 0 (dac.rs:80-93)
   DCDF_DEVINL i64 get(u32 index) const {
-    if (slow.d->n_levels == 0) return 0;
+    if (empty) return 0;
     if (!more0.get(index)) return unzigzag64((u64)bytes0[index]);
     return slow.get(index);
+  }
+  // Same lookup in the expansion's value type: a one-byte code decodes in 32-bit arithmetic.
+  template <typename V>
+  DCDF_DEVINL V getv(u32 index) const {
+    if (empty) return (V)0;
+    if (!more0.get(index)) {
+      const int b = (int)bytes0[index];
+      return (V)((b >> 1) ^ -(b & 1));
+    }
+    return (V)slow.get(index);
   }
 };
 DCDF_DEVINL DacFast dac_fast(const u8* chunk, const DacDir* d) {
   const u32 len = d->len[0], base = d->base[0];
   const u32 words = base + 8u + 4u * (len / 128u);
-  return DacFast{chunk + words + 4u * ((len + 31u) / 32u), BitsFast{chunk + words}, DacRef{chunk, d}};
+  return DacFast{chunk + words + 4u * ((len + 31u) / 32u), BitsFast{chunk + words}, DacRef{chunk, d}, d->n_levels == 0};
 }
 
 // ------------------------------------------------------------------ directory builder (Chunk::read_from)

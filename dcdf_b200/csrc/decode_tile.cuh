@@ -102,7 +102,7 @@ DCDF_DEVINL void expand_snapshot(const ChunkView& cv, const InstDir& s, int L, T
   const BitsFast nm = bits_fast(cv.chunk, s.nm_len, s.nm_base);
   const DacFast mx = dac_fast(cv.chunk, &s.max);
   if (tid == 0) {
-    S.sval[0] = (V)mx.get(0);
+    S.sval[0] = mx.getv<V>(0);
     S.scb[0] = nm.get(0) ? 1 : 0xffff;
   }
   __syncthreads();
@@ -118,7 +118,7 @@ DCDF_DEVINL void expand_snapshot(const ChunkView& cv, const InstDir& s, int L, T
       bool in = false;
       if (cb != 0xffffu) {
         const u32 idx = cb + (p1 & 3u);
-        v -= (V)mx.get(idx);
+        v -= mx.getv<V>(idx);
         in = has_bits && idx < s.nm_len && nm.get(idx);
       }
       S.sval[o1 + cell_index(p1, L, !has_bits)] = v;
@@ -138,7 +138,7 @@ DCDF_DEVINL void expand_log(const ChunkView& cv, const ChunkView& cv_snap, const
   const BitMapRef nm_rank{cv.chunk, l.nm_len, l.nm_base}, eq{cv.chunk, l.eq_len, l.eq_base};
   const DacFast mx = dac_fast(cv.chunk, &l.max);
   if (tid == 0) {
-    const V d0 = (V)mx.get(0);
+    const V d0 = mx.getv<V>(0);
     const bool single_t = !nm.get(0);
     if (!single_t) {
       S.lmode[0] = 0; S.lpay[0] = d0; S.lcb[0] = 1;
@@ -166,7 +166,7 @@ DCDF_DEVINL void expand_log(const ChunkView& cv, const ChunkView& cv_snap, const
       bool in = false;
       if (mode == 0) {
         const u32 idx = S.lcb[o0 + p] + (p1 & 3u);
-        const V d = (V)mx.get(idx);  // max_t is replaced, not accumulated (log.rs:233)
+        const V d = mx.getv<V>(idx);  // max_t is replaced, not accumulated (log.rs:233)
         in = has_bits && idx < l.nm_len && nm.get(idx);
         if (in) {
           mode = 0; pay = d;
@@ -199,6 +199,13 @@ struct CellOut {
     kind = (raw || Q.encoding == 8) ? 0 : Q.encoding == 4 ? 1 : Q.encoding == 32 ? 2 : 3;
     inv32 = __int_as_float((126 - bits) << 23);                          // 2^-(bits+1)
     inv64 = __longlong_as_double((long long)(1022 - bits) << 52);
+  }
+  // 32-bit values (narrow expansion): the same conversions without 64-bit arithmetic
+  DCDF_DEVINL void put(u64 i, int32_t fixed) const {
+    if (kind == 2) static_cast<float*>(out)[i] = fixed == 0 ? __int_as_float(0x7fc00000) : __int2float_rn(fixed - 1) * inv32;
+    else if (kind == 0) static_cast<i64*>(out)[i] = (i64)fixed;
+    else if (kind == 1) static_cast<int32_t*>(out)[i] = fixed;
+    else static_cast<double*>(out)[i] = fixed == 0 ? __longlong_as_double(0x7ff8000000000000ll) : __int2double_rn(fixed - 1) * inv64;
   }
   DCDF_DEVINL void put(u64 i, i64 fixed) const {
     if (kind == 2) static_cast<float*>(out)[i] = fixed == 0 ? __int_as_float(0x7fc00000) : __ll2float_rn(fixed - 1) * inv32;
@@ -299,7 +306,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_window_tiles(const TileWindowPar
         // rows of the window inside this tile; consecutive threads write consecutive columns
         for (int r = top + (tid / 64); r < bottom; r += DT_THREADS / 64) {
           const int col = left + (tid & 63);
-          if (col < right) co.put(out_index(t, r, col), (i64)S.sval[oL + ((u32)r << L) + (u32)col]);
+          if (col < right) co.put(out_index(t, r, col), S.sval[oL + ((u32)r << L) + (u32)col]);
         }
       } else {
         // fused cell pass: one thread per 2x2 quad (row-major over quads so that a warp writes whole row segments);
@@ -315,16 +322,18 @@ __global__ void __launch_bounds__(DT_THREADS) k_window_tiles(const TileWindowPar
           const u8 mode = S.lmode[oQ + q];
           const V pay = S.lpay[oQ + q];
           const u32 cb = S.lcb[oQ + q];
+          const u64 i00 = out_index(t, r0q, c0q);  // the quad's cells are i00, +1, +W_cols, +W_cols+1
+          const bool inside = r0q >= top && r0q + 1 < bottom && c0q >= left && c0q + 1 < right;
 #pragma unroll
           for (int c = 0; c < 4; c++) {
             const int r = r0q + (c >> 1), col = c0q + (c & 1);
-            if (r < top || r >= bottom || col < left || col >= right) continue;
+            if (!inside && (r < top || r >= bottom || col < left || col >= right)) continue;
             const V sc = S.sval[oL + ((u32)r << L) + (u32)col];
             V v;
             if (mode == 1) v = pay;
             else if (mode == 2) v = pay + sc;
-            else v = (V)mxl.get(cb + (u32)c) + sc;
-            co.put(out_index(t, r, col), (i64)v);
+            else v = mxl.getv<V>(cb + (u32)c) + sc;
+            co.put(i00 + (u64)((c >> 1) ? W_cols : 0) + (u64)(c & 1), v);
           }
         }
       }
