@@ -7,6 +7,7 @@
 #include "decode_tile.cuh"
 #include "decode_tile2.cuh"
 #include "decode_tile3.cuh"
+#include "decode_tile4.cuh"
 #include "host.hpp"
 
 using namespace dcdf;
@@ -396,7 +397,11 @@ void do_window_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
     static const bool walk_v1 = getenv("DCDF_WINDOW_WALK") == nullptr;
     const bool narrow = mb->max_dac_levels <= 3 && getenv("DCDF_WINDOW_WIDE") == nullptr;
     static const bool tiles_v1 = getenv("DCDF_WINDOW_V1") != nullptr;  // first-generation expansion (decode_tile.cuh)
-    if (walk_v1 && !tiles_v1) {
+    static const bool tiles_v3 = getenv("DCDF_WINDOW_V3") != nullptr;  // level-synchronous second generation (decode_tile3.cuh)
+    if (walk_v1 && !tiles_v1 && !tiles_v3) {
+      CK(cudaFuncSetAttribute(k_window_tiles4<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile4Smem<i64>)));
+      CK(cudaFuncSetAttribute(k_window_tiles4<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile4Smem<int32_t>)));
+    } else if (walk_v1 && !tiles_v1) {
       CK(cudaFuncSetAttribute(k_window_tiles3<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile3Smem<i64>)));
       CK(cudaFuncSetAttribute(k_window_tiles3<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile3Smem<int32_t>)));
     } else if (walk_v1) {
@@ -405,7 +410,11 @@ void do_window_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
     }
     tbegin(ctx, KT_WINDOW);
     if (n_jobs) {
-      if (walk_v1 && !tiles_v1) {
+      if (walk_v1 && !tiles_v1 && !tiles_v3) {
+        const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
+        if (narrow) k_window_tiles4<int32_t><<<grid, DT_THREADS, sizeof(Tile4Smem<int32_t>), ctx->stream>>>(TP);
+        else k_window_tiles4<i64><<<grid, DT_THREADS, sizeof(Tile4Smem<i64>), ctx->stream>>>(TP);
+      } else if (walk_v1 && !tiles_v1) {
         const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
         if (narrow) k_window_tiles3<int32_t><<<grid, DT_THREADS, sizeof(Tile3Smem<int32_t>), ctx->stream>>>(TP);
         else k_window_tiles3<i64><<<grid, DT_THREADS, sizeof(Tile3Smem<i64>), ctx->stream>>>(TP);

@@ -1,0 +1,370 @@
+// decode_tile4.cuh -- window decode of whole <=64x64 tiles, barrier-free expansion.
+//
+// Same contract as k_window_tiles / k_window_tiles3 (Snapshot::fill_window snapshot.rs:204-301, Log::fill_window
+// log.rs:311-508, Chunk::fill_window chunk.rs:152-158, Superchunk::fill_window superchunk.rs:402-457).
+//
+// One thread owns one 4x4 block of cells (a node of level L-2) for the whole job.  Per instant it walks from the root to
+// that node the way Snapshot::get / Log::get do (snapshot.rs:165-188, log.rs:207-293: child = 1 + rank(idx) * k^2 + c),
+// then decodes the node's four quads and sixteen cells with 4-entry fetches (decode_tile3.cuh).  Threads of a warp
+// share their ancestors, so the walk's loads are broadcasts; nothing a thread reads was written by another thread
+// (snapshot values of its ancestors and cells are rewritten, identically, by every thread below them), hence no
+// barrier inside an instant.  rank() comes from a per-warp table over the staged nodemap (ones before each 32-bit
+// word + the word itself, MSB first): two shared-memory loads and a popcount instead of the byte-order-dependent walk
+// over the serialized rank directory (bitmap.rs:186-212).  The only block barrier per instant publishes the bytes
+// that cp.async brought in while the previous instant was being decoded.
+#pragma once
+#include "decode_tile3.cuh"
+
+namespace dcdf {
+
+constexpr int W4_TABW = 48;  // nodemap words of a 64x64 tree: ceil(1365 / 32) = 43
+
+struct RankTab {
+  u32 R[W4_TABW];  // ones before word j
+  u32 W[W4_TABW];  // word j, bit i of the stream at position 31 - (i % 32)
+};
+
+template <typename V>
+struct Tile4Smem {
+  static constexpr int BUF = sizeof(V) == 4 ? 10 * 1024 : 16 * 1024;
+  __align__(16) V cells[4096];     // snapshot values of the cells, Morton order (quad q = cells[4q .. 4q+3])
+  __align__(16) V sup[W3_UPPER];   // snapshot max values of the levels above the cells (off3 layout)
+  RankTab tab[DT_WARPS];
+  u32 snap_single, pad_[3];
+  __align__(16) InstDir dir[2];    // directory entries of the staged structures
+  __align__(16) u8 stage[2][BUF + 32];
+};
+
+// Per warp: rank table of the nodemap whose words start at byte pointer `bits` (any alignment).
+DCDF_DEVINL void build_rank(const u8* bits, u32 nm_len, RankTab& T) {
+  const u32 lane = threadIdx.x & 31u;
+  const u32 nw = min((nm_len + 31u) / 32u, (u32)(W4_TABW - 2));
+  const u32 j = 2u * lane;
+  const u32 w0 = j < nw ? load_be32(bits + 4u * j) : 0u;
+  const u32 w1 = j + 1u < nw ? load_be32(bits + 4u * j + 4u) : 0u;
+  const u32 c0 = __popc(w0), s = c0 + __popc(w1);
+  u32 inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 y = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((int)lane >= o) inc += y;
+  }
+  __syncwarp();  // the previous instant's readers of this table are done
+  if (j < (u32)W4_TABW) {
+    T.W[j] = w0; T.R[j] = inc - s;
+    T.W[j + 1u] = w1; T.R[j + 1u] = inc - s + c0;
+  }
+  __syncwarp();
+}
+DCDF_DEVINL u32 tab_word(u32 idx) { return min(idx >> 5, (u32)(W4_TABW - 2)); }
+DCDF_DEVINL u32 tab_rank(const RankTab& T, u32 idx) {  // ones in [0, idx)  (bitmap.rs:186-212)
+  const u32 w = tab_word(idx);
+  return T.R[w] + __popc(T.W[w] & ~(0xffffffffu >> (idx & 31u)));
+}
+DCDF_DEVINL bool tab_bit(const RankTab& T, u32 idx) { return (T.W[tab_word(idx)] >> (31u - (idx & 31u))) & 1u; }
+DCDF_DEVINL u32 tab_bits4(const RankTab& T, u32 idx) {  // bits idx .. idx+3 as a mask, bit c = stream bit idx + c
+  const u32 w = tab_word(idx);
+  return __brev(__funnelshift_l(T.W[w + 1u], T.W[w], idx & 31u)) & 15u;
+}
+
+// Cells of this thread's 4x4 block for one instant, given the state of its level L-2 node: mode 0 internal (r = rank1 of
+// the node, its quads start at BFS index 1 + 4r), 1 uniform (value = pay), 2 equal (value = pay + snapshot cell).
+template <typename V>
+DCDF_DEVINL void block4(const Dac4& mx, const u8* eq, const RankTab& T, u32 nm_len, u32 mode, V pay, u32 r, u32 p, u32 oQ,
+                       const Tile4Smem<V>& S, const QuadOut& O) {
+  const int R0 = 4 * (int)morton_row(p), C0 = 4 * (int)morton_col(p);
+  if (!O.touches(R0, C0, 4)) return;
+  const bool fast = O.vec4 && O.inside(R0, C0, 4);
+  V dq[4] = {0, 0, 0, 0};
+  u32 inb = 0, rq = 0, idx0 = 0, win = 0, e0 = 0;
+  Quad<V> sn;
+#pragma unroll
+  for (int c = 0; c < 4; c++) sn.c[c] = 0;
+  if (mode == 0) {
+    idx0 = 1u + 4u * r;
+    dac_get4<V>(mx, idx0, dq);
+    if (idx0 < nm_len) { inb = tab_bits4(T, idx0); rq = tab_rank(T, idx0); }
+    if (inb != 15u) {
+      sn = *reinterpret_cast<const Quad<V>*>(&S.sup[oQ + 4u * p]);
+      e0 = idx0 - rq;  // rank0(idx + 1) - 1 of the first quad that stops here (log.rs:265)
+      win = eq_window(eq, e0);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    V v[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int c = 2 * h + j;
+      u32 m = mode;
+      V py = pay;
+      const u32 bl = below(inb, c);
+      if (mode == 0 && !((inb >> c) & 1u)) {
+        const bool e = eq_bit(win, e0, (u32)c - bl);
+        m = e ? 2u : 1u;
+        py = e ? dq[c] : dq[c] + sn.c[c];  // uniform: max_t + max_s of the quad (log.rs:266-268)
+      }
+      if (m == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[j][i] = py;
+      } else {
+        const Quad<V> q = reinterpret_cast<const Quad<V>*>(S.cells)[4u * p + (u32)c];
+        if (m == 2) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) v[j][i] = py + q.c[i];
+        } else {
+          V dd[4];
+          dac_get4<V>(mx, 1u + 4u * (rq + bl), dd);  // leaves: max_t + max_s (log.rs:233,246)
+#pragma unroll
+          for (int i = 0; i < 4; i++) v[j][i] = dd[i] + q.c[i];
+        }
+      }
+    }
+    O.put_pair(fast, R0 + 2 * h, C0, v[0], v[1]);
+  }
+}
+
+// Snapshot at `chunk + d.off`: every thread walks to its level L-2 node, writes the snapshot values of its ancestors,
+// of its four quads and of its sixteen cells; with `emit` the cells also go to the window (the instant is the snapshot).
+template <typename V>
+DCDF_DEVINL void snapshot4(const u8* chunk, const InstDir& d, int L, Tile4Smem<V>& S, bool emit, const QuadOut& O) {
+  const u32 p = threadIdx.x;
+  RankTab& T = S.tab[threadIdx.x >> 5];
+  const u32 nm_len = d.nm_len;
+  build_rank(bitmap_bits(chunk, nm_len, d.nm_base), nm_len, T);
+  const Dac4 mx = dac4_of(chunk, &d.max);
+  bool has = T.W[0] >> 31;
+  V val = dac_get1<V>(mx, 0);
+  u32 r = 0;
+  if (p == 0) { S.sup[0] = val; S.snap_single = has ? 0u : 1u; }
+  if (L == 1) {
+    if (p == 0) {
+      V dd[4] = {0, 0, 0, 0};
+      if (has) dac_get4<V>(mx, 1u, dd);
+      Quad<V> q;
+#pragma unroll
+      for (int i = 0; i < 4; i++) q.c[i] = val - dd[i];
+      reinterpret_cast<Quad<V>*>(S.cells)[0] = q;
+      if (emit) O.put(0, 0, q.c);
+    }
+    return;
+  }
+  const int lvp = L - 2;
+  if (p >= (1u << (2 * lvp))) return;
+  for (int k = 1; k <= lvp; k++) {
+    const u32 pk = p >> (2 * (lvp - k));
+    if (has) {
+      const u32 cidx = 1u + 4u * r + (pk & 3u);
+      val -= dac_get1<V>(mx, cidx);  // snapshot.rs:179
+      has = cidx < nm_len && tab_bit(T, cidx);
+      if (has) r = tab_rank(T, cidx);
+    }
+    S.sup[off3(k) + pk] = val;
+  }
+  V dq[4] = {0, 0, 0, 0};
+  u32 inb = 0, rq = 0;
+  if (has) {
+    const u32 idx0 = 1u + 4u * r;
+    dac_get4<V>(mx, idx0, dq);
+    if (idx0 < nm_len) { inb = tab_bits4(T, idx0); rq = tab_rank(T, idx0); }
+  }
+  Quad<V> qv;
+#pragma unroll
+  for (int c = 0; c < 4; c++) qv.c[c] = val - dq[c];
+  *reinterpret_cast<Quad<V>*>(&S.sup[off3(L - 1) + 4u * p]) = qv;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    V dd[4] = {0, 0, 0, 0};
+    if ((inb >> c) & 1u) dac_get4<V>(mx, 1u + 4u * (rq + below(inb, c)), dd);
+    Quad<V> q;
+#pragma unroll
+    for (int i = 0; i < 4; i++) q.c[i] = qv.c[c] - dd[i];
+    reinterpret_cast<Quad<V>*>(S.cells)[4u * p + (u32)c] = q;
+  }
+  if (emit) block4<V>(mx, chunk, T, nm_len, 2u, (V)0, 0u, p, off3(L - 1), S, O);  // "equal to the snapshot, offset 0"
+}
+
+// Log at `chunk + d.off` against the snapshot pyramid in S: walk to the level L-2 node, then the block's cells.
+template <typename V>
+DCDF_DEVINL void log4(const u8* chunk, const InstDir& d, int L, Tile4Smem<V>& S, const QuadOut& O) {
+  const u32 p = threadIdx.x;
+  RankTab& T = S.tab[threadIdx.x >> 5];
+  const u32 nm_len = d.nm_len;
+  build_rank(bitmap_bits(chunk, nm_len, d.nm_base), nm_len, T);
+  const u8* eq = bitmap_bits(chunk, d.eq_len, d.eq_base);
+  const Dac4 mx = dac4_of(chunk, &d.max);
+  u32 mode = 0, r = 0;
+  V pay = dac_get1<V>(mx, 0);
+  if (!(T.W[0] >> 31)) {
+    // log.rs:180-186: a single-node log is uniform unless its equal bit says "snapshot + constant"
+    const bool uniform = S.snap_single || !bit_at(eq, 0);
+    mode = uniform ? 1u : 2u;
+    if (uniform) pay += S.sup[0];
+  }
+  if (L == 1) {
+    if (p == 0) {
+      const Quad<V> q = reinterpret_cast<const Quad<V>*>(S.cells)[0];
+      V v[4], dd[4] = {0, 0, 0, 0};
+      if (mode == 0) dac_get4<V>(mx, 1u, dd);
+#pragma unroll
+      for (int i = 0; i < 4; i++) v[i] = mode == 1 ? pay : mode == 2 ? pay + q.c[i] : dd[i] + q.c[i];
+      O.put(0, 0, v);
+    }
+    return;
+  }
+  const int lvp = L - 2;
+  if (p >= (1u << (2 * lvp))) return;
+  for (int k = 1; k <= lvp; k++) {
+    if (mode == 0) {
+      const u32 pk = p >> (2 * (lvp - k));
+      const u32 cidx = 1u + 4u * r + (pk & 3u);
+      pay = dac_get1<V>(mx, cidx);  // max_t is replaced, not accumulated (log.rs:233)
+      const bool known = cidx < nm_len;
+      const u32 rc = known ? tab_rank(T, cidx) : 0u;
+      if (known && tab_bit(T, cidx)) {
+        r = rc;
+      } else {
+        const bool e = bit_at(eq, cidx - rc);  // rank0(idx + 1) - 1 (log.rs:265)
+        mode = e ? 2u : 1u;
+        if (!e) pay += S.sup[off3(k) + pk];    // uniform: max_t + max_s of this node (log.rs:266-268)
+      }
+    }
+  }
+  block4<V>(mx, eq, T, nm_len, mode, pay, r, p, off3(L - 1), S, O);
+}
+
+template <typename V>
+DCDF_DEVINL void instant4(const u8* chunk, const InstDir& d, bool is_snap, int L, Tile4Smem<V>& S, const QuadOut& O) {
+  if (is_snap) snapshot4<V>(chunk, d, L, S, true, O);
+  else log4<V>(chunk, d, L, S, O);
+}
+template <typename V>
+__device__ __noinline__ void instant4_global(const u8* chunk, const InstDir* d, bool is_snap, int L, Tile4Smem<V>* S, const QuadOut* O) {
+  instant4<V>(chunk, *d, is_snap, L, *S, *O);
+}
+template <typename V>
+__device__ __noinline__ void snapshot4_global(const u8* chunk, const InstDir* d, int L, Tile4Smem<V>* S, const QuadOut* O) {
+  snapshot4<V>(chunk, *d, L, *S, false, *O);
+}
+
+// Start the copy of a structure and of its directory entry into staging half b.
+template <typename V>
+DCDF_DEVINL void prefetch4(const u8* chunk, const InstDir* dg, u32 off, u32 size, Tile4Smem<V>& S, int b) {
+  const int tid = threadIdx.x;
+  if (tid < W3_DIRW) cp_async4(reinterpret_cast<u32*>(&S.dir[b]) + tid, reinterpret_cast<const u32*>(dg) + tid);
+  const u8* src = chunk + off;
+  const u32 mis = (u32)((uintptr_t)src & 15u);
+  if (size + mis + 4u > (u32)Tile4Smem<V>::BUF + 32u) return;
+  const u8* g = src - mis;
+  const u32 n16 = (size + mis + 4u + 15u) / 16u;  // +4: a few bytes past the end may be read
+  for (u32 i = tid; i < n16; i += DT_THREADS) cp_async16(S.stage[b] + 16u * i, g + 16u * i);
+}
+template <typename V>
+DCDF_DEVINL bool staged4(const u8* chunk, const InstDir& d, u32& delta) {
+  const u32 mis = (u32)((uintptr_t)(chunk + d.off) & 15u);
+  delta = mis - d.off;
+  return d.size + mis + 4u <= (u32)Tile4Smem<V>::BUF + 32u;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_window_tiles4(const TileWindowParams P) {
+  extern __shared__ __align__(16) unsigned char dt4_smem_raw[];
+  Tile4Smem<V>& S = *reinterpret_cast<Tile4Smem<V>*>(dt4_smem_raw);
+  const QuerySet& Q = P.Q;
+  const int tid = threadIdx.x;
+  for (u64 ji = blockIdx.x; ji < P.n_jobs; ji += gridDim.x) {
+    u64 lo_q = 0, hi_q = P.n_queries;
+    while (hi_q - lo_q > 1) {
+      const u64 mid = (lo_q + hi_q) >> 1;
+      if (P.job_base[mid] <= ji) lo_q = mid; else hi_q = mid;
+    }
+    const u64 q = lo_q;
+    const CubeDev c = P.cubes[q];
+    const u64 local = ji - P.job_base[q];
+    const i64 cs = Q.chunks_sidelen;
+    const i64 cr0 = c.top / cs, cc0 = c.left / cs;
+    const i64 ncr = (c.bottom - 1) / cs - cr0 + 1, ncc = (c.right - 1) / cs - cc0 + 1;
+    const u64 nsub = (u64)(ncr * ncc);
+    const u32 s = (u32)(c.start / Q.chunk_size) + (u32)(local / nsub);
+    const u64 sub = local % nsub;
+    const i64 cr = cr0 + (i64)(sub / (u64)ncc), cc = cc0 + (i64)(sub % (u64)ncc);
+    const SliceMeta sm = Q.slices[s];
+    const i64 t_lo = max(c.start, sm.t0), t_hi = min(c.end, sm.t0 + (i64)sm.instants);
+    const i64 chunk_top = cr * cs, chunk_left = cc * cs;
+    const i64 W_rows = c.bottom - c.top, W_cols = c.right - c.left;
+    const u64 obase = P.out_off[q];
+    const u32 slot = (u32)(cr * Q.subsidelen + cc);
+    const int32_t u = Q.slot_unit[sm.slot_base + slot];
+    const UnitMeta m = u >= 0 ? Q.units[u] : UnitMeta{};
+    const bool stored = u >= 0 && m.stored;
+    const i64 tile_org = (chunk_top - c.top) * W_cols + (chunk_left - c.left);  // element offset of tile cell (0, 0)
+    QuadOut O;
+    O.co.init(Q, P.out, P.raw, m.bits);
+    O.pitch = W_cols;
+    O.top = (int)(max(chunk_top, c.top) - chunk_top); O.bottom = (int)(min(chunk_top + cs, c.bottom) - chunk_top);
+    O.left = (int)(max(chunk_left, c.left) - chunk_left); O.right = (int)(min(chunk_left + cs, c.right) - chunk_left);
+    O.vec = O.co.kind == 2 && !(W_cols & 1) && !((obase + (u64)tile_org) & 1ull) && !((uintptr_t)P.out & 7u);
+    O.vec4 = O.co.kind == 2 && !(W_cols & 3) && !((obase + (u64)tile_org) & 3ull) && !((uintptr_t)P.out & 15u);
+    O.base = 0;
+    if (!stored) {
+      // Elided: one value per instant from the max table, parent's fractional bits (superchunk.rs:426-433)
+      const SlotDesc sdsc = Q.slot_desc[sm.slot_base + slot];
+      const int wr = O.bottom - O.top, wc = O.right - O.left;
+      for (i64 t = t_lo; t < t_hi; t++) {
+        const i64 v = Q.tbl_max[sdsc.tbl0 + (u64)(t - sm.t0) * sdsc.stride];
+        const u64 tb = obase + (u64)((t - c.start) * W_rows * W_cols + tile_org);
+        for (int i = tid; i < wr * wc; i += DT_THREADS)
+          emit(Q, P.out, tb + (u64)((i64)(O.top + i / wc) * W_cols + (O.left + i % wc)), v, sdsc.bits, P.raw);
+      }
+      continue;
+    }
+    const u8* chunk = Q.blob + m.blob_off;
+    const InstDir* dir = Q.dir + m.dir_base;
+    const int L = 31 - __clz(m.sidelen);
+    if (t_hi <= t_lo) continue;
+    const u32 ti0 = (u32)(t_lo - sm.t0), n_t = (u32)(t_hi - t_lo);
+    __syncthreads();  // the previous job's readers are done with the staging buffers
+    const u32 snap0 = dir[ti0].snap;
+    if (snap0 != ti0) {
+      // the window starts inside a block: expand the block's snapshot first
+      prefetch4<V>(chunk, dir + snap0, dir[snap0].off, dir[snap0].size, S, 1);
+      cp_async_wait_all();
+      __syncthreads();
+      u32 delta;
+      if (staged4<V>(chunk, S.dir[1], delta)) {
+        snapshot4<V>(S.stage[1] + (int32_t)delta, S.dir[1], L, S, false, O);
+      } else {
+        const QuadOut O2 = O;
+        snapshot4_global<V>(chunk, &S.dir[1], L, &S, &O2);
+      }
+      __syncthreads();
+    }
+    prefetch4<V>(chunk, dir + ti0, dir[ti0].off, dir[ti0].size, S, 0);
+    u32 noff = 0, nsize = 0;  // offset and size of the structure after the one being processed
+    if (n_t > 1) { noff = dir[ti0 + 1].off; nsize = dir[ti0 + 1].size; }
+    const u64 t_stride = (u64)(W_rows * W_cols);
+    u64 tbase = obase + (u64)((t_lo - c.start) * W_rows * W_cols + tile_org);
+    for (u32 i = 0; i < n_t; i++, tbase += t_stride) {
+      const int b = (int)(i & 1u);
+      const u32 ti = ti0 + i;
+      cp_async_wait_all();
+      __syncthreads();  // structure i has landed; everyone is done with instant i-1 (the other half can be overwritten)
+      if (i + 1 < n_t) {
+        prefetch4<V>(chunk, dir + ti + 1, noff, nsize, S, b ^ 1);
+        if (i + 2 < n_t) { noff = dir[ti + 2].off; nsize = dir[ti + 2].size; }
+      }
+      O.base = tbase;
+      const InstDir& D = S.dir[b];
+      const bool is_snap = D.snap == ti;
+      u32 delta;
+      if (staged4<V>(chunk, D, delta)) {
+        instant4<V>(S.stage[b] + (int32_t)delta, D, is_snap, L, S, O);
+      } else {
+        const QuadOut O2 = O;  // only the copy has its address taken
+        instant4_global<V>(chunk, &D, is_snap, L, &S, &O2);
+      }
+    }
+  }
+}
+
+}  // namespace dcdf
