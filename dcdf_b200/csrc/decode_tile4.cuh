@@ -31,7 +31,7 @@ struct Tile4Smem {
   __align__(16) V sup[W3_UPPER];   // snapshot max values of the levels above the cells (off3 layout)
   RankTab tab[DT_WARPS];
   u32 snap_single, pad_[3];
-  __align__(16) InstDir dir[2];    // directory entries of the staged structures
+  __align__(16) InstDir dir[3];    // ring of directory entries: instant i in dir[i % 3], fetched two instants ahead
   __align__(16) u8 stage[2][BUF + 32];
 };
 
@@ -40,8 +40,17 @@ DCDF_DEVINL void build_rank(const u8* bits, u32 nm_len, RankTab& T) {
   const u32 lane = threadIdx.x & 31u;
   const u32 nw = min((nm_len + 31u) / 32u, (u32)(W4_TABW - 2));
   const u32 j = 2u * lane;
-  const u32 w0 = j < nw ? load_be32(bits + 4u * j) : 0u;
-  const u32 w1 = j + 1u < nw ? load_be32(bits + 4u * j + 4u) : 0u;
+  // big-endian words at any byte alignment from three aligned loads (the misalignment is the same for every word)
+  const uintptr_t a = (uintptr_t)bits + 8u * lane;
+  const u32* al = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+  const u32 mis = (u32)(a & 3u);
+  const u32 sel = (mis + 3u) | ((mis + 2u) << 4) | ((mis + 1u) << 8) | (mis << 12);
+  u32 w0 = 0, w1 = 0;
+  if (j < nw) {
+    const u32 x0 = al[0], x1 = al[1], x2 = al[2];  // x2 may lie past the bitmap, inside the staged structure
+    w0 = __byte_perm(x0, x1, sel);
+    if (j + 1u < nw) w1 = __byte_perm(x1, x2, sel);
+  }
   const u32 c0 = __popc(w0), s = c0 + __popc(w1);
   u32 inc = s;
 #pragma unroll
@@ -249,9 +258,13 @@ __device__ __noinline__ void snapshot4_global(const u8* chunk, const InstDir* d,
 
 // Start the copy of a structure and of its directory entry into staging half b.
 template <typename V>
-DCDF_DEVINL void prefetch4(const u8* chunk, const InstDir* dg, u32 off, u32 size, Tile4Smem<V>& S, int b) {
+DCDF_DEVINL void prefetch_dir4(const InstDir* dg, Tile4Smem<V>& S, u32 slot) {
   const int tid = threadIdx.x;
-  if (tid < W3_DIRW) cp_async4(reinterpret_cast<u32*>(&S.dir[b]) + tid, reinterpret_cast<const u32*>(dg) + tid);
+  if (tid < W3_DIRW) cp_async4(reinterpret_cast<u32*>(&S.dir[slot]) + tid, reinterpret_cast<const u32*>(dg) + tid);
+}
+template <typename V>
+DCDF_DEVINL void prefetch4(const u8* chunk, u32 off, u32 size, Tile4Smem<V>& S, int b) {
+  const int tid = threadIdx.x;
   const u8* src = chunk + off;
   const u32 mis = (u32)((uintptr_t)src & 15u);
   if (size + mis + 4u > (u32)Tile4Smem<V>::BUF + 32u) return;
@@ -327,34 +340,38 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_window_t
     const u32 snap0 = dir[ti0].snap;
     if (snap0 != ti0) {
       // the window starts inside a block: expand the block's snapshot first
-      prefetch4<V>(chunk, dir + snap0, dir[snap0].off, dir[snap0].size, S, 1);
+      prefetch_dir4<V>(dir + snap0, S, 2);
+      prefetch4<V>(chunk, dir[snap0].off, dir[snap0].size, S, 1);
       cp_async_wait_all();
       __syncthreads();
       u32 delta;
-      if (staged4<V>(chunk, S.dir[1], delta)) {
-        snapshot4<V>(S.stage[1] + (int32_t)delta, S.dir[1], L, S, false, O);
+      if (staged4<V>(chunk, S.dir[2], delta)) {
+        snapshot4<V>(S.stage[1] + (int32_t)delta, S.dir[2], L, S, false, O);
       } else {
         const QuadOut O2 = O;
-        snapshot4_global<V>(chunk, &S.dir[1], L, &S, &O2);
+        snapshot4_global<V>(chunk, &S.dir[2], L, &S, &O2);
       }
       __syncthreads();
     }
-    prefetch4<V>(chunk, dir + ti0, dir[ti0].off, dir[ti0].size, S, 0);
-    u32 noff = 0, nsize = 0;  // offset and size of the structure after the one being processed
-    if (n_t > 1) { noff = dir[ti0 + 1].off; nsize = dir[ti0 + 1].size; }
+    prefetch_dir4<V>(dir + ti0, S, 0);
+    prefetch4<V>(chunk, dir[ti0].off, dir[ti0].size, S, 0);
+    if (n_t > 1) prefetch_dir4<V>(dir + ti0 + 1, S, 1);
     const u64 t_stride = (u64)(W_rows * W_cols);
     u64 tbase = obase + (u64)((t_lo - c.start) * W_rows * W_cols + tile_org);
+    u32 rs = 0;  // i % 3
     for (u32 i = 0; i < n_t; i++, tbase += t_stride) {
       const int b = (int)(i & 1u);
       const u32 ti = ti0 + i;
+      const u32 slot1 = rs == 2 ? 0u : rs + 1u, slot2 = slot1 == 2 ? 0u : slot1 + 1u;
       cp_async_wait_all();
-      __syncthreads();  // structure i has landed; everyone is done with instant i-1 (the other half can be overwritten)
+      __syncthreads();  // structure i and directory entry i+1 have landed; everyone is done with instant i-1
       if (i + 1 < n_t) {
-        prefetch4<V>(chunk, dir + ti + 1, noff, nsize, S, b ^ 1);
-        if (i + 2 < n_t) { noff = dir[ti + 2].off; nsize = dir[ti + 2].size; }
+        prefetch4<V>(chunk, S.dir[slot1].off, S.dir[slot1].size, S, b ^ 1);
+        if (i + 2 < n_t) prefetch_dir4<V>(dir + ti + 2, S, slot2);
       }
       O.base = tbase;
-      const InstDir& D = S.dir[b];
+      const InstDir& D = S.dir[rs];
+      rs = slot1;
       const bool is_snap = D.snap == ti;
       u32 delta;
       if (staged4<V>(chunk, D, delta)) {
