@@ -8,6 +8,7 @@
 #include "decode_tile2.cuh"
 #include "decode_tile3.cuh"
 #include "decode_tile4.cuh"
+#include "decode_tile5.cuh"
 #include "host.hpp"
 
 using namespace dcdf;
@@ -398,7 +399,14 @@ void do_window_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
     const bool narrow = mb->max_dac_levels <= 3 && getenv("DCDF_WINDOW_WIDE") == nullptr;
     static const bool tiles_v1 = getenv("DCDF_WINDOW_V1") != nullptr;  // first-generation expansion (decode_tile.cuh)
     static const bool tiles_v3 = getenv("DCDF_WINDOW_V3") != nullptr;  // level-synchronous second generation (decode_tile3.cuh)
-    if (walk_v1 && !tiles_v1 && !tiles_v3) {
+    // default: per-thread walk with one block barrier per instant (decode_tile4.cuh).  DCDF_WINDOW_V5=1: the same walk behind a
+    // TMA bulk-copy / mbarrier ring (decode_tile5.cuh) -- bit-exact, measured slower (the elected producer thread's warp
+    // paces every other warp), kept as an experiment
+    static const bool tiles_v4 = getenv("DCDF_WINDOW_V5") == nullptr;
+    if (walk_v1 && !tiles_v1 && !tiles_v3 && !tiles_v4) {
+      CK(cudaFuncSetAttribute(k_window_tiles5<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile5Smem<i64>)));
+      CK(cudaFuncSetAttribute(k_window_tiles5<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile5Smem<int32_t>)));
+    } else if (walk_v1 && !tiles_v1 && !tiles_v3) {
       CK(cudaFuncSetAttribute(k_window_tiles4<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile4Smem<i64>)));
       CK(cudaFuncSetAttribute(k_window_tiles4<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile4Smem<int32_t>)));
     } else if (walk_v1 && !tiles_v1) {
@@ -410,7 +418,11 @@ void do_window_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
     }
     tbegin(ctx, KT_WINDOW);
     if (n_jobs) {
-      if (walk_v1 && !tiles_v1 && !tiles_v3) {
+      if (walk_v1 && !tiles_v1 && !tiles_v3 && !tiles_v4) {
+        const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
+        if (narrow) k_window_tiles5<int32_t><<<grid, DT_THREADS, sizeof(Tile5Smem<int32_t>), ctx->stream>>>(TP);
+        else k_window_tiles5<i64><<<grid, DT_THREADS, sizeof(Tile5Smem<i64>), ctx->stream>>>(TP);
+      } else if (walk_v1 && !tiles_v1 && !tiles_v3) {
         const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
         if (narrow) k_window_tiles4<int32_t><<<grid, DT_THREADS, sizeof(Tile4Smem<int32_t>), ctx->stream>>>(TP);
         else k_window_tiles4<i64><<<grid, DT_THREADS, sizeof(Tile4Smem<i64>), ctx->stream>>>(TP);

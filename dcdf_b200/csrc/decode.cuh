@@ -19,14 +19,16 @@ struct DacDir {
   u32 len[8];   // entries on level j
   u32 base[8];  // byte offset (from chunk start) of level j's BitMap
 };
-struct InstDir {
+struct alignas(16) InstDir {  // 176 bytes: one entry is a 16-byte aligned bulk copy
   u32 off;      // structure start (from chunk start)
   u32 size;     // serialized bytes of the structure
   u32 snap;     // directory index (within the chunk) of the block's Snapshot; == own index for snapshots
   u32 nm_len, nm_base;
   u32 eq_len, eq_base;  // logs only (eq_base == 0 for snapshots)
   DacDir max, min;
+  u32 pad_[3];
 };
+static_assert(sizeof(InstDir) == 176, "InstDir is copied with 16-byte bulk copies");
 struct UnitMeta {
   u64 blob_off;   // chunk start inside the blob
   u64 size;       // chunk bytes
@@ -221,6 +223,7 @@ __global__ void k_build_dir(const DirParams P) {
     const u32 snap_idx = inst;
     for (u32 i = 0; i < n_inst && c.ok; i++) {
       InstDir d;
+      d.pad_[0] = d.pad_[1] = d.pad_[2] = 0;
       d.off = (u32)c.pos;
       d.snap = snap_idx;
       const u32 k = c.u8_();

@@ -27,10 +27,12 @@ struct RankTab {
 template <typename V>
 struct Tile4Smem {
   static constexpr int BUF = sizeof(V) == 4 ? 10 * 1024 : 16 * 1024;
+  static constexpr bool PRIVATE_TOP = false;  // one block barrier per instant: warps share levels 0 and 1 of `sup`
   __align__(16) V cells[4096];     // snapshot values of the cells, Morton order (quad q = cells[4q .. 4q+3])
   __align__(16) V sup[W3_UPPER];   // snapshot max values of the levels above the cells (off3 layout)
   RankTab tab[DT_WARPS];
-  u32 snap_single, pad_[3];
+  V suptop[DT_WARPS][8];           // per-warp copies of the snapshot values of levels 0 and 1 (nodes shared between warps)
+  u32 single[DT_WARPS];            // per warp: the block's snapshot is a single node
   __align__(16) InstDir dir[3];    // ring of directory entries: instant i in dir[i % 3], fetched two instants ahead
   __align__(16) u8 stage[2][BUF + 32];
 };
@@ -76,11 +78,22 @@ DCDF_DEVINL u32 tab_bits4(const RankTab& T, u32 idx) {  // bits idx .. idx+3 as 
   return __brev(__funnelshift_l(T.W[w + 1u], T.W[w], idx & 31u)) & 15u;
 }
 
+// Snapshot value of node pk of level k: levels 0 and 1 are shared between warps, every warp keeps its own copy so that
+// no warp ever reads what another one wrote (k_window_tiles5 lets warps drift apart by more than one instant).
+template <typename S_>
+DCDF_DEVINL auto& sup_at(S_& S, int k, u32 pk) {
+  if (!S_::PRIVATE_TOP) return S.sup[off3(k) + pk];
+  const u32 warp = threadIdx.x >> 5;
+  return k <= 1 ? S.suptop[warp][k ? 1u + (pk & 3u) : 0u] : S.sup[off3(k) + pk];
+}
+template <typename S_>
+DCDF_DEVINL u32 top_slot() { return S_::PRIVATE_TOP ? threadIdx.x >> 5 : 0u; }
+
 // Cells of this thread's 4x4 block for one instant, given the state of its level L-2 node: mode 0 internal (r = rank1 of
 // the node, its quads start at BFS index 1 + 4r), 1 uniform (value = pay), 2 equal (value = pay + snapshot cell).
-template <typename V>
+template <typename V, typename S_>
 DCDF_DEVINL void block4(const Dac4& mx, const u8* eq, const RankTab& T, u32 nm_len, u32 mode, V pay, u32 r, u32 p, u32 oQ,
-                       const Tile4Smem<V>& S, const QuadOut& O) {
+                       const S_& S, const QuadOut& O) {
   const int R0 = 4 * (int)morton_row(p), C0 = 4 * (int)morton_col(p);
   if (!O.touches(R0, C0, 4)) return;
   const bool fast = O.vec4 && O.inside(R0, C0, 4);
@@ -135,8 +148,8 @@ DCDF_DEVINL void block4(const Dac4& mx, const u8* eq, const RankTab& T, u32 nm_l
 
 // Snapshot at `chunk + d.off`: every thread walks to its level L-2 node, writes the snapshot values of its ancestors,
 // of its four quads and of its sixteen cells; with `emit` the cells also go to the window (the instant is the snapshot).
-template <typename V>
-DCDF_DEVINL void snapshot4(const u8* chunk, const InstDir& d, int L, Tile4Smem<V>& S, bool emit, const QuadOut& O) {
+template <typename V, typename S_>
+DCDF_DEVINL void snapshot4(const u8* chunk, const InstDir& d, int L, S_& S, bool emit, const QuadOut& O) {
   const u32 p = threadIdx.x;
   RankTab& T = S.tab[threadIdx.x >> 5];
   const u32 nm_len = d.nm_len;
@@ -145,7 +158,7 @@ DCDF_DEVINL void snapshot4(const u8* chunk, const InstDir& d, int L, Tile4Smem<V
   bool has = T.W[0] >> 31;
   V val = dac_get1<V>(mx, 0);
   u32 r = 0;
-  if (p == 0) { S.sup[0] = val; S.snap_single = has ? 0u : 1u; }
+  if (S_::PRIVATE_TOP ? (p & 31u) == 0 : p == 0) { sup_at(S, 0, 0) = val; S.single[top_slot<S_>()] = has ? 0u : 1u; }
   if (L == 1) {
     if (p == 0) {
       V dd[4] = {0, 0, 0, 0};
@@ -168,7 +181,7 @@ DCDF_DEVINL void snapshot4(const u8* chunk, const InstDir& d, int L, Tile4Smem<V
       has = cidx < nm_len && tab_bit(T, cidx);
       if (has) r = tab_rank(T, cidx);
     }
-    S.sup[off3(k) + pk] = val;
+    sup_at(S, k, pk) = val;
   }
   V dq[4] = {0, 0, 0, 0};
   u32 inb = 0, rq = 0;
@@ -190,12 +203,12 @@ DCDF_DEVINL void snapshot4(const u8* chunk, const InstDir& d, int L, Tile4Smem<V
     for (int i = 0; i < 4; i++) q.c[i] = qv.c[c] - dd[i];
     reinterpret_cast<Quad<V>*>(S.cells)[4u * p + (u32)c] = q;
   }
-  if (emit) block4<V>(mx, chunk, T, nm_len, 2u, (V)0, 0u, p, off3(L - 1), S, O);  // "equal to the snapshot, offset 0"
+  if (emit) block4<V, S_>(mx, chunk, T, nm_len, 2u, (V)0, 0u, p, off3(L - 1), S, O);  // "equal to the snapshot, offset 0"
 }
 
 // Log at `chunk + d.off` against the snapshot pyramid in S: walk to the level L-2 node, then the block's cells.
-template <typename V>
-DCDF_DEVINL void log4(const u8* chunk, const InstDir& d, int L, Tile4Smem<V>& S, const QuadOut& O) {
+template <typename V, typename S_>
+DCDF_DEVINL void log4(const u8* chunk, const InstDir& d, int L, S_& S, const QuadOut& O) {
   const u32 p = threadIdx.x;
   RankTab& T = S.tab[threadIdx.x >> 5];
   const u32 nm_len = d.nm_len;
@@ -206,9 +219,9 @@ DCDF_DEVINL void log4(const u8* chunk, const InstDir& d, int L, Tile4Smem<V>& S,
   V pay = dac_get1<V>(mx, 0);
   if (!(T.W[0] >> 31)) {
     // log.rs:180-186: a single-node log is uniform unless its equal bit says "snapshot + constant"
-    const bool uniform = S.snap_single || !bit_at(eq, 0);
+    const bool uniform = S.single[top_slot<S_>()] || !bit_at(eq, 0);
     mode = uniform ? 1u : 2u;
-    if (uniform) pay += S.sup[0];
+    if (uniform) pay += sup_at(S, 0, 0);
   }
   if (L == 1) {
     if (p == 0) {
@@ -235,25 +248,21 @@ DCDF_DEVINL void log4(const u8* chunk, const InstDir& d, int L, Tile4Smem<V>& S,
       } else {
         const bool e = bit_at(eq, cidx - rc);  // rank0(idx + 1) - 1 (log.rs:265)
         mode = e ? 2u : 1u;
-        if (!e) pay += S.sup[off3(k) + pk];    // uniform: max_t + max_s of this node (log.rs:266-268)
+        if (!e) pay += sup_at(S, k, pk);       // uniform: max_t + max_s of this node (log.rs:266-268)
       }
     }
   }
-  block4<V>(mx, eq, T, nm_len, mode, pay, r, p, off3(L - 1), S, O);
+  block4<V, S_>(mx, eq, T, nm_len, mode, pay, r, p, off3(L - 1), S, O);
 }
 
-template <typename V>
-DCDF_DEVINL void instant4(const u8* chunk, const InstDir& d, bool is_snap, int L, Tile4Smem<V>& S, const QuadOut& O) {
-  if (is_snap) snapshot4<V>(chunk, d, L, S, true, O);
-  else log4<V>(chunk, d, L, S, O);
+template <typename V, typename S_>
+DCDF_DEVINL void instant4(const u8* chunk, const InstDir& d, bool is_snap, bool emit, int L, S_& S, const QuadOut& O) {
+  if (is_snap) snapshot4<V, S_>(chunk, d, L, S, emit, O);
+  else log4<V, S_>(chunk, d, L, S, O);
 }
-template <typename V>
-__device__ __noinline__ void instant4_global(const u8* chunk, const InstDir* d, bool is_snap, int L, Tile4Smem<V>* S, const QuadOut* O) {
-  instant4<V>(chunk, *d, is_snap, L, *S, *O);
-}
-template <typename V>
-__device__ __noinline__ void snapshot4_global(const u8* chunk, const InstDir* d, int L, Tile4Smem<V>* S, const QuadOut* O) {
-  snapshot4<V>(chunk, *d, L, *S, false, *O);
+template <typename V, typename S_>
+__device__ __noinline__ void instant4_global(const u8* chunk, const InstDir* d, bool is_snap, bool emit, int L, S_* S, const QuadOut* O) {
+  instant4<V, S_>(chunk, *d, is_snap, emit, L, *S, *O);
 }
 
 // Start the copy of a structure and of its directory entry into staging half b.
@@ -346,10 +355,10 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_window_t
       __syncthreads();
       u32 delta;
       if (staged4<V>(chunk, S.dir[2], delta)) {
-        snapshot4<V>(S.stage[1] + (int32_t)delta, S.dir[2], L, S, false, O);
+        instant4<V, Tile4Smem<V>>(S.stage[1] + (int32_t)delta, S.dir[2], true, false, L, S, O);
       } else {
         const QuadOut O2 = O;
-        snapshot4_global<V>(chunk, &S.dir[2], L, &S, &O2);
+        instant4_global<V, Tile4Smem<V>>(chunk, &S.dir[2], true, false, L, &S, &O2);
       }
       __syncthreads();
     }
@@ -375,10 +384,10 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_window_t
       const bool is_snap = D.snap == ti;
       u32 delta;
       if (staged4<V>(chunk, D, delta)) {
-        instant4<V>(S.stage[b] + (int32_t)delta, D, is_snap, L, S, O);
+        instant4<V, Tile4Smem<V>>(S.stage[b] + (int32_t)delta, D, is_snap, true, L, S, O);
       } else {
         const QuadOut O2 = O;  // only the copy has its address taken
-        instant4_global<V>(chunk, &D, is_snap, L, &S, &O2);
+        instant4_global<V, Tile4Smem<V>>(chunk, &D, is_snap, true, L, &S, &O2);
       }
     }
   }
