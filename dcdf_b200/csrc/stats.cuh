@@ -99,6 +99,35 @@ struct FloatBits<double> {
   }
 };
 
+// Running maximum of FloatBits::fast over the values fed to add().  For f32 the per-value work avoids the bit scan:
+// the lowest set bit of |v| as a float is |v| - (|v| with that mantissa bit cleared) -- exact, a power of two
+// 2^(E' - 150 + tz(M)) -- and the most fractional bits belong to the smallest such power.
+// Bit patterns of positive floats order like the values, so one unsigned min over (bits - 1) keeps it; zeros wrap to
+// 0xffffffff and inf / NaN stay above every finite value, so none of them needs a branch.
+template <typename T>
+struct FracAcc {
+  int fb = 0;
+  DCDF_DEVINL void add(T v) { fb = max(fb, FloatBits<T>::fast(v)); }
+  DCDF_DEVINL int result() const { return fb; }
+};
+template <>
+struct FracAcc<float> {
+  u32 acc = 0xffffffffu;
+  DCDF_DEVINL void add(float v) {
+    const u32 b = __float_as_uint(v) & 0x7fffffffu;
+    const u32 c = (b & 0x7fffffu) ? (b & (b - 1u)) : 0u;  // mantissa field != 0: b - 1 only borrows inside it
+    const float l = __uint_as_float(b) - __uint_as_float(c);
+    acc = min(acc, __float_as_uint(l) - 1u);
+  }
+  DCDF_DEVINL int result() const {
+    const u32 lb = acc + 1u;                   // bits of the smallest lowest-set-bit value: 2^e
+    if (lb == 0u || lb >= 0x7f800000u) return 0;  // nothing finite and non-zero
+    const int E = (int)(lb >> 23);
+    const int e = E ? E - 127 : (31 - __clz((int)(lb & 0x7fffffu))) - 149;
+    return e < 0 ? -e : 0;
+  }
+};
+
 // whole_bits = 1 + (floor(log2(max)) as usize)  (fixed.rs:126; `as` saturates: NaN / negatives -> 0)
 DCDF_DEVINL int whole_bits_of(double vmax) {
   if (!(vmax > 0.0)) return 1;
@@ -207,6 +236,7 @@ __global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams
   InT umax = Lim<InT>::lo(), umin = Lim<InT>::hi();  // unit extrema over non-NaN values
   InT uneg = (InT)0;                                 // most negative value
   int has = 0, fnn = 0, fng = 0, nonfinite = 0;
+  FracAcc<InT> facc;  // fractional bits: only max(frac_nonneg, frac_neg) is ever used, so one accumulator serves both
 
   // vec4 path: the next instant's four 128-bit loads are in flight while the current one is reduced
   uint4 nxt[4];
@@ -233,6 +263,7 @@ __global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams
         for (int j = 0; j < 4; j++) qv[j] = nxt[j];
         if (i0 + bi + 1 < unit.instants) fetch4(i0 + bi + 1);
         bool anynan = false;
+        u32 nanacc = 0;  // f32: largest |bits| seen; a NaN is anything above the infinity pattern
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int row = (tid >> 4) + 16 * j;
@@ -243,15 +274,13 @@ __global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams
             const InT v = *reinterpret_cast<const InT*>(&wv[e]);
             if (IS_FLOAT) {
               // fmin / fmax skip NaN operands, which is what the reference's comparisons do (mmbuffer.rs:465-499);
-              // the NaN positions are only worked out (below) for warps that saw one
-              anynan = anynan || v != v;
+              // the NaN positions are only worked out (below) for warps that saw one; the most negative value of the
+              // unit follows from the per-instant minima
+              if (sizeof(InT) == 4) nanacc = max(nanacc, wv[e] & 0x7fffffffu);
+              else anynan = anynan || v != v;
               mn = stat_fmin(mn, v);
               mx = stat_fmax(mx, v);
-              uneg = stat_fmin(uneg, v);
-              const int fb = FloatBits<InT>::fast(v);
-              const bool neg = v < (InT)0;
-              fng = max(fng, neg ? fb : 0);
-              fnn = max(fnn, neg ? 0 : fb);
+              facc.add(v);
             } else {
               mn = v < mn ? v : mn;
               mx = v > mx ? v : mx;
@@ -259,6 +288,7 @@ __global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams
           }
         }
         if (IS_FLOAT) {
+          if (sizeof(InT) == 4) anynan = nanacc > 0x7f800000u;
           if (__any_sync(0xffffffffu, anynan)) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -304,11 +334,7 @@ __global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams
               first = min(first, isn ? 0xffffffffu : (u32)idx);
               mn = (isn || v > mn) ? mn : v;
               mx = (isn || v < mx) ? mx : v;
-              uneg = (isn || v > uneg) ? uneg : v;
-              const int fb = FloatBits<InT>::fast(v);
-              const bool neg = v < (InT)0;
-              fng = max(fng, neg ? fb : 0);
-              fnn = max(fnn, neg ? 0 : fb);
+              facc.add(v);
             } else {
               mn = v < mn ? v : mn;
               mx = v > mx ? v : mx;
@@ -336,6 +362,7 @@ __global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams
         if (first != 0xffffffffu) {
           has = 1;
           umax = mx > umax ? mx : umax;
+          uneg = mn < uneg ? mn : uneg;  // most negative value of the unit (mn skips NaN)
           if (mx - mx != (InT)0 || mn - mn != (InT)0) nonfinite = 1;  // +-inf among the extrema
         }
       } else {
@@ -351,6 +378,7 @@ __global__ void __launch_bounds__(STAT_THREADS, 3) k_unit_stats(const StatParams
 
   // unit-level reductions of the thread-local accumulators
   umax = warp_max(umax); umin = warp_min(umin); uneg = warp_min(uneg);
+  fnn = facc.result();
   for (int o = 16; o > 0; o >>= 1) {
     fnn = max(fnn, __shfl_xor_sync(0xffffffffu, fnn, o));
     fng = max(fng, __shfl_xor_sync(0xffffffffu, fng, o));
