@@ -284,11 +284,18 @@ def run_ours(args):
         ok = bool(torch.equal(out[:tspan], data[:tspan]))
         cells = tspan * rows * cols
         s_in = s_out * tspan / T
+        dtraffic = None
+        try:  # DRAM bytes per decoded cell of k_window_tiles4 from the committed ncu capture, scaled to this launch
+            dtraffic = json.load(open(os.path.join(ROOT, "profiles", "r1_decode_traffic.json")))["dram_bytes_per_cell"] * cells
+        except Exception:
+            pass
         dec = {"metric": "window_decode_cells_per_s", "value": _sum_over_ranks(cells, world, dev) / (_max_over_ranks(dms, world, dev) * 1e-3),
                "unit": "cells/s", "ms": dms, "cells": cells, "round_trip_equal": ok,
                "roofline": {"bound": "hbm", "achieved": (s_in + 4 * cells) / (dms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                            "frac": (s_in + 4 * cells) / (dms * 1e-3) / 1e9 / peak, "traffic": None,
-                            "kernel_ms": ctx.last_kernel_ms(_ffi.KT_WINDOW)}}
+                            "frac": (s_in + 4 * cells) / (dms * 1e-3) / 1e9 / peak, "traffic": dtraffic,
+                            "frac_of_nominal_8TBps": (s_in + 4 * cells) / (dms * 1e-3) / 1e9 / 8000.0,
+                            "kernel": "k_window_tiles4<int> (one launch: every 64x64 tile of 8 slices, f32 output resident in HBM)",
+                            "algorithmic_bytes": int(s_in + 4 * cells), "kernel_ms": ctx.last_kernel_ms(_ffi.KT_WINDOW)}}
         del out
     except Exception as e:  # decode is the second half of the metric; never hide an encode number behind it
         dec = {"error": str(e)}

@@ -511,9 +511,12 @@ void do_search_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
   k_pick_u64<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(d_offsets, d_jb, n + 1, d_pick);
   CK(cudaGetLastError());
   ctx->launches += 3;
+  tend(ctx, KT_SEARCH);  // the timer covers the kernels of both passes, not the host round trip / output allocation between them
   std::vector<u64> pick(n + 1);
   CK(cudaMemcpyAsync(pick.data(), d_pick, sizeof(u64) * (n + 1), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  tcollect(ctx, KT_SEARCH);
+  const float ms_count = ctx->kernel_ms[KT_SEARCH];
   const u64 total = pick[n];
   if (n_found) *n_found = total;
   if (counts) for (uint64_t i = 0; i < n; i++) counts[i] = pick[i + 1] - pick[i];
@@ -522,16 +525,15 @@ void do_search_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
     OutTarget ot = out_begin(ctx, out_irc, sizeof(i64) * 3 * total, mem);
     SP.out = static_cast<i64*>(ot.dev);
     SP.cap = total;
+    tbegin(ctx, KT_SEARCH);
     k_search<<<grid, 128, 0, st>>>(SP, 1);
     CK(cudaGetLastError());
     ctx->launches++;
     tend(ctx, KT_SEARCH);
     out_end(ctx, ot);
-  } else {
-    tend(ctx, KT_SEARCH);
-    CK(cudaStreamSynchronize(st));
+    tcollect(ctx, KT_SEARCH);
+    ctx->kernel_ms[KT_SEARCH] += ms_count;
   }
-  tcollect(ctx, KT_SEARCH);
 }
 
 }  // namespace
