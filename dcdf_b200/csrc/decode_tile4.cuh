@@ -92,7 +92,7 @@ DCDF_DEVINL u32 top_slot() { return S_::PRIVATE_TOP ? threadIdx.x >> 5 : 0u; }
 // Cells of this thread's 4x4 block for one instant, given the state of its level L-2 node: mode 0 internal (r = rank1 of
 // the node, its quads start at BFS index 1 + 4r), 1 uniform (value = pay), 2 equal (value = pay + snapshot cell).
 template <typename V, typename S_>
-DCDF_DEVINL void block4(const Dac4& mx, const u8* eq, const RankTab& T, u32 nm_len, u32 mode, V pay, u32 r, u32 p, u32 oQ,
+DCDF_DEVINL void block4(const Dac4& mx, const u8* eq, u32 eq_len, const RankTab& T, u32 nm_len, u32 mode, V pay, u32 r, u32 p, u32 oQ,
                        const S_& S, const QuadOut& O) {
   const int R0 = 4 * (int)morton_row(p), C0 = 4 * (int)morton_col(p);
   if (!O.touches(R0, C0, 4)) return;
@@ -109,7 +109,7 @@ DCDF_DEVINL void block4(const Dac4& mx, const u8* eq, const RankTab& T, u32 nm_l
     if (inb != 15u) {
       sn = *reinterpret_cast<const Quad<V>*>(&S.sup[oQ + 4u * p]);
       e0 = idx0 - rq;  // rank0(idx + 1) - 1 of the first quad that stops here (log.rs:265)
-      win = eq_window(eq, e0);
+      win = e0 < eq_len ? eq_window(eq, e0) : 0u;  // malformed input guard: a bit past the bitmap reads as 0
     }
   }
 #pragma unroll
@@ -122,7 +122,7 @@ DCDF_DEVINL void block4(const Dac4& mx, const u8* eq, const RankTab& T, u32 nm_l
       V py = pay;
       const u32 bl = below(inb, c);
       if (mode == 0 && !((inb >> c) & 1u)) {
-        const bool e = eq_bit(win, e0, (u32)c - bl);
+        const bool e = e0 + ((u32)c - bl) < eq_len && eq_bit(win, e0, (u32)c - bl);
         m = e ? 2u : 1u;
         py = e ? dq[c] : dq[c] + sn.c[c];  // uniform: max_t + max_s of the quad (log.rs:266-268)
       }
@@ -203,7 +203,7 @@ DCDF_DEVINL void snapshot4(const u8* chunk, const InstDir& d, int L, S_& S, bool
     for (int i = 0; i < 4; i++) q.c[i] = qv.c[c] - dd[i];
     reinterpret_cast<Quad<V>*>(S.cells)[4u * p + (u32)c] = q;
   }
-  if (emit) block4<V, S_>(mx, chunk, T, nm_len, 2u, (V)0, 0u, p, off3(L - 1), S, O);  // "equal to the snapshot, offset 0"
+  if (emit) block4<V, S_>(mx, chunk, 0u, T, nm_len, 2u, (V)0, 0u, p, off3(L - 1), S, O);  // "equal to the snapshot, offset 0"
 }
 
 // Log at `chunk + d.off` against the snapshot pyramid in S: walk to the level L-2 node, then the block's cells.
@@ -246,13 +246,13 @@ DCDF_DEVINL void log4(const u8* chunk, const InstDir& d, int L, S_& S, const Qua
       if (known && tab_bit(T, cidx)) {
         r = rc;
       } else {
-        const bool e = bit_at(eq, cidx - rc);  // rank0(idx + 1) - 1 (log.rs:265)
+        const bool e = cidx - rc < d.eq_len && bit_at(eq, cidx - rc);  // rank0(idx + 1) - 1 (log.rs:265)
         mode = e ? 2u : 1u;
         if (!e) pay += sup_at(S, k, pk);       // uniform: max_t + max_s of this node (log.rs:266-268)
       }
     }
   }
-  block4<V, S_>(mx, eq, T, nm_len, mode, pay, r, p, off3(L - 1), S, O);
+  block4<V, S_>(mx, eq, d.eq_len, T, nm_len, mode, pay, r, p, off3(L - 1), S, O);
 }
 
 template <typename V, typename S_>
