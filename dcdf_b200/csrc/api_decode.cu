@@ -9,6 +9,7 @@
 #include "decode_tile3.cuh"
 #include "decode_tile4.cuh"
 #include "decode_tile5.cuh"
+#include "decode_search4.cuh"
 #include "host.hpp"
 
 using namespace dcdf;
@@ -503,8 +504,46 @@ void do_search_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
   SP.counts = d_counts; SP.offsets = d_offsets;
   SP.out = nullptr; SP.cap = 0;
   const unsigned grid = (unsigned)((n_jobs + 127) / 128);
+  // default for trees up to 64x64: one CTA per (window, time slice, subchunk) with the per-thread walk (decode_search4.cuh);
+  // DCDF_SEARCH_V1=1: one thread per (window, subchunk, instant) replaying the depth-first traversal (k_search)
+  static const bool search_v1 = getenv("DCDF_SEARCH_V1") != nullptr;
+  const bool tiles = mb->max_sidelen <= 64 && !search_v1;
+  const bool narrow = mb->max_dac_levels <= 3 && getenv("DCDF_WINDOW_WIDE") == nullptr;
+  TileSearchParams TS;
+  unsigned tgrid = 0;
+  if (tiles) {
+    std::vector<u64> tile_base(n + 1);
+    u64 n_tiles = 0;
+    for (uint64_t i = 0; i < n; i++) {
+      const CubeDev& c = cubes[i];
+      tile_base[i] = n_tiles;
+      if (c.end > c.start && c.bottom > c.top && c.right > c.left) {
+        const u64 nsub = (u64)((c.bottom - 1) / cs - c.top / cs + 1) * (u64)((c.right - 1) / cs - c.left / cs + 1);
+        const u64 nsl = (u64)((c.end - 1) / mb->Q.chunk_size - c.start / mb->Q.chunk_size + 1);
+        n_tiles += nsub * nsl;
+      }
+    }
+    tile_base[n] = n_tiles;
+    ctx->query_aux2.reserve(sizeof(u64) * (n + 1));
+    CK(cudaMemcpyAsync(ctx->query_aux2.p, tile_base.data(), sizeof(u64) * (n + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // tile_base is a local
+    TS.Q = mb->Q; TS.cubes = d_c; TS.job_base = d_jb; TS.tile_base = ctx->query_aux2.as<u64>();
+    TS.n_queries = n; TS.n_tiles = n_tiles; TS.lower = d_lo; TS.upper = d_hi;
+    TS.counts = d_counts; TS.offsets = d_offsets; TS.out = nullptr; TS.cap = 0;
+    tgrid = (unsigned)std::min<u64>(n_tiles, (u64)ctx->sm_count * 64);
+    CK(cudaFuncSetAttribute(k_search_tiles4<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Search4Smem<i64>)));
+    CK(cudaFuncSetAttribute(k_search_tiles4<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Search4Smem<int32_t>)));
+  }
+  auto launch_search = [&](int write) {
+    if (tiles) {
+      if (narrow) k_search_tiles4<int32_t><<<tgrid, DT_THREADS, sizeof(Search4Smem<int32_t>), st>>>(TS);
+      else k_search_tiles4<i64><<<tgrid, DT_THREADS, sizeof(Search4Smem<i64>), st>>>(TS);
+    } else {
+      k_search<<<grid, 128, 0, st>>>(SP, write);
+    }
+  };
   tbegin(ctx, KT_SEARCH);
-  k_search<<<grid, 128, 0, st>>>(SP, 0);
+  launch_search(0);
   CK(cudaGetLastError());
   k_scan_u64<<<1, 1024, 0, st>>>(d_counts, n_jobs, d_offsets);
   CK(cudaGetLastError());
@@ -525,8 +564,9 @@ void do_search_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
     OutTarget ot = out_begin(ctx, out_irc, sizeof(i64) * 3 * total, mem);
     SP.out = static_cast<i64*>(ot.dev);
     SP.cap = total;
+    TS.out = SP.out; TS.cap = total;
     tbegin(ctx, KT_SEARCH);
-    k_search<<<grid, 128, 0, st>>>(SP, 1);
+    launch_search(1);
     CK(cudaGetLastError());
     ctx->launches++;
     tend(ctx, KT_SEARCH);

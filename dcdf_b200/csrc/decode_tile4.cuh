@@ -266,17 +266,17 @@ __device__ __noinline__ void instant4_global(const u8* chunk, const InstDir* d, 
 }
 
 // Start the copy of a structure and of its directory entry into staging half b.
-template <typename V>
-DCDF_DEVINL void prefetch_dir4(const InstDir* dg, Tile4Smem<V>& S, u32 slot) {
+template <typename V, typename S_>
+DCDF_DEVINL void prefetch_dir4(const InstDir* dg, S_& S, u32 slot) {
   const int tid = threadIdx.x;
   if (tid < W3_DIRW) cp_async4(reinterpret_cast<u32*>(&S.dir[slot]) + tid, reinterpret_cast<const u32*>(dg) + tid);
 }
-template <typename V>
-DCDF_DEVINL void prefetch4(const u8* chunk, u32 off, u32 size, Tile4Smem<V>& S, int b) {
+template <typename V, typename S_>
+DCDF_DEVINL void prefetch4(const u8* chunk, u32 off, u32 size, S_& S, int b) {
   const int tid = threadIdx.x;
   const u8* src = chunk + off;
   const u32 mis = (u32)((uintptr_t)src & 15u);
-  if (size + mis + 4u > (u32)Tile4Smem<V>::BUF + 32u) return;
+  if (size + mis + 4u > (u32)S_::BUF + 32u) return;
   const u8* g = src - mis;
   const u32 n16 = (size + mis + 4u + 15u) / 16u;  // +4: a few bytes past the end may be read
   for (u32 i = tid; i < n16; i += DT_THREADS) cp_async16(S.stage[b] + 16u * i, g + 16u * i);
@@ -349,8 +349,8 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_window_t
     const u32 snap0 = dir[ti0].snap;
     if (snap0 != ti0) {
       // the window starts inside a block: expand the block's snapshot first
-      prefetch_dir4<V>(dir + snap0, S, 2);
-      prefetch4<V>(chunk, dir[snap0].off, dir[snap0].size, S, 1);
+      prefetch_dir4<V, Tile4Smem<V>>(dir + snap0, S, 2);
+      prefetch4<V, Tile4Smem<V>>(chunk, dir[snap0].off, dir[snap0].size, S, 1);
       cp_async_wait_all();
       __syncthreads();
       u32 delta;
@@ -362,9 +362,9 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_window_t
       }
       __syncthreads();
     }
-    prefetch_dir4<V>(dir + ti0, S, 0);
-    prefetch4<V>(chunk, dir[ti0].off, dir[ti0].size, S, 0);
-    if (n_t > 1) prefetch_dir4<V>(dir + ti0 + 1, S, 1);
+    prefetch_dir4<V, Tile4Smem<V>>(dir + ti0, S, 0);
+    prefetch4<V, Tile4Smem<V>>(chunk, dir[ti0].off, dir[ti0].size, S, 0);
+    if (n_t > 1) prefetch_dir4<V, Tile4Smem<V>>(dir + ti0 + 1, S, 1);
     const u64 t_stride = (u64)(W_rows * W_cols);
     u64 tbase = obase + (u64)((t_lo - c.start) * W_rows * W_cols + tile_org);
     u32 rs = 0;  // i % 3
@@ -375,8 +375,8 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_window_t
       cp_async_wait_all();
       __syncthreads();  // structure i and directory entry i+1 have landed; everyone is done with instant i-1
       if (i + 1 < n_t) {
-        prefetch4<V>(chunk, S.dir[slot1].off, S.dir[slot1].size, S, b ^ 1);
-        if (i + 2 < n_t) prefetch_dir4<V>(dir + ti + 2, S, slot2);
+        prefetch4<V, Tile4Smem<V>>(chunk, S.dir[slot1].off, S.dir[slot1].size, S, b ^ 1);
+        if (i + 2 < n_t) prefetch_dir4<V, Tile4Smem<V>>(dir + ti + 2, S, slot2);
       }
       O.base = tbase;
       const InstDir& D = S.dir[rs];

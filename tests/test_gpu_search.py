@@ -1,0 +1,116 @@
+"""GPU parity tests of the tile search kernel (k_search_tiles4, decode_search4.cuh) through the C-ABI: result cells AND
+their order must equal the reference traversal (Snapshot::search_window snapshot.rs:310-421, Log::search_window
+log.rs:519-702, Chunk::iter_search chunk.rs:213-228) as restated by the oracle.  The rasters have large uniform areas,
+areas that equal the snapshot plus a constant, smooth gradients (whole sub-trees inside the band: the reference then
+pushes a node's rectangle row-major) and per-cell noise, on 64x64 tiles, clipped tiles and small trees."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+from test_gpu_window import _field
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from dcdf_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _bands(fixed, rng, n):
+    lo, hi = int(fixed.min()), int(fixed.max())
+    out = [(lo, hi), (lo - 5, lo - 1), (hi + 1, hi + 9), (int(np.median(fixed)), int(np.median(fixed)))]
+    for _ in range(n):
+        a, b = sorted(int(x) for x in rng.integers(lo - 3, hi + 4, 2))
+        out.append((a, b))
+        c = int(rng.integers(lo, hi + 1))
+        out.append((c, c + int(rng.integers(0, max(2, (hi - lo) // 6)))))
+    return out
+
+
+@pytest.mark.parametrize("rows,cols,kind", [(64, 64, "float"), (64, 64, "int"), (50, 64, "float"), (64, 37, "int"), (32, 32, "float"),
+                                            (17, 9, "int"), (8, 8, "float"), (4, 4, "int"), (3, 2, "int"), (2, 2, "int")])
+def test_chunk_search_order_exact(ctx, rows, cols, kind):
+    from dcdf_b200 import Chunk
+    T = 12
+    rng = np.random.default_rng(rows * 1000 + cols)
+    if kind == "float":
+        data = _field(T, rows, cols, 77 + rows + cols, nan_frac=0.04 if rows * cols > 16 else 0.0, flat=rows >= 8)
+        got, ref = Chunk.build(ctx, data, fractional_bits=4), orc.chunk_build(data, fractional_bits=4)
+    else:
+        y, x = np.mgrid[0:rows, 0:cols]
+        data = np.stack([(100 + 2 * y + x + 3 * t + (rng.integers(-2, 3, (rows, cols)) * (rng.random((rows, cols)) < 0.3))) for t in range(T)]).astype(np.int32)
+        data[:, : rows // 2, : cols // 2] = 250                      # uniform quadrant
+        data[5] = data[4] + 11                                       # a whole instant "equal + constant"
+        data[7] = 999                                                # a single-node instant
+        data[8] = 999                                                # single-node log over a single-node snapshot (or its log)
+        got, ref = Chunk.build(ctx, data), orc.chunk_build(data)
+    assert got.write_to() == ref.serialize()
+    fixed = ref.window(0, T, 0, rows, 0, cols)
+    wins = [(0, T, 0, rows, 0, cols), (1, T - 1, rows // 4, rows, 0, max(1, cols - 1)), (3, 9, 0, max(1, rows // 2 + 1), cols // 3, cols),
+            (T - 1, T, rows - 1, rows, cols - 1, cols)]
+    for (a, b, t, bo, l, r) in wins:
+        for lo, hi in _bands(fixed, rng, 6):
+            g = got.search(a, b, t, bo, l, r, lo, hi)
+            o = ref.search(a, b, t, bo, l, r, lo, hi)
+            assert np.array_equal(g, o), f"window {(a, b, t, bo, l, r)} band {(lo, hi)}: {len(g)} vs {len(o)} cells or order differs"
+
+
+def test_superchunk_search_batch_against_oracle_chunks(ctx):
+    """Per (window, subchunk) the cells of one instant come out in the chunk's traversal order; subchunks row-major,
+    instants ascending inside a subchunk (decode.cuh: job order)."""
+    from dcdf_b200 import Superchunk
+    T, R, C = 10, 150, 140
+    data = _field(T, R, C, 4, nan_frac=0.03)
+    data[:, 64:128, 0:64] = 2.25                                     # an elided subchunk
+    sc = Superchunk.build(ctx, data, [2, 6], chunk_size=4)
+    bits = sc.info(0).fractional_bits
+    cubes = [[0, T, 0, R, 0, C], [1, 9, 30, 131, 20, 139], [3, 4, 64, 128, 0, 64], [2, 10, 100, 150, 100, 140]]
+    rng = np.random.default_rng(3)
+    for lo_f, hi_f in [(2.25, 2.25), (240.0, 251.0), (0.0, 1000.0), (247.0, 247.5)]:
+        lo, hi = orc.to_fixed(lo_f, bits, False, np.float32), orc.to_fixed(hi_f, bits, False, np.float32)
+        counts, cells = sc.search_batch(cubes, lo, hi)
+        pos = 0
+        for c, n in zip(cubes, counts):
+            mine = cells[pos:pos + int(n)]
+            pos += int(n)
+            want = []
+            for cr in range(c[2] // 64, (c[3] - 1) // 64 + 1):
+                for cc in range(c[4] // 64, (c[5] - 1) // 64 + 1):
+                    tile = np.ascontiguousarray(data[:, cr * 64:min(cr * 64 + 64, R), cc * 64:min(cc * 64 + 64, C)])
+                    t_, b_ = max(c[2], cr * 64) - cr * 64, min(c[3], cr * 64 + 64) - cr * 64
+                    l_, r_ = max(c[4], cc * 64) - cc * 64, min(c[5], cc * 64 + 64) - cc * 64
+                    for s0 in range(0, T, 4):                          # one Chunk per time slice
+                        a, b = max(c[0], s0), min(c[1], s0 + 4)
+                        if a >= b:
+                            continue
+                        ref = orc.chunk_build(np.ascontiguousarray(tile[s0:s0 + 4]), fractional_bits=bits)
+                        hits = ref.search(a - s0, b - s0, t_, b_, l_, r_, lo, hi)
+                        want += [(int(t) + s0, int(r) + cr * 64, int(cl) + cc * 64) for t, r, cl in hits]
+            assert [tuple(x) for x in mine.tolist()] == want, f"cube {c} band {(lo_f, hi_f)}"
+    sc.close()
+
+
+def test_depth_first_search_kernel_stays_bit_exact():
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
+        "import oracle_lib as orc, test_gpu_window as t\n"
+        "from dcdf_b200 import Context, Chunk\n"
+        "ctx = Context(0)\n"
+        "data = t._field(9, 64, 50, 5, nan_frac=0.04)\n"
+        "got, ref = Chunk.build(ctx, data, fractional_bits=4), orc.chunk_build(data, fractional_bits=4)\n"
+        "for lo, hi in ((7900, 8000), (0, 0), (7000, 9000)):\n"
+        "    assert np.array_equal(got.search(1, 9, 3, 60, 2, 49, lo, hi), ref.search(1, 9, 3, 60, 2, 49, lo, hi))\n"
+        "print('ok')\n"
+    )
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, "DCDF_SEARCH_V1": "1"}, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
