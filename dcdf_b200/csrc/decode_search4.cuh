@@ -38,6 +38,8 @@ struct SearchJob {
   i64 lower, upper;
   int top, bottom, left, right;  // window clipped to the tile, tile coordinates, exclusive ends
   i64 row0, col0;                // raster coordinates of the tile's origin
+  bool act, warp_act;            // this thread's 4x4 block / some block of this warp touches the window: the others never
+                                 // need their part of any pyramid (a thread only reads what it wrote itself)
 };
 
 // what a thread found for its 4x4 block: e_lvl >= 0: an ancestor of level e_lvl (or the block itself) emits its whole
@@ -56,12 +58,14 @@ DCDF_DEVINL Hit snapshot4s(const u8* chunk, const InstDir& d, int L, S_& S, bool
   const u32 p = threadIdx.x;
   RankTab& T = S.tab[threadIdx.x >> 5];
   const u32 nm_len = d.nm_len;
-  build_rank(bitmap_bits(chunk, nm_len, d.nm_base), nm_len, T);
+  const u8* nmb = bitmap_bits(chunk, nm_len, d.nm_base);
   const Dac4 mx = dac4_of(chunk, &d.max), mn = dac4_of(chunk, &d.min);
-  bool has = T.W[0] >> 31;
+  bool has = bit_at(nmb, 0);
   V val = dac_get1<V>(mx, 0), mnv = dac_get1<V>(mn, 0);  // an empty min DAC yields 0 (dac.rs:80-93)
   u32 r = 0;
   if (p == 0) { S.sup[0] = val; S.smin[0] = mnv; S.single[0] = has ? 0u : 1u; }
+  if (!J.warp_act) return Hit{-1, 0u};
+  build_rank(nmb, nm_len, T);
   Hit h{-1, 0u};
   bool live = search;  // still descending
   if (search && !has) {  // single node (snapshot.rs:318-326)
@@ -69,7 +73,7 @@ DCDF_DEVINL Hit snapshot4s(const u8* chunk, const InstDir& d, int L, S_& S, bool
     h.e_lvl = in_band(val, J) ? 0 : -1;
   }
   const int lvp = L - 2;
-  if (p >= (1u << (2 * lvp))) return Hit{-1, 0u};
+  if (p >= (1u << (2 * lvp)) || !J.act) return Hit{-1, 0u};
   for (int k = 1; k <= lvp; k++) {
     const u32 pk = p >> (2 * (lvp - k));
     if (has) {
@@ -142,16 +146,21 @@ DCDF_DEVINL Hit log4s(const u8* chunk, const InstDir& d, int L, S_& S, const Sea
   const u32 p = threadIdx.x;
   RankTab& T = S.tab[threadIdx.x >> 5];
   const u32 nm_len = d.nm_len;
-  build_rank(bitmap_bits(chunk, nm_len, d.nm_base), nm_len, T);
+  const u8* nmb = bitmap_bits(chunk, nm_len, d.nm_base);
   const u8* eq = bitmap_bits(chunk, d.eq_len, d.eq_base);
   const Dac4 mx = dac4_of(chunk, &d.max), mn = dac4_of(chunk, &d.min);
+  // the root's test is the same for every thread: a disjoint root ends the instant for the whole CTA (e_lvl = -2)
+  // before the rank table is built
+  V max_t = dac_get1<V>(mx, 0), min_t = dac_get1<V>(mn, 0);
+  int st = log_test<V>(S.smin[0], min_t, S.sup[0], max_t, J);
+  if (st < 0) return Hit{-2, 0u};
+  if (!J.warp_act) return Hit{-1, 0u};
+  build_rank(nmb, nm_len, T);
   const int lvp = L - 2;
-  if (p >= (1u << (2 * lvp))) return Hit{-1, 0u};
+  if (p >= (1u << (2 * lvp)) || !J.act) return Hit{-1, 0u};
   bool has_t = T.W[0] >> 31;  // index_t is Some
   u32 r = 0;                  // rank1 of the current log node (its children start at 1 + 4r)
-  V max_t = dac_get1<V>(mx, 0), min_t = dac_get1<V>(mn, 0);
   Hit h{-1, 0u};
-  int st = log_test<V>(S.smin[0], min_t, S.sup[0], max_t, J);
   if (st > 0) h.e_lvl = 0;
   // one step of the children loop: node with BFS index cidx (when the parent is internal) over snapshot (min_s, max_s)
   auto step = [&](u32 c, V min_s, V max_s) {
@@ -329,6 +338,11 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_search_t
     J.top = (int)(max(chunk_top, c.top) - chunk_top); J.bottom = (int)(min(chunk_top + cs, c.bottom) - chunk_top);
     J.left = (int)(max(chunk_left, c.left) - chunk_left); J.right = (int)(min(chunk_left + cs, c.right) - chunk_left);
     J.row0 = chunk_top; J.col0 = chunk_left;
+    {
+      const int R0 = 4 * (int)morton_row((u32)tid), C0 = 4 * (int)morton_col((u32)tid);
+      J.act = R0 + 4 > J.top && R0 < J.bottom && C0 + 4 > J.left && C0 < J.right;
+      J.warp_act = __any_sync(0xffffffffu, J.act);
+    }
     const u64 T_all = (u64)(c.end - c.start);
     const u64 job0 = P.job_base[q] + sub * T_all;  // + (t - c.start)
     const u32 slot = (u32)(cr * Q.subsidelen + cc);
@@ -413,11 +427,20 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_search_t
       }
       const InstDir& D = S.dir[rs];
       rs = slot1;
+      const u64 jb = job0 + (u64)(t_lo + i - c.start);
+      const bool is_snap = D.snap == ti;
+      // writing pass: an instant the counting pass found empty is skipped (a Snapshot is still expanded for its Logs)
+      const bool want = !P.out || P.offsets[jb + 1] != P.offsets[jb];
+      if (!want && !is_snap) continue;
       u32 delta;
       Hit h;
-      if (staged4<V>(chunk, D, delta)) h = instant4s<V, SM>(S.stage[b] + (int32_t)delta, D, D.snap == ti, true, L, S, J);
-      else { const SearchJob J2 = J; instant4s_global<V, SM>(chunk, &D, D.snap == ti, true, L, &S, &J2, &h); }
-      const u64 jb = job0 + (u64)(t_lo + i - c.start);
+      if (staged4<V>(chunk, D, delta)) h = instant4s<V, SM>(S.stage[b] + (int32_t)delta, D, is_snap, want, L, S, J);
+      else { const SearchJob J2 = J; instant4s_global<V, SM>(chunk, &D, is_snap, want, L, &S, &J2, &h); }
+      if (!want) continue;
+      if (h.e_lvl == -2) {  // CTA-uniform: nothing of this instant is inside the band
+        if (!P.out && tid == 0) P.counts[jb] = 0ull;
+        continue;
+      }
       emit_hits<V, SM>(h, L, S, J, t_lo + (i64)i, P.counts + jb, P.out, P.out ? P.offsets[jb] : 0ull, P.cap);
     }
   }
