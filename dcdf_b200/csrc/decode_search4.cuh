@@ -17,6 +17,17 @@
 
 namespace dcdf {
 
+struct SearchJob {
+  i64 lower, upper;
+  int top, bottom, left, right;  // window clipped to the tile, tile coordinates, exclusive ends
+  i64 row0, col0;                // raster coordinates of the tile's origin
+};
+// per thread: its 4x4 block / some block of its warp touches the window -- the others never need their part of any
+// pyramid (a thread only reads what it wrote itself)
+struct SearchAct {
+  bool act, warp_act;
+};
+
 template <typename V>
 struct Search4Smem {
   static constexpr int BUF = sizeof(V) == 4 ? 10 * 1024 : 16 * 1024;
@@ -30,17 +41,11 @@ struct Search4Smem {
   u32 single[DT_WARPS];
   u32 base[DT_THREADS];            // exclusive prefix of the per-thread hit counts of the current instant
   u32 wsum[DT_WARPS];
+  SearchJob job;                   // the CTA's current job (uniform; kept here instead of in every thread's registers)
   __align__(16) InstDir dir[3];
   __align__(16) u8 stage[2][BUF + 32];
 };
 
-struct SearchJob {
-  i64 lower, upper;
-  int top, bottom, left, right;  // window clipped to the tile, tile coordinates, exclusive ends
-  i64 row0, col0;                // raster coordinates of the tile's origin
-  bool act, warp_act;            // this thread's 4x4 block / some block of this warp touches the window: the others never
-                                 // need their part of any pyramid (a thread only reads what it wrote itself)
-};
 
 // what a thread found for its 4x4 block: e_lvl >= 0: an ancestor of level e_lvl (or the block itself) emits its whole
 // rectangle; otherwise m16 = hits in Morton order (bit 4 * quad + cell)
@@ -54,7 +59,7 @@ DCDF_DEVINL bool in_band(V v, const SearchJob& J) { return J.lower <= (i64)v && 
 
 // Snapshot: expansion of the pyramid (max, min, cells) and, with `search`, the tests of snapshot.rs:371-413 on the way.
 template <typename V, typename S_>
-DCDF_DEVINL Hit snapshot4s(const u8* chunk, const InstDir& d, int L, S_& S, bool search, const SearchJob& J) {
+DCDF_DEVINL Hit snapshot4s(const u8* chunk, const InstDir& d, int L, S_& S, bool search, const SearchJob& J, const SearchAct A) {
   const u32 p = threadIdx.x;
   RankTab& T = S.tab[threadIdx.x >> 5];
   const u32 nm_len = d.nm_len;
@@ -64,7 +69,7 @@ DCDF_DEVINL Hit snapshot4s(const u8* chunk, const InstDir& d, int L, S_& S, bool
   V val = dac_get1<V>(mx, 0), mnv = dac_get1<V>(mn, 0);  // an empty min DAC yields 0 (dac.rs:80-93)
   u32 r = 0;
   if (p == 0) { S.sup[0] = val; S.smin[0] = mnv; S.single[0] = has ? 0u : 1u; }
-  if (!J.warp_act) return Hit{-1, 0u};
+  if (!A.warp_act) return Hit{-1, 0u};
   build_rank(nmb, nm_len, T);
   Hit h{-1, 0u};
   bool live = search;  // still descending
@@ -73,7 +78,7 @@ DCDF_DEVINL Hit snapshot4s(const u8* chunk, const InstDir& d, int L, S_& S, bool
     h.e_lvl = in_band(val, J) ? 0 : -1;
   }
   const int lvp = L - 2;
-  if (p >= (1u << (2 * lvp)) || !J.act) return Hit{-1, 0u};
+  if (p >= (1u << (2 * lvp)) || !A.act) return Hit{-1, 0u};
   for (int k = 1; k <= lvp; k++) {
     const u32 pk = p >> (2 * (lvp - k));
     if (has) {
@@ -142,7 +147,7 @@ DCDF_DEVINL int log_test(V min_s, V min_t, V max_s, V max_t, const SearchJob& J)
 
 // Log: the recursion's state down the thread's path, against the snapshot pyramid in S (log.rs:593-700).
 template <typename V, typename S_>
-DCDF_DEVINL Hit log4s(const u8* chunk, const InstDir& d, int L, S_& S, const SearchJob& J) {
+DCDF_DEVINL Hit log4s(const u8* chunk, const InstDir& d, int L, S_& S, const SearchJob& J, const SearchAct A) {
   const u32 p = threadIdx.x;
   RankTab& T = S.tab[threadIdx.x >> 5];
   const u32 nm_len = d.nm_len;
@@ -154,10 +159,10 @@ DCDF_DEVINL Hit log4s(const u8* chunk, const InstDir& d, int L, S_& S, const Sea
   V max_t = dac_get1<V>(mx, 0), min_t = dac_get1<V>(mn, 0);
   int st = log_test<V>(S.smin[0], min_t, S.sup[0], max_t, J);
   if (st < 0) return Hit{-2, 0u};
-  if (!J.warp_act) return Hit{-1, 0u};
+  if (!A.warp_act) return Hit{-1, 0u};
   build_rank(nmb, nm_len, T);
   const int lvp = L - 2;
-  if (p >= (1u << (2 * lvp)) || !J.act) return Hit{-1, 0u};
+  if (p >= (1u << (2 * lvp)) || !A.act) return Hit{-1, 0u};
   bool has_t = T.W[0] >> 31;  // index_t is Some
   u32 r = 0;                  // rank1 of the current log node (its children start at 1 + 4r)
   Hit h{-1, 0u};
@@ -282,13 +287,13 @@ DCDF_DEVINL void emit_hits(const Hit h, int L, S_& S, const SearchJob& J, i64 in
 }
 
 template <typename V, typename S_>
-DCDF_DEVINL Hit instant4s(const u8* base, const InstDir& d, bool is_snap, bool search, int L, S_& S, const SearchJob& J) {
-  return is_snap ? snapshot4s<V, S_>(base, d, L, S, search, J) : log4s<V, S_>(base, d, L, S, J);
+DCDF_DEVINL Hit instant4s(const u8* base, const InstDir& d, bool is_snap, bool search, int L, S_& S, const SearchJob& J, const SearchAct A) {
+  return is_snap ? snapshot4s<V, S_>(base, d, L, S, search, J, A) : log4s<V, S_>(base, d, L, S, J, A);
 }
 // structures that do not fit the staging buffer are read from global memory by an out-of-line copy of the same code
 template <typename V, typename S_>
-__device__ __noinline__ void instant4s_global(const u8* chunk, const InstDir* d, bool is_snap, bool search, int L, S_* S, const SearchJob* J, Hit* h) {
-  *h = instant4s<V, S_>(chunk, *d, is_snap, search, L, *S, *J);
+__device__ __noinline__ void instant4s_global(const u8* chunk, const InstDir* d, bool is_snap, bool search, int L, S_* S, int act, Hit* h) {
+  *h = instant4s<V, S_>(chunk, *d, is_snap, search, L, *S, S->job, SearchAct{(act & 1) != 0, (act & 2) != 0});
 }
 
 struct TileSearchParams {
@@ -332,17 +337,19 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_search_t
     const i64 t_lo = max(c.start, sm.t0), t_hi = min(c.end, sm.t0 + (i64)sm.instants);
     if (t_hi <= t_lo) continue;
     const i64 chunk_top = cr * cs, chunk_left = cc * cs;
-    SearchJob J;
+    SearchJob J;  // local copy: the elided / tiny-tile paths use it, the walk reads the CTA's copy in shared memory
     J.lower = P.lower[q]; J.upper = P.upper[q];
     if (J.lower > J.upper) { const i64 t = J.lower; J.lower = J.upper; J.upper = t; }  // helpers.rs:7-16 via chunk.rs:214
     J.top = (int)(max(chunk_top, c.top) - chunk_top); J.bottom = (int)(min(chunk_top + cs, c.bottom) - chunk_top);
     J.left = (int)(max(chunk_left, c.left) - chunk_left); J.right = (int)(min(chunk_left + cs, c.right) - chunk_left);
     J.row0 = chunk_top; J.col0 = chunk_left;
+    SearchAct A;
     {
       const int R0 = 4 * (int)morton_row((u32)tid), C0 = 4 * (int)morton_col((u32)tid);
-      J.act = R0 + 4 > J.top && R0 < J.bottom && C0 + 4 > J.left && C0 < J.right;
-      J.warp_act = __any_sync(0xffffffffu, J.act);
+      A.act = R0 + 4 > J.top && R0 < J.bottom && C0 + 4 > J.left && C0 < J.right;
+      A.warp_act = __any_sync(0xffffffffu, A.act);
     }
+    const int act_bits = (A.act ? 1 : 0) | (A.warp_act ? 2 : 0);
     const u64 T_all = (u64)(c.end - c.start);
     const u64 job0 = P.job_base[q] + sub * T_all;  // + (t - c.start)
     const u32 slot = (u32)(cr * Q.subsidelen + cc);
@@ -397,7 +404,10 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_search_t
     const u8* chunk = Q.blob + m.blob_off;
     const InstDir* dir = Q.dir + m.dir_base;
     const u32 ti0 = (u32)(t_lo - sm.t0), n_t = (u32)(t_hi - t_lo);
-    __syncthreads();  // the previous job's readers are done with the staging buffers
+    __syncthreads();  // the previous job's readers are done with the staging buffers and the job description
+    if (tid == 0) S.job = J;
+    __syncthreads();
+    const SearchJob& JS = S.job;
     const u32 snap0 = dir[ti0].snap;
     if (snap0 != ti0) {
       // the window starts inside a block: expand the block's snapshot first
@@ -407,8 +417,8 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_search_t
       __syncthreads();
       u32 delta;
       Hit hg;
-      if (staged4<V>(chunk, S.dir[2], delta)) instant4s<V, SM>(S.stage[1] + (int32_t)delta, S.dir[2], true, false, L, S, J);
-      else { const SearchJob J2 = J; instant4s_global<V, SM>(chunk, &S.dir[2], true, false, L, &S, &J2, &hg); }
+      if (staged4<V>(chunk, S.dir[2], delta)) instant4s<V, SM>(S.stage[1] + (int32_t)delta, S.dir[2], true, false, L, S, JS, A);
+      else instant4s_global<V, SM>(chunk, &S.dir[2], true, false, L, &S, act_bits, &hg);
       __syncthreads();
     }
     prefetch_dir4<V, SM>(dir + ti0, S, 0);
@@ -434,14 +444,14 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_search_t
       if (!want && !is_snap) continue;
       u32 delta;
       Hit h;
-      if (staged4<V>(chunk, D, delta)) h = instant4s<V, SM>(S.stage[b] + (int32_t)delta, D, is_snap, want, L, S, J);
-      else { const SearchJob J2 = J; instant4s_global<V, SM>(chunk, &D, is_snap, want, L, &S, &J2, &h); }
+      if (staged4<V>(chunk, D, delta)) h = instant4s<V, SM>(S.stage[b] + (int32_t)delta, D, is_snap, want, L, S, JS, A);
+      else instant4s_global<V, SM>(chunk, &D, is_snap, want, L, &S, act_bits, &h);
       if (!want) continue;
       if (h.e_lvl == -2) {  // CTA-uniform: nothing of this instant is inside the band
         if (!P.out && tid == 0) P.counts[jb] = 0ull;
         continue;
       }
-      emit_hits<V, SM>(h, L, S, J, t_lo + (i64)i, P.counts + jb, P.out, P.out ? P.offsets[jb] : 0ull, P.cap);
+      emit_hits<V, SM>(h, L, S, JS, t_lo + (i64)i, P.counts + jb, P.out, P.out ? P.offsets[jb] : 0ull, P.cap);
     }
   }
 }
