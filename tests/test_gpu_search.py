@@ -99,7 +99,8 @@ def test_superchunk_search_batch_against_oracle_chunks(ctx):
     sc.close()
 
 
-def test_depth_first_search_kernel_stays_bit_exact():
+@pytest.mark.parametrize("env", ["DCDF_SEARCH_V1", "DCDF_WINDOW_WIDE"])
+def test_depth_first_search_kernel_and_wide_expansion_stay_bit_exact(env):
     code = (
         "import sys, numpy as np\n"
         f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
@@ -112,5 +113,5 @@ def test_depth_first_search_kernel_stays_bit_exact():
         "    assert np.array_equal(got.search(1, 9, 3, 60, 2, 49, lo, hi), ref.search(1, 9, 3, 60, 2, 49, lo, hi))\n"
         "print('ok')\n"
     )
-    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, "DCDF_SEARCH_V1": "1"}, capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, env: "1"}, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

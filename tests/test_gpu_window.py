@@ -138,7 +138,7 @@ def test_device_output_and_elided_tiles(ctx):
     sc.close()
 
 
-@pytest.mark.parametrize("env", ["DCDF_WINDOW_V1", "DCDF_WINDOW_V3", "DCDF_WINDOW_V5", "DCDF_WINDOW_CELLS"])
+@pytest.mark.parametrize("env", ["DCDF_WINDOW_V1", "DCDF_WINDOW_V3", "DCDF_WINDOW_V5", "DCDF_WINDOW_CELLS", "DCDF_WINDOW_WIDE"])
 def test_other_window_kernels_stay_bit_exact(env):
     """The earlier generations (and the per-cell kernel used for trees larger than 64x64) are selected once per process."""
     code = (
