@@ -530,6 +530,12 @@ void do_search_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
     TS.Q = mb->Q; TS.cubes = d_c; TS.job_base = d_jb; TS.tile_base = ctx->query_aux2.as<u64>();
     TS.n_queries = n; TS.n_tiles = n_tiles; TS.lower = d_lo; TS.upper = d_hi;
     TS.counts = d_counts; TS.offsets = d_offsets; TS.out = nullptr; TS.cap = 0;
+    // 1 KB per (window, subchunk, instant) keeps the counting pass's findings for the writing pass (up to 2 GB)
+    TS.hit_cache = nullptr;
+    if (out_irc && n_jobs * (u64)DT_THREADS * 4ull <= (2ull << 30) && getenv("DCDF_SEARCH_NO_CACHE") == nullptr) {
+      ctx->search_cache.reserve(n_jobs * (size_t)DT_THREADS * 4);
+      TS.hit_cache = ctx->search_cache.as<u32>();
+    }
     tgrid = (unsigned)std::min<u64>(n_tiles, (u64)ctx->sm_count * 64);
     CK(cudaFuncSetAttribute(k_search_tiles4<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Search4Smem<i64>)));
     CK(cudaFuncSetAttribute(k_search_tiles4<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Search4Smem<int32_t>)));

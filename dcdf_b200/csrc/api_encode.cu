@@ -899,7 +899,7 @@ int32_t dcdf_ctx_destroy(dcdf_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->input_copy, &ctx->units, &ctx->ustats, &ctx->istats, &ctx->slices, &ctx->sstate, &ctx->tbl_scratch,
                     &ctx->order, &ctx->pieces, &ctx->results, &ctx->stored, &ctx->chunk_off, &ctx->arena, &ctx->small,
-                    &ctx->exact, &ctx->query_in, &ctx->query_out, &ctx->query_aux, &ctx->query_aux2, &ctx->tree_buf};
+                    &ctx->exact, &ctx->query_in, &ctx->query_out, &ctx->query_aux, &ctx->query_aux2, &ctx->search_cache, &ctx->tree_buf};
   for (auto* b : bufs) b->release();
   ctx->pin.release();
   ctx->pin2.release();

@@ -308,6 +308,8 @@ struct TileSearchParams {
   const u64* offsets;
   i64* out;                  // null in the counting pass
   u64 cap;
+  u32* hit_cache;            // [n_jobs][256] what every thread found in the counting pass ((e_lvl + 1) << 16 | m16), or null:
+                             // the writing pass then places the hits without staging or expanding anything again
 };
 
 template <typename V>
@@ -408,6 +410,17 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_search_t
     if (tid == 0) S.job = J;
     __syncthreads();
     const SearchJob& JS = S.job;
+    if (P.out && P.hit_cache) {
+      for (u32 i = 0; i < n_t; i++) {
+        const u64 jb = job0 + (u64)(t_lo + i - c.start);
+        if (P.offsets[jb + 1] == P.offsets[jb]) continue;  // uniform
+        const u32 pk = P.hit_cache[jb * DT_THREADS + (u64)tid];
+        const Hit h{(int)(pk >> 16) - 1, pk & 0xffffu};
+        emit_hits<V, SM>(h, L, S, JS, t_lo + (i64)i, P.counts + jb, P.out, P.offsets[jb], P.cap);
+        __syncthreads();  // wsum / base are reused by the next instant
+      }
+      continue;
+    }
     const u32 snap0 = dir[ti0].snap;
     if (snap0 != ti0) {
       // the window starts inside a block: expand the block's snapshot first
@@ -451,6 +464,7 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_search_t
         if (!P.out && tid == 0) P.counts[jb] = 0ull;
         continue;
       }
+      if (!P.out && P.hit_cache) P.hit_cache[jb * DT_THREADS + (u64)tid] = ((u32)(h.e_lvl + 1) << 16) | (h.m16 & 0xffffu);
       emit_hits<V, SM>(h, L, S, JS, t_lo + (i64)i, P.counts + jb, P.out, P.out ? P.offsets[jb] : 0ull, P.cap);
     }
   }

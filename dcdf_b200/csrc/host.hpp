@@ -112,7 +112,7 @@ struct dcdf_ctx {
   int sm_count = 148;
   // scratch
   dcdf::DevBuf input_copy, units, ustats, istats, slices, sstate, tbl_scratch, order, pieces, results, stored, chunk_off,
-      arena, small, exact, query_in, query_out, query_aux, query_aux2, tree_buf;
+      arena, small, exact, query_in, query_out, query_aux, query_aux2, search_cache, tree_buf;
   dcdf::PinBuf pin, pin2;
   size_t arena_hint = 0;
   // small transfers through mapped pinned memory (xfer.cuh)

@@ -99,7 +99,7 @@ def test_superchunk_search_batch_against_oracle_chunks(ctx):
     sc.close()
 
 
-@pytest.mark.parametrize("env", ["DCDF_SEARCH_V1", "DCDF_WINDOW_WIDE"])
+@pytest.mark.parametrize("env", ["DCDF_SEARCH_V1", "DCDF_WINDOW_WIDE", "DCDF_SEARCH_NO_CACHE"])
 def test_depth_first_search_kernel_and_wide_expansion_stay_bit_exact(env):
     code = (
         "import sys, numpy as np\n"
