@@ -542,6 +542,7 @@ void do_search_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
   }
   auto launch_search = [&](int write) {
     if (tiles) {
+      if (!write) CK(cudaMemsetAsync(d_counts, 0, sizeof(u64) * n_jobs, st));  // the counting pass adds per warp
       if (narrow) k_search_tiles4<int32_t><<<tgrid, DT_THREADS, sizeof(Search4Smem<int32_t>), st>>>(TS);
       else k_search_tiles4<i64><<<tgrid, DT_THREADS, sizeof(Search4Smem<i64>), st>>>(TS);
     } else {

@@ -236,6 +236,12 @@ DCDF_DEVINL void emit_hits(const Hit h, int L, S_& S, const SearchJob& J, i64 in
   }
   const u32 mine = h.e_lvl >= 0 ? w16 : (h.m16 & w16);
   const u32 n = __popc(mine);
+  if (!out) {
+    // counting pass: the instant's total is all that is needed -- one atomic per warp into the zeroed count, no barrier
+    const u32 wt = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0 && wt) atomicAdd(reinterpret_cast<unsigned long long*>(count_out), (unsigned long long)wt);
+    return;
+  }
   u32 inc = n;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -252,10 +258,6 @@ DCDF_DEVINL void emit_hits(const Hit h, int L, S_& S, const SearchJob& J, i64 in
     total += x;
   }
   const u32 base = before + inc - n;
-  if (!out) {
-    if (p == 0) *count_out = total;
-    return;  // wsum is rewritten after the next instant's first barrier
-  }
   S.base[p] = base;
   __syncthreads();
   if (!mine || off + total > cap) return;
@@ -460,10 +462,7 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_search_t
       if (staged4<V>(chunk, D, delta)) h = instant4s<V, SM>(S.stage[b] + (int32_t)delta, D, is_snap, want, L, S, JS, A);
       else instant4s_global<V, SM>(chunk, &D, is_snap, want, L, &S, act_bits, &h);
       if (!want) continue;
-      if (h.e_lvl == -2) {  // CTA-uniform: nothing of this instant is inside the band
-        if (!P.out && tid == 0) P.counts[jb] = 0ull;
-        continue;
-      }
+      if (h.e_lvl == -2) continue;  // CTA-uniform: nothing of this instant is inside the band (its count stays 0)
       if (!P.out && P.hit_cache) P.hit_cache[jb * DT_THREADS + (u64)tid] = ((u32)(h.e_lvl + 1) << 16) | (h.m16 & 0xffffu);
       emit_hits<V, SM>(h, L, S, JS, t_lo + (i64)i, P.counts + jb, P.out, P.out ? P.offsets[jb] : 0ull, P.cap);
     }
