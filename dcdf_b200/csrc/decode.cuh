@@ -280,14 +280,18 @@ DCDF_DEVINL i64 snapshot_get(const ChunkView& cv, const InstDir& s, u32 row, u32
   }
 }
 
-DCDF_DEVINL i64 log_get(const ChunkView& cv, const InstDir& l, const InstDir& s, u32 row, u32 col) {  // log.rs:176-293
+// `is_snap`: the instant is the block's Snapshot itself (l == s).  It takes the same walk as a Log whose tree ends at the
+// root with offset 0 -- Snapshot::get (snapshot.rs:165-188) is exactly the snapshot half of this loop -- so that the lanes
+// of a warp (consecutive instants of one cell series) stay on one code path instead of running snapshot_get and log_get
+// one after the other.
+DCDF_DEVINL i64 log_get(const ChunkView& cv, const InstDir& l, const InstDir& s, u32 row, u32 col, bool is_snap = false) {  // log.rs:176-293
   BitMapRef nm_t{cv.chunk, l.nm_len, l.nm_base}, nm_s{cv.chunk, s.nm_len, s.nm_base};
   BitMapRef eq{cv.chunk, l.eq_len, l.eq_base};
   DacRef mx_t{cv.chunk, &l.max}, mx_s{cv.chunk, &s.max};
-  i64 max_t = mx_t.get(0), max_s = mx_s.get(0);
-  const bool single_t = !nm_t.get(0), single_s = !nm_s.get(0);
+  i64 max_t = is_snap ? 0 : mx_t.get(0), max_s = mx_s.get(0);
+  const bool single_t = is_snap || !nm_t.get(0), single_s = !nm_s.get(0);
   if (single_t && single_s) return max_t + max_s;
-  if (single_t && !eq.get(0)) return max_t + max_s;
+  if (!is_snap && single_t && !eq.get(0)) return max_t + max_s;
   bool has_t = !single_t, has_s = !single_s;
   u32 it = 0, is = 0, sl = (u32)cv.sidelen;
   for (;;) {
@@ -319,8 +323,7 @@ DCDF_DEVINL i64 log_get(const ChunkView& cv, const InstDir& l, const InstDir& s,
 
 DCDF_DEVINL i64 chunk_get(const ChunkView& cv, u32 instant, u32 row, u32 col) {  // chunk.rs:127-131 + block.rs:42-47
   const InstDir& d = cv.dir[instant];
-  if (d.snap == instant) return snapshot_get(cv, d, row, col);
-  return log_get(cv, d, cv.dir[d.snap], row, col);
+  return log_get(cv, d, cv.dir[d.snap], row, col, d.snap == instant);
 }
 
 // Route a global (instant,row,col) to (fixed value, fractional bits)  -- superchunk.rs:313-351 + span.rs:121-137
