@@ -287,7 +287,9 @@ DCDF_DEVINL i64 snapshot_get(const ChunkView& cv, const InstDir& s, u32 row, u32
 DCDF_DEVINL i64 log_get(const ChunkView& cv, const InstDir& l, const InstDir& s, u32 row, u32 col, bool is_snap = false) {  // log.rs:176-293
   BitMapRef nm_t{cv.chunk, l.nm_len, l.nm_base}, nm_s{cv.chunk, s.nm_len, s.nm_base};
   BitMapRef eq{cv.chunk, l.eq_len, l.eq_base};
-  DacRef mx_t{cv.chunk, &l.max}, mx_s{cv.chunk, &s.max};
+  // level 0 of both max DACs located once: a one-byte code is then a bit test and a byte load that do not wait for the
+  // directory entry (DacRef re-reads its level table from global memory at every lookup)
+  const DacFast mx_t = dac_fast(cv.chunk, &l.max), mx_s = dac_fast(cv.chunk, &s.max);
   i64 max_t = is_snap ? 0 : mx_t.get(0), max_s = mx_s.get(0);
   const bool single_t = is_snap || !nm_t.get(0), single_s = !nm_s.get(0);
   if (single_t && single_s) return max_t + max_s;
