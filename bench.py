@@ -327,7 +327,7 @@ def run_ours(args):
         rng = np.random.default_rng(7)
         nq = 4096
         q = np.stack([np.zeros(nq, np.int64), np.full(nq, T, np.int64), rng.integers(0, rows, nq), rng.integers(0, cols, nq)], axis=1)
-        sc.cell_batch(q[:64])
+        sc.cell_batch(q)  # warm-up at full size: the context's staging buffers grow here, not inside the timed call
         tq = time.perf_counter()
         series = sc.cell_batch(q)
         t_cell = time.perf_counter() - tq
@@ -339,7 +339,7 @@ def run_ours(args):
         t0s = rng.integers(0, max(T - CHUNK_SIZE, 1), nw)
         cubes = np.stack([t0s, np.minimum(t0s + CHUNK_SIZE, T), top, np.minimum(top + side, rows), left, np.minimum(left + side, cols)], axis=1)
         lo_v = rng.integers(270 * 32, 300 * 32, nw)      # fixed point with 4 fractional bits: value * 32 + 1
-        counts, _ = sc.search_batch(cubes[:32], lo_v[:32], lo_v[:32] + 48, want_cells=False)
+        sc.search_batch(cubes, lo_v, lo_v + 48)  # warm-up at full size (result / cache buffers are allocated here)
         ts = time.perf_counter()
         counts, cells = sc.search_batch(cubes, lo_v, lo_v + 48)
         t_search = time.perf_counter() - ts
