@@ -30,7 +30,34 @@ def _is_torch(a):
     return hasattr(a, "data_ptr") and hasattr(a, "is_cuda")
 
 
-def _describe(a):
+def _order_after_torch(ctx, t):
+    """A Context runs on its own stream: before the library touches a CUDA tensor, wait for the work torch has queued
+    on that device's current stream (a producer kernel may still be writing it) -- unless the context was told to use
+    that very stream (Context.set_stream).  Calls return after the context's stream has drained, so torch may consume
+    outputs right away."""
+    if not t.is_cuda:
+        return
+    import torch
+    if ctx is not None and t.device.index != ctx.device:
+        raise ValueError(f"tensor lives on cuda:{t.device.index}, the context on cuda:{ctx.device}")
+    cur = torch.cuda.current_stream(t.device)
+    if ctx is None or ctx._stream_ptr != cur.cuda_stream:
+        cur.synchronize()
+
+
+def _check_out(out, n, enc, raw):
+    """`out` must be a contiguous buffer of exactly the element type and at least the size the C call writes."""
+    want = np.dtype(np.int64 if raw else _DTYPE_OF_ENC[enc])
+    if _is_torch(out):
+        name = str(out.dtype).replace("torch.", "")
+        if name != want.name or not out.is_contiguous() or out.numel() < n:
+            raise ValueError(f"out must be a contiguous {want.name} tensor with at least {n} elements")
+    else:
+        if out.dtype != want or not out.flags["C_CONTIGUOUS"] or out.size < n:
+            raise ValueError(f"out must be a C-contiguous {want.name} array with at least {n} elements")
+
+
+def _describe(a, ctx=None):
     """-> (Array3, keepalive)"""
     d = Array3()
     if _is_torch(a):
@@ -39,6 +66,7 @@ def _describe(a):
         name = str(a.dtype).replace("torch.", "")
         if name not in _ENC_OF_DTYPE:
             raise TypeError(f"unsupported dtype {a.dtype}")
+        _order_after_torch(ctx, a)
         d.base = a.data_ptr()
         d.shape = (C.c_int64 * 3)(*a.shape)
         d.strides = (C.c_int64 * 3)(*a.stride())
@@ -73,6 +101,7 @@ class Context:
             raise DcdfError(code, f"cannot create a CUDA context on device {device} (no CPU fallback exists)")
         self._h = h
         self.device = device
+        self._stream_ptr = None   # a borrowed stream (set_stream), else the context's private one
 
     def close(self):
         if getattr(self, "_h", None):
@@ -91,6 +120,11 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         self.check(self._lib.dcdf_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+        self._stream_ptr = cuda_stream_ptr or None
+
+    def set_option(self, name, value):
+        """dcdf_ctx_set_option: select between equivalent code paths (tests, A/B measurements)."""
+        self.check(self._lib.dcdf_ctx_set_option(self._h, name.encode(), int(value)))
 
     def synchronize(self):
         self.check(self._lib.dcdf_ctx_synchronize(self._h))
@@ -106,13 +140,13 @@ class Context:
 
     # ---- fixed.rs
     def suggest_fraction(self, a):
-        d, keep = _describe(a)
+        d, keep = _describe(a, self)
         kind, bits = C.c_int32(), C.c_int32()
         self.check(self._lib.dcdf_suggest_fraction(self._h, C.byref(d), C.byref(kind), C.byref(bits)))
         return ("Round" if kind.value else "Precise", bits.value)
 
     def min_max(self, a, fractional_bits=0, round=False):
-        d, keep = _describe(a)
+        d, keep = _describe(a, self)
         mn = np.empty(d.shape[0], np.int64)
         mx = np.empty(d.shape[0], np.int64)
         self.check(self._lib.dcdf_min_max(self._h, C.byref(d), fractional_bits, int(round), _ptr(mn), _ptr(mx)))
@@ -173,8 +207,11 @@ class _Queryable:
             out = _out_array(shape, self.encoding, raw)
             ptr = _ptr(out)
         elif _is_torch(out):
+            _check_out(out, shape[0] * shape[1] * shape[2], self.encoding, raw)
+            _order_after_torch(self.ctx, out)
             ptr, mem = C.c_void_p(out.data_ptr()), (MEM_DEVICE if out.is_cuda else MEM_HOST)
         else:
+            _check_out(out, shape[0] * shape[1] * shape[2], self.encoding, raw)
             ptr = _ptr(out)
         self.ctx.check(self._fn("window")(self.ctx._h, self._h, C.byref(cube), ptr, ENC_I64 if raw else self.encoding, mem))
         return out
@@ -195,7 +232,7 @@ class Chunk(_Queryable):
     @classmethod
     def build(cls, ctx, array, k=2, fractional_bits=0, round=False):
         """Chunk::build chunk.rs:42-96 (fractional_bits / round are the MMBuffer3 fields)."""
-        d, keep = _describe(array)
+        d, keep = _describe(array, ctx)
         h = C.c_void_p()
         st = BuildStats()
         ctx.check(ctx._lib.dcdf_chunk_build(ctx._h, C.byref(d), k, fractional_bits, int(round), C.byref(h), C.byref(st)))
@@ -261,7 +298,7 @@ class Superchunk(_Queryable):
     @classmethod
     def build(cls, ctx, array, levels, k=2, fractional_bits=0, round=False, compute_bits=True, chunk_size=0):
         """Superchunk::build superchunk.rs:88-270 for every chunk_size slice (dataset.rs:834-851)."""
-        d, keep = _describe(array)
+        d, keep = _describe(array, ctx)
         lv = (C.c_uint32 * len(levels))(*levels)
         h = C.c_void_p()
         ctx.check(ctx._lib.dcdf_superchunk_build(ctx._h, C.byref(d), lv, len(levels), k, fractional_bits, int(round),
@@ -325,8 +362,11 @@ class Superchunk(_Queryable):
             out = _out_array(int(off[-1]), self.encoding, raw)
             ptr = _ptr(out)
         elif _is_torch(out):
+            _check_out(out, int(off[-1]), self.encoding, raw)
+            _order_after_torch(self.ctx, out)
             ptr, mem = C.c_void_p(out.data_ptr()), (MEM_DEVICE if out.is_cuda else MEM_HOST)
         else:
+            _check_out(out, int(off[-1]), self.encoding, raw)
             ptr = _ptr(out)
         self.ctx.check(self.ctx._lib.dcdf_superchunk_window_batch(self.ctx._h, self._h, len(cubes), _ptr(cubes), _ptr(off), ptr,
                                                                   ENC_I64 if raw else self.encoding, mem))

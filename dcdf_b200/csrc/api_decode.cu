@@ -2,13 +2,10 @@
 // fill_window / iter_search at chunk and superchunk level, flat to_fixed / from_fixed).
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 #include "decode.cuh"
-#include "decode_tile.cuh"
-#include "decode_tile2.cuh"
-#include "decode_tile3.cuh"
 #include "decode_tile4.cuh"
-#include "decode_tile5.cuh"
 #include "decode_search4.cuh"
 #include "host.hpp"
 
@@ -33,6 +30,12 @@ int32_t guarded(dcdf_ctx* ctx, Fn&& fn) {
     return DCDF_ERR_CUDA;
   } catch (const std::bad_alloc&) {
     ctx->last_error = "host out of memory";
+    return DCDF_ERR_BAD_ARG;
+  } catch (const std::exception& e) {  // nothing may unwind across the C ABI
+    ctx->last_error = std::string("unexpected exception: ") + e.what();
+    return DCDF_ERR_BAD_ARG;
+  } catch (...) {
+    ctx->last_error = "unexpected exception";
     return DCDF_ERR_BAD_ARG;
   }
 }
@@ -62,6 +65,10 @@ void check_err_word(dcdf_ctx* ctx, u32* d_err, const char* what) {
   CK(cudaMemcpyAsync(&f, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (f & EF_BAD_FORMAT) api_fail(DCDF_ERR_BAD_FORMAT, "%s: malformed chunk bytes", what);
+  if (f & EF_OUT_OF_BOUNDS) {
+    CK(cudaMemsetAsync(d_err, 0, 4, ctx->stream));
+    api_fail(DCDF_ERR_OUT_OF_BOUNDS, "%s: query out of bounds", what);
+  }
   if (f & EF_NONFINITE) api_fail(DCDF_ERR_NONFINITE, "%s: non-finite input", what);
   if (f & EF_OVERFLOW) api_fail(DCDF_ERR_OVERFLOW, "%s: overflow", what);
   if (f & EF_PRECISION) api_fail(DCDF_ERR_PRECISION_LOSS, "%s: loss of precision", what);
@@ -70,9 +77,10 @@ void check_err_word(dcdf_ctx* ctx, u32* d_err, const char* what) {
 
 MetaBlock* make_meta(dcdf_ctx* ctx, const u8* blob, std::vector<UnitMeta>& units, const std::vector<SliceMeta>& slices,
                      const std::vector<int32_t>& slot_unit, const std::vector<SlotDesc>& slot_desc, u32 n_slots, i64 chunk_size, int chunks_sidelen, int subsidelen,
-                     int encoding, const i64* shape, const i64* tbl_max, void** dir_out, bool count_first) {
+                     int encoding, const i64* shape, const i64* tbl_max, void** dir_out, bool count_first, bool validate) {
   cudaStream_t st = ctx->stream;
   MetaBlock* mb = new MetaBlock();
+  *dir_out = nullptr;
   try {
     const size_t ub = sizeof(UnitMeta) * units.size(), sb = sizeof(SliceMeta) * slices.size(),
                  mbytes = (sizeof(int32_t) * slot_unit.size() + 15) & ~size_t(15), db = sizeof(SlotDesc) * slot_desc.size();
@@ -93,6 +101,7 @@ MetaBlock* make_meta(dcdf_ctx* ctx, const u8* blob, std::vector<UnitMeta>& units
     DP.units = mb->d.units;
     DP.dir = nullptr;
     DP.n_units = (u32)units.size();
+    DP.validate = validate ? 1 : 0;
     DP.err = mb->d.err;
     const u32 grid = ((u32)units.size() + 63) / 64;
     if (count_first) {
@@ -139,15 +148,23 @@ MetaBlock* make_meta(dcdf_ctx* ctx, const u8* blob, std::vector<UnitMeta>& units
     for (int i = 0; i < 3; i++) Q.shape[i] = shape[i];
     return mb;
   } catch (...) {
+    cudaStreamSynchronize(st);
+    pool_free(*dir_out);
+    *dir_out = nullptr;
     pool_free(mb->d.units);
     delete mb;
     throw;
   }
 }
 
+// Built objects are immutable and may be queried from several contexts / host threads (dcdf_cuda.h): the lazily built
+// device directory of a handle is created under this lock.
+std::mutex g_meta_mutex;
+
 // ---- handle -> MetaBlock (lazily for built objects)
 MetaBlock* chunk_meta(dcdf_ctx* ctx, const dcdf_chunk* cc) {
   dcdf_chunk* c = const_cast<dcdf_chunk*>(cc);
+  std::lock_guard<std::mutex> lock(g_meta_mutex);
   if (c->dir) return static_cast<MetaBlock*>(c->dir);
   std::vector<UnitMeta> units(1);
   memset(&units[0], 0, sizeof(UnitMeta));
@@ -160,7 +177,8 @@ MetaBlock* chunk_meta(dcdf_ctx* ctx, const dcdf_chunk* cc) {
   std::vector<SlotDesc> slot_desc(1, SlotDesc{0, 0, 0});
   void* dir = nullptr;
   const bool count_first = c->shape[0] == 0;
-  MetaBlock* mb = make_meta(ctx, c->bytes, units, slices, slot_unit, slot_desc, 1, 0, 1 << 30, 1, c->encoding, c->shape, nullptr, &dir, count_first);
+  MetaBlock* mb = make_meta(ctx, c->bytes, units, slices, slot_unit, slot_desc, 1, 0, 1 << 30, 1, c->encoding, c->shape, nullptr, &dir, count_first,
+                            /*validate=*/count_first);  // opened from outside bytes
   if (count_first) {
     c->shape[0] = units[0].instants; c->shape[1] = units[0].rows; c->shape[2] = units[0].cols;
     c->fractional_bits = units[0].bits;
@@ -179,6 +197,7 @@ MetaBlock* chunk_meta(dcdf_ctx* ctx, const dcdf_chunk* cc) {
 
 MetaBlock* super_meta(dcdf_ctx* ctx, const dcdf_superchunk* scc) {
   dcdf_superchunk* sc = const_cast<dcdf_superchunk*>(scc);
+  std::lock_guard<std::mutex> lock(g_meta_mutex);
   if (sc->dev_meta) return static_cast<MetaBlock*>(sc->dev_meta);
   std::vector<UnitMeta> units(sc->units.size());
   for (size_t u = 0; u < units.size(); u++) {
@@ -228,7 +247,7 @@ MetaBlock* super_meta(dcdf_ctx* ctx, const dcdf_superchunk* scc) {
   }
   void* dir = nullptr;
   MetaBlock* mb = make_meta(ctx, sc->chunk_blob, units, slices, sc->slot_unit, slot_desc, sc->n_slots, sc->chunk_size, sc->leaf_side,
-                            (int)sc->leaf_grid, sc->encoding, sc->shape, sc->tbl_max, &dir, false);
+                            (int)sc->leaf_grid, sc->encoding, sc->shape, sc->tbl_max, &dir, false, sc->opened);
   sc->dir = dir;
   sc->dev_meta = mb;
   return mb;
@@ -311,12 +330,13 @@ void do_get_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const int64_t* irc, 
   const i64* d_q = static_cast<const i64*>(to_device(ctx, ctx->query_in, irc, sizeof(i64) * 3 * n, mem));
   OutTarget ot = out_begin(ctx, out, os.esize * n, mem);
   tbegin(ctx, KT_CELL);
-  k_get_batch<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(mb->Q, d_q, n, ot.dev, os.raw);
+  k_get_batch<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(mb->Q, d_q, n, ot.dev, os.raw, mb->d.err);
   CK(cudaGetLastError());
   ctx->launches++;
   tend(ctx, KT_CELL);
   out_end(ctx, ot);
   tcollect(ctx, KT_CELL);
+  if (mem == DCDF_MEM_DEVICE) check_err_word(ctx, mb->d.err, "get_batch");  // host queries were checked above
 }
 
 void do_cell_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const int64_t* q, const uint64_t* out_off, void* out,
@@ -374,9 +394,9 @@ void do_window_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
   CK(cudaMemcpyAsync(d_c, cubes.data(), sizeof(CubeDev) * n, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_off, out_off, sizeof(u64) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
   OutTarget ot = out_begin(ctx, out, os.esize * total, mem);
-  const bool tiles = mb->max_sidelen <= 64 && getenv("DCDF_WINDOW_CELLS") == nullptr;
+  const bool tiles = mb->max_sidelen <= 64 && !ctx->opt.window_cells;
   if (tiles) {
-    // one CTA per (window, slice, subchunk)
+    // one CTA per (window, slice, subchunk): per-thread walk with one block barrier per instant (decode_tile4.cuh)
     std::vector<u64> job_base(n + 1);
     u64 n_jobs = 0;
     const i64 cs = mb->Q.chunks_sidelen;
@@ -395,50 +415,14 @@ void do_window_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
     TileWindowParams TP;
     TP.Q = mb->Q; TP.cubes = d_c; TP.out_off = d_off; TP.job_base = ctx->query_aux.as<u64>();
     TP.n_queries = n; TP.n_jobs = n_jobs; TP.out = ot.dev; TP.raw = os.raw;
-    // default: level-synchronous expansion (decode_tile.cuh); DCDF_WINDOW_WALK=1: per-thread sub-tree walk (decode_tile2.cuh)
-    static const bool walk_v1 = getenv("DCDF_WINDOW_WALK") == nullptr;
-    const bool narrow = mb->max_dac_levels <= 3 && getenv("DCDF_WINDOW_WIDE") == nullptr;
-    static const bool tiles_v1 = getenv("DCDF_WINDOW_V1") != nullptr;  // first-generation expansion (decode_tile.cuh)
-    static const bool tiles_v3 = getenv("DCDF_WINDOW_V3") != nullptr;  // level-synchronous second generation (decode_tile3.cuh)
-    // default: per-thread walk with one block barrier per instant (decode_tile4.cuh).  DCDF_WINDOW_V5=1: the same walk behind a
-    // TMA bulk-copy / mbarrier ring (decode_tile5.cuh) -- bit-exact, measured slower (the elected producer thread's warp
-    // paces every other warp), kept as an experiment
-    static const bool tiles_v4 = getenv("DCDF_WINDOW_V5") == nullptr;
-    if (walk_v1 && !tiles_v1 && !tiles_v3 && !tiles_v4) {
-      CK(cudaFuncSetAttribute(k_window_tiles5<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile5Smem<i64>)));
-      CK(cudaFuncSetAttribute(k_window_tiles5<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile5Smem<int32_t>)));
-    } else if (walk_v1 && !tiles_v1 && !tiles_v3) {
-      CK(cudaFuncSetAttribute(k_window_tiles4<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile4Smem<i64>)));
-      CK(cudaFuncSetAttribute(k_window_tiles4<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile4Smem<int32_t>)));
-    } else if (walk_v1 && !tiles_v1) {
-      CK(cudaFuncSetAttribute(k_window_tiles3<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile3Smem<i64>)));
-      CK(cudaFuncSetAttribute(k_window_tiles3<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile3Smem<int32_t>)));
-    } else if (walk_v1) {
-      CK(cudaFuncSetAttribute(k_window_tiles<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<i64>)));
-      CK(cudaFuncSetAttribute(k_window_tiles<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<int32_t>)));
-    }
+    const bool narrow = mb->max_dac_levels <= 3 && !ctx->opt.window_wide;  // 32-bit expansion (4 CTAs / SM instead of 2)
+    CK(cudaFuncSetAttribute(k_window_tiles4<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile4Smem<i64>)));
+    CK(cudaFuncSetAttribute(k_window_tiles4<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile4Smem<int32_t>)));
     tbegin(ctx, KT_WINDOW);
     if (n_jobs) {
-      if (walk_v1 && !tiles_v1 && !tiles_v3 && !tiles_v4) {
-        const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
-        if (narrow) k_window_tiles5<int32_t><<<grid, DT_THREADS, sizeof(Tile5Smem<int32_t>), ctx->stream>>>(TP);
-        else k_window_tiles5<i64><<<grid, DT_THREADS, sizeof(Tile5Smem<i64>), ctx->stream>>>(TP);
-      } else if (walk_v1 && !tiles_v1 && !tiles_v3) {
-        const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
-        if (narrow) k_window_tiles4<int32_t><<<grid, DT_THREADS, sizeof(Tile4Smem<int32_t>), ctx->stream>>>(TP);
-        else k_window_tiles4<i64><<<grid, DT_THREADS, sizeof(Tile4Smem<i64>), ctx->stream>>>(TP);
-      } else if (walk_v1 && !tiles_v1) {
-        const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
-        if (narrow) k_window_tiles3<int32_t><<<grid, DT_THREADS, sizeof(Tile3Smem<int32_t>), ctx->stream>>>(TP);
-        else k_window_tiles3<i64><<<grid, DT_THREADS, sizeof(Tile3Smem<i64>), ctx->stream>>>(TP);
-      } else if (walk_v1) {
-        const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
-        if (narrow) k_window_tiles<int32_t><<<grid, DT_THREADS, sizeof(TileSmemT<int32_t>), ctx->stream>>>(TP);
-        else k_window_tiles<i64><<<grid, DT_THREADS, sizeof(TileSmemT<i64>), ctx->stream>>>(TP);
-      } else {
-        const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
-        k_window_tiles2<<<grid, DW_THREADS, 0, ctx->stream>>>(TP);
-      }
+      const unsigned grid = (unsigned)std::min<u64>(n_jobs, (u64)ctx->sm_count * 64);
+      if (narrow) k_window_tiles4<int32_t><<<grid, DT_THREADS, sizeof(Tile4Smem<int32_t>), ctx->stream>>>(TP);
+      else k_window_tiles4<i64><<<grid, DT_THREADS, sizeof(Tile4Smem<i64>), ctx->stream>>>(TP);
       CK(cudaGetLastError());
       ctx->launches++;
     }
@@ -505,10 +489,9 @@ void do_search_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
   SP.out = nullptr; SP.cap = 0;
   const unsigned grid = (unsigned)((n_jobs + 127) / 128);
   // default for trees up to 64x64: one CTA per (window, time slice, subchunk) with the per-thread walk (decode_search4.cuh);
-  // DCDF_SEARCH_V1=1: one thread per (window, subchunk, instant) replaying the depth-first traversal (k_search)
-  static const bool search_v1 = getenv("DCDF_SEARCH_V1") != nullptr;
-  const bool tiles = mb->max_sidelen <= 64 && !search_v1;
-  const bool narrow = mb->max_dac_levels <= 3 && getenv("DCDF_WINDOW_WIDE") == nullptr;
+  // option "search_dfs": one thread per (window, subchunk, instant) replaying the depth-first traversal (k_search)
+  const bool tiles = mb->max_sidelen <= 64 && !ctx->opt.search_dfs;
+  const bool narrow = mb->max_dac_levels <= 3 && !ctx->opt.window_wide;
   TileSearchParams TS;
   unsigned tgrid = 0;
   if (tiles) {
@@ -532,7 +515,7 @@ void do_search_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
     TS.counts = d_counts; TS.offsets = d_offsets; TS.out = nullptr; TS.cap = 0;
     // 1 KB per (window, subchunk, instant) keeps the counting pass's findings for the writing pass (up to 2 GB)
     TS.hit_cache = nullptr;
-    if (out_irc && n_jobs * (u64)DT_THREADS * 4ull <= (2ull << 30) && getenv("DCDF_SEARCH_NO_CACHE") == nullptr) {
+    if (out_irc && n_jobs * (u64)DT_THREADS * 4ull <= (2ull << 30) && !ctx->opt.search_no_cache) {
       ctx->search_cache.reserve(n_jobs * (size_t)DT_THREADS * 4);
       TS.hit_cache = ctx->search_cache.as<u32>();
     }
@@ -598,6 +581,7 @@ int32_t dcdf_chunk_open(dcdf_ctx* ctx, const uint8_t* bytes, uint64_t len, int32
     if (!out) api_fail(DCDF_ERR_BAD_ARG, "null out");
     *out = nullptr;
     if (!bytes || len < 6) api_fail(DCDF_ERR_BAD_FORMAT, "chunk bytes too short");
+    if (len > 0xfffffff0ull) api_fail(DCDF_ERR_BAD_FORMAT, "a Chunk larger than 4 GiB cannot be addressed by the decode directory");
     dcdf_chunk* c = new dcdf_chunk();
     c->device = ctx->device;
     try {

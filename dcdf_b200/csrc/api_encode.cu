@@ -54,6 +54,12 @@ int32_t guarded(dcdf_ctx* ctx, Fn&& fn) {
   } catch (const std::bad_alloc&) {
     ctx->last_error = "host out of memory";
     return DCDF_ERR_BAD_ARG;
+  } catch (const std::exception& e) {  // nothing may unwind across the C ABI
+    ctx->last_error = std::string("unexpected exception: ") + e.what();
+    return DCDF_ERR_BAD_ARG;
+  } catch (...) {
+    ctx->last_error = "unexpected exception";
+    return DCDF_ERR_BAD_ARG;
   }
 }
 
@@ -213,18 +219,13 @@ void launch_encode_one(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   ctx->launches++;
 }
 // Full 64x64 tiles with 31-bit values: 64-thread CTAs, 64 cells per thread (encode_v4.cuh).
-// DCDF_ENCODE_V2=1 routes them through k_encode_tiles instead; DCDF_STAGE_LIMIT=<bytes> lowers the size above
+// Option "encode_tiles256" routes them through k_encode_tiles instead; option "stage_limit" lowers the size above
 // which a structure is emitted straight into the arena (tests use it to cover that path).
 template <typename InT, bool FULL>
 void launch_encode_v4(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   constexpr int MINB = 4;
-  static const u32 stage_limit = [] {
-    const char* e = getenv("DCDF_STAGE_LIMIT");
-    const long v = e ? atol(e) : (long)E4_POOL;
-    return (u32)std::min<long>(std::max<long>(v, 0), (long)E4_POOL);
-  }();
-  static const size_t pad = getenv("DCDF_V4_PAD") ? (size_t)atol(getenv("DCDF_V4_PAD")) : 0;  // occupancy experiments
-  const size_t smem = sizeof(E4Smem) + pad;
+  const u32 stage_limit = std::min<u32>(ctx->opt.stage_limit, (u32)E4_POOL);
+  const size_t smem = sizeof(E4Smem);
   CK(cudaFuncSetAttribute(k_encode_v4<InT, MINB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_encode_v4<InT, MINB, FULL><<<grid, E4_THREADS, smem, FULL ? ctx->stream : ctx->aux_stream>>>(P, stage_limit);
   CK(cudaGetLastError());
@@ -234,7 +235,7 @@ void launch_encode_v4(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
 template <typename InT>
 void launch_encode(dcdf_ctx* ctx, const EncParams& P, u32 grid, int list) {
   if (grid == 0) return;
-  static const bool force_v2 = getenv("DCDF_ENCODE_V2") != nullptr;
+  const bool force_v2 = ctx->opt.encode_tiles256 != 0;
   if (list == 0 && !force_v2) { launch_encode_v4<InT, true>(ctx, P, grid); return; }
   if (list == 4 && !force_v2) { launch_encode_v4<InT, false>(ctx, P, grid); return; }
   switch (list) {
@@ -260,12 +261,12 @@ void time_collect(dcdf_ctx* ctx, int which) {
   else cudaGetLastError();
 }
 
-// DCDF_TRACE=1 prints host-side phase times of run_encode to stderr (adds stream syncs).
+// Option "trace" prints host-side phase times of run_encode to stderr (adds stream syncs).
 struct Tracer {
   bool on;
   cudaStream_t st;
   std::chrono::steady_clock::time_point t0;
-  Tracer(cudaStream_t s) : on(getenv("DCDF_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+  Tracer(cudaStream_t s, bool on_) : on(on_), st(s), t0(std::chrono::steady_clock::now()) {}
   void mark(const char* what) {
     if (!on) return;
     cudaStreamSynchronize(st);
@@ -278,7 +279,7 @@ struct Tracer {
 // The whole encode pipeline for a list of <=64x64 units grouped in slices.
 void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces) {
   cudaStream_t st = ctx->stream;
-  Tracer tr(st);
+  Tracer tr(st, ctx->opt.trace != 0);
   const u32 n_units = (u32)job.units.size();
   const u32 n_slices = (u32)job.slices.size();
   if (n_units == 0) api_fail(DCDF_ERR_BAD_ARG, "nothing to encode");
@@ -471,6 +472,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   // ---- K_enc (+ table DACs), with arena growth on overflow
   if (ctx->arena_hint == 0) ctx->arena_hint = std::max<size_t>(job.input_bytes / 2 + (8u << 20), 16u << 20);
   std::vector<uint8_t> head_buf(64);
+  u32 sticky = 0;  // flags raised before the emission (finalize / fraction passes) survive an arena retry
   for (int attempt = 0;; attempt++) {
     ctx->arena.reserve(ctx->arena_hint);
     const u64 arena_cap = ctx->arena.cap;
@@ -525,14 +527,16 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     u64 head;
     memcpy(&flags, head_buf.data(), 4);
     memcpy(&head, head_buf.data() + 8, 8);
-    if (flags & EF_ARENA_FULL) {
-      if (attempt >= 2) api_fail(DCDF_ERR_CUDA, "arena overflow persisted after growth");
+    sticky |= flags & ~(u32)EF_ARENA_FULL;
+    std::string msg;
+    if ((flags & EF_ARENA_FULL) && status_from_flags(sticky, msg) == DCDF_OK) {
+      if (attempt >= 3) api_fail(DCDF_ERR_CUDA, "arena overflow persisted after growth");
       ctx->arena_hint = (size_t)head + (size_t)head / 16 + (1u << 20);
       CK(cudaMemsetAsync(d_err, 0, 4, st));
       // phase-2 outputs (order lists, unit bits) are still valid; only the emission is repeated
       continue;
     }
-    std::string msg;
+    flags = sticky;
     int32_t code = status_from_flags(flags, msg);
     if (code != DCDF_OK) {
       pool_free(d_tbl_max);
@@ -615,6 +619,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   tr.mark("gather");
   u32 flags;
   memcpy(&flags, head_buf.data(), 4);
+  flags |= sticky;
   std::string msg;
   int32_t code = status_from_flags(flags, msg);
   if (code != DCDF_OK) throw ApiFail{code, msg};
@@ -871,6 +876,8 @@ int32_t dcdf_ctx_create(int32_t device, dcdf_ctx** out) {
   ctx->device = device;
   try {
     CK(cudaSetDevice(device));
+    upload_log2_roundup_table();  // a1: floor(log2(max)) exactly as the host libm rounds it (fixed.rs:126)
+    CK(cudaGetLastError());
     CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     for (auto& ev : ctx->ev) CK(cudaEventCreate(&ev));
@@ -917,6 +924,24 @@ int32_t dcdf_ctx_destroy(dcdf_ctx* ctx) {
 int32_t dcdf_ctx_set_stream(dcdf_ctx* ctx, void* cuda_stream) {
   if (!ctx) return DCDF_ERR_BAD_ARG;
   ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return DCDF_OK;
+}
+
+int32_t dcdf_ctx_set_option(dcdf_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return DCDF_ERR_BAD_ARG;
+  const std::string n(name);
+  if (n == "stage_limit") ctx->opt.stage_limit = value < 0 ? 0xffffffffu : (uint32_t)std::min<int64_t>(value, 0xffffffffll);
+  else if (n == "arena_hint") ctx->arena_hint = value < 0 ? 0 : (size_t)value;
+  else if (n == "encode_tiles256") ctx->opt.encode_tiles256 = value != 0;
+  else if (n == "window_cells") ctx->opt.window_cells = value != 0;
+  else if (n == "window_wide") ctx->opt.window_wide = value != 0;
+  else if (n == "search_dfs") ctx->opt.search_dfs = value != 0;
+  else if (n == "search_no_cache") ctx->opt.search_no_cache = value != 0;
+  else if (n == "trace") ctx->opt.trace = value != 0;
+  else {
+    ctx->last_error = "unknown option " + n;
+    return DCDF_ERR_BAD_ARG;
+  }
   return DCDF_OK;
 }
 

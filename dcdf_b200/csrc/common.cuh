@@ -22,6 +22,7 @@ enum : u32 {
   EF_OUT_CAP = 1u << 5,
   EF_BAD_LEVELS = 1u << 6,    // superchunk.rs:105-110 inside a recursion
   EF_REGION_EXACT = 1u << 7,  // nested region needs the exact saturating-cast pass (not built yet)
+  EF_OUT_OF_BOUNDS = 1u << 8, // a device-resident query outside the array (mmarray.rs:218-229)
 };
 
 #define DCDF_DEVINL __device__ __forceinline__

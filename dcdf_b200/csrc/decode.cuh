@@ -164,6 +164,7 @@ struct DirParams {
   InstDir* dir;      // may be null in counting mode
   u32 n_units;
   int count_only;    // 1: only walk and count instants (dcdf_chunk_open pass 1)
+  int validate;      // 1: bytes come from outside (dcdf_chunk_open / dcdf_superchunk_open): check every count the walks rely on
   u32* err;
 };
 
@@ -205,6 +206,30 @@ DCDF_DEVINL void parse_dac(Cursor& c, DacDir& d) {
   }
 }
 
+// Ones among the first `len` bits of a serialized BitMap, checking its rank directory on the way
+// (index[b] == ones in words [0, 4(b+1)), bitmap.rs:97-104).  The walks trust both.
+DCDF_DEVINL u32 checked_popcount(const u8* chunk, u32 len, u32 base, bool& ok) {
+  const u32 blocks = len / 128u, words = (len + 31u) / 32u;
+  const u32 wo = base + 8u + 4u * blocks;
+  u32 ones = 0;
+  for (u32 w = 0; w < words; w++) {
+    u32 v = be32_at(chunk, wo + 4u * w);
+    if (w == words - 1u && (len & 31u)) v &= ~(0xffffffffu >> (len & 31u));
+    ones += __popc(v);
+    if ((w & 3u) == 3u && (w >> 2) < blocks && be32_at(chunk, base + 8u + 4u * (w >> 2)) != ones) ok = false;
+  }
+  return ones;
+}
+// Dac::from invariants (dac.rs:96-132): level j + 1 holds one byte per continuation bit of level j.
+DCDF_DEVINL void check_dac(const u8* chunk, const DacDir& d, u32 expect_len0, bool& ok) {
+  if ((d.n_levels ? d.len[0] : 0u) != expect_len0) ok = false;
+  for (u32 j = 0; j < d.n_levels && ok; j++) {
+    const u32 ones = checked_popcount(chunk, d.len[j], d.base[j], ok);
+    const u32 next = j + 1u < d.n_levels ? d.len[j + 1u] : 0u;
+    if (ones != next) ok = false;
+  }
+}
+
 __global__ void k_build_dir(const DirParams P) {
   const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= P.n_units) return;
@@ -239,6 +264,20 @@ __global__ void k_build_dir(const DirParams P) {
       dac_levels = max(dac_levels, d.max.n_levels);
       d.size = (u32)c.pos - d.off;
       if (c.ok && d.nm_len == 0) c.ok = false;
+      if (c.ok && P.validate && !P.count_only) {
+        // one max entry for the root and four per internal node, one min entry per internal node, one `equal` bit per
+        // node that is not internal (snapshot.rs:122-147, log.rs:128-158): the walks index with ranks of the nodemap
+        bool ok = (d.nm_len & 3u) == 1u;
+        const u32 ones = checked_popcount(c.p, d.nm_len, d.nm_base, ok);
+        check_dac(c.p, d.max, 1u + 4u * ones, ok);
+        check_dac(c.p, d.min, ones, ok);
+        if (i > 0) {
+          if (d.eq_len != d.nm_len - ones) ok = false;
+          else checked_popcount(c.p, d.eq_len, d.eq_base, ok);
+        }
+        if (d.nm_len > 1u + 4u * ones) ok = false;
+        if (!ok) c.ok = false;
+      }
       if (c.ok && !P.count_only) {
         if (inst >= (u32)m.instants) c.ok = false;
         else P.dir[m.dir_base + inst] = d;
@@ -364,11 +403,16 @@ DCDF_DEVINL void emit(const QuerySet& Q, void* out, u64 i, i64 fixed, int bits, 
 }
 
 // Chunk::get batched: one thread per (instant,row,col)
-__global__ void k_get_batch(const QuerySet Q, const i64* irc, u64 n, void* out, int raw) {
+// Queries may live in device memory the host never saw: bounds are checked here (mmarray.rs:218-229); an offending
+// query writes 0 and raises EF_OUT_OF_BOUNDS.
+__global__ void k_get_batch(const QuerySet Q, const i64* irc, u64 n, void* out, int raw, u32* err) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int bits;
-  const i64 v = set_get(Q, irc[3 * i], irc[3 * i + 1], irc[3 * i + 2], bits);
+  int bits = 0;
+  const i64 t = irc[3 * i], r = irc[3 * i + 1], c = irc[3 * i + 2];
+  i64 v = 0;
+  if (t < 0 || r < 0 || c < 0 || t >= Q.shape[0] || r >= Q.shape[1] || c >= Q.shape[2]) atomicOr(err, (u32)EF_OUT_OF_BOUNDS);
+  else v = set_get(Q, t, r, c, bits);
   emit(Q, out, i, v, bits, raw);
 }
 

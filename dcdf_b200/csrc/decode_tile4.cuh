@@ -13,7 +13,7 @@
 // over the serialized rank directory (bitmap.rs:186-212).  The only block barrier per instant publishes the bytes
 // that cp.async brought in while the previous instant was being decoded.
 #pragma once
-#include "decode_tile3.cuh"
+#include "decode_tile_common.cuh"
 
 namespace dcdf {
 

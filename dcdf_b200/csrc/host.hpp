@@ -110,6 +110,16 @@ struct dcdf_ctx {
   float kernel_ms[dcdf::KT_COUNT] = {0, 0, 0, 0, 0, 0};
   cudaEvent_t ev[2 * dcdf::KT_COUNT] = {};
   int sm_count = 148;
+  // dcdf_ctx_set_option (include/dcdf_cuda.h)
+  struct Options {
+    uint32_t stage_limit = 0xffffffffu;  // encoder: structures above this many bytes are emitted straight into the arena
+    int encode_tiles256 = 0;             // full tiles through the 256-thread tile encoder instead of the 64-thread one
+    int window_cells = 0;                // windows through the per-cell walker (the path of trees larger than 64x64)
+    int window_wide = 0;                 // 64-bit expansion even when every DAC code fits three bytes
+    int search_dfs = 0;                  // depth-first search kernel instead of the tile search
+    int search_no_cache = 0;             // the search's writing pass recomputes instead of reading cached findings
+    int trace = 0;                       // host-side phase times of the encode pipeline on stderr (adds stream syncs)
+  } opt;
   // scratch
   dcdf::DevBuf input_copy, units, ustats, istats, slices, sstate, tbl_scratch, order, pieces, results, stored, chunk_off,
       arena, small, exact, query_in, query_out, query_aux, query_aux2, search_cache, tree_buf;
@@ -177,4 +187,5 @@ struct dcdf_superchunk {
   uint64_t tbl_len = 0;
   void* dir = nullptr;         // device decode directory over all stored units
   void* dev_meta = nullptr;    // device copies of unit / slot tables for the query kernels
+  bool opened = false;         // built from stored bytes by dcdf_superchunk_open (validated like Chunk::read_from)
 };

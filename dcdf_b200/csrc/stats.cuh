@@ -5,6 +5,8 @@
 // and the per-slice finalisation of Superchunk::build (superchunk.rs:127-198): parent/sub fractional
 // bits, fixed-point (min,max) tables in instant-major order, elision flags, narrow/wide work lists.
 #pragma once
+#include <cmath>
+
 #include "common.cuh"
 #include "encode_tile.cuh"
 #include "tree_types.hpp"
@@ -128,11 +130,31 @@ struct FracAcc<float> {
   }
 };
 
-// whole_bits = 1 + (floor(log2(max)) as usize)  (fixed.rs:126; `as` saturates: NaN / negatives -> 0)
+// whole_bits = 1 + (floor(log2(max)) as usize)  (fixed.rs:126; `as` saturates: NaN / negatives -> 0).
+// The reference takes log2 with the host's libm, whose result ROUNDS UP to the integer k for the last few doubles below
+// 2^k (8 - 2^-50 -> log2 == 3.0), so floor(log2(x)) is not ilogb(x) there.  c_log2_roundup[k] has bit j-1 set when
+// floor(std::log2(2^k - j * 2^(k-53))) == k on THIS host (filled by dcdf_ctx_create with std::log2, the libm call
+// behind Rust's f64::log2); only f64 inputs can come that close to a power of two.
+__constant__ u64 c_log2_roundup[64];
 DCDF_DEVINL int whole_bits_of(double vmax) {
   if (!(vmax > 0.0)) return 1;
   int e = ilogb(vmax);
+  if (e >= 0 && e < 63) {
+    const double j = (ldexp(1.0, e + 1) - vmax) * ldexp(1.0, 52 - e);  // exact: vmax is the j-th double below 2^(e+1)
+    if (j <= 64.0 && ((c_log2_roundup[e + 1] >> ((int)j - 1)) & 1ull)) e += 1;
+  }
   return 1 + (e > 0 ? e : 0);
+}
+inline void upload_log2_roundup_table() {
+  u64 tab[64];
+  for (int k = 0; k < 64; k++) {
+    tab[k] = 0;
+    for (int j = 1; j <= 64 && k >= 1; j++) {
+      const double x = std::ldexp(1.0, k) - (double)j * std::ldexp(1.0, k - 53);
+      if (std::floor(std::log2(x)) == (double)k) tab[k] |= 1ull << (j - 1);
+    }
+  }
+  cudaMemcpyToSymbol(c_log2_roundup, tab, sizeof tab);
 }
 
 // Evaluate suggest_fraction from a (max, frac_nonneg, frac_neg, most-negative) summary.

@@ -40,8 +40,14 @@ def _triangle(v, period, amp):
 
 
 def raster_slice(t0, t1, rows, cols, *, seed=0xDCDF0002, frac_bits=4, base=280, hourly=True, nan_ocean=False,
-                 noise_every=16, noise_mask=3, device="cpu", dtype=torch.float32):
-    """float raster [t1-t0, rows, cols] of the synthetic field for instants t0..t1."""
+                 noise_every=16, noise_mask=3, scale=None, device="cpu", dtype=torch.float32):
+    """float raster [t1-t0, rows, cols] of the synthetic field for instants t0..t1.
+
+    noise_every=1 jitters every cell (SURVEY 8d's per-cell noise; the default touches every 16th cell).
+    scale: multiply the finished field by this factor IN THE OUTPUT dtype (one IEEE multiply, identical on CPU and
+    CUDA).  A non-dyadic factor such as 0.1 gives what un-rounded real data looks like: full mantissas, ~29
+    fractional bits, fixed-point values beyond 32 bits (the int64 encode path) -- SURVEY 8d's variant v2; the same
+    data with round=True and a small fractional_bits is variant v3."""
     dev = torch.device(device)
     t = torch.arange(t0, t1, device=dev, dtype=torch.int64).view(-1, 1, 1)
     y = torch.arange(rows, device=dev, dtype=torch.int64).view(1, -1, 1)
@@ -71,7 +77,10 @@ def raster_slice(t0, t1, rows, cols, *, seed=0xDCDF0002, frac_bits=4, base=280, 
         out = torch.clamp(out - float(base), min=0.0)
         ocean = (_hash3(seed ^ 0xAAAA, torch.zeros_like(t), y // 16, x // 16) & 0xFF) < 154
         out = torch.where(ocean.expand_as(out), torch.full_like(out, float("nan")), out)
-    return out.to(dtype)
+    out = out.to(dtype)
+    if scale is not None:
+        out = out * torch.tensor(scale, dtype=dtype, device=dev)
+    return out
 
 
 def raster(instants, rows, cols, *, slice_instants=64, out=None, **kw):

@@ -82,6 +82,18 @@ int32_t dcdf_ctx_create(int32_t device, dcdf_ctx** out);
 int32_t dcdf_ctx_destroy(dcdf_ctx* ctx);
 /* Borrow a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the private one. */
 int32_t dcdf_ctx_set_stream(dcdf_ctx* ctx, void* cuda_stream);
+/* Per-context knobs (the reference has no configuration system: all knobs are arguments; these
+ * select between code paths that produce identical bytes / results and exist for tests and A/B measurements):
+ *   "stage_limit" <bytes>   encoder: structures larger than this are emitted straight into the arena (default 16384)
+ *   "arena_hint"  <bytes>   first size of the encoder's output arena (grown and retried when it overflows)
+ *   "encode_tiles256" 0|1   full 64x64 tiles through the 256-thread tile encoder
+ *   "window_cells" 0|1      windows through the per-cell walker (the path of trees larger than 64x64)
+ *   "window_wide" 0|1       64-bit tile expansion even when every DAC code fits three bytes
+ *   "search_dfs" 0|1        depth-first search kernel instead of the tile search
+ *   "search_no_cache" 0|1   search's writing pass recomputes instead of reading the counting pass's findings
+ *   "trace" 0|1             host-side phase times of the encode pipeline on stderr
+ * Unknown names return DCDF_ERR_BAD_ARG. */
+int32_t dcdf_ctx_set_option(dcdf_ctx* ctx, const char* name, int64_t value);
 int32_t dcdf_ctx_synchronize(dcdf_ctx* ctx);
 const char* dcdf_last_error(const dcdf_ctx* ctx);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */

@@ -14,10 +14,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["staged", "direct"])
+def ctx(request):
+    """Every test of this module runs twice: with the shared-memory emission image (default) and with option
+    stage_limit = 0, which forces every structure through the direct (global-memory) emission path."""
     from dcdf_b200 import Context
     c = Context(0)
+    if request.param == "direct":
+        c.set_option("stage_limit", 0)
     yield c
     c.close()
 
@@ -182,11 +186,3 @@ def test_superchunk_many_full_tiles(ctx):
         if k:
             assert chunks[slot] == ref.node_bytes(int(c)), f"slot {slot}"
     assert np.array_equal(sc.window(0, 70, 0, 150, 0, 230), data)
-
-
-def test_direct_to_arena_emission():
-    """DCDF_STAGE_LIMIT=0 forces every structure through the direct (global-memory) emission path."""
-    env = dict(os.environ, DCDF_STAGE_LIMIT="0")
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
-                        "full_tile_int or uniform_levels or float_nan"], cwd=ROOT, env=env, capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -99,19 +99,15 @@ def test_superchunk_search_batch_against_oracle_chunks(ctx):
     sc.close()
 
 
-@pytest.mark.parametrize("env", ["DCDF_SEARCH_V1", "DCDF_WINDOW_WIDE", "DCDF_SEARCH_NO_CACHE"])
-def test_depth_first_search_kernel_and_wide_expansion_stay_bit_exact(env):
-    code = (
-        "import sys, numpy as np\n"
-        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
-        "import oracle_lib as orc, test_gpu_window as t\n"
-        "from dcdf_b200 import Context, Chunk\n"
-        "ctx = Context(0)\n"
-        "data = t._field(9, 64, 50, 5, nan_frac=0.04)\n"
-        "got, ref = Chunk.build(ctx, data, fractional_bits=4), orc.chunk_build(data, fractional_bits=4)\n"
-        "for lo, hi in ((7900, 8000), (0, 0), (7000, 9000)):\n"
-        "    assert np.array_equal(got.search(1, 9, 3, 60, 2, 49, lo, hi), ref.search(1, 9, 3, 60, 2, 49, lo, hi))\n"
-        "print('ok')\n"
-    )
-    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, env: "1"}, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+@pytest.mark.parametrize("option", ["search_dfs", "window_wide", "search_no_cache"])
+def test_depth_first_search_kernel_and_wide_expansion_stay_bit_exact(option):
+    import test_gpu_window as t
+    from dcdf_b200 import Chunk, Context
+    ctx = Context(0)
+    ctx.set_option(option, 1)
+    data = t._field(9, 64, 50, 5, nan_frac=0.04)
+    got, ref = Chunk.build(ctx, data, fractional_bits=4), orc.chunk_build(data, fractional_bits=4)
+    for lo, hi in ((7900, 8000), (0, 0), (7000, 9000)):
+        assert np.array_equal(got.search(1, 9, 3, 60, 2, 49, lo, hi), ref.search(1, 9, 3, 60, 2, 49, lo, hi))
+    got.close()
+    ctx.close()

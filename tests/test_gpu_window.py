@@ -138,21 +138,16 @@ def test_device_output_and_elided_tiles(ctx):
     sc.close()
 
 
-@pytest.mark.parametrize("env", ["DCDF_WINDOW_V1", "DCDF_WINDOW_V3", "DCDF_WINDOW_V5", "DCDF_WINDOW_CELLS", "DCDF_WINDOW_WIDE"])
-def test_other_window_kernels_stay_bit_exact(env):
-    """The earlier generations (and the per-cell kernel used for trees larger than 64x64) are selected once per process."""
-    code = (
-        "import sys, numpy as np\n"
-        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
-        "import test_gpu_window as t\n"
-        "from dcdf_b200 import Context, Superchunk\n"
-        "ctx = Context(0)\n"
-        "data = t._field(19, 150, 203, 3, nan_frac=0.05)\n"
-        "sc = Superchunk.build(ctx, data, [2, 6], chunk_size=8)\n"
-        "for c in ([0, 19, 0, 150, 0, 203], [3, 18, 5, 149, 7, 202], [9, 10, 64, 128, 0, 64]):\n"
-        "    w = sc.window(*c)\n"
-        "    assert t._same(t._canon(w), t._canon(data[c[0]:c[1], c[2]:c[3], c[4]:c[5]])), c\n"
-        "print('ok')\n"
-    )
-    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, env: "1"}, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+@pytest.mark.parametrize("option", ["window_cells", "window_wide"])
+def test_other_window_kernels_stay_bit_exact(option):
+    """The per-cell kernel (used for trees larger than 64x64) and the 64-bit tile expansion, selected per context."""
+    from dcdf_b200 import Context, Superchunk
+    ctx = Context(0)
+    ctx.set_option(option, 1)
+    data = _field(19, 150, 203, 3, nan_frac=0.05)
+    sc = Superchunk.build(ctx, data, [2, 6], chunk_size=8)
+    for c in ([0, 19, 0, 150, 0, 203], [3, 18, 5, 149, 7, 202], [9, 10, 64, 128, 0, 64]):
+        w = sc.window(*c)
+        assert _same(_canon(w), _canon(data[c[0]:c[1], c[2]:c[3], c[4]:c[5]])), c
+    sc.close()
+    ctx.close()
