@@ -457,7 +457,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     TP.nstate = d_nstate;
     TP.units = ctx->units.as<EncUnit>();
     TP.ustats = SP.ustats; TP.istats = SP.istats; TP.t_max = job.t_max;
-    TP.encoding = job.encoding; TP.round = job.round;
+    TP.encoding = job.encoding; TP.round = job.round; TP.req_bits = job.req_bits;
     TP.tbl_min = d_tbl_min; TP.tbl_max = d_tbl_max;
     TP.order = FP.order; TP.order_pitch = FP.order_pitch; TP.order_counts = FP.order_counts;
     TP.stored = FP.stored; TP.err = d_err;

@@ -163,6 +163,9 @@ DCDF_DEVINL bool suggest_from_summary(bool has_value, double vmax, double vneg, 
                                       int& bits, int& err) {
   err = 0;
   if (!has_value) { round_ = 0; bits = 0; return true; }  // all NaN -> Precise(0)  (fixed.rs:121-124)
+  // max == +inf: log2 is inf, the `as usize` cast saturates and 1 + usize::MAX wraps to 0 in a release build, so
+  // max_fraction_bits = 62; inf.fract() is NaN != 0.0 -> Round(62)  (fixed.rs:126-148)
+  if (isinf(vmax)) { round_ = 1; bits = 62; return true; }
   int whole = whole_bits_of(vmax);
   if (whole > 62) { err = EF_OVERFLOW; round_ = 0; bits = 0; return true; }
   int maxfb = 62 - whole;
@@ -700,7 +703,10 @@ __global__ void k_finalize_phase2(const FinalizeParams P, u32 n_slices) {
   }
   if (n_el) atomicAdd(&P.state[s].n_elided, n_el);
   if (n_st) atomicAdd(&P.state[s].n_stored, n_st);
-  if (err) atomicOr(&s_err, err);
+  // a panic of the slice-level compute_fractional_bits (dataset.rs:842) comes before anything Superchunk::build raises
+  const bool slice_failed = P.state[s].err != 0;
+  __syncthreads();
+  if (err && !slice_failed) atomicOr(&s_err, err);
   __syncthreads();
   if (tid == 0 && s_err) { P.state[s].err = s_err; atomicOr(P.err, s_err); }
 }
@@ -789,7 +795,7 @@ struct TreeParams {
   const UnitStats* ustats;
   const InstStats* istats;
   u32 t_max;
-  int encoding, round;
+  int encoding, round, req_bits;
   i64* tbl_min;
   i64* tbl_max;
   u32* order;
@@ -810,12 +816,26 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
   NodeState* ns = P.nstate + (size_t)s * P.n_nodes;
   u32 err = 0;
   u32 n_el = 0, n_st = 0;
+  __shared__ int s_slice_failed;
   if (tid == 0) {
+    // slice-level compute_fractional_bits (dataset.rs:842): resolve the exact pass and surface its panic, which comes
+    // before anything Superchunk::build raises
+    SliceState st = P.state[s];
+    if (st.need_exact) {
+      const int rnd = st.round_exact, bits = rnd ? st.maxfb : st.f_exact;
+      if (round) st.bits = min(bits, P.req_bits);              // mmbuffer.rs:602-603
+      else { if (rnd) st.err |= EF_PRECISION; st.bits = bits; }  // mmbuffer.rs:605-609
+      P.state[s].bits = st.bits;
+      P.state[s].err = st.err;
+    }
+    s_slice_failed = st.err != 0;
+    if (st.err) atomicOr(P.err, st.err);
     ns[0].alive = 1;
-    ns[0].bits = P.state[s].bits;
+    ns[0].bits = st.bits;
     for (u32 n = 1; n < P.n_nodes; n++) { ns[n].alive = 0; ns[n].bits = 0; }
   }
   __syncthreads();
+  const bool slice_failed = s_slice_failed != 0;
   for (u32 n = 0; n < P.n_nodes; n++) {
     const TreeNode nd = P.nodes[n];
     const bool alive = ns[n].alive != 0;
@@ -961,7 +981,7 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
   }
   if (n_el) atomicAdd(&P.state[s].n_elided, n_el);
   if (n_st) atomicAdd(&P.state[s].n_stored, n_st);
-  if (err) { atomicOr(&P.state[s].err, err); atomicOr(P.err, err); }
+  if (err && !slice_failed) { atomicOr(&P.state[s].err, err); atomicOr(P.err, err); }
 }
 
 }  // namespace dcdf

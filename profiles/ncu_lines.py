@@ -2,7 +2,7 @@
 import csv, subprocess, sys, io
 rep, kre = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", ] + (["--kernel-id", ":::" + kre] if kre != "all" else []),
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", ] + (["--kernel-id", "::regex:" + kre + ":" + (sys.argv[4] if len(sys.argv) > 4 else "1")] if kre != "all" else []),
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 agg, cur, hdr = {}, None, None

@@ -43,7 +43,7 @@ def test_c3_shaped_whole_slice(ctx):
     assert 0.5 < np.isnan(data).mean() < 0.7
     got = _check_superchunk(ctx, data, [5, 6])
     st = got.info(0).stats
-    assert st.external + st.elided == 1024 and st.elided > 1024 - 220      # all-NaN / all-zero tiles are elided
+    assert st.external + st.elided == 1024 and st.external <= 220           # 10 x 22 in-bounds tiles of 32 x 32 slots
     rng = np.random.default_rng(2)
     q = np.stack([np.zeros(200, np.int64), np.full(200, 64, np.int64), rng.integers(0, 621, 200), rng.integers(0, 1405, 200)], axis=1)
     for qi, series in zip(q, got.cell_batch(q)):
@@ -106,11 +106,31 @@ def test_whole_bits_follow_the_host_libm_log2(ctx):
     rng = np.random.default_rng(4)
     data = rng.integers(0, 2 ** 20, (5, 40, 50)).astype(np.float64) / 2.0 ** 20 * 7.0
     data[2, 7, 9] = below8
-    data[0, 0, 0] = 1.0 / 3.0                                              # forces Round(max_fraction_bits)
+    data[0, 0, 0] = 0.0123                                                 # 59 fractional bits > 62 - 4: Round(58)
     kind, bits = orc.suggest_fraction(data)
     assert ctx.suggest_fraction(data) == (kind, bits) and kind == "Round"
     _check_chunk(ctx, data, fractional_bits=bits, round_=True)
     _check_superchunk(ctx, data, [1, 5], fractional_bits=60, round_=True).close()     # per-slice and per-subchunk bits
+
+
+def test_slice_level_fraction_panics_and_exact_pass_through_superchunk_build(ctx):
+    """compute_fractional_bits of the whole slice (dataset.rs:842) can fail where no single subchunk does, and its
+    saturating-cast corner (fixed.rs:150) needs the exact pass; both must reach Superchunk::build's result."""
+    from dcdf_b200 import DcdfError, Superchunk
+    rng = np.random.default_rng(12)
+    data = 280.0 + rng.integers(0, 64, (4, 128, 128)).astype(np.float64) / 16.0
+    data[:, :64, :64] = 0.1 + rng.integers(0, 8, (4, 64, 64)) / 8.0        # this tile alone is Precise(55); the slice is Round(53)
+    assert orc.suggest_fraction(np.ascontiguousarray(data[:, :64, :64]))[0] == "Precise" and orc.suggest_fraction(data)[0] == "Round"
+    with pytest.raises(orc.OracleError) as eo:
+        orc.superchunk_build(data, [1, 6])
+    with pytest.raises(DcdfError) as eg:
+        Superchunk.build(ctx, data, [1, 6])
+    assert eg.value.code == eo.value.code == 2
+    _check_superchunk(ctx, data, [1, 6], fractional_bits=20, round_=True).close()
+    neg = rng.integers(0, 32, (3, 128, 128)).astype(np.float64) / 16.0
+    neg[1, 70, 70] = -100.5                                                # -100.5 * 2^60 saturates `as i64`
+    _check_superchunk(ctx, neg, [1, 6]).close()
+    _check_superchunk(ctx, neg.astype(np.float32), [1, 6]).close()
 
 
 # ----------------------------------------------------------------------------- arena retry keeps earlier flags
@@ -167,7 +187,7 @@ def test_out_buffers_are_validated_and_ordered_after_torch(ctx):
     import torch
     from dcdf_b200 import Superchunk, synth
     dev = synth.raster_slice(0, 8, 100, 130, device="cuda")
-    sc = Superchunk.build(ctx, dev * 1.0, [1, 6])                          # input produced by a kernel still in flight on torch's stream
+    sc = Superchunk.build(ctx, dev * 1.0, [2, 6])                          # input produced by a kernel still in flight on torch's stream
     host = dev.cpu().numpy()
     assert np.array_equal(sc.window(0, 8, 0, 100, 0, 130), host)
     with pytest.raises(ValueError):
