@@ -70,6 +70,7 @@ def _declare(lib):
         "dcdf_ctx_destroy": (i32, [vp]),
         "dcdf_ctx_set_stream": (i32, [vp, vp]),
         "dcdf_ctx_set_option": (i32, [vp, C.c_char_p, i64]),
+        "dcdf_ctx_get_stat": (i32, [vp, C.c_char_p, _P(i64)]),
         "dcdf_ctx_synchronize": (i32, [vp]),
         "dcdf_last_error": (C.c_char_p, [vp]),
         "dcdf_ctx_launch_count": (u64, [vp]),

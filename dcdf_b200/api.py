@@ -126,6 +126,12 @@ class Context:
         """dcdf_ctx_set_option: select between equivalent code paths (tests, A/B measurements)."""
         self.check(self._lib.dcdf_ctx_set_option(self._h, name.encode(), int(value)))
 
+    def get_stat(self, name):
+        """dcdf_ctx_get_stat: counters of the last build (e.g. "encode_units_fast")."""
+        v = C.c_int64()
+        self.check(self._lib.dcdf_ctx_get_stat(self._h, name.encode(), C.byref(v)))
+        return v.value
+
     def synchronize(self):
         self.check(self._lib.dcdf_ctx_synchronize(self._h))
 

@@ -9,6 +9,7 @@
 
 #include "encode_big.cuh"
 #include "encode_v4.cuh"
+#include "encode_v5.cuh"
 #include "gather.cuh"
 #include "host.hpp"
 #include "stats.cuh"
@@ -231,10 +232,25 @@ void launch_encode_v4(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   CK(cudaGetLastError());
   ctx->launches++;
 }
-// list = wide * 2 + clipped  (narrow kernels are compiled for two resident CTAs per SM)
+// Full f32 tiles that qualify for the small fast-path kernel (encode_v5.cuh; list 5, filled by k_finalize_tree).
+void launch_encode_v5(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
+  constexpr int G = 6;  // tiles per CTA, one CTA per SM
+  const u32 stage_limit = std::min<u32>(ctx->opt.stage_limit, (u32)E5_POOL);
+  const size_t smem = sizeof(E5Smem) * G;
+  CK(cudaFuncSetAttribute(k_encode_v5<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_encode_v5<G><<<(grid + G - 1) / G, E5_THREADS * G, smem, ctx->stream>>>(P, stage_limit);
+  CK(cudaGetLastError());
+  ctx->launches++;
+}
+// list = wide * 2 + clipped  (narrow kernels are compiled for two resident CTAs per SM); 4 = clipped 64-side trees,
+// 5 = fast path
 template <typename InT>
 void launch_encode(dcdf_ctx* ctx, const EncParams& P, u32 grid, int list) {
   if (grid == 0) return;
+  if (list == 5) {
+    if (sizeof(InT) == 4) launch_encode_v5(ctx, P, grid);  // k_finalize_tree only fills the list for f32 input
+    return;
+  }
   const bool force_v2 = ctx->opt.encode_tiles256 != 0;
   if (list == 0 && !force_v2) { launch_encode_v4<InT, true>(ctx, P, grid); return; }
   if (list == 4 && !force_v2) { launch_encode_v4<InT, false>(ctx, P, grid); return; }
@@ -306,7 +322,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   ctx->istats.reserve(sizeof(InstStats) * (size_t)n_units * job.t_max);
   ctx->slices.reserve(sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_tables);
   ctx->sstate.reserve(sizeof(SliceState) * n_slices);
-  ctx->order.reserve(sizeof(u32) * (5 * (size_t)n_units + 8));
+  ctx->order.reserve(sizeof(u32) * (6 * (size_t)n_units + 8));
   ctx->pieces.reserve(sizeof(Piece) * (n_pieces + 2 * (size_t)n_tables));
   ctx->results.reserve(sizeof(UnitResult) * n_units);
   ctx->stored.reserve(n_units);
@@ -458,6 +474,10 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     TP.units = ctx->units.as<EncUnit>();
     TP.ustats = SP.ustats; TP.istats = SP.istats; TP.t_max = job.t_max;
     TP.encoding = job.encoding; TP.round = job.round; TP.req_bits = job.req_bits;
+    // k_encode_v5 reads rows of four cells with 128-bit loads
+    TP.allow_fast = job.encoding == DCDF_ENC_F32 && !ctx->opt.no_fast_encode && job.strides[2] == 1 && job.strides[1] % 4 == 0 &&
+                    job.strides[0] % 4 == 0 && ((uintptr_t)job.dev_data & 15) == 0;
+    for (const auto& u : job.units) if (u.base % 4 != 0) { TP.allow_fast = 0; break; }
     TP.tbl_min = d_tbl_min; TP.tbl_max = d_tbl_max;
     TP.order = FP.order; TP.order_pitch = FP.order_pitch; TP.order_counts = FP.order_counts;
     TP.stored = FP.stored; TP.err = d_err;
@@ -490,7 +510,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     time_begin(ctx, KT_ENCODE);
     CK(cudaEventRecord(ctx->fork_ev, st));  // clipped-tile lists run on the auxiliary stream beside the full-tile lists
     CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));
-    for (int list = 0; list < 5; list++) {
+    for (int list = 5; list >= 0; list--) {  // the fast-path list (most units of a typical raster) goes first
       EP.order = FP.order + (size_t)list * n_units;
       EP.order_count = d_counts + list;
       switch (job.encoding) {
@@ -527,6 +547,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     u64 head;
     memcpy(&flags, head_buf.data(), 4);
     memcpy(&head, head_buf.data() + 8, 8);
+    memcpy(ctx->last_list_counts, head_buf.data() + 16, sizeof ctx->last_list_counts);
     sticky |= flags & ~(u32)EF_ARENA_FULL;
     std::string msg;
     if ((flags & EF_ARENA_FULL) && status_from_flags(sticky, msg) == DCDF_OK) {
@@ -933,6 +954,7 @@ int32_t dcdf_ctx_set_option(dcdf_ctx* ctx, const char* name, int64_t value) {
   if (n == "stage_limit") ctx->opt.stage_limit = value < 0 ? 0xffffffffu : (uint32_t)std::min<int64_t>(value, 0xffffffffll);
   else if (n == "arena_hint") ctx->arena_hint = value < 0 ? 0 : (size_t)value;
   else if (n == "encode_tiles256") ctx->opt.encode_tiles256 = value != 0;
+  else if (n == "no_fast_encode") ctx->opt.no_fast_encode = value != 0;
   else if (n == "window_cells") ctx->opt.window_cells = value != 0;
   else if (n == "window_wide") ctx->opt.window_wide = value != 0;
   else if (n == "search_dfs") ctx->opt.search_dfs = value != 0;
@@ -942,6 +964,18 @@ int32_t dcdf_ctx_set_option(dcdf_ctx* ctx, const char* name, int64_t value) {
     ctx->last_error = "unknown option " + n;
     return DCDF_ERR_BAD_ARG;
   }
+  return DCDF_OK;
+}
+
+int32_t dcdf_ctx_get_stat(const dcdf_ctx* ctx, const char* name, int64_t* value) {
+  if (!ctx || !name || !value) return DCDF_ERR_BAD_ARG;
+  const std::string n(name);
+  const uint32_t* c = ctx->last_list_counts;
+  if (n == "encode_units_fast") *value = c[5];
+  else if (n == "encode_units_general") *value = (int64_t)c[0] + c[1] + c[2] + c[3] + c[4];
+  else if (n == "encode_units_wide") *value = (int64_t)c[2] + c[3];
+  else if (n == "encode_units_clipped") *value = (int64_t)c[1] + c[3] + c[4];
+  else return DCDF_ERR_BAD_ARG;
   return DCDF_OK;
 }
 

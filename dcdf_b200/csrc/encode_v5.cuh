@@ -1,0 +1,905 @@
+// encode_v5.cuh -- Chunk::build (chunk.rs:42-96) for the common case of a full 64x64 f32 tile whose to_fixed is exact
+// (fixed.rs:47-57 never rounds), that holds no NaN, whose fixed-point values are below 2^22 in magnitude and lie within
+// 32767 of each other over the whole unit (k_finalize_tree decides; everything else stays with k_encode_v4).  Under
+// those conditions every DAC entry below the root takes at most two bytes, float -> fixed is one FFMA and one integer
+// add, and the kernel can be small:
+//   * same mapping as encode_v4.cuh (one 64-thread CTA per unit, thread t = level-3 node t in Morton order, 8x8 cells),
+//     same masks / packed counters / BFS layout arithmetic, same bytes;
+//   * ONE fused pass per Log instant: a thread reads its four level-4 nodes (4x4 cells each, four 128-bit loads)
+//     straight from global memory, converts, and while the cells are in registers computes the differences to the
+//     block's snapshot, the equal / uniform flags, the length classes AND the low bytes of every zigzag code, which
+//     go to a 6 KB payload in shared memory.  The instant itself is never stored: emission copies payload words to
+//     their scan-computed positions (the recomputation pass of v4 -- second read of both images, second min/max
+//     pyramid, second zigzag -- is gone);
+//   * entries longer than one byte (rare below the root) are re-derived at emission time from a second, L2-resident
+//     read of just that level-4 node;
+//   * a Snapshot is needed for one instant in several (first of a block): its exact size (only when the Log does not
+//     already beat the one-byte-per-entry lower bound) and its emission each take their own pass over the tile from
+//     L2; the emission pass also rewrites the snapshot image the following Logs refer to;
+//   * the emission image is placed so that byte 1 of the max DAC's level 0 is 4-byte aligned: every sibling group
+//     (BFS positions 1 + 4k .. 4 + 4k) is then one aligned 32-bit store; the copy to the arena re-aligns with funnel
+//     shifts.
+// 36 KB of shared memory per tile and <= 168 registers: six tiles per SM (v4: four).
+// Reference functions restated: snapshot.rs:108-156 + 439-500, log.rs:112-165 + 725-817, bitmap.rs:66-113,
+// dac.rs:96-132, chunk.rs:55-78, serializers snapshot.rs:48-58 / log.rs:53-64 / dac.rs:37-44 / bitmap.rs:128-138.
+#pragma once
+#include "encode_v4.cuh"
+
+namespace dcdf {
+
+constexpr int E5_THREADS = 64;
+constexpr int E5_POOL = 9 * 1024;
+
+struct E5Smem {
+  __align__(16) u8 pool[E5_POOL + 16];  // emission image (+ room for the alignment shift)
+  int4 cell[16][E5_THREADS];            // cells of the block's snapshot: [quad q][thread]
+  int2 l4s[4][E5_THREADS];              // (max, min) of the snapshot's level-4 nodes
+  int2 l4t[4][E5_THREADS];              // ... of the instant being encoded
+  u32 leaf[16][E5_THREADS];             // Log payload: low bytes of the four leaf codes of quad q
+  u32 qx[4][E5_THREADS];                // Log payload: low bytes of the four quad max codes of level-4 node a
+  u32 qn[4][E5_THREADS];                // ... and of the four quad min codes
+  int4 rec1[4];                         // level-1 nodes: tmax, tmin, first-cell diff, equal
+  int2 ent1[4];                         // level-1 log entries
+  u32 wt[2][2][4];                      // [warp][0 = snapshot, 1 = log][STRUCT, a1, b1, c1]
+  u32 bm_off[12], bm_len[12];
+  u32 n_bm;
+  unsigned long long piece_off;
+};
+
+struct E5Cand {
+  u32 in5, in4;        // internal flags: quad q = bit 15-q, level-4 node a = bit 3-a
+  bool in3, in2, in1;
+  u64 ml;              // leaves longer than one byte (cell m = bit 63-m)
+  u32 mq;              // quads: max entries bits 15..0, min entries bits 31..16
+  u32 mu;              // level 4 max (3..0) / min (7..4), level 3 max (8) / min (9), level 2 max (10) / min (11)
+};
+
+DCDF_DEVINL void e5_count(const E5Cand& C, bool owner2, u32* w /* [4] */) {
+  const bool e2 = C.in1, e3 = e2 && C.in2, e4 = e3 && C.in3;
+  const u32 ai4 = e4 ? C.in4 : 0u;
+  const u32 X5 = e4_expand4(ai4);
+  const u32 ai5 = C.in5 & X5;
+  const u64 X6 = e4_expand16(ai5);
+  const u32 mu = C.mu, mq = C.mq;
+  w[0] = ((owner2 && e2 && C.in2) ? E4_F2 : 0u) + ((e3 && C.in3) ? E4_F3 : 0u) + (u32)__popc(ai4) * E4_F4 + (u32)__popc(ai5) * E4_F5;
+  w[1] = ((owner2 && e2 && ((mu >> 10) & 1u)) ? E4_F2 : 0u) + ((e3 && ((mu >> 8) & 1u)) ? E4_F3 : 0u) +
+         (e4 ? (u32)__popc(mu & 0xfu) : 0u) * E4_F4 + (u32)__popc(mq & 0xffffu & X5) * E4_F5;
+  w[2] = (u32)__popcll(C.ml & X6);
+  w[3] = ((owner2 && e2 && C.in2 && ((mu >> 11) & 1u)) ? E4_F2 : 0u) + ((e3 && C.in3 && ((mu >> 9) & 1u)) ? E4_F3 : 0u) +
+         (u32)__popc((mu >> 4) & ai4) * E4_F4 + (u32)__popc((mq >> 16) & ai5) * E4_F5;
+}
+
+struct E5Tot {
+  u32 tot[4];
+  u32 cmax[4], cmin[4];
+  u32 I0, I1, nm_len, n_int;
+};
+// Block totals of one candidate and the entry counts of its two DACs (snapshot.rs:71-79, log.rs:77-86): below the
+// level-1 nodes nothing is longer than two bytes, so DAC levels 2 and 3 only hold bytes of the root / level-1 entries.
+DCDF_DEVINL void e5_totals(E5Tot& T, const E5Smem& S, int cand, bool in0, u32 in1m, const int (&e1max)[4], const int (&e1min)[4],
+                           int e0max, int e0min) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) T.tot[i] = in0 ? S.wt[0][cand][i] + S.wt[1][cand][i] : 0u;
+  T.I0 = in0 ? 1u : 0u;
+  T.I1 = in0 ? (u32)__popc(in1m) : 0u;
+  const u32 upper = T.I0 + T.I1 + e4_f2(T.tot[0]) + e4_f3(T.tot[0]) + e4_f4(T.tot[0]);
+  T.n_int = upper + e4_f5(T.tot[0]);
+  T.nm_len = 1u + 4u * upper;
+  T.cmax[0] = 1u + 4u * T.n_int;
+  T.cmin[0] = T.n_int;
+#pragma unroll
+  for (int j = 1; j < 4; j++) {
+    u32 tm = e4_longer_j(e0max, j) ? 1u : 0u, tn = 0;
+    if (in0) {
+      tn = e4_longer_j(e0min, j) ? 1u : 0u;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        tm += e4_longer_j(e1max[k], j) ? 1u : 0u;
+        tn += (((in1m >> (3 - k)) & 1u) && e4_longer_j(e1min[k], j)) ? 1u : 0u;
+      }
+    }
+    T.cmax[j] = tm + (j == 1 ? e4_fsum(T.tot[1]) + T.tot[2] : 0u);
+    T.cmin[j] = tn + (j == 1 ? e4_fsum(T.tot[3]) : 0u);
+  }
+}
+// Number of max-DAC entries longer than one byte that precede this thread's entries of tree level `level` (2..6).
+DCDF_DEVINL u32 e5_base_x(const E5Tot& T, const u32 (&pre)[4], int level) {
+  const u32 t = T.tot[1], p = pre[1];
+  u32 b = T.cmax[1] - e4_fsum(t) - T.tot[2];  // root and level-1 entries come first
+  if (level == 2) return b + e4_f2(p);
+  b += e4_f2(t);
+  if (level == 3) return b + e4_f3(p);
+  b += e4_f3(t);
+  if (level == 4) return b + e4_f4(p);
+  b += e4_f4(t);
+  if (level == 5) return b + e4_f5(p);
+  return b + e4_f5(t) + pre[2];
+}
+DCDF_DEVINL u32 e5_base_n(const E5Tot& T, const u32 (&pre)[4], int level) {
+  const u32 t = T.tot[3], p = pre[3];
+  u32 b = T.cmin[1] - e4_fsum(t);
+  if (level == 2) return b + e4_f2(p);
+  b += e4_f2(t);
+  if (level == 3) return b + e4_f3(p);
+  b += e4_f3(t);
+  if (level == 4) return b + e4_f4(p);
+  return b + e4_f4(t) + e4_f5(p);
+}
+
+// second byte of a two-byte code (DAC level 1): rare, out of line; returns the next position
+__device__ __noinline__ u32 e5_hi(u8* b1, u32 z, u32 r1) {
+  b1[r1] = (u8)(z >> 8);
+  return r1 + 1u;
+}
+
+// Root / level-1 entries are written by one thread: out of line, so the code every warp runs stays small.
+__device__ __noinline__ void e5_top_bits(u8* w0, u8* w1, u8* w2, u32* p, int e) {
+  u32 q[4] = {p[0], p[1], p[2], p[3]};
+  e4_top_bits(w0, w1, w2, q, e);
+  p[0] = q[0]; p[1] = q[1]; p[2] = q[2]; p[3] = q[3];
+}
+__device__ __noinline__ void e5_top_bytes(u8* b0, u8* b1, u8* b2, u8* b3, u32 at, u32* r, int e) {
+  const u32 z = zigzag32(e);
+  b0[at] = (u8)z;
+  if (z > 0xffu) {
+    u32 r1 = r[0], r2 = r[1], r3 = r[2];
+    e4_emit_hi(b1, b2, b3, z, r1, r2, r3);
+    r[0] = r1; r[1] = r2; r[2] = r3;
+  }
+}
+__device__ __noinline__ void e5_set_bit_cold(u8* bytes, u32 bitpos) { e4_set_bit(bytes, bitpos); }
+__device__ __noinline__ void e5_bitmap_hdr(u8* out, u32 hdr, u32 len) {
+  store_be32(out + hdr, len);
+  store_be32(out + hdr + 4, 4u);  // k = 4 (bitmap.rs:69)
+}
+// OR a run of bits into a bit stream (e4_or_run), one shared copy for every call site
+__device__ __noinline__ void e5_or_run(u8* bytes, u32 bitpos, u64 V) { e4_or_run(bytes, bitpos, V); }
+DCDF_DEVINL void e5_or_bits(u8* bytes, u32 bitpos, u32 bits, int n) {  // n <= 32 bits, right-aligned in `bits`
+  if (n > 0 && bits) e5_or_run(bytes, bitpos, (u64)bits << (64 - n));
+}
+
+// to_fixed (a3) of an exact, finite, small value: n * 2^(bits+1) is an integer below 2^22, so adding 1.5 * 2^23
+// leaves it in the low mantissa bits (fixed.rs:59-70: trunc(2 * shifted) + 1).
+DCDF_DEVINL int e5_conv(float x, float scale2) { return __float_as_int(__fmaf_rn(x, scale2, 12582912.0f)) - (0x4B400000 - 1); }
+
+// One level-4 node (4x4 cells at pn, row stride sr) as four quads (x, y = upper row; z, w = lower row).
+DCDF_DEVINL void e5_load_node(const float* pn, i64 sr, uint4 (&raw)[4]) {
+#pragma unroll
+  for (int r = 0; r < 4; r++) raw[r] = __ldg(reinterpret_cast<const uint4*>(pn + (i64)r * sr));
+}
+DCDF_DEVINL void e5_quads(const uint4 (&raw)[4], float scale2, int4 (&q)[4]) {
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const uint4 u = raw[2 * h], l = raw[2 * h + 1];
+    q[2 * h] = make_int4(e5_conv(__uint_as_float(u.x), scale2), e5_conv(__uint_as_float(u.y), scale2),
+                         e5_conv(__uint_as_float(l.x), scale2), e5_conv(__uint_as_float(l.y), scale2));
+    q[2 * h + 1] = make_int4(e5_conv(__uint_as_float(u.z), scale2), e5_conv(__uint_as_float(u.w), scale2),
+                             e5_conv(__uint_as_float(l.z), scale2), e5_conv(__uint_as_float(l.w), scale2));
+  }
+}
+DCDF_DEVINL const float* e5_node_ptr(const float* pt, i64 sr, int a) { return pt + (i64)(4 * (a >> 1)) * sr + 4 * (a & 1); }
+
+DCDF_DEVINL u32 e5_pack4(u32 z0, u32 z1, u32 z2, u32 z3) { return (z0 & 0xffu) | ((z1 & 0xffu) << 8) | ((z2 & 0xffu) << 16) | (z3 << 24); }
+DCDF_DEVINL void e5_store_word(u8* p, u32 w) {
+  if ((((uintptr_t)p) & 3u) == 0) *reinterpret_cast<u32*>(p) = w;
+  else { p[0] = (u8)w; p[1] = (u8)(w >> 8); p[2] = (u8)(w >> 16); p[3] = (u8)(w >> 24); }
+}
+
+// Entries of one level-4 node that take two bytes (rare), re-derived from the node's cells: leaves of the internal
+// quads, then the four quad max entries, then the min entries of the internal quads -- the order in which their second
+// bytes sit in DAC level 1 (dac.rs:109-121).  Log: cells of the instant come from a second (L2-resident) read of the
+// node, the snapshot's from shared memory.  Snapshot: the emission pass has just stored the cells in shared memory.
+__device__ __noinline__ void e5_long_node(bool as_snapshot, const float* pn, i64 sr, float scale2, const int4* scell, int2 n4, u32 in5a,
+                                          u8* xb1, u8* nb1, u32* pos /* lx1, rx1, rn1 */) {
+  int4 q[4];
+  if (!as_snapshot) {
+    uint4 raw[4];
+    e5_load_node(pn, sr, raw);
+    e5_quads(raw, scale2, q);
+  }
+  u32 lx1 = pos[0], rx1 = pos[1], rn1 = pos[2];
+  u32 zx[4], zn[4];
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    const int4 s = scell[b * E5_THREADS];
+    const int4 t = as_snapshot ? s : q[b];
+    const int qmax = max(max(t.x, t.y), max(t.z, t.w)), qmin = min(min(t.x, t.y), min(t.z, t.w));
+    const int sqmax = max(max(s.x, s.y), max(s.z, s.w)), sqmin = min(min(s.x, s.y), min(s.z, s.w));
+    zx[b] = zigzag32(as_snapshot ? n4.x - qmax : qmax - sqmax);
+    zn[b] = zigzag32(as_snapshot ? qmin - n4.y : qmin - sqmin);
+    if ((in5a >> (3 - b)) & 1u) {
+      const u32 z0 = zigzag32(as_snapshot ? qmax - t.x : t.x - s.x), z1 = zigzag32(as_snapshot ? qmax - t.y : t.y - s.y);
+      const u32 z2 = zigzag32(as_snapshot ? qmax - t.z : t.z - s.z), z3 = zigzag32(as_snapshot ? qmax - t.w : t.w - s.w);
+      if (z0 > 0xffu) xb1[lx1++] = (u8)(z0 >> 8);
+      if (z1 > 0xffu) xb1[lx1++] = (u8)(z1 >> 8);
+      if (z2 > 0xffu) xb1[lx1++] = (u8)(z2 >> 8);
+      if (z3 > 0xffu) xb1[lx1++] = (u8)(z3 >> 8);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < 4; b++)
+    if (zx[b] > 0xffu) xb1[rx1++] = (u8)(zx[b] >> 8);
+#pragma unroll
+  for (int b = 0; b < 4; b++)
+    if (((in5a >> (3 - b)) & 1u) && zn[b] > 0xffu) nb1[rn1++] = (u8)(zn[b] >> 8);
+  pos[0] = lx1; pos[1] = rx1; pos[2] = rn1;
+}
+
+// barrier over the 64 threads of one tile (named barrier 1 + tile slot; barrier 0 stays the CTA-wide one)
+DCDF_DEVINL void e5_tile_sync(int slot) { asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory"); }
+
+// G tiles per CTA, one per 64-thread group.  The tiles are independent (own shared-memory slab, own named barrier);
+// what they share is the instruction stream: one CTA-wide barrier per instant keeps all 2G warps of the SM inside the
+// same stretch of code, so instruction-cache lines fetched for one warp are hits for the others (with unsynchronised
+// CTAs the kernel spent a quarter of its issue slots waiting for instruction fetches).
+template <int G>
+__global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams P, const u32 stage_limit) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int slot = threadIdx.x / E5_THREADS;
+  E5Smem& S = *reinterpret_cast<E5Smem*>(smem_raw + (size_t)slot * sizeof(E5Smem));
+
+  const u32 n_order = *P.order_count;
+  if (blockIdx.x * (u32)G >= n_order) return;
+  const u32 order_idx = blockIdx.x * (u32)G + (u32)slot;
+  const bool tile_live = order_idx < n_order;
+  const u32 unit_idx = P.order[tile_live ? order_idx : blockIdx.x * (u32)G];
+  EncUnit unit = P.units[unit_idx];
+  if (!tile_live) unit.instants = 0;
+  // every tile of the CTA takes the CTA-wide barrier the same number of times
+  int max_instants = 0;
+  for (int g = 0; g < G; g++) {
+    const u32 oi = blockIdx.x * (u32)G + (u32)g;
+    if (oi < n_order) max_instants = max(max_instants, P.units[P.order[oi]].instants);
+  }
+  const int tid = threadIdx.x % E5_THREADS, lane = tid & 31, warp = tid >> 5;
+  const float scale2 = (float)((i64)2 << unit.bits);
+  const i64 sr = P.stride_r;
+  // the thread's 8x8 block
+  const float* const base = static_cast<const float*>(P.data) + unit.base + (i64)(8 * (int)morton_row(tid)) * sr + 8 * (int)morton_col(tid);
+  const bool owner2 = (lane & 3) == 0;
+  const int k1 = tid >> 4;  // own level-1 node
+
+  {  // the emission image starts out all zero; every copy-out re-zeroes what it used
+    uint4* z = reinterpret_cast<uint4*>(S.pool);
+    for (int i = tid; i < (E5_POOL + 16) / 16; i += E5_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+
+  u32 err = 0;
+  int s3max = 0, s3min = 0, s2max = 0, s2min = 0, s1max = 0, s1min = 0, s0max = 0, s0min = 0;
+  u32 n_logs = 0, n_snap = 0, n_log_total = 0;
+  u64 total_bytes = 0;
+
+#pragma unroll 1
+  for (int inst = 0; inst < max_instants; inst++) {
+    __syncthreads();  // all tiles of the CTA start the instant together (shared instruction stream)
+    if (inst >= unit.instants) continue;
+    const bool first = inst == 0;
+    const float* const pt = base + (i64)inst * P.stride_t;
+    const bool forced = first || n_logs == 254u;  // chunk.rs:62 (Block caps logs at 254)
+
+    u32 u5 = 0, eq5 = 0, u4 = 0, eq4 = 0;
+    E5Cand L, C;
+    L.ml = 0; L.mq = 0; L.mu = 0; L.in5 = 0; L.in4 = 0; L.in3 = L.in2 = L.in1 = false;
+    C.ml = 0; C.mq = 0; C.mu = 0; C.in5 = 0; C.in4 = 0; C.in3 = C.in2 = C.in1 = false;
+    int t3max = 0, t3min = 0, diff3 = 0;
+    bool eq3 = false, u3 = false;
+    int t2max = 0, t2min = 0, t1max = 0, t1min = 0, t0max = 0, t0min = 0;
+    bool u2 = false, eq2 = false, u0 = false, eq0 = false;
+    int n1max[4], n1min[4];
+    u32 n1flags = 0;             // bit k: level-1 node k is `equal`
+    u32 l_in1 = 0, s_in1 = 0;    // level-1 internal flags, node k = bit 3-k
+    bool l_in0 = false, s_in0 = false;
+    int l_e1max[4], l_e1min[4];
+    u32 wl[4] = {0, 0, 0, 0}, ws[4] = {0, 0, 0, 0};
+    E5Tot T;
+    bool as_snapshot = forced;
+    u32 my_size = 0, log_size = 0;
+
+    // Pass 0: the fused Log pass and the Log's exact size against a lower bound of the Snapshot's.  Pass 1 (first
+    // instant of a block, the 254-log cap, or a Log that does not beat the bound): the Snapshot's exact size.
+#pragma unroll 1
+    for (int pass = forced ? 1 : 0; pass < 2; pass++) {
+      t3max = INT32_MIN; t3min = INT32_MAX;
+      u5 = 0; u4 = 0;
+      uint4 raw[4];
+      e5_load_node(e5_node_ptr(pt, sr, 0), sr, raw);
+      if (pass == 0) {
+        // ---------------- load, convert, differences, flags, length classes, payload
+        eq3 = true;
+#pragma unroll 1
+        for (int a = 0; a < 4; a++) {
+          int4 q[4];
+          e5_quads(raw, scale2, q);
+          if (a < 3) e5_load_node(e5_node_ptr(pt, sr, a + 1), sr, raw);
+          const int2 s4 = S.l4s[a][tid];
+          int amax = INT32_MIN, amin = INT32_MAX, dfirst = 0;
+          bool aeq = true;
+          u32 leaf16 = 0, u5n = 0, e5n = 0, qx = 0, qn = 0, zxw = 0, znw = 0;
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const int4 t = q[b], sq = S.cell[4 * a + b][tid];
+            const int qmax = max(max(t.x, t.y), max(t.z, t.w)), qmin = min(min(t.x, t.y), min(t.z, t.w));
+            const int sqmax = max(max(sq.x, sq.y), max(sq.z, sq.w)), sqmin = min(min(sq.x, sq.y), min(sq.z, sq.w));
+            const int d0 = t.x - sq.x, d1 = t.y - sq.y, d2 = t.z - sq.z, d3 = t.w - sq.w;
+            const int ex = qmax - sqmax, en = qmin - sqmin;
+            const bool e5 = (((d1 ^ d0) | (d2 ^ d0) | (d3 ^ d0)) == 0);  // all four leaf diffs equal (log.rs:780-806)
+            if (qmax == qmin) u5n |= 1u << (3 - b);
+            if (e5) e5n |= 1u << (3 - b);
+            // one test for "some entry of this quad needs two bytes" (zigzag code above 255  <=>  value outside -128..127)
+            if ((((u32)d0 + 128u) | ((u32)d1 + 128u) | ((u32)d2 + 128u) | ((u32)d3 + 128u) | ((u32)ex + 128u) | ((u32)en + 128u)) > 255u) {
+              if (e4_longer<1>(d0)) leaf16 |= 1u << (15 - 4 * b);
+              if (e4_longer<1>(d1)) leaf16 |= 1u << (14 - 4 * b);
+              if (e4_longer<1>(d2)) leaf16 |= 1u << (13 - 4 * b);
+              if (e4_longer<1>(d3)) leaf16 |= 1u << (12 - 4 * b);
+              if (e4_longer<1>(ex)) qx |= 1u << (3 - b);
+              if (e4_longer<1>(en)) qn |= 1u << (3 - b);
+              if ((((u32)d0 + 32768u) | ((u32)d1 + 32768u) | ((u32)d2 + 32768u) | ((u32)d3 + 32768u)) > 65535u) err |= EF_BAD_FORMAT;  // not eligible
+            }
+            S.leaf[4 * a + b][tid] = e5_pack4(zigzag32(d0), zigzag32(d1), zigzag32(d2), zigzag32(d3));
+            zxw |= (zigzag32(ex) & 0xffu) << (8 * b);
+            znw |= (zigzag32(en) & 0xffu) << (8 * b);
+            amax = max(amax, qmax); amin = min(amin, qmin);
+            if (b == 0) dfirst = d0;
+            aeq = aeq && e5 && d0 == dfirst;
+          }
+          S.qx[a][tid] = zxw;
+          S.qn[a][tid] = znw;
+          S.l4t[a][tid] = make_int2(amax, amin);
+          L.ml |= (u64)leaf16 << (48 - 16 * a);
+          L.mq |= (qx << (12 - 4 * a)) | (qn << (28 - 4 * a));
+          u5 |= u5n << (12 - 4 * a);
+          eq5 |= e5n << (12 - 4 * a);
+          if (amax == amin) u4 |= 1u << (3 - a);
+          if (aeq) eq4 |= 1u << (3 - a);
+          if (e4_longer<1>(amax - s4.x)) L.mu |= 1u << (3 - a);
+          if (e4_longer<1>(amin - s4.y)) L.mu |= 1u << (7 - a);
+          t3max = max(t3max, amax); t3min = min(t3min, amin);
+          if (a == 0) diff3 = dfirst;
+          eq3 = eq3 && aeq && dfirst == diff3;
+        }
+        if (e4_longer<1>(t3max - s3max)) L.mu |= 1u << 8;
+        if (e4_longer<1>(t3min - s3min)) L.mu |= 1u << 9;
+      } else {
+        // ---------------- Snapshot entry masks of levels 6 and 5 (snapshot.rs:122-147: parent_max - child_max,
+        // child_min - parent_min); the uniform flags and the level-4 records come out the same as in pass 0
+        C.ml = 0; C.mq = 0;
+#pragma unroll 1
+        for (int a = 0; a < 4; a++) {
+          int4 q[4];
+          e5_quads(raw, scale2, q);
+          if (a < 3) e5_load_node(e5_node_ptr(pt, sr, a + 1), sr, raw);
+          int qmax[4], qmin[4];
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            qmax[b] = max(max(q[b].x, q[b].y), max(q[b].z, q[b].w));
+            qmin[b] = min(min(q[b].x, q[b].y), min(q[b].z, q[b].w));
+          }
+          const int amax = max(max(qmax[0], qmax[1]), max(qmax[2], qmax[3])), amin = min(min(qmin[0], qmin[1]), min(qmin[2], qmin[3]));
+          u32 leaf16 = 0, qx = 0, qn = 0, u5n = 0;
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const int4 t = q[b];
+            if (qmax[b] == qmin[b]) u5n |= 1u << (3 - b);
+            if (((u32)(qmax[b] - qmin[b]) | (u32)(amax - qmax[b]) | (u32)(qmin[b] - amin)) > 127u) {  // all differences are >= 0
+              if (e4_longer<1>(qmax[b] - t.x)) leaf16 |= 1u << (15 - 4 * b);
+              if (e4_longer<1>(qmax[b] - t.y)) leaf16 |= 1u << (14 - 4 * b);
+              if (e4_longer<1>(qmax[b] - t.z)) leaf16 |= 1u << (13 - 4 * b);
+              if (e4_longer<1>(qmax[b] - t.w)) leaf16 |= 1u << (12 - 4 * b);
+              if (e4_longer<1>(amax - qmax[b])) qx |= 1u << (3 - b);
+              if (e4_longer<1>(qmin[b] - amin)) qn |= 1u << (3 - b);
+            }
+          }
+          S.l4t[a][tid] = make_int2(amax, amin);
+          C.ml |= (u64)leaf16 << (48 - 16 * a);
+          C.mq |= (qx << (12 - 4 * a)) | (qn << (28 - 4 * a));
+          u5 |= u5n << (12 - 4 * a);
+          if (amax == amin) u4 |= 1u << (3 - a);
+          t3max = max(t3max, amax); t3min = min(t3min, amin);
+        }
+        if ((u32)(t3max - t3min) > 32767u) err |= EF_BAD_FORMAT;  // not eligible
+      }
+      u3 = t3max == t3min;
+
+      // ---------------- levels 2 and 1 with shuffles (4 resp. 16 consecutive lanes)
+      t2max = max(t3max, shfl_xor(t3max, 1)); t2max = max(t2max, shfl_xor(t2max, 2));
+      t2min = min(t3min, shfl_xor(t3min, 1)); t2min = min(t2min, shfl_xor(t2min, 2));
+      const int diff2 = shfl(diff3, lane & ~3);
+      const u32 ok3 = __ballot_sync(0xffffffffu, eq3 && diff3 == diff2);
+      eq2 = ((ok3 >> (lane & ~3)) & 0xfu) == 0xfu;
+      u2 = t2max == t2min;
+      t1max = max(t2max, shfl_xor(t2max, 4)); t1max = max(t1max, shfl_xor(t1max, 8));
+      t1min = min(t2min, shfl_xor(t2min, 4)); t1min = min(t1min, shfl_xor(t1min, 8));
+      const int diff1 = shfl(diff2, lane & ~15);
+      const u32 ok2 = __ballot_sync(0xffffffffu, eq2 && diff2 == diff1);
+      const bool eq1 = ((ok2 >> (lane & ~15)) & 0xffffu) == 0xffffu;
+      const bool u1 = t1max == t1min;
+
+      // structure flags: snapshot internal = !uniform (snapshot.rs:133); log internal = !uniform && !equal (log.rs:137-152)
+      C.in5 = ~u5 & 0xffffu; C.in4 = ~u4 & 0xfu; C.in3 = !u3; C.in2 = !u2; C.in1 = !u1;
+      if (pass == 0) {
+        if (e4_longer<1>(t2max - s2max)) L.mu |= 1u << 10;
+        if (e4_longer<1>(t2min - s2min)) L.mu |= 1u << 11;
+        L.in5 = ~u5 & ~eq5 & 0xffffu; L.in4 = ~u4 & ~eq4 & 0xfu; L.in3 = !u3 && !eq3; L.in2 = !u2 && !eq2; L.in1 = !u1 && !eq1;
+        e5_count(L, owner2, wl);
+      } else {
+        C.mu = 0;  // entry masks of the Snapshot above the quads
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          const int2 n4 = S.l4t[a][tid];
+          if (e4_longer<1>(t3max - n4.x)) C.mu |= 1u << (3 - a);
+          if (e4_longer<1>(n4.y - t3min)) C.mu |= 1u << (7 - a);
+        }
+        if (e4_longer<1>(t2max - t3max)) C.mu |= 1u << 8;
+        if (e4_longer<1>(t3min - t2min)) C.mu |= 1u << 9;
+        if (e4_longer<1>(t1max - t2max)) C.mu |= 1u << 10;
+        if (e4_longer<1>(t2min - t1min)) C.mu |= 1u << 11;
+      }
+      e5_count(C, owner2, ws);  // pass 0: structure only (the masks are still empty) -> the lower bound
+
+      // ---------------- per-warp totals and the four level-1 records go through shared memory
+      if (pass == 1 && !forced) e5_tile_sync(slot);  // the other warp may still be reading the totals of pass 0
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const u32 rs = __reduce_add_sync(0xffffffffu, ws[i]);
+        if (lane == 0) S.wt[warp][0][i] = rs;
+        if (pass == 0) {
+          const u32 rl = __reduce_add_sync(0xffffffffu, wl[i]);
+          if (lane == 0) S.wt[warp][1][i] = rl;
+        }
+      }
+      if ((lane & 15) == 0) {
+        S.rec1[k1] = make_int4(t1max, t1min, diff1, eq1 ? 1 : 0);
+        if (pass == 0) S.ent1[k1] = make_int2(t1max - s1max, t1min - s1min);
+      }
+      e5_tile_sync(slot);  // B1
+
+      // ---------------- root (every thread, redundantly)
+      int n1dif[4];
+      n1flags = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int4 r = S.rec1[k];
+        n1max[k] = r.x; n1min[k] = r.y; n1dif[k] = r.z;
+        if (r.w != 0) n1flags |= 1u << k;
+      }
+      t0max = max(max(n1max[0], n1max[1]), max(n1max[2], n1max[3]));
+      t0min = min(min(n1min[0], n1min[1]), min(n1min[2], n1min[3]));
+      u0 = t0max == t0min;
+      eq0 = n1flags == 0xfu && n1dif[1] == n1dif[0] && n1dif[2] == n1dif[0] && n1dif[3] == n1dif[0];
+      l_in1 = 0; s_in1 = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const bool un = n1max[k] == n1min[k];
+        if (!un) s_in1 |= 1u << (3 - k);
+        if (!un && !((n1flags >> k) & 1u)) l_in1 |= 1u << (3 - k);
+      }
+      l_in0 = !u0 && !eq0; s_in0 = !u0;
+      if (pass == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int2 e = S.ent1[k]; l_e1max[k] = e.x; l_e1min[k] = e.y; }
+      }
+
+      // ---------------- exact size of this pass's candidate (snapshot.rs:84-93, log.rs:92-98)
+      const bool as_log = pass == 0;
+      int c_e1max[4], c_e1min[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) { c_e1max[k] = as_log ? l_e1max[k] : t0max - n1max[k]; c_e1min[k] = as_log ? l_e1min[k] : n1min[k] - t0min; }
+      E5Tot Tc;
+      e5_totals(Tc, S, as_log ? 1 : 0, as_log ? l_in0 : s_in0, as_log ? l_in1 : s_in1, c_e1max, c_e1min, as_log ? t0max - s0max : t0max,
+                as_log ? t0min - s0min : t0min);
+      const u32 size = 13u + bitmap_size(Tc.nm_len) + (as_log ? bitmap_size(Tc.nm_len - Tc.n_int) : 0u) + e4_dac_size(Tc.cmax) + e4_dac_size(Tc.cmin);
+      if (as_log) {
+        T = Tc;
+        log_size = size; my_size = size;
+        // lower bound of the Snapshot: every entry takes at least one byte
+        const u32 st = s_in0 ? S.wt[0][0][0] + S.wt[1][0][0] : 0u;
+        const u32 s_upper = (s_in0 ? 1u + (u32)__popc(s_in1) : 0u) + e4_f2(st) + e4_f3(st) + e4_f4(st);
+        const u32 s_int = s_upper + e4_f5(st), s_nm = 1u + 4u * s_upper, s_nmax = 1u + 4u * s_int;
+        const u32 snap_lb = 13u + bitmap_size(s_nm) + 1u + bitmap_size(s_nmax) + s_nmax + (s_int ? 1u + bitmap_size(s_int) + s_int : 1u);
+        if (!(snap_lb <= log_size)) break;  // the Log wins without looking closer
+      } else {
+        as_snapshot = forced || size <= log_size;  // ties go to the snapshot (chunk.rs:62)
+        if (as_snapshot) { T = Tc; my_size = size; }
+      }
+    }
+
+    // ---------------- the winner, generic from here on
+    E5Cand W;
+    W.in5 = as_snapshot ? C.in5 : L.in5; W.in4 = as_snapshot ? C.in4 : L.in4;
+    W.in3 = as_snapshot ? C.in3 : L.in3; W.in2 = as_snapshot ? C.in2 : L.in2; W.in1 = as_snapshot ? C.in1 : L.in1;
+    W.ml = as_snapshot ? C.ml : L.ml; W.mq = as_snapshot ? C.mq : L.mq; W.mu = as_snapshot ? C.mu : L.mu;
+    int e1x[4], e1n[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { e1x[k] = as_snapshot ? t0max - n1max[k] : l_e1max[k]; e1n[k] = as_snapshot ? n1min[k] - t0min : l_e1min[k]; }
+    const int e0x = as_snapshot ? t0max : t0max - s0max, e0n = as_snapshot ? t0min : t0min - s0min;
+    const u32 nm_len = T.nm_len, n_int = T.n_int, I0 = T.I0, I1 = T.I1;
+    const bool in0 = as_snapshot ? s_in0 : l_in0;
+    const u32 in1m = as_snapshot ? s_in1 : l_in1;
+    const int cand = as_snapshot ? 0 : 1;
+    const bool staged = my_size <= stage_limit;
+    if (tid == 0) {
+      const u64 need = ((u64)my_size + 15ull) & ~15ull;
+      const u64 off = atomicAdd(P.arena_head, (unsigned long long)need);
+      S.piece_off = off;
+      Piece pc;
+      pc.off = off; pc.size = my_size; pc.kind = as_snapshot ? 1u : 0u;
+      P.pieces[unit.piece_base + inst] = pc;
+    }
+    // stream layout (snapshot.rs:48-58 / log.rs:53-64)
+    const u32 eq_len = nm_len - n_int;
+    const u32 nm_hdr = 13u;
+    const u32 eq_hdr = nm_hdr + bitmap_size(nm_len);
+    E4Dac DX, DN;
+    u32 end = e4_lay_dac(DX, as_snapshot ? eq_hdr : eq_hdr + bitmap_size(eq_len), T.cmax);
+    end = e4_lay_dac(DN, end, T.cmin);
+    if (end != my_size) err |= EF_BAD_FORMAT;
+    // the image starts `shift` bytes into the pool so that entry 1 of the max DAC's level 0 is 4-byte aligned
+    const u32 shift = staged ? ((4u - ((DX.bytes[0] + 1u) & 3u)) & 3u) : 0u;
+    if (!staged) e5_tile_sync(slot);
+    u64 piece_off = 0;
+    bool fits = true;
+    u8* out = S.pool + shift;
+    if (!staged) {
+      piece_off = S.piece_off;
+      fits = piece_off + (((u64)my_size + 15ull) & ~15ull) <= P.arena_cap;
+      if (!fits) err |= EF_ARENA_FULL;
+      out = P.arena + piece_off;
+      if (fits) {
+        uint4* z = reinterpret_cast<uint4*>(out);
+        for (u32 i = tid; i < (my_size + 15u) / 16u; i += E5_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+      }
+      e5_tile_sync(slot);
+    }
+    const bool emit = staged || fits;
+
+    u8* const nm_words = e4_words_of(out, nm_hdr, nm_len);
+    u8* const eq_words = e4_words_of(out, eq_hdr, eq_len);
+    u8* const xw0 = e4_words_of(out, DX.hdr[0], T.cmax[0]);  // continuation bits of DAC level 0
+    u8* const nw0 = e4_words_of(out, DN.hdr[0], T.cmin[0]);
+    u8* const xb0 = out + DX.bytes[0];
+    u8* const xb1 = out + DX.bytes[1];
+    u8* const nb0 = out + DN.bytes[0];
+    u8* const nb1 = out + DN.bytes[1];
+
+    // block-wide positions
+    const u32 T0 = T.tot[0];
+    const u32 I2 = e4_f2(T0), I3 = e4_f3(T0), I4 = e4_f4(T0);
+    const u32 Pn2 = 1u + 4u * I0, Pn3 = Pn2 + 4u * I1, Pn4 = Pn3 + 4u * I2, Pn5 = Pn4 + 4u * I3, Pn6 = Pn5 + 4u * I4;
+    const u32 Mn2 = I0 + I1, Mn3 = Mn2 + I2, Mn4 = Mn3 + I3, Mn5 = Mn4 + I4;
+    const u32 R1 = (u32)__popc(in1m >> (4 - k1));  // internal level-1 nodes before the own one
+    const bool x2 = in0 && ((in1m >> (3 - k1)) & 1u);
+    const bool x3 = x2 && W.in2, x4 = x3 && W.in3;
+    const u32 ai4 = x4 ? W.in4 : 0u;
+    const u32 X5 = e4_expand4(ai4);
+    const u32 ai5 = W.in5 & X5;
+    // prefix over earlier threads (Morton order) of the packed counters
+    u32 pre[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      pre[i] = e4_warp_excl(as_snapshot ? ws[i] : wl[i], lane) + ((warp == 1 && in0) ? S.wt[0][cand][i] : 0u);
+    const u32 R2own = e4_f2(pre[0]);                       // internal level-2 nodes before the own group (valid on owner lanes)
+    const u32 R2p = e4_f2(shfl(pre[0], lane & ~3));        // the same, seen by every lane of the group
+    const u32 R3 = e4_f3(pre[0]), R4 = e4_f4(pre[0]), R5 = e4_f5(pre[0]);
+    // positions of this thread's second bytes (DAC level 1) per tree level: entries longer than one byte before them
+    const u32 tx = T.tot[1], tn = T.tot[3];
+    const u32 bx2 = T.cmax[1] - e4_fsum(tx) - T.tot[2], bx3 = bx2 + e4_f2(tx), bx4 = bx3 + e4_f3(tx), bx5 = bx4 + e4_f4(tx), bx6 = bx5 + e4_f5(tx);
+    const u32 bn2 = T.cmin[1] - e4_fsum(tn), bn3 = bn2 + e4_f2(tn), bn4 = bn3 + e4_f3(tn), bn5 = bn4 + e4_f4(tn);
+    // log "equal" flags of nodes that are neither uniform nor internal
+    const u32 eqb5 = ~u5 & eq5 & 0xffffu, eqb4 = ~u4 & eq4 & 0xfu;
+    const bool eqb3 = !u3 && eq3, eqb2 = !u2 && eq2;
+
+    if (emit) {
+      // ================= phase A: every bitmap bit (OR of runs; no byte store is in flight) =================
+      {  // quads and leaves
+        const u32 mqn = (W.mq >> 16) & ai5;
+        if ((W.ml != 0) | (mqn != 0)) {  // some leaf or quad-min entry takes two bytes: compress their flags
+          u64 accL = 0; int nL = 0;
+          u32 accM = 0; int nM = 0;
+#pragma unroll 1
+          for (int bit = 15; bit >= 0; bit--) {  // quad q = 15 - bit
+            if ((ai5 >> bit) & 1u) {
+              accL = (accL << 4) | ((W.ml >> (4 * bit)) & 0xfull); nL += 4;
+              accM = (accM << 1) | ((mqn >> bit) & 1u); nM += 1;
+            }
+          }
+          if (nL) e5_or_run(xw0, Pn6 + 4u * R5, accL << (64 - nL));
+          e5_or_bits(nw0, Mn5 + R5, accM, nM);
+        }
+        if (!as_snapshot) {
+          // `equal` flags of the quads that exist but are not internal, in quad order
+          const u32 sel = X5 & ~ai5 & 0xffffu;
+          u32 m = eqb5 & sel, accE = 0;
+          const int nE = __popc(sel);
+          while (m) {
+            const int b = 31 - __clz((int)m);
+            m ^= 1u << b;
+            accE |= 1u << (nE - 1 - __popc(sel >> (b + 1)));
+          }
+          e5_or_bits(eq_words, (Pn5 - Mn5) + 4u * R4 - R5, accE, nE);
+        }
+        u32 accN = 0, accC = 0; int nN = 0;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          if ((ai4 >> (3 - a)) & 1u) {
+            accN = (accN << 4) | ((W.in5 >> (12 - 4 * a)) & 0xfu);
+            accC = (accC << 4) | ((W.mq >> (12 - 4 * a)) & 0xfu);
+            nN += 4;
+          }
+        }
+        e5_or_bits(nm_words, Pn5 + 4u * R4, accN, nN);
+        e5_or_bits(xw0, Pn5 + 4u * R4, accC, nN);
+      }
+      if (x4) {  // the four level-4 nodes
+        e5_or_bits(nm_words, Pn4 + 4u * R3, W.in4, 4);
+        e5_or_bits(xw0, Pn4 + 4u * R3, W.mu & 0xfu, 4);
+        u32 accM = 0, accE = 0; int nM = 0, nE = 0;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          if ((W.in4 >> (3 - a)) & 1u) { accM = (accM << 1) | ((W.mu >> (7 - a)) & 1u); nM++; }
+          else { accE = (accE << 1) | ((eqb4 >> (3 - a)) & 1u); nE++; }
+        }
+        e5_or_bits(nw0, Mn4 + R4, accM, nM);
+        if (!as_snapshot) e5_or_bits(eq_words, (Pn4 - Mn4) + 4u * R3 - R4, accE, nE);
+      }
+      if (x3) {  // own level-3 node
+        const u32 pos = Pn3 + 4u * R2p + (u32)(tid & 3);
+        if (W.in3) {
+          e5_or_run(nm_words, pos, 1ull << 63);
+          if ((W.mu >> 9) & 1u) e5_or_run(nw0, Mn3 + R3, 1ull << 63);
+        } else if (!as_snapshot && eqb3) {
+          e5_or_run(eq_words, pos - (Mn3 + R3), 1ull << 63);
+        }
+        if ((W.mu >> 8) & 1u) e5_or_run(xw0, pos, 1ull << 63);
+      }
+      if (x2 && owner2) {  // level-2 node of the group
+        const u32 pos = Pn2 + 4u * R1 + (u32)((tid >> 2) & 3);
+        if (W.in2) {
+          e5_or_run(nm_words, pos, 1ull << 63);
+          if ((W.mu >> 11) & 1u) e5_or_run(nw0, Mn2 + R2own, 1ull << 63);
+        } else if (!as_snapshot && eqb2) {
+          e5_or_run(eq_words, pos - (Mn2 + R2own), 1ull << 63);
+        }
+        if ((W.mu >> 10) & 1u) e5_or_run(xw0, pos, 1ull << 63);
+      }
+      if (tid == 0) {
+        // root and level-1 nodes: nodemap, equal, continuation bits of every DAC level
+        u8* const xw1 = e4_words_of(out, DX.hdr[1], T.cmax[1]);
+        u8* const xw2 = e4_words_of(out, DX.hdr[2], T.cmax[2]);
+        u8* const nw1 = e4_words_of(out, DN.hdr[1], T.cmin[1]);
+        u8* const nw2 = e4_words_of(out, DN.hdr[2], T.cmin[2]);
+        if (in0) e5_set_bit_cold(nm_words, 0);
+        else if (!as_snapshot && !u0 && eq0) e5_set_bit_cold(eq_words, 0);
+        u32 px[4] = {0, 0, 0, 0}, pn[4] = {0, 0, 0, 0};  // running positions in DAC levels 0..3
+        e5_top_bits(xw0, xw1, xw2, px, e0x);
+        if (in0) {
+          e5_top_bits(nw0, nw1, nw2, pn, e0n);
+#pragma unroll 1
+          for (int k = 0; k < 4; k++) {
+            const bool ik = (in1m >> (3 - k)) & 1u;
+            if (ik) e5_set_bit_cold(nm_words, 1u + (u32)k);
+            else if (!as_snapshot && !(n1max[k] == n1min[k]) && ((n1flags >> k) & 1u)) e5_set_bit_cold(eq_words, (u32)k - (u32)__popc(in1m >> (4 - k)));
+            e5_top_bits(xw0, xw1, xw2, px, e1x[k]);
+            if (ik) e5_top_bits(nw0, nw1, nw2, pn, e1n[k]);
+          }
+        }
+      }
+    }
+    e5_tile_sync(slot);  // B2a: all word-wide ORs done before the first byte store
+
+    // ================= phase B: DAC bytes =================
+    {
+      u32 pos[3] = {bx6 + pre[2], bx5 + e4_f5(pre[1]), bn5 + e4_f5(pre[3])};  // lx1, rx1, rn1: second bytes of leaves / quad max / quad min
+      u8* dst6 = xb0 + Pn6 + 4u * R5;
+      u8* dst5 = xb0 + Pn5 + 4u * R4;
+      u8* dmn = nb0 + Mn5 + R5;
+      uint4 raw[4];
+      if (as_snapshot) e5_load_node(e5_node_ptr(pt, sr, 0), sr, raw);
+#pragma unroll 1
+      for (int a = 0; a < 4; a++) {
+        const int2 n4 = S.l4t[a][tid];
+        const u32 in5a = (W.in5 >> (12 - 4 * a)) & 0xfu;
+        const bool alive = emit && ((ai4 >> (3 - a)) & 1u);
+        u32 zxw, znw;
+        if (as_snapshot) {
+          // quads and leaves of the Snapshot from a pass over the tile, which also installs the instant as the snapshot
+          // image the following Logs are built against (even when nothing can be emitted: the sizes must stay exact)
+          int4 q[4];
+          e5_quads(raw, scale2, q);
+          if (a < 3) e5_load_node(e5_node_ptr(pt, sr, a + 1), sr, raw);
+          S.l4s[a][tid] = n4;
+          zxw = 0; znw = 0;
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const int4 t = q[b];
+            S.cell[4 * a + b][tid] = t;
+            const int qmax = max(max(t.x, t.y), max(t.z, t.w)), qmin = min(min(t.x, t.y), min(t.z, t.w));
+            zxw |= (zigzag32(n4.x - qmax) & 0xffu) << (8 * b);
+            znw |= (zigzag32(qmin - n4.y) & 0xffu) << (8 * b);
+            if (alive && ((in5a >> (3 - b)) & 1u))
+              e5_store_word(dst6 + 4u * (u32)__popc(in5a >> (4 - b)),
+                            e5_pack4(zigzag32(qmax - t.x), zigzag32(qmax - t.y), zigzag32(qmax - t.z), zigzag32(qmax - t.w)));
+          }
+        } else {
+          // quads and leaves of the Log from the payload of the fused pass
+          zxw = S.qx[a][tid]; znw = S.qn[a][tid];
+          if (alive) {
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+              if ((in5a >> (3 - b)) & 1u) e5_store_word(dst6 + 4u * (u32)__popc(in5a >> (4 - b)), S.leaf[4 * a + b][tid]);
+          }
+        }
+        if (!alive) continue;
+        e5_store_word(dst5, zxw);
+        dst5 += 4;
+        dst6 += 4u * (u32)__popc(in5a);
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+          if ((in5a >> (3 - b)) & 1u) *dmn++ = (u8)(znw >> (8 * b));
+        const u32 ml16 = (u32)(W.ml >> (48 - 16 * a)) & 0xffffu;
+        const u32 lq = ((W.mq >> (12 - 4 * a)) & 0xfu) | (((W.mq >> (28 - 4 * a)) & 0xfu) & in5a);
+        if ((ml16 & (e4_expand4(in5a) & 0xffffu)) | lq)
+          e5_long_node(as_snapshot, e5_node_ptr(pt, sr, a), sr, scale2, &S.cell[4 * a][tid], n4, in5a, xb1, nb1, pos);
+      }
+    }
+    if (emit) {
+      if (x4) {  // ---- level-4 nodes
+        u32 rx1 = bx4 + e4_f4(pre[1]), rn1 = bn4 + e4_f4(pre[3]);
+        u32 zx[4], zn[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          const int2 n4 = S.l4t[a][tid];
+          // the Snapshot pass has already installed l4s = l4t, and a Snapshot's entries do not refer to it
+          const int2 s4 = as_snapshot ? make_int2(0, 0) : S.l4s[a][tid];
+          zx[a] = zigzag32(as_snapshot ? t3max - n4.x : n4.x - s4.x);
+          zn[a] = zigzag32(as_snapshot ? n4.y - t3min : n4.y - s4.y);
+        }
+        e5_store_word(xb0 + Pn4 + 4u * R3, e5_pack4(zx[0], zx[1], zx[2], zx[3]));
+        u8* dmn = nb0 + Mn4 + R4;
+        if (W.mu & 0xffu) {
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+            if (zx[a] > 0xffu) rx1 = e5_hi(xb1, zx[a], rx1);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          if ((W.in4 >> (3 - a)) & 1u) {
+            *dmn++ = (u8)zn[a];
+            if (zn[a] > 0xffu) rn1 = e5_hi(nb1, zn[a], rn1);
+          }
+        }
+      }
+      if (x3) {
+        const u32 zx = zigzag32(as_snapshot ? t2max - t3max : t3max - s3max);
+        xb0[Pn3 + 4u * R2p + (u32)(tid & 3)] = (u8)zx;
+        if (zx > 0xffu) e5_hi(xb1, zx, bx3 + e4_f3(pre[1]));
+        if (W.in3) {
+          const u32 zn = zigzag32(as_snapshot ? t3min - t2min : t3min - s3min);
+          nb0[Mn3 + R3] = (u8)zn;
+          if (zn > 0xffu) e5_hi(nb1, zn, bn3 + e4_f3(pre[3]));
+        }
+      }
+      if (x2 && owner2) {
+        const u32 zx = zigzag32(as_snapshot ? t1max - t2max : t2max - s2max);
+        xb0[Pn2 + 4u * R1 + (u32)((tid >> 2) & 3)] = (u8)zx;
+        if (zx > 0xffu) e5_hi(xb1, zx, bx2 + e4_f2(pre[1]));
+        if (W.in2) {
+          const u32 zn = zigzag32(as_snapshot ? t2min - t1min : t2min - s2min);
+          nb0[Mn2 + R2own] = (u8)zn;
+          if (zn > 0xffu) e5_hi(nb1, zn, bn2 + e4_f2(pre[3]));
+        }
+      }
+      if (tid == 0) {
+        // root, level-1 entries (any length), every header field
+        u8* const xb2 = out + DX.bytes[2];
+        u8* const xb3 = out + DX.bytes[3];
+        u8* const nb2 = out + DN.bytes[2];
+        u8* const nb3 = out + DN.bytes[3];
+        u32 rx[3] = {0, 0, 0}, rn[3] = {0, 0, 0};
+        e5_top_bytes(xb0, xb1, xb2, xb3, 0, rx, e0x);
+        if (in0) {
+          e5_top_bytes(nb0, nb1, nb2, nb3, 0, rn, e0n);
+          u32 rm = 1;
+#pragma unroll 1
+          for (int k = 0; k < 4; k++) {
+            e5_top_bytes(xb0, xb1, xb2, xb3, 1u + (u32)k, rx, e1x[k]);
+            if ((in1m >> (3 - k)) & 1u) e5_top_bytes(nb0, nb1, nb2, nb3, rm++, rn, e1n[k]);
+          }
+        }
+        out[0] = 2;  // k
+        store_be32(out + 1, 64u);  // rows
+        store_be32(out + 5, 64u);  // cols
+        store_be32(out + 9, 64u);  // sidelen
+        u32 nb_ = 0;
+        auto bitmap_hdr = [&](u32 hdr, u32 len) {
+          e5_bitmap_hdr(out, hdr, len);
+          S.bm_off[nb_] = hdr; S.bm_len[nb_] = len; nb_++;
+        };
+        bitmap_hdr(nm_hdr, nm_len);
+        if (!as_snapshot) bitmap_hdr(eq_hdr, eq_len);
+        out[DX.hdr[0] - 1] = (u8)DX.levels;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (j < DX.levels) bitmap_hdr(DX.hdr[j], T.cmax[j]);
+        out[DN.hdr[0] - 1] = (u8)DN.levels;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (j < DN.levels) bitmap_hdr(DN.hdr[j], T.cmin[j]);
+        S.n_bm = nb_;
+      }
+    }
+    e5_tile_sync(slot);  // B2
+
+    if (emit) {
+      // ================= rank directories: index[b] = ones in bits [0, 128(b+1))  (bitmap.rs:97-104) =================
+      const u32 n_bm = S.n_bm;
+#pragma unroll 1
+      for (u32 i = warp; i < n_bm; i += 2) {
+        const u32 hdr = S.bm_off[i], len = S.bm_len[i];
+        const u32 blocks = len >> 7;
+        u8* const index = out + hdr + 8u;
+        const u8* const words = index + 4u * blocks;
+        u32 carry = 0;
+#pragma unroll 1
+        for (u32 b0 = 0; b0 < blocks; b0 += 32u) {
+          const u32 b = b0 + lane;
+          u32 c = b < blocks ? e4_popc_bytes16(words + 16u * b) : 0u;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const u32 n = __shfl_up_sync(0xffffffffu, c, d);
+            if (lane >= d) c += n;
+          }
+          if (b < blocks) e4_store_be32(index + 4u * b, carry + c);
+          carry += shfl(c, 31);
+        }
+      }
+    }
+    e5_tile_sync(slot);  // B3
+
+    // ================= copy-out (re-aligning by `shift` bytes) and re-zero the image =================
+    if (staged) {
+      piece_off = S.piece_off;
+      fits = piece_off + (((u64)my_size + 15ull) & ~15ull) <= P.arena_cap;
+      if (!fits) err |= EF_ARENA_FULL;
+      u32* src = reinterpret_cast<u32*>(S.pool);
+      uint4* dst = reinterpret_cast<uint4*>(P.arena + piece_off);
+      const u32 sh = 8u * shift;
+      const u32 n16 = (my_size + 15u) / 16u;
+#pragma unroll 1
+      for (u32 i = tid; i < n16; i += E5_THREADS) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + 4u * i);
+        const u32 nx = src[4u * i + 4u];
+        uint4 o;
+        o.x = __funnelshift_r(v.x, v.y, sh); o.y = __funnelshift_r(v.y, v.z, sh);
+        o.z = __funnelshift_r(v.z, v.w, sh); o.w = __funnelshift_r(v.w, nx, sh);
+        if (fits) dst[i] = o;
+      }
+      e5_tile_sync(slot);  // every word has been read (a chunk's last word belongs to the next one's first)
+#pragma unroll 1
+      for (u32 i = tid; i < n16 + 1u; i += E5_THREADS) *reinterpret_cast<uint4*>(src + 4u * i) = make_uint4(0, 0, 0, 0);
+    }
+
+    // ---------------- bookkeeping: start a new block or extend the current one
+    if (as_snapshot) {
+      s3max = t3max; s3min = t3min; s2max = t2max; s2min = t2min; s1max = t1max; s1min = t1min; s0max = t0max; s0min = t0min;
+      n_snap++;
+      n_logs = 0;
+      total_bytes += 1;  // Block's n_instants byte (block.rs:88-95)
+    } else {
+      n_logs++;
+      n_log_total++;
+    }
+    total_bytes += my_size;
+  }
+
+  if (tid == 0 && tile_live) {
+    UnitResult r;
+    r.bytes = total_bytes + 6;  // encoding + fractional_bits + n_blocks (chunk.rs:235-243)
+    r.snapshots = n_snap;
+    r.logs = n_log_total;
+    P.results[unit_idx] = r;
+  }
+  err = __reduce_or_sync(0xffffffffu, err);
+  if (lane == 0 && err) atomicOr(P.err, err);
+}
+
+}  // namespace dcdf

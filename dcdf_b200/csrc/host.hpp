@@ -113,6 +113,7 @@ struct dcdf_ctx {
   // dcdf_ctx_set_option (include/dcdf_cuda.h)
   struct Options {
     uint32_t stage_limit = 0xffffffffu;  // encoder: structures above this many bytes are emitted straight into the arena
+    int no_fast_encode = 0;              // keep eligible tiles away from the fast-path encoder (k_encode_v5)
     int encode_tiles256 = 0;             // full tiles through the 256-thread tile encoder instead of the 64-thread one
     int window_cells = 0;                // windows through the per-cell walker (the path of trees larger than 64x64)
     int window_wide = 0;                 // 64-bit expansion even when every DAC code fits three bytes
@@ -120,6 +121,7 @@ struct dcdf_ctx {
     int search_no_cache = 0;             // the search's writing pass recomputes instead of reading cached findings
     int trace = 0;                       // host-side phase times of the encode pipeline on stderr (adds stream syncs)
   } opt;
+  uint32_t last_list_counts[6] = {0, 0, 0, 0, 0, 0};  // units per encoder work list of the last build (dcdf_ctx_get_stat)
   // scratch
   dcdf::DevBuf input_copy, units, ustats, istats, slices, sstate, tbl_scratch, order, pieces, results, stored, chunk_off,
       arena, small, exact, query_in, query_out, query_aux, query_aux2, search_cache, tree_buf;

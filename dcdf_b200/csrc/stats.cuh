@@ -796,6 +796,7 @@ struct TreeParams {
   const InstStats* istats;
   u32 t_max;
   int encoding, round, req_bits;
+  int allow_fast;            // the input layout allows k_encode_v5's 128-bit loads
   i64* tbl_min;
   i64* tbl_max;
   u32* order;
@@ -865,6 +866,8 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
       int fnn = 0, fng = 0;
       i64 imax = INT64_MIN, imin = INT64_MAX;
       bool can_elide = true;
+      bool any_nan = false;                        // some cell of some instant is NaN
+      double rmin = INFINITY, rmax = -INFINITY;    // raw extrema over every instant (fast-path eligibility)
       const i64 region_cols = (i64)(ch.gc1 - ch.gc0) * P.leaf_side;
       for (int t = 0; t < sd.instants; t++) {
         double mn = INFINITY, mx = -INFINITY;
@@ -898,6 +901,8 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
         i64 fmn, fmx;
         if (is_float) {
           const bool all_nan = first == ~0ull;
+          any_nan = any_nan || all_nan || last != 0;
+          rmin = fmin(rmin, mn); rmax = fmax(rmax, mx);
           const bool quirk = !all_nan && last > first;  // mmbuffer.rs:485-487
           if (P.encoding == 32) {
             fmn = (all_nan || quirk) ? 0 : to_fixed_dev<float>((float)mn, nbits, round, err);
@@ -966,12 +971,20 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
         }
         const bool full = unit.rows == 64 && unit.cols == 64 && unit.lo == 0;
         if (full) flags |= UF_FULL;
+        // k_encode_v5 (encode_v5.cuh): full f32 tiles whose to_fixed is exact, without NaN, every fixed value below
+        // 2^22 in magnitude and all of them within 32767 of each other -> every entry below the root takes <= 2 bytes
+        bool fast = false;
+        if (P.allow_fast && !can_elide && full && narrow && P.encoding == 32 && (flags & UF_EXACT) && !any_nan && has) {
+          const double sc = ldexp(1.0, cbits + 1);
+          fast = (rmax - rmin) * sc <= 32767.0 && fabs(rmax) * sc < 4194303.0 && fabs(rmin) * sc < 4194303.0;
+        }
         unit.bits = cbits;
         unit.flags = flags;
         P.units[u] = unit;
         P.stored[u] = can_elide ? 0 : 1;
         if (!can_elide) {
           u32 list = (narrow ? 0u : 2u) + (full ? 0u : 1u);
+          if (fast) list = 5u;
           if (narrow && !full && unit.lo == 0) list = 4u;  // clipped, but still a 64-side tree: k_encode_v4<.., false>
           P.order[(size_t)list * P.order_pitch + atomicAdd(&P.order_counts[list], 1u)] = u;
         }

@@ -86,6 +86,7 @@ int32_t dcdf_ctx_set_stream(dcdf_ctx* ctx, void* cuda_stream);
  * select between code paths that produce identical bytes / results and exist for tests and A/B measurements):
  *   "stage_limit" <bytes>   encoder: structures larger than this are emitted straight into the arena (default 16384)
  *   "arena_hint"  <bytes>   first size of the encoder's output arena (grown and retried when it overflows)
+ *   "no_fast_encode" 0|1    eligible full f32 tiles through the general encoder instead of the fast-path kernel
  *   "encode_tiles256" 0|1   full 64x64 tiles through the 256-thread tile encoder
  *   "window_cells" 0|1      windows through the per-cell walker (the path of trees larger than 64x64)
  *   "window_wide" 0|1       64-bit tile expansion even when every DAC code fits three bytes
@@ -94,6 +95,9 @@ int32_t dcdf_ctx_set_stream(dcdf_ctx* ctx, void* cuda_stream);
  *   "trace" 0|1             host-side phase times of the encode pipeline on stderr
  * Unknown names return DCDF_ERR_BAD_ARG. */
 int32_t dcdf_ctx_set_option(dcdf_ctx* ctx, const char* name, int64_t value);
+/* Counters of the last build call: "encode_units_fast" (units encoded by the fast-path kernel), "encode_units_general",
+ * "encode_units_wide" (64-bit values), "encode_units_clipped". */
+int32_t dcdf_ctx_get_stat(const dcdf_ctx* ctx, const char* name, int64_t* value);
 int32_t dcdf_ctx_synchronize(dcdf_ctx* ctx);
 const char* dcdf_last_error(const dcdf_ctx* ctx);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */

@@ -8,9 +8,13 @@ R = int(sys.argv[2]) if len(sys.argv) > 2 else 721
 C = int(sys.argv[3]) if len(sys.argv) > 3 else 1440
 data = synth.raster(T, R, C, device="cuda")
 ctx = Context(0)
+for opt in sys.argv[4:]:          # e.g. no_fast_encode=1
+    k, v = opt.split("=")
+    ctx.set_option(k, int(v))
 for i in range(2):
     sc = Superchunk.build(ctx, data, [5, 6], compute_bits=True, chunk_size=64)
-    print("encode ms", ctx.last_kernel_ms(_ffi.KT_ENCODE), "stats ms", ctx.last_kernel_ms(_ffi.KT_STATS), "bytes", sc.total_bytes())
+    print("encode ms", ctx.last_kernel_ms(_ffi.KT_ENCODE), "stats ms", ctx.last_kernel_ms(_ffi.KT_STATS), "bytes", sc.total_bytes(),
+          "fast units", ctx.get_stat("encode_units_fast"), "general", ctx.get_stat("encode_units_general"))
     if i == 0:
         sc.close()
 out = torch.empty((T, R, C), device="cuda", dtype=torch.float32)
