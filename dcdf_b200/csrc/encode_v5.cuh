@@ -132,30 +132,55 @@ __device__ __noinline__ u32 e5_hi(u8* b1, u32 z, u32 r1) {
   return r1 + 1u;
 }
 
-// Root / level-1 entries are written by one thread: out of line, so the code every warp runs stays small.
-__device__ __noinline__ void e5_top_bits(u8* w0, u8* w1, u8* w2, u32* p, int e) {
-  u32 q[4] = {p[0], p[1], p[2], p[3]};
-  e4_top_bits(w0, w1, w2, q, e);
-  p[0] = q[0]; p[1] = q[1]; p[2] = q[2]; p[3] = q[3];
-}
-__device__ __noinline__ void e5_top_bytes(u8* b0, u8* b1, u8* b2, u8* b3, u32 at, u32* r, int e) {
-  const u32 z = zigzag32(e);
-  b0[at] = (u8)z;
-  if (z > 0xffu) {
-    u32 r1 = r[0], r2 = r[1], r3 = r[2];
-    e4_emit_hi(b1, b2, b3, z, r1, r2, r3);
-    r[0] = r1; r[1] = r2; r[2] = r3;
-  }
-}
-__device__ __noinline__ void e5_set_bit_cold(u8* bytes, u32 bitpos) { e4_set_bit(bytes, bitpos); }
-__device__ __noinline__ void e5_bitmap_hdr(u8* out, u32 hdr, u32 len) {
-  store_be32(out + hdr, len);
-  store_be32(out + hdr + 4, 4u);  // k = 4 (bitmap.rs:69)
-}
-// OR a run of bits into a bit stream (e4_or_run), one shared copy for every call site
+// OR a run of bits into a bit stream (e4_or_run): the 64-bit form is rare (leaf flags), out of line
 __device__ __noinline__ void e5_or_run(u8* bytes, u32 bitpos, u64 V) { e4_or_run(bytes, bitpos, V); }
-DCDF_DEVINL void e5_or_bits(u8* bytes, u32 bitpos, u32 bits, int n) {  // n <= 32 bits, right-aligned in `bits`
-  if (n > 0 && bits) e5_or_run(bytes, bitpos, (u64)bits << (64 - n));
+// ... a run of n <= 32 bits, right-aligned in `bits` (at most two containers)
+DCDF_DEVINL void e5_or_bits(u8* bytes, u32 bitpos, u32 bits, int n) {
+  if (n <= 0 || !bits) return;
+  const u32 hi = bits << (32 - n);
+  const uintptr_t A = (uintptr_t)bytes;
+  const u32 g = bitpos + 8u * (u32)(A & 3u);
+  const u32 sft = g & 31u;
+  u32* w = reinterpret_cast<u32*>(A & ~(uintptr_t)3) + (g >> 5);
+  const u32 w0 = hi >> sft, w1 = __funnelshift_r(0u, hi, sft);
+  if (w0) e4_red_or(w, e4_bswap(w0));
+  if (w1) e4_red_or(w + 1, e4_bswap(w1));
+}
+// ... one bit
+DCDF_DEVINL void e5_or_bit(u8* bytes, u32 bitpos) {
+  const uintptr_t A = (uintptr_t)bytes;
+  const u32 g = bitpos + 8u * (u32)(A & 3u);
+  e4_red_or(reinterpret_cast<u32*>(A & ~(uintptr_t)3) + (g >> 5), e4_bswap(0x80000000u >> (g & 31u)));
+}
+// bits of `src` at the positions where `sel` is set, packed to the right in order (both MSB-first over n entries)
+DCDF_DEVINL u32 e5_compress(u32 src, u32 sel, int n) {
+  u32 out = 0;
+#pragma unroll
+  for (int i = 4; i >= 0; i--)
+    if (i < n && ((sel >> i) & 1u)) out = (out << 1) | ((src >> i) & 1u);
+  return out;
+}
+// The first entries of a DAC are the root's and the level-1 nodes' (BFS order), so their continuation bits are the
+// first bits of every level's bitmap: three short runs per DAC instead of one call per bit.  e[i], i < n (n <= 5).
+__device__ __noinline__ void e5_top_bits(u8* w0, u8* w1, u8* w2, const int* e, int n) {
+  u32 m1 = 0, m2 = 0, m3 = 0;  // entry i = bit n-1-i: longer than 1 / 2 / 3 bytes
+  for (int i = 0; i < n; i++) {
+    m1 = (m1 << 1) | (e4_longer<1>(e[i]) ? 1u : 0u);
+    m2 = (m2 << 1) | (e4_longer<2>(e[i]) ? 1u : 0u);
+    m3 = (m3 << 1) | (e4_longer<3>(e[i]) ? 1u : 0u);
+  }
+  e5_or_bits(w0, 0, m1, n);
+  if (m2) e5_or_bits(w1, 0, e5_compress(m2, m1, n), __popc(m1));
+  if (m3) e5_or_bits(w2, 0, e5_compress(m3, m2, n), __popc(m2));
+}
+// ... and their bytes are the first bytes of every level (dac.rs:109-121)
+__device__ __noinline__ void e5_top_bytes(u8* b0, u8* b1, u8* b2, u8* b3, const int* e, int n) {
+  u32 r1 = 0, r2 = 0, r3 = 0;
+  for (int i = 0; i < n; i++) {
+    const u32 z = zigzag32(e[i]);
+    b0[i] = (u8)z;
+    if (z > 0xffu) e4_emit_hi(b1, b2, b3, z, r1, r2, r3);
+  }
 }
 
 // to_fixed (a3) of an exact, finite, small value: n * 2^(bits+1) is an integer below 2^22, so adding 1.5 * 2^23
@@ -644,22 +669,22 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
       if (x3) {  // own level-3 node
         const u32 pos = Pn3 + 4u * R2p + (u32)(tid & 3);
         if (W.in3) {
-          e5_or_run(nm_words, pos, 1ull << 63);
-          if ((W.mu >> 9) & 1u) e5_or_run(nw0, Mn3 + R3, 1ull << 63);
+          e5_or_bit(nm_words, pos);
+          if ((W.mu >> 9) & 1u) e5_or_bit(nw0, Mn3 + R3);
         } else if (!as_snapshot && eqb3) {
-          e5_or_run(eq_words, pos - (Mn3 + R3), 1ull << 63);
+          e5_or_bit(eq_words, pos - (Mn3 + R3));
         }
-        if ((W.mu >> 8) & 1u) e5_or_run(xw0, pos, 1ull << 63);
+        if ((W.mu >> 8) & 1u) e5_or_bit(xw0, pos);
       }
       if (x2 && owner2) {  // level-2 node of the group
         const u32 pos = Pn2 + 4u * R1 + (u32)((tid >> 2) & 3);
         if (W.in2) {
-          e5_or_run(nm_words, pos, 1ull << 63);
-          if ((W.mu >> 11) & 1u) e5_or_run(nw0, Mn2 + R2own, 1ull << 63);
+          e5_or_bit(nm_words, pos);
+          if ((W.mu >> 11) & 1u) e5_or_bit(nw0, Mn2 + R2own);
         } else if (!as_snapshot && eqb2) {
-          e5_or_run(eq_words, pos - (Mn2 + R2own), 1ull << 63);
+          e5_or_bit(eq_words, pos - (Mn2 + R2own));
         }
-        if ((W.mu >> 10) & 1u) e5_or_run(xw0, pos, 1ull << 63);
+        if ((W.mu >> 10) & 1u) e5_or_bit(xw0, pos);
       }
       if (tid == 0) {
         // root and level-1 nodes: nodemap, equal, continuation bits of every DAC level
@@ -667,20 +692,23 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
         u8* const xw2 = e4_words_of(out, DX.hdr[2], T.cmax[2]);
         u8* const nw1 = e4_words_of(out, DN.hdr[1], T.cmin[1]);
         u8* const nw2 = e4_words_of(out, DN.hdr[2], T.cmin[2]);
-        if (in0) e5_set_bit_cold(nm_words, 0);
-        else if (!as_snapshot && !u0 && eq0) e5_set_bit_cold(eq_words, 0);
-        u32 px[4] = {0, 0, 0, 0}, pn[4] = {0, 0, 0, 0};  // running positions in DAC levels 0..3
-        e5_top_bits(xw0, xw1, xw2, px, e0x);
+        int ex[5] = {e0x, e1x[0], e1x[1], e1x[2], e1x[3]};
+        e5_top_bits(xw0, xw1, xw2, ex, in0 ? 5 : 1);
         if (in0) {
-          e5_top_bits(nw0, nw1, nw2, pn, e0n);
-#pragma unroll 1
+          e5_or_bits(nm_words, 0, 0x10u | in1m, 5);
+          int en[5];
+          int nn = 1;
+          en[0] = e0n;
+          u32 accE = 0; int nE = 0;
+#pragma unroll
           for (int k = 0; k < 4; k++) {
-            const bool ik = (in1m >> (3 - k)) & 1u;
-            if (ik) e5_set_bit_cold(nm_words, 1u + (u32)k);
-            else if (!as_snapshot && !(n1max[k] == n1min[k]) && ((n1flags >> k) & 1u)) e5_set_bit_cold(eq_words, (u32)k - (u32)__popc(in1m >> (4 - k)));
-            e5_top_bits(xw0, xw1, xw2, px, e1x[k]);
-            if (ik) e5_top_bits(nw0, nw1, nw2, pn, e1n[k]);
+            if ((in1m >> (3 - k)) & 1u) en[nn++] = e1n[k];
+            else { accE = (accE << 1) | ((!(n1max[k] == n1min[k]) && ((n1flags >> k) & 1u)) ? 1u : 0u); nE++; }
           }
+          e5_top_bits(nw0, nw1, nw2, en, nn);
+          if (!as_snapshot) e5_or_bits(eq_words, 0, accE, nE);
+        } else if (!as_snapshot && !u0 && eq0) {
+          e5_or_bit(eq_words, 0);
         }
       }
     }
@@ -789,52 +817,51 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
         }
       }
       if (tid == 0) {
-        // root, level-1 entries (any length), every header field
-        u8* const xb2 = out + DX.bytes[2];
-        u8* const xb3 = out + DX.bytes[3];
-        u8* const nb2 = out + DN.bytes[2];
-        u8* const nb3 = out + DN.bytes[3];
-        u32 rx[3] = {0, 0, 0}, rn[3] = {0, 0, 0};
-        e5_top_bytes(xb0, xb1, xb2, xb3, 0, rx, e0x);
+        // root and level-1 entries (any length), structure header
+        int ex[5] = {e0x, e1x[0], e1x[1], e1x[2], e1x[3]};
+        e5_top_bytes(xb0, xb1, out + DX.bytes[2], out + DX.bytes[3], ex, in0 ? 5 : 1);
         if (in0) {
-          e5_top_bytes(nb0, nb1, nb2, nb3, 0, rn, e0n);
-          u32 rm = 1;
-#pragma unroll 1
-          for (int k = 0; k < 4; k++) {
-            e5_top_bytes(xb0, xb1, xb2, xb3, 1u + (u32)k, rx, e1x[k]);
-            if ((in1m >> (3 - k)) & 1u) e5_top_bytes(nb0, nb1, nb2, nb3, rm++, rn, e1n[k]);
-          }
+          int en[5];
+          int nn = 1;
+          en[0] = e0n;
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if ((in1m >> (3 - k)) & 1u) en[nn++] = e1n[k];
+          e5_top_bytes(nb0, nb1, out + DN.bytes[2], out + DN.bytes[3], en, nn);
         }
         out[0] = 2;  // k
         store_be32(out + 1, 64u);  // rows
         store_be32(out + 5, 64u);  // cols
         store_be32(out + 9, 64u);  // sidelen
-        u32 nb_ = 0;
-        auto bitmap_hdr = [&](u32 hdr, u32 len) {
-          e5_bitmap_hdr(out, hdr, len);
-          S.bm_off[nb_] = hdr; S.bm_len[nb_] = len; nb_++;
-        };
-        bitmap_hdr(nm_hdr, nm_len);
-        if (!as_snapshot) bitmap_hdr(eq_hdr, eq_len);
         out[DX.hdr[0] - 1] = (u8)DX.levels;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (j < DX.levels) bitmap_hdr(DX.hdr[j], T.cmax[j]);
         out[DN.hdr[0] - 1] = (u8)DN.levels;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (j < DN.levels) bitmap_hdr(DN.hdr[j], T.cmin[j]);
-        S.n_bm = nb_;
       }
     }
     e5_tile_sync(slot);  // B2
 
     if (emit) {
-      // ================= rank directories: index[b] = ones in bits [0, 128(b+1))  (bitmap.rs:97-104) =================
-      const u32 n_bm = S.n_bm;
+      // ================= bitmap headers and rank directories: index[b] = ones in bits [0, 128(b+1))  (bitmap.rs:97-104)
+      // bitmaps in stream order: nodemap, equal (Logs), the levels of the max DAC, the levels of the min DAC
+      const u32 n_fix = as_snapshot ? 1u : 2u;
+      const u32 n_bm = n_fix + (u32)DX.levels + (u32)DN.levels;
 #pragma unroll 1
       for (u32 i = warp; i < n_bm; i += 2) {
-        const u32 hdr = S.bm_off[i], len = S.bm_len[i];
+        u32 hdr, len;
+        if (i == 0) { hdr = nm_hdr; len = nm_len; }
+        else if (i < n_fix) { hdr = eq_hdr; len = eq_len; }
+        else if (i < n_fix + (u32)DX.levels) {
+          const u32 j = i - n_fix;
+          hdr = j == 0 ? DX.hdr[0] : j == 1 ? DX.hdr[1] : j == 2 ? DX.hdr[2] : DX.hdr[3];
+          len = j == 0 ? T.cmax[0] : j == 1 ? T.cmax[1] : j == 2 ? T.cmax[2] : T.cmax[3];
+        } else {
+          const u32 j = i - n_fix - (u32)DX.levels;
+          hdr = j == 0 ? DN.hdr[0] : j == 1 ? DN.hdr[1] : j == 2 ? DN.hdr[2] : DN.hdr[3];
+          len = j == 0 ? T.cmin[0] : j == 1 ? T.cmin[1] : j == 2 ? T.cmin[2] : T.cmin[3];
+        }
+        if (lane == 0) {
+          store_be32(out + hdr, len);
+          store_be32(out + hdr + 4, 4u);  // k = 4 (bitmap.rs:69)
+        }
         const u32 blocks = len >> 7;
         u8* const index = out + hdr + 8u;
         const u8* const words = index + 4u * blocks;
