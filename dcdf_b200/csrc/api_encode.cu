@@ -238,7 +238,7 @@ void launch_encode_v5(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   const u32 stage_limit = std::min<u32>(ctx->opt.stage_limit, (u32)E5_POOL);
   const size_t smem = sizeof(E5Smem) * G;
   CK(cudaFuncSetAttribute(k_encode_v5<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_encode_v5<G><<<(grid + G - 1) / G, E5_THREADS * G, smem, ctx->stream>>>(P, stage_limit);
+  k_encode_v5<G><<<(grid + G - 1) / G, E5_THREADS * G, smem, ctx->stream>>>(P, stage_limit, ctx->opt.fast_sync_mask);
   CK(cudaGetLastError());
   ctx->launches++;
 }
@@ -955,6 +955,7 @@ int32_t dcdf_ctx_set_option(dcdf_ctx* ctx, const char* name, int64_t value) {
   else if (n == "arena_hint") ctx->arena_hint = value < 0 ? 0 : (size_t)value;
   else if (n == "encode_tiles256") ctx->opt.encode_tiles256 = value != 0;
   else if (n == "no_fast_encode") ctx->opt.no_fast_encode = value != 0;
+  else if (n == "fast_sync_mask") ctx->opt.fast_sync_mask = (int)value;
   else if (n == "window_cells") ctx->opt.window_cells = value != 0;
   else if (n == "window_wide") ctx->opt.window_wide = value != 0;
   else if (n == "search_dfs") ctx->opt.search_dfs = value != 0;

@@ -23,6 +23,8 @@
 // Reference functions restated: snapshot.rs:108-156 + 439-500, log.rs:112-165 + 725-817, bitmap.rs:66-113,
 // dac.rs:96-132, chunk.rs:55-78, serializers snapshot.rs:48-58 / log.rs:53-64 / dac.rs:37-44 / bitmap.rs:128-138.
 #pragma once
+#include <type_traits>
+
 #include "encode_v4.cuh"
 
 namespace dcdf {
@@ -204,6 +206,10 @@ DCDF_DEVINL void e5_quads(const uint4 (&raw)[4], float scale2, int4 (&q)[4]) {
 }
 DCDF_DEVINL const float* e5_node_ptr(const float* pt, i64 sr, int a) { return pt + (i64)(4 * (a >> 1)) * sr + 4 * (a & 1); }
 
+// low bytes of four values as one word, and the zigzag codes of four signed bytes at once (dac.rs:134-137 on values in
+// -128..127: (b << 1) ^ (b >> 7) per byte; the carries of p + p land in the cleared low bits)
+DCDF_DEVINL u32 e5_low4(int a, int b, int c, int d) { return __byte_perm(__byte_perm((u32)a, (u32)b, 0x0040), __byte_perm((u32)c, (u32)d, 0x0040), 0x5410); }
+DCDF_DEVINL u32 e5_zz4(u32 p) { return ((p + p) & 0xfefefefeu) ^ (((p >> 7) & 0x01010101u) * 0xffu); }
 DCDF_DEVINL u32 e5_pack4(u32 z0, u32 z1, u32 z2, u32 z3) { return (z0 & 0xffu) | ((z1 & 0xffu) << 8) | ((z2 & 0xffu) << 16) | (z3 << 24); }
 DCDF_DEVINL void e5_store_word(u8* p, u32 w) {
   if ((((uintptr_t)p) & 3u) == 0) *reinterpret_cast<u32*>(p) = w;
@@ -258,7 +264,7 @@ DCDF_DEVINL void e5_tile_sync(int slot) { asm volatile("bar.sync %0, 64;" ::"r"(
 // same stretch of code, so instruction-cache lines fetched for one warp are hits for the others (with unsynchronised
 // CTAs the kernel spent a quarter of its issue slots waiting for instruction fetches).
 template <int G>
-__global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams P, const u32 stage_limit) {
+__global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams P, const u32 stage_limit, const int sync_mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int slot = threadIdx.x / E5_THREADS;
   E5Smem& S = *reinterpret_cast<E5Smem*>(smem_raw + (size_t)slot * sizeof(E5Smem));
@@ -296,10 +302,14 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
 
 #pragma unroll 1
   for (int inst = 0; inst < max_instants; inst++) {
-    __syncthreads();  // all tiles of the CTA start the instant together (shared instruction stream)
+    if ((inst & sync_mask) == 0) __syncthreads();  // all tiles of the CTA start the instant together (shared instruction stream)
     if (inst >= unit.instants) continue;
     const bool first = inst == 0;
     const float* const pt = base + (i64)inst * P.stride_t;
+    if (inst + 1 < unit.instants) {  // the next instant's cells on their way into L2 (the tiles of a CTA all load at once)
+#pragma unroll
+      for (int r = 0; r < 8; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + P.stride_t + (i64)r * sr));
+    }
     const bool forced = first || n_logs == 254u;  // chunk.rs:62 (Block caps logs at 254)
 
     u32 u5 = 0, eq5 = 0, u4 = 0, eq4 = 0;
@@ -339,7 +349,9 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
           const int2 s4 = S.l4s[a][tid];
           int amax = INT32_MIN, amin = INT32_MAX, dfirst = 0;
           bool aeq = true;
-          u32 leaf16 = 0, u5n = 0, e5n = 0, qx = 0, qn = 0, zxw = 0, znw = 0;
+          u32 leaf16 = 0, u5n = 0, e5n = 0, qx = 0, qn = 0;
+          u32 exw = 0, enw = 0;          // low bytes of the four quad max / min entries
+          u32 ovx = 0, ovn = 0, ovm = 0; // exact low bytes of the zigzag codes of entries outside -128..127
 #pragma unroll
           for (int b = 0; b < 4; b++) {
             const int4 t = q[b], sq = S.cell[4 * a + b][tid];
@@ -350,6 +362,9 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
             const bool e5 = (((d1 ^ d0) | (d2 ^ d0) | (d3 ^ d0)) == 0);  // all four leaf diffs equal (log.rs:780-806)
             if (qmax == qmin) u5n |= 1u << (3 - b);
             if (e5) e5n |= 1u << (3 - b);
+            u32 leafw = e5_zz4(e5_low4(d0, d1, d2, d3));
+            exw = __byte_perm(exw, (u32)ex, b == 0 ? 0x3214 : b == 1 ? 0x3240 : b == 2 ? 0x3410 : 0x4210);
+            enw = __byte_perm(enw, (u32)en, b == 0 ? 0x3214 : b == 1 ? 0x3240 : b == 2 ? 0x3410 : 0x4210);
             // one test for "some entry of this quad needs two bytes" (zigzag code above 255  <=>  value outside -128..127)
             if ((((u32)d0 + 128u) | ((u32)d1 + 128u) | ((u32)d2 + 128u) | ((u32)d3 + 128u) | ((u32)ex + 128u) | ((u32)en + 128u)) > 255u) {
               if (e4_longer<1>(d0)) leaf16 |= 1u << (15 - 4 * b);
@@ -359,14 +374,17 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
               if (e4_longer<1>(ex)) qx |= 1u << (3 - b);
               if (e4_longer<1>(en)) qn |= 1u << (3 - b);
               if ((((u32)d0 + 32768u) | ((u32)d1 + 32768u) | ((u32)d2 + 32768u) | ((u32)d3 + 32768u)) > 65535u) err |= EF_BAD_FORMAT;  // not eligible
+              leafw = e5_pack4(zigzag32(d0), zigzag32(d1), zigzag32(d2), zigzag32(d3));
+              ovx |= (zigzag32(ex) & 0xffu) << (8 * b);
+              ovn |= (zigzag32(en) & 0xffu) << (8 * b);
+              ovm |= 0xffu << (8 * b);
             }
-            S.leaf[4 * a + b][tid] = e5_pack4(zigzag32(d0), zigzag32(d1), zigzag32(d2), zigzag32(d3));
-            zxw |= (zigzag32(ex) & 0xffu) << (8 * b);
-            znw |= (zigzag32(en) & 0xffu) << (8 * b);
+            S.leaf[4 * a + b][tid] = leafw;
             amax = max(amax, qmax); amin = min(amin, qmin);
             if (b == 0) dfirst = d0;
             aeq = aeq && e5 && d0 == dfirst;
           }
+          const u32 zxw = (e5_zz4(exw) & ~ovm) | ovx, znw = (e5_zz4(enw) & ~ovm) | ovn;
           S.qx[a][tid] = zxw;
           S.qn[a][tid] = znw;
           S.l4t[a][tid] = make_int2(amax, amin);
@@ -563,20 +581,23 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
     if (!staged) e5_tile_sync(slot);
     u64 piece_off = 0;
     bool fits = true;
-    u8* out = S.pool + shift;
     if (!staged) {
       piece_off = S.piece_off;
       fits = piece_off + (((u64)my_size + 15ull) & ~15ull) <= P.arena_cap;
       if (!fits) err |= EF_ARENA_FULL;
-      out = P.arena + piece_off;
       if (fits) {
-        uint4* z = reinterpret_cast<uint4*>(out);
+        uint4* z = reinterpret_cast<uint4*>(P.arena + piece_off);
         for (u32 i = tid; i < (my_size + 15u) / 16u; i += E5_THREADS) z[i] = make_uint4(0, 0, 0, 0);
       }
       e5_tile_sync(slot);
     }
     const bool emit = staged || fits;
 
+    // Everything that touches the image, once for the shared-memory image (the compiler then knows the address space of
+    // every pointer: 32-bit addressing, shared-memory reductions) and once for a structure too large for it, emitted
+    // straight into its zeroed piece of the arena.
+    auto emission = [&](auto in_shared) {
+    u8* const out = decltype(in_shared)::value ? S.pool + shift : P.arena + piece_off;
     u8* const nm_words = e4_words_of(out, nm_hdr, nm_len);
     u8* const eq_words = e4_words_of(out, eq_hdr, eq_len);
     u8* const xw0 = e4_words_of(out, DX.hdr[0], T.cmax[0]);  // continuation bits of DAC level 0
@@ -600,8 +621,11 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
     // prefix over earlier threads (Morton order) of the packed counters
     u32 pre[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-      pre[i] = e4_warp_excl(as_snapshot ? ws[i] : wl[i], lane) + ((warp == 1 && in0) ? S.wt[0][cand][i] : 0u);
+    for (int i = 0; i < 4; i++) {
+      pre[i] = 0;
+      if (i == 0 || T.tot[i] != 0)  // tile-uniform: without two-byte entries there is nothing to scan
+        pre[i] = e4_warp_excl(as_snapshot ? ws[i] : wl[i], lane) + ((warp == 1 && in0) ? S.wt[0][cand][i] : 0u);
+    }
     const u32 R2own = e4_f2(pre[0]);                       // internal level-2 nodes before the own group (valid on owner lanes)
     const u32 R2p = e4_f2(shfl(pre[0], lane & ~3));        // the same, seen by every lane of the group
     const u32 R3 = e4_f3(pre[0]), R4 = e4_f4(pre[0]), R5 = e4_f5(pre[0]);
@@ -883,7 +907,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
     e5_tile_sync(slot);  // B3
 
     // ================= copy-out (re-aligning by `shift` bytes) and re-zero the image =================
-    if (staged) {
+    if constexpr (decltype(in_shared)::value) {
       piece_off = S.piece_off;
       fits = piece_off + (((u64)my_size + 15ull) & ~15ull) <= P.arena_cap;
       if (!fits) err |= EF_ARENA_FULL;
@@ -904,6 +928,10 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
 #pragma unroll 1
       for (u32 i = tid; i < n16 + 1u; i += E5_THREADS) *reinterpret_cast<uint4*>(src + 4u * i) = make_uint4(0, 0, 0, 0);
     }
+
+    };
+    if (staged) emission(std::true_type{});
+    else emission(std::false_type{});
 
     // ---------------- bookkeeping: start a new block or extend the current one
     if (as_snapshot) {
