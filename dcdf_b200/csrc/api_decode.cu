@@ -77,7 +77,7 @@ void check_err_word(dcdf_ctx* ctx, u32* d_err, const char* what) {
 
 MetaBlock* make_meta(dcdf_ctx* ctx, const u8* blob, std::vector<UnitMeta>& units, const std::vector<SliceMeta>& slices,
                      const std::vector<int32_t>& slot_unit, const std::vector<SlotDesc>& slot_desc, u32 n_slots, i64 chunk_size, int chunks_sidelen, int subsidelen,
-                     int encoding, const i64* shape, const i64* tbl_max, void** dir_out, bool count_first, bool validate) {
+                     int encoding, const i64* shape, const i64* tbl_max, const i64* tbl_min, void** dir_out, bool count_first, bool validate) {
   cudaStream_t st = ctx->stream;
   MetaBlock* mb = new MetaBlock();
   *dir_out = nullptr;
@@ -139,6 +139,7 @@ MetaBlock* make_meta(dcdf_ctx* ctx, const u8* blob, std::vector<UnitMeta>& units
     Q.slot_unit = mb->d.slot_unit;
     Q.slot_desc = mb->d.slot_desc;
     Q.tbl_max = tbl_max;
+    Q.tbl_min = tbl_min;
     Q.n_slices = (u32)slices.size();
     Q.n_slots = n_slots;
     Q.chunk_size = chunk_size;
@@ -174,10 +175,11 @@ MetaBlock* chunk_meta(dcdf_ctx* ctx, const dcdf_chunk* cc) {
   memset(&slices[0], 0, sizeof(SliceMeta));
   slices[0].t0 = 0; slices[0].instants = (int)c->shape[0]; slices[0].bits = c->fractional_bits;
   std::vector<int32_t> slot_unit(1, 0);
-  std::vector<SlotDesc> slot_desc(1, SlotDesc{0, 0, 0});
+  std::vector<SlotDesc> slot_desc(1);
+  memset(&slot_desc[0], 0, sizeof(SlotDesc));
   void* dir = nullptr;
   const bool count_first = c->shape[0] == 0;
-  MetaBlock* mb = make_meta(ctx, c->bytes, units, slices, slot_unit, slot_desc, 1, 0, 1 << 30, 1, c->encoding, c->shape, nullptr, &dir, count_first,
+  MetaBlock* mb = make_meta(ctx, c->bytes, units, slices, slot_unit, slot_desc, 1, 0, 1 << 30, 1, c->encoding, c->shape, nullptr, nullptr, &dir, count_first,
                             /*validate=*/count_first);  // opened from outside bytes
   if (count_first) {
     c->shape[0] = units[0].instants; c->shape[1] = units[0].rows; c->shape[2] = units[0].cols;
@@ -211,7 +213,8 @@ MetaBlock* super_meta(dcdf_ctx* ctx, const dcdf_superchunk* scc) {
   }
   const uint32_t n_nodes = (uint32_t)sc->nodes.size();
   std::vector<SliceMeta> slices(sc->slices.size());
-  std::vector<SlotDesc> slot_desc(sc->slot_unit.size(), SlotDesc{0, 0, 0});
+  std::vector<SlotDesc> slot_desc(sc->slot_unit.size());
+  if (!slot_desc.empty()) memset(slot_desc.data(), 0, sizeof(SlotDesc) * slot_desc.size());
   for (size_t s = 0; s < slices.size(); s++) {
     SliceMeta& m = slices[s];
     memset(&m, 0, sizeof m);
@@ -227,17 +230,22 @@ MetaBlock* super_meta(dcdf_ctx* ctx, const dcdf_superchunk* scc) {
         const size_t slot = s * sc->n_slots + (size_t)gr * sc->leaf_grid + gc;
         const int64_t row = (int64_t)gr * sc->leaf_side, col = (int64_t)gc * sc->leaf_side;
         uint32_t node = 0;
+        SlotDesc d;
+        memset(&d, 0, sizeof d);
         for (;;) {
           const TreeNode& nd = sc->nodes[node];
           const auto& g = sc->geom[node];
           const int64_t cr = (row - g.top) / g.chunks_sidelen, cc = (col - g.left) / g.chunks_sidelen;
           const u32 c = (u32)(cr * g.subsidelen + cc);
           const TreeChild& ch = sc->children[nd.first_child + c];
-          bool descend = false;
-          if (ch.kind == 2 && sc->nstate[s * n_nodes + ch.index].alive) { node = (uint32_t)ch.index; descend = true; }
-          if (descend) continue;
-          SlotDesc d;
-          d.tbl0 = sc->slices[s].table_base + (u64)nd.tbl_off * (u64)m.instants + c;
+          const u64 tbl0 = sc->slices[s].table_base + (u64)nd.tbl_off * (u64)m.instants + c;
+          if (ch.kind == 2 && sc->nstate[s * n_nodes + ch.index].alive) {
+            if (d.n_up >= 3) api_fail(DCDF_ERR_BAD_ARG, "superchunks nested more than four levels deep are not supported by the query kernels");
+            d.up_tbl0[d.n_up] = tbl0; d.up_stride[d.n_up] = nd.n_children; d.n_up++;
+            node = (uint32_t)ch.index;
+            continue;
+          }
+          d.tbl0 = tbl0;
           d.stride = nd.n_children;
           d.bits = sc->nstate[s * n_nodes + node].bits;
           slot_desc[slot] = d;
@@ -247,7 +255,7 @@ MetaBlock* super_meta(dcdf_ctx* ctx, const dcdf_superchunk* scc) {
   }
   void* dir = nullptr;
   MetaBlock* mb = make_meta(ctx, sc->chunk_blob, units, slices, sc->slot_unit, slot_desc, sc->n_slots, sc->chunk_size, sc->leaf_side,
-                            (int)sc->leaf_grid, sc->encoding, sc->shape, sc->tbl_max, &dir, false, sc->opened);
+                            (int)sc->leaf_grid, sc->encoding, sc->shape, sc->tbl_max, sc->tbl_min, &dir, false, sc->opened);
   sc->dir = dir;
   sc->dev_meta = mb;
   return mb;

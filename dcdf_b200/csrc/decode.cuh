@@ -55,6 +55,11 @@ struct SlotDesc {
   u64 tbl0;
   u32 stride;
   int bits;
+  // the same entry coordinates in the tables of the superchunk nodes ABOVE that node (nested superchunks), root first:
+  // Superchunk::search prunes a subchunk with its node's min / max Dacs at every level of the recursion
+  u64 up_tbl0[3];
+  u32 up_stride[3];
+  int n_up;
 };
 struct QuerySet {
   const u8* blob;
@@ -64,6 +69,7 @@ struct QuerySet {
   const int32_t* slot_unit;  // [n_slices][n_slots] unit index or -1
   const SlotDesc* slot_desc; // [n_slices][n_slots] source of elided values
   const i64* tbl_max;
+  const i64* tbl_min;        // null for a plain Chunk
   u32 n_slices, n_slots;
   i64 chunk_size;            // instants per slice
   int chunks_sidelen, subsidelen;
@@ -388,6 +394,21 @@ DCDF_DEVINL i64 set_get(const QuerySet& Q, i64 instant, i64 row, i64 col, int& b
   return Q.tbl_max[sdsc.tbl0 + (u64)ti * sdsc.stride];  // Elided: superchunk.rs:325-330
 }
 
+// Superchunk::search's has_cells (superchunk.rs:480-493): some instant of [t_lo, t_hi) -- slice-local indices -- has
+// upper >= min && lower <= max in the subchunk's entry of the node's min / max tables; applied at every level of a
+// nested superchunk.  Each caller tests the instants t_lo + first, t_lo + first + step, ... and ORs the results.
+DCDF_DEVINL bool slot_has_cells_part(const QuerySet& Q, const SlotDesc& d, i64 t_lo, i64 t_hi, i64 lower, i64 upper, int first, int step,
+                                     int level /* 0 .. n_up: n_up = the slot's own node */) {
+  const u64 tbl0 = level < d.n_up ? d.up_tbl0[level] : d.tbl0;
+  const u64 stride = level < d.n_up ? d.up_stride[level] : d.stride;
+  bool any = false;
+  for (i64 t = t_lo + first; t < t_hi; t += step) {
+    const u64 idx = tbl0 + (u64)t * stride;
+    any = any || (upper >= Q.tbl_min[idx] && lower <= Q.tbl_max[idx]);
+  }
+  return any;
+}
+
 template <typename OutT>
 DCDF_DEVINL void store_value(void* out, u64 i, i64 fixed, int bits, int out_enc) {
   if (out_enc == 8) static_cast<i64*>(out)[i] = fixed;
@@ -666,6 +687,15 @@ __global__ void k_search(const SearchParams P, int write) {
   const u32 ti = (u32)(instant - sm.t0);
   const u32 slot = (u32)(cr * Q.subsidelen + cc);
   const int32_t u = Q.slot_unit[sm.slot_base + slot];
+  if (Q.tbl_min) {  // superchunk.rs:480-493: the subchunk is searched only if some instant of the window can have cells in range
+    const SlotDesc sd = Q.slot_desc[sm.slot_base + slot];
+    const i64 t_lo = max(c.start, sm.t0) - sm.t0, t_hi = min(c.end, sm.t0 + (i64)sm.instants) - sm.t0;
+    for (int lv = 0; lv <= sd.n_up; lv++)
+      if (!slot_has_cells_part(Q, sd, t_lo, t_hi, lower, upper, 0, 1, lv)) {
+        if (!write) P.counts[ji] = 0;
+        return;
+      }
+  }
   bool done = false;
   if (u >= 0) {
     const UnitMeta m = Q.units[u];

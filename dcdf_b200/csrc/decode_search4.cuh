@@ -357,6 +357,15 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_search_t
     const u64 T_all = (u64)(c.end - c.start);
     const u64 job0 = P.job_base[q] + sub * T_all;  // + (t - c.start)
     const u32 slot = (u32)(cr * Q.subsidelen + cc);
+    if (Q.tbl_min) {
+      // Superchunk::search only looks into subchunks whose min / max entries say that some instant of the window can have
+      // cells in range (superchunk.rs:480-493), at every level of a nested superchunk; the counts of a pruned job stay 0
+      const SlotDesc sd = Q.slot_desc[sm.slot_base + slot];
+      bool pruned = false;
+      for (int lv = 0; lv <= sd.n_up; lv++)
+        if (!__syncthreads_or(slot_has_cells_part(Q, sd, t_lo - sm.t0, t_hi - sm.t0, J.lower, J.upper, tid, DT_THREADS, lv) ? 1 : 0)) pruned = true;
+      if (pruned) continue;
+    }
     const int32_t u = Q.slot_unit[sm.slot_base + slot];
     const UnitMeta m = u >= 0 ? Q.units[u] : UnitMeta{};
     const bool stored = u >= 0 && m.stored;

@@ -18,6 +18,8 @@
 // stand-in for the reference's CPU path.
 #pragma once
 #include <algorithm>
+#include <array>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -309,27 +311,53 @@ struct Reader {
   }
 };
 
+// ---------------------------------------------------------------- sector model (measurement, not reference)
+// Random-access queries are bound by the distinct 32-byte sectors of SERIALIZED chunk bytes a query touches.  When a
+// tracker is installed (thread local), BitMap::get / rank and Dac::get record the byte ranges they read, expressed
+// as offsets into their chunk's serialization (assign_offsets below walks a chunk in write_to order).  Header fields
+// (lengths, k) are read once when a chunk is opened, not per query, and are not counted.
+struct SectorTracker {
+  std::vector<u64> keys;        // (chunk uid << 32) | sector index, with repeats
+  void touch(u64 uid, u64 off, u64 len) {
+    if (len == 0) return;
+    for (u64 sct = off / 32; sct <= (off + len - 1) / 32; sct++) keys.push_back((uid << 32) | sct);
+  }
+  u64 distinct() {
+    std::sort(keys.begin(), keys.end());
+    return (u64)(std::unique(keys.begin(), keys.end()) - keys.begin());
+  }
+  void clear() { keys.clear(); }
+};
+inline SectorTracker*& sector_tracker() {
+  static thread_local SectorTracker* t = nullptr;
+  return t;
+}
+
 // ---------------------------------------------------------------- bitmap.rs
 struct BitMap {
   usize length = 0;
   usize k = 4;
   std::vector<u32> index;
   std::vector<u32> bitmap;
-  mutable std::vector<usize>* touched = nullptr;  // instrumentation hook (unused by default)
+  u64 uid = 0, base = 0;        // sector model: owning chunk and offset of this BitMap in its serialization
 
+  void touch_index(usize i) const { if (SectorTracker* t = sector_tracker()) t->touch(uid, base + 8 + 4 * i, 4); }
+  void touch_word(usize w) const { if (SectorTracker* t = sector_tracker()) t->touch(uid, base + 8 + 4 * index.size() + 4 * w, 4); }
   bool get(usize i) const {                                     // bitmap.rs:176-183
     usize word_index = i / 32;
     if (word_index >= bitmap.size()) fail(OUT_OF_BOUNDS, "bitmap index out of bounds");
+    touch_word(word_index);
     return ((bitmap[word_index] >> (31 - i % 32)) & 1u) != 0;
   }
   usize rank(usize i) const {                                   // bitmap.rs:186-212
     if (i > length) fail(OUT_OF_BOUNDS, "rank index out of bounds");
     usize block = i / 32 / k;
+    if (block > 0) touch_index(block - 1);
     u32 count = block > 0 ? index[block - 1] : 0;
     usize start = block * k, end = i / 32;
-    for (usize w = start; w < end; w++) count += (u32)__builtin_popcount(bitmap[w]);
+    for (usize w = start; w < end; w++) { touch_word(w); count += (u32)__builtin_popcount(bitmap[w]); }
     usize leftover = i - end * 32;
-    if (leftover > 0) count += (u32)__builtin_popcount(bitmap[end] >> (32 - leftover));
+    if (leftover > 0) { touch_word(end); count += (u32)__builtin_popcount(bitmap[end] >> (32 - leftover)); }
     return count;
   }
   usize rank0(usize i) const { return i - rank(i); }            // bitmap.rs:215-217
@@ -394,11 +422,21 @@ inline i64 zigzag_decode(u64 zz) { return (i64)((zz >> 1) ^ ((zz & 1) ? ~u64(0) 
 struct Dac {
   std::vector<std::pair<BitMap, std::vector<u8>>> levels;
 
+  // sector model: offsets of every level inside the owning chunk's serialization; returns the offset past the Dac
+  u64 assign_offsets(u64 uid, u64 off) {
+    off += 1;
+    for (auto& lv : levels) {
+      lv.first.uid = uid; lv.first.base = off;
+      off += lv.first.size() + lv.second.size();
+    }
+    return off;
+  }
   i64 get(usize index) const {                                  // dac.rs:80-93
     u64 n = 0;
     usize i = 0;
     for (auto& lv : levels) {
       if (index >= lv.second.size()) fail(OUT_OF_BOUNDS, "dac index out of bounds");
+      if (SectorTracker* t = sector_tracker()) t->touch(lv.first.uid, lv.first.base + lv.first.size() + index, 1);
       n |= u64(lv.second[index]) << (i * 8);
       if (lv.first.get(index)) index = lv.first.rank(index);
       else break;
@@ -1117,6 +1155,27 @@ struct Chunk {
     for (auto& b : blocks) s += b.size();
     return s;
   }
+  // sector model: give every BitMap / Dac level its offset inside this chunk's serialization (write_to order)
+  void assign_offsets() {
+    static std::atomic<u64> next_uid{1};
+    const u64 uid = next_uid.fetch_add(1);
+    u64 off = 6;
+    for (auto& b : blocks) {
+      off += 1;
+      off += 13;
+      b.snapshot.nodemap.uid = uid; b.snapshot.nodemap.base = off; off += b.snapshot.nodemap.size();
+      off = b.snapshot.max.assign_offsets(uid, off);
+      off = b.snapshot.min.assign_offsets(uid, off);
+      for (auto& l : b.logs) {
+        off += 13;
+        l.nodemap.uid = uid; l.nodemap.base = off; off += l.nodemap.size();
+        l.equal.uid = uid; l.equal.base = off; off += l.equal.size();
+        off = l.max.assign_offsets(uid, off);
+        off = l.min.assign_offsets(uid, off);
+      }
+    }
+    if (off != size()) fail(BAD_FORMAT, "sector model: offsets do not add up to the chunk size");
+  }
   void write_to(Writer& w) const {                              // chunk.rs:235-243
     w.byte((u8)encoding);
     w.byte((u8)fractional_bits);
@@ -1250,6 +1309,71 @@ struct SuperNode {
     if (ref.kind == 0) { *bits = fractional_bits; return max.get(ci + instant * subsidelen * subsidelen); }
     if (ref.chunk) { *bits = ref.chunk->fractional_bits; return ref.chunk->get(instant, local_row, local_col); }
     return ref.super->get(instant, local_row, local_col, bits);
+  }
+  // Superchunk::fill_cell  superchunk.rs:356-398 (Elided: SuperCellIter over the max Dac :787-824)
+  template <class S2>
+  void fill_cell(usize start, usize end, usize row, usize col, S2&& set) const {  // set(i, fixed, bits)
+    usize chunk_row = row / chunks_sidelen, local_row = row % chunks_sidelen;
+    usize chunk_col = col / chunks_sidelen, local_col = col % chunks_sidelen;
+    usize ci = chunk_row * subsidelen + chunk_col;
+    const SubRef& ref = refs[ci];
+    if (ref.kind == 0) {
+      usize stride = subsidelen * subsidelen;
+      for (usize i = start; i < end; i++) set(i - start, max.get(ci + i * stride), fractional_bits);
+    } else if (ref.chunk) {
+      usize fb = ref.chunk->fractional_bits;
+      ref.chunk->fill_cell(start, end, local_row, local_col, [&](usize i, i64 v) { set(i, v, fb); });
+    } else {
+      ref.super->fill_cell(start, end, local_row, local_col, set);
+    }
+  }
+  // Superchunk::search  superchunk.rs:464-585.  The reference gathers the subchunks' streams with FuturesUnordered
+  // (order across subchunks not defined); here: subchunks in subchunks_for order (row-major), each one's cells in its
+  // own order.  `lower` / `upper` are applied as they are to every level (the superchunk's min / max Dacs in ITS
+  // fractional bits prune subchunks first, :480-493; Elided subchunks are answered from the max Dac, :541-559).
+  void search(const Cube& bounds, i64 lower, i64 upper, std::vector<std::array<usize, 3>>& out, usize top0 = 0, usize left0 = 0) const {
+    rearrange(lower, upper);                                    // :477
+    usize r0 = bounds.top / chunks_sidelen, r1 = (bounds.bottom - 1) / chunks_sidelen;
+    usize c0 = bounds.left / chunks_sidelen, c1 = (bounds.right - 1) / chunks_sidelen;
+    usize stride = subsidelen * subsidelen;
+    for (usize row = r0; row <= r1; row++) {                    // subchunks_for :589-633
+      usize chunk_top = row * chunks_sidelen;
+      usize wt = std::max(chunk_top, bounds.top), wb = std::min(chunk_top + chunks_sidelen, bounds.bottom);
+      for (usize col = c0; col <= c1; col++) {
+        usize chunk_left = col * chunks_sidelen;
+        usize wl = std::max(chunk_left, bounds.left), wr = std::min(chunk_left + chunks_sidelen, bounds.right);
+        usize ci = row * subsidelen + col;
+        bool has_cells = false;                                 // :480-493
+        for (usize i = bounds.start, idx = ci + bounds.start * stride; i < bounds.end && !has_cells; i++, idx += stride)
+          has_cells = upper >= min.get(idx) && lower <= max.get(idx);
+        if (!has_cells) continue;
+        Cube local(bounds.start, bounds.end, wt - chunk_top, wb - chunk_top, wl - chunk_left, wr - chunk_left);
+        const SubRef& ref = refs[ci];
+        if (ref.kind == 0) {                                    // :541-559
+          for (usize i = local.start; i < local.end; i++) {
+            i64 v = max.get(ci + i * stride);
+            if (lower <= v && v <= upper)
+              for (usize r = local.top; r < local.bottom; r++)
+                for (usize c = local.left; c < local.right; c++) out.push_back({i, r + chunk_top + top0, c + chunk_left + left0});
+          }
+        } else if (ref.chunk) {
+          for (auto& irc : ref.chunk->search(local, lower, upper)) out.push_back({irc[0], irc[1] + chunk_top + top0, irc[2] + chunk_left + left0});
+        } else {
+          ref.super->search(local, lower, upper, out, chunk_top + top0, chunk_left + left0);
+        }
+      }
+    }
+  }
+  // sector model: chunks get offsets into their own serialization; the superchunk's own Dacs are counted against a
+  // serialization of their own (they are part of the superchunk node, read like any other bytes)
+  void assign_offsets() {
+    static std::atomic<u64> next_uid{1ull << 30};
+    u64 off = max.assign_offsets(next_uid.fetch_add(1), 0);
+    min.assign_offsets(next_uid.fetch_add(1), off);
+    for (auto& r : refs) {
+      if (r.chunk) r.chunk->assign_offsets();
+      if (r.super) r.super->assign_offsets();
+    }
   }
   // Superchunk::fill_window  superchunk.rs:403-457 with subchunks_for :589-633
   using Set5 = std::function<void(usize, usize, usize, i64, usize)>;

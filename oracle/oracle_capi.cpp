@@ -473,6 +473,71 @@ int32_t dcdf_oracle_super_window_f32(const void* obj, const int64_t* cube, float
   });
 }
 
+// Raw fixed-point window at superchunk level + the fractional bits of every cell's source.
+int32_t dcdf_oracle_super_window_raw(const void* obj, const int64_t* cube, int64_t* out) {
+  return guard([&] {
+    const Obj* o = static_cast<const Obj*>(obj);
+    Cube b((usize)cube[0], (usize)cube[1], (usize)cube[2], (usize)cube[3], (usize)cube[4], (usize)cube[5]);
+    usize rows = b.rows(), cols = b.cols();
+    o->super->fill_window(b, [&](usize i, usize r, usize c, i64 v, usize) { out[(i * rows + r) * cols + c] = v; });
+  });
+}
+// Superchunk::fill_cell batched: q = n x (start, end, row, col), out_off[n + 1] element offsets.  `sectors` (may be
+// null): SURVEY 8d's sector model -- sum over the queries of the distinct 32-byte sectors of serialized bytes touched.
+int32_t dcdf_oracle_super_cell_batch(const void* obj, uint64_t n, const int64_t* q, const uint64_t* out_off, int64_t* out_fixed,
+                                     uint64_t* sectors) {
+  return guard([&] {
+    const Obj* o = static_cast<const Obj*>(obj);
+    SectorTracker tr;
+    if (sectors) { *sectors = 0; o->super->assign_offsets(); sector_tracker() = &tr; }
+    try {
+      for (uint64_t i = 0; i < n; i++) {
+        usize start = (usize)q[4 * i], end = (usize)q[4 * i + 1];
+        if (start > end) std::swap(start, end);
+        i64* dst = out_fixed ? out_fixed + out_off[i] : nullptr;
+        o->super->fill_cell(start, end, (usize)q[4 * i + 2], (usize)q[4 * i + 3], [&](usize t, i64 v, usize) { if (dst) dst[t] = v; });
+        if (sectors) { *sectors += tr.distinct(); tr.clear(); }
+      }
+    } catch (...) { sector_tracker() = nullptr; throw; }
+    sector_tracker() = nullptr;
+  });
+}
+// Superchunk::search batched over n windows with per-window [lower, upper]; counts[n]; out_irc (may be null) receives
+// the triplets window after window (up to cap).  `sectors` as above.
+int32_t dcdf_oracle_super_search_batch(const void* obj, uint64_t n, const int64_t* cubes, const int64_t* lower, const int64_t* upper,
+                                       uint64_t* counts, int64_t* out_irc, uint64_t cap, uint64_t* n_found, uint64_t* sectors) {
+  return guard([&] {
+    const Obj* o = static_cast<const Obj*>(obj);
+    SectorTracker tr;
+    if (sectors) { *sectors = 0; o->super->assign_offsets(); sector_tracker() = &tr; }
+    uint64_t total = 0;
+    try {
+      for (uint64_t i = 0; i < n; i++) {
+        const int64_t* c = cubes + 6 * i;
+        Cube b((usize)c[0], (usize)c[1], (usize)c[2], (usize)c[3], (usize)c[4], (usize)c[5]);
+        std::vector<std::array<usize, 3>> hits;
+        if (b.instants() && b.rows() && b.cols()) o->super->search(b, lower[i], upper[i], hits);
+        if (counts) counts[i] = hits.size();
+        for (auto& h : hits) {
+          if (out_irc && total < cap) { out_irc[3 * total] = (int64_t)h[0]; out_irc[3 * total + 1] = (int64_t)h[1]; out_irc[3 * total + 2] = (int64_t)h[2]; }
+          total++;
+        }
+        if (sectors) { *sectors += tr.distinct(); tr.clear(); }
+      }
+    } catch (...) { sector_tracker() = nullptr; throw; }
+    sector_tracker() = nullptr;
+    if (n_found) *n_found = total;
+  });
+}
+// Sector model of a full-extent window read: every serialized byte of every structure the window needs is read once
+// (S_in of SURVEY 8d); here simply the stored bytes of the superchunk.
+int32_t dcdf_oracle_super_stored_bytes(const void* obj, uint64_t* nbytes) {
+  return guard([&] {
+    const Obj* o = static_cast<const Obj*>(obj);
+    *nbytes = o->super->stats.size;
+  });
+}
+
 // ---- CPU baseline helper: encode `n_units` independent [T,r,c] sub-arrays of one strided raster with
 // `threads` host threads (the reference itself never spawns: superchunk.rs:123-188; threads=1 is faithful).
 // Returns total serialized bytes and elapsed seconds.

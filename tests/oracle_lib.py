@@ -336,6 +336,43 @@ class SuperH(_Handle):
         _check(lib().dcdf_oracle_super_get_batch(self.ptr, C.c_uint64(len(irc)), _p(irc), _p(out), _p(bits)))
         return out, bits
 
+    def window_raw(self, start, end, top, bottom, left, right):
+        cube = (C.c_int64 * 6)(start, end, top, bottom, left, right)
+        out = np.zeros((abs(end - start), abs(bottom - top), abs(right - left)), np.int64)
+        _check(lib().dcdf_oracle_super_window_raw(self.ptr, cube, _p(out)))
+        return out
+
+    def cell_batch(self, queries, sectors=False, want_values=True):
+        """Superchunk::fill_cell for n x (start, end, row, col) -> (list of raw fixed series, sector count or None)."""
+        q = np.ascontiguousarray(queries, dtype=np.int64).reshape(-1, 4)
+        lens = np.abs(q[:, 1] - q[:, 0]).astype(np.uint64)
+        off = np.zeros(len(q) + 1, np.uint64)
+        np.cumsum(lens, out=off[1:])
+        out = np.zeros(int(off[-1]) if want_values else 1, np.int64)
+        sec = C.c_uint64()
+        _check(lib().dcdf_oracle_super_cell_batch(self.ptr, C.c_uint64(len(q)), _p(q), _p(off), _p(out) if want_values else None,
+                                                  C.byref(sec) if sectors else None))
+        series = [out[int(off[i]):int(off[i + 1])] for i in range(len(q))] if want_values else None
+        return series, (sec.value if sectors else None)
+
+    def search_batch(self, cubes, lower, upper, sectors=False, want_cells=True):
+        """Superchunk::search per window -> (counts, [n,3] cells or None, sector count or None)."""
+        cubes = np.ascontiguousarray(cubes, dtype=np.int64).reshape(-1, 6)
+        n = len(cubes)
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lower, np.int64), (n,)))
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(upper, np.int64), (n,)))
+        counts = np.zeros(n, np.uint64)
+        found, sec = C.c_uint64(), C.c_uint64()
+        fn = lib().dcdf_oracle_super_search_batch
+        _check(fn(self.ptr, C.c_uint64(n), _p(cubes), _p(lo), _p(hi), _p(counts), None, C.c_uint64(0), C.byref(found),
+                  C.byref(sec) if sectors else None))
+        cells = None
+        if want_cells:
+            cells = np.zeros((found.value, 3), np.int64)
+            if found.value:
+                _check(fn(self.ptr, C.c_uint64(n), _p(cubes), _p(lo), _p(hi), _p(counts), _p(cells), C.c_uint64(found.value), C.byref(found), None))
+        return counts, cells, (sec.value if sectors else None)
+
     def window_f32(self, start, end, top, bottom, left, right):
         cube = (C.c_int64 * 6)(start, end, top, bottom, left, right)
         out = np.zeros((abs(end - start), abs(bottom - top), abs(right - left)), np.float32)

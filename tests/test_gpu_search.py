@@ -111,3 +111,31 @@ def test_depth_first_search_kernel_and_wide_expansion_stay_bit_exact(option):
         assert np.array_equal(got.search(1, 9, 3, 60, 2, 49, lo, hi), ref.search(1, 9, 3, 60, 2, 49, lo, hi))
     got.close()
     ctx.close()
+
+
+def test_superchunk_search_prunes_with_the_superchunk_min_max_like_the_reference(ctx):
+    """Superchunk::search first asks the superchunk's own min / max Dacs -- in the SUPERCHUNK's fractional bits --
+    whether a subchunk can have cells in range (superchunk.rs:480-493) and only then searches the subchunk with the same
+    bounds in the SUBCHUNK's bits.  When the two differ the pruning changes the answer, so it has to be reproduced:
+    results and order against the oracle's Superchunk::search, two-level and nested."""
+    from dcdf_b200 import Superchunk
+    rng = np.random.default_rng(77)
+    data = (rng.integers(1600, 1920, (9, 128, 192)) / 16.0).astype(np.float32)        # 4 fractional bits
+    data[:, :64, 64:128] = (rng.integers(200, 240, (9, 64, 64)) / 2.0).astype(np.float32)   # this subchunk alone: 1 bit
+    data[:, 64:, :64] = 107.5                                                           # elided subchunk
+    for levels in ([2, 6], [1, 1, 6]):
+        got = Superchunk.build(ctx, data, levels)
+        ref = orc.superchunk_build(data, levels)
+        assert got.info(0).fractional_bits == 4
+        cubes = [[0, 9, 0, 128, 0, 192], [2, 7, 10, 100, 50, 150], [0, 9, 64, 128, 0, 64], [3, 4, 0, 64, 64, 128]]
+        bands = [(400, 500), (3300, 3500), (3441, 3441), (3201, 3841), (0, 10 ** 6), (430, 431), (6000, 100)]
+        for lo, hi in bands:
+            counts, cells = got.search_batch(cubes, lo, hi)
+            rcounts, rcells, _ = ref.search_batch(cubes, lo, hi)
+            assert counts.tolist() == rcounts.tolist(), (levels, lo, hi, counts.tolist(), rcounts.tolist())
+            assert np.array_equal(cells, rcells), (levels, lo, hi)
+        series, _ = ref.cell_batch([[0, 9, 3, 70], [2, 8, 100, 5], [0, 9, 127, 191]])
+        mine = got.cell_batch([[0, 9, 3, 70], [2, 8, 100, 5], [0, 9, 127, 191]], raw=True)
+        for a, b in zip(mine, series):
+            assert np.array_equal(a, b)
+        got.close()
