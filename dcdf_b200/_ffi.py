@@ -42,6 +42,11 @@ class SuperchunkInfo(C.Structure):
                 ("min_dac_bytes", C.c_uint64), ("chunk_bytes", C.c_uint64), ("stats", BuildStats)]
 
 
+CID_BYTES = 36
+NODE_LINKS, NODE_SUBCHUNK, NODE_SUPERCHUNK = 1, 4, 5
+FETCH_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_uint64))
+
+
 def build_library(force=False, verbose=False):
     """Compile csrc/*.cu for sm_100a into libdcdf_cuda.so (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".sh"))]
@@ -106,6 +111,13 @@ def _declare(lib):
         "dcdf_superchunk_window": (i32, [vp, vp, _P(Cube), vp, i32, i32]),
         "dcdf_superchunk_window_batch": (i32, [vp, vp, u64, vp, vp, vp, i32, i32]),
         "dcdf_superchunk_search_batch": (i32, [vp, vp, u64, vp, vp, vp, vp, vp, u64, _P(u64), i32]),
+        "dcdf_superchunk_save": (i32, [vp, vp, u32, _P(vp)]),
+        "dcdf_saved_free": (i32, [vp]),
+        "dcdf_saved_count": (i32, [vp, _P(u32)]),
+        "dcdf_saved_node": (i32, [vp, u32, vp, _P(i32), _P(u64)]),
+        "dcdf_saved_node_bytes": (i32, [vp, vp, u32, vp, u64, i32]),
+        "dcdf_saved_stats": (i32, [vp, _P(BuildStats)]),
+        "dcdf_superchunk_open": (i32, [vp, u32, vp, FETCH_FN, vp, _P(vp)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

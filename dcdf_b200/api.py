@@ -358,6 +358,68 @@ class Superchunk(_Queryable):
         self.ctx.check(self.ctx._lib.dcdf_superchunk_total_bytes(self._h, C.byref(n)))
         return n.value
 
+    def save(self, slice_=0):
+        """The tail of Superchunk::build + Resolver::save (superchunk.rs:199-270, resolver.rs:126-138): the stored
+        objects of one time slice in first-save order as (cid, node_type, bytes) -- the last one is the superchunk node
+        -- and the reference's MMStruct3Build counters (External references de-duplicated by CID)."""
+        lib = self.ctx._lib
+        h = C.c_void_p()
+        self.ctx.check(lib.dcdf_superchunk_save(self.ctx._h, self._h, slice_, C.byref(h)))
+        try:
+            n = C.c_uint32()
+            self.ctx.check(lib.dcdf_saved_count(h, C.byref(n)))
+            nodes = []
+            for i in range(n.value):
+                cid = np.zeros(_ffi.CID_BYTES, np.uint8)
+                t, size = C.c_int32(), C.c_uint64()
+                self.ctx.check(lib.dcdf_saved_node(h, i, _ptr(cid), C.byref(t), C.byref(size)))
+                buf = np.empty(max(size.value, 1), np.uint8)
+                self.ctx.check(lib.dcdf_saved_node_bytes(self.ctx._h, h, i, _ptr(buf), size.value, MEM_HOST))
+                nodes.append((cid.tobytes(), t.value, buf[:size.value].tobytes()))
+            st = BuildStats()
+            self.ctx.check(lib.dcdf_saved_stats(h, C.byref(st)))
+            stats = dict(size=st.size, elided=st.elided, local=st.local, external=st.external, snapshots=st.snapshots, logs=st.logs)
+        finally:
+            lib.dcdf_saved_free(h)
+        return nodes, stats
+
+    @classmethod
+    def open(cls, ctx, root_cids, store):
+        """Superchunk::load_from (superchunk.rs:713-768) for the superchunk nodes of consecutive time slices: `store`
+        maps a CID (bytes) to the stored bytes of a node -- the Mapper::load of mapper.rs:10-38."""
+        keep = {}
+
+        def fetch(user, cid_p, bytes_pp, len_p):
+            try:
+                cid = C.string_at(cid_p, _ffi.CID_BYTES)
+                data = store.get(cid) if hasattr(store, "get") else store[cid]
+                if data is None:
+                    return 1
+                arr = keep.get(cid)
+                if arr is None:
+                    arr = np.frombuffer(bytes(data), dtype=np.uint8)
+                    keep[cid] = arr
+                bytes_pp[0] = C.cast(arr.ctypes.data, C.POINTER(C.c_uint8))
+                len_p[0] = len(arr)
+                return 0
+            except Exception:
+                return 1
+
+        cb = _ffi.FETCH_FN(fetch)
+        roots = np.frombuffer(b"".join(bytes(c) for c in root_cids), dtype=np.uint8)
+        h = C.c_void_p()
+        ctx.check(ctx._lib.dcdf_superchunk_open(ctx._h, len(root_cids), _ptr(roots), cb, None, C.byref(h)))
+        info = SuperchunkInfo()
+        ctx.check(ctx._lib.dcdf_superchunk_get_info(h, 0, C.byref(info)))
+        n = C.c_uint32()
+        ctx.check(ctx._lib.dcdf_superchunk_count(h, C.byref(n)))
+        total = 0
+        for s in range(n.value):
+            si = SuperchunkInfo()
+            ctx.check(ctx._lib.dcdf_superchunk_get_info(h, s, C.byref(si)))
+            total += si.shape[0]
+        return cls(ctx, h, info.encoding, (total, info.shape[1], info.shape[2]))
+
     def window_batch(self, cubes, raw=False, out=None):
         cubes = np.ascontiguousarray(cubes, dtype=np.int64).reshape(-1, 6)
         sizes = (np.abs(cubes[:, 1] - cubes[:, 0]) * np.abs(cubes[:, 3] - cubes[:, 2]) * np.abs(cubes[:, 5] - cubes[:, 4])).astype(np.uint64)

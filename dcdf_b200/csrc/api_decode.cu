@@ -577,6 +577,7 @@ void do_search_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
 }  // namespace
 
 namespace dcdf {
+void build_super_meta(dcdf_ctx* ctx, const dcdf_superchunk* sc) { super_meta(ctx, sc); }
 void free_chunk_meta(void* p) { free_meta(p, true); }
 void free_super_meta(void* p) { free_meta(p, false); }
 }  // namespace dcdf

@@ -191,4 +191,5 @@ struct dcdf_superchunk {
   void* dir = nullptr;         // device decode directory over all stored units
   void* dev_meta = nullptr;    // device copies of unit / slot tables for the query kernels
   bool opened = false;         // built from stored bytes by dcdf_superchunk_open (validated like Chunk::read_from)
+  std::vector<uint8_t> unit_digests;  // SHA2-256 of every stored chunk node, 32 bytes per unit (dcdf_superchunk_save)
 };

@@ -225,6 +225,40 @@ int32_t dcdf_superchunk_search_batch(dcdf_ctx* ctx, const dcdf_superchunk* sc, u
                                      const int64_t* lower, const int64_t* upper, uint64_t* counts, int64_t* out_irc,
                                      uint64_t cap, uint64_t* n_found, int32_t mem);
 
+/* ------------------------------------------------------------------ storage side */
+/* Content address of a stored node as the reference's in-memory store computes it (testing.rs:172-183):
+ * CIDv1 = version 0x01, codec 0x12, multihash { code 0x12 (sha2-256), length 0x20, 32 digest bytes }. */
+#define DCDF_CID_BYTES 36
+/* node types (node.rs:9-15) of the objects a saved superchunk consists of */
+enum { DCDF_NODE_LINKS = 1, DCDF_NODE_SUBCHUNK = 4, DCDF_NODE_SUPERCHUNK = 5 };
+typedef struct dcdf_saved dcdf_saved;
+
+/* What Superchunk::build + Resolver::save store for one time slice (superchunk.rs:199-270, 678-710; links.rs:65-76;
+ * resolver.rs:126-138; mmstruct.rs:199-222): every distinct subchunk node, the Links node(s), nested superchunk nodes
+ * and, last, the superchunk node itself -- in the order of their first save.  Chunk nodes are hashed on the device
+ * (SHA2-256 over bytes that never leave HBM); External references are de-duplicated by CID exactly as
+ * superchunk.rs:222-232 does, so dcdf_saved_stats returns the reference's MMStruct3Build (size, elided, external =
+ * DISTINCT subchunks, snapshots, logs).  `sc` must outlive the returned object. */
+int32_t dcdf_superchunk_save(dcdf_ctx* ctx, const dcdf_superchunk* sc, uint32_t slice, dcdf_saved** out);
+int32_t dcdf_saved_free(dcdf_saved* saved);
+int32_t dcdf_saved_count(const dcdf_saved* saved, uint32_t* n_nodes);
+/* CID, node type (DCDF_NODE_*) and stored size of object i; the last object is the slice's superchunk node. */
+int32_t dcdf_saved_node(const dcdf_saved* saved, uint32_t i, uint8_t* cid /* DCDF_CID_BYTES */, int32_t* node_type, uint64_t* size);
+/* The stored bytes of object i (header included), into host or device memory. */
+int32_t dcdf_saved_node_bytes(dcdf_ctx* ctx, const dcdf_saved* saved, uint32_t i, uint8_t* dst, uint64_t cap, int32_t mem);
+int32_t dcdf_saved_stats(const dcdf_saved* saved, dcdf_build_stats* stats);
+
+/* Mapper::load stand-in (mapper.rs:10-38): hand out the stored bytes of a node; they must stay valid until the call that
+ * received the callback returns.  Return 0 on success. */
+typedef int32_t (*dcdf_fetch_fn)(void* user, const uint8_t* cid /* DCDF_CID_BYTES */, const uint8_t** bytes, uint64_t* len);
+/* Superchunk::load_from (superchunk.rs:713-768) + Resolver::get_mmstruct3 / get_links for every External reference, for
+ * the n_slices superchunk nodes of consecutive time slices of one array (what a Span holds, span.rs:50-110): every
+ * stored Chunk is uploaded once and validated like Chunk::read_from, the min / max Dacs are decoded into the tables the
+ * Elided cells and the search pruning read, and the result answers every dcdf_superchunk_* query.  All slices but the
+ * last must have the same number of instants. */
+int32_t dcdf_superchunk_open(dcdf_ctx* ctx, uint32_t n_slices, const uint8_t* root_cids /* n_slices x DCDF_CID_BYTES */,
+                             dcdf_fetch_fn fetch, void* user, dcdf_superchunk** out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1194,6 +1194,97 @@ struct Chunk {
   }
 };
 
+// ---------------------------------------------------------------- content addressing (testing.rs:91-184)
+// SHA2-256 (FIPS 180-4), written independently of the product's copy; pinned by the FIPS known answers in
+// tests/test_oracle_golden.py.  The `cid` / `multihash` crates the reference uses are storage-side dependencies that
+// are not vendored; their published byte layouts: CIDv1 = varint(1) varint(codec) multihash,
+// multihash = varint(code) varint(length) digest.
+struct OSha256 {
+  u32 st[8];
+  std::vector<u8> pending;
+  u64 total = 0;
+  OSha256() {
+    static const u32 init[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    for (int i = 0; i < 8; i++) st[i] = init[i];
+  }
+  static u32 ror(u32 x, int n) { return (x >> n) | (x << (32 - n)); }
+  void block(const u8* p) {
+    static const u32 K[64] = {
+        0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+        0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+        0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+        0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+        0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+        0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    u32 w[64];
+    for (int i = 0; i < 16; i++) w[i] = (u32(p[4 * i]) << 24) | (u32(p[4 * i + 1]) << 16) | (u32(p[4 * i + 2]) << 8) | u32(p[4 * i + 3]);
+    for (int i = 16; i < 64; i++) {
+      u32 s0 = ror(w[i - 15], 7) ^ ror(w[i - 15], 18) ^ (w[i - 15] >> 3), s1 = ror(w[i - 2], 17) ^ ror(w[i - 2], 19) ^ (w[i - 2] >> 10);
+      w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    u32 v[8];
+    for (int i = 0; i < 8; i++) v[i] = st[i];
+    for (int i = 0; i < 64; i++) {
+      u32 t1 = v[7] + (ror(v[4], 6) ^ ror(v[4], 11) ^ ror(v[4], 25)) + ((v[4] & v[5]) ^ (~v[4] & v[6])) + K[i] + w[i];
+      u32 t2 = (ror(v[0], 2) ^ ror(v[0], 13) ^ ror(v[0], 22)) + ((v[0] & v[1]) ^ (v[0] & v[2]) ^ (v[1] & v[2]));
+      for (int j = 7; j > 0; j--) v[j] = v[j - 1];
+      v[4] += t1;
+      v[0] = t1 + t2;
+    }
+    for (int i = 0; i < 8; i++) st[i] += v[i];
+  }
+  void feed(const u8* p, usize n) {
+    pending.insert(pending.end(), p, p + n);
+    usize off = 0;
+    while (pending.size() - off >= 64) { block(pending.data() + off); off += 64; }
+    pending.erase(pending.begin(), pending.begin() + off);
+  }
+  void update(const u8* p, usize n) { total += n; feed(p, n); }
+  std::array<u8, 32> finish() {
+    u64 bits = total * 8;
+    std::vector<u8> pad(1, 0x80);
+    while ((pending.size() + pad.size()) % 64 != 56) pad.push_back(0);
+    for (int i = 7; i >= 0; i--) pad.push_back(u8(bits >> (8 * i)));
+    feed(pad.data(), pad.size());
+    std::array<u8, 32> d;
+    for (int i = 0; i < 8; i++) { d[4 * i] = u8(st[i] >> 24); d[4 * i + 1] = u8(st[i] >> 16); d[4 * i + 2] = u8(st[i] >> 8); d[4 * i + 3] = u8(st[i]); }
+    return d;
+  }
+};
+typedef std::array<u8, 36> CidB;
+// MemoryMapperStoreWrite::finish  testing.rs:170-183: Cid::new_v1(SHA2_256, Multihash::wrap(SHA2_256, digest)), SHA2_256 = 0x12
+inline CidB cid_for_bytes(const std::vector<u8>& bytes) {
+  OSha256 h;
+  h.update(bytes.data(), bytes.size());
+  auto d = h.finish();
+  CidB c;
+  c[0] = 1; c[1] = 0x12; c[2] = 0x12; c[3] = 0x20;
+  std::copy(d.begin(), d.end(), c.begin() + 4);
+  return c;
+}
+// MemoryMapper  testing.rs:91-134: content-addressed objects, kept in first-save order for comparison
+struct MemoryStore {
+  std::vector<std::pair<CidB, std::vector<u8>>> objects;
+  std::vector<int> types;
+  CidB put(std::vector<u8> bytes, int type) {
+    CidB c = cid_for_bytes(bytes);
+    for (auto& o : objects) if (o.first == c) return c;
+    objects.emplace_back(c, std::move(bytes));
+    types.push_back(type);
+    return c;
+  }
+  const std::vector<u8>* get(const CidB& c) const {
+    for (auto& o : objects) if (o.first == c) return &o.second;
+    return nullptr;
+  }
+};
+const u8 NODE_LINKS = 1, NODE_MMSTRUCT3 = 2, NODE_SUBCHUNK = 4, NODE_SUPERCHUNK = 5;  // node.rs:9-15
+inline void write_header(Writer& w, u8 node_type) {              // resolver.rs:130-132
+  w.byte(0xDC); w.byte(0xE0);                                   // MAGIC_NUMBER = 0xDCDF + 1 (u16, big-endian)
+  w.u32be(1);                                                   // FORMAT_VERSION
+  w.byte(node_type);
+}
+
 // ---------------------------------------------------------------- superchunk.rs (compute part)
 // Superchunk::build  superchunk.rs:88-270 minus CIDs / resolver.save / Links (host storage side).
 struct SuperNode;
@@ -1363,6 +1454,76 @@ struct SuperNode {
         }
       }
     }
+  }
+  // The storage tail of Superchunk::build (superchunk.rs:199-270) + Resolver::save of every node (resolver.rs:126-138,
+  // mmstruct.rs:199-222, links.rs:65-76): saves subchunks in reference order, de-duplicates External references by
+  // CID, saves Links, and returns the body of this superchunk's own node (NODE_SUPERCHUNK byte + save_to :683-707).
+  struct Saved {
+    std::vector<u8> body;
+    u64 data_size;      // Superchunk::size()  :654-669
+    BuildStats stats;   // MMStruct3Build  :261-269
+  };
+  Saved save(MemoryStore& store) const {
+    Saved R;
+    std::vector<CidB> external;
+    std::vector<std::pair<int, u32>> references;
+    u64 sizes = 0;
+    for (auto& ref : refs) {
+      if (ref.kind == 0) { R.stats.elided++; references.emplace_back(0, 0); continue; }
+      CidB cid;
+      if (ref.chunk) {
+        Writer w;
+        write_header(w, NODE_MMSTRUCT3);
+        w.byte(NODE_SUBCHUNK);                                    // mmstruct.rs:209-212
+        ref.chunk->write_to(w);
+        sizes += ref.chunk->size() + 1;                           // build.data.size()  mmstruct.rs:186-196
+        cid = store.put(std::move(w.buf), NODE_SUBCHUNK);
+        for (auto& b : ref.chunk->blocks) { R.stats.snapshots++; R.stats.logs += b.logs.size(); }
+      } else {
+        Saved sub = ref.super->save(store);
+        Writer w;
+        write_header(w, NODE_MMSTRUCT3);
+        w.bytes(sub.body);
+        sizes += sub.data_size + 1;
+        cid = store.put(std::move(w.buf), NODE_SUPERCHUNK);
+        R.stats.snapshots += sub.stats.snapshots; R.stats.logs += sub.stats.logs;
+      }
+      usize index = external.size();
+      for (usize i = 0; i < external.size(); i++) if (external[i] == cid) { index = i; break; }  // :222-232
+      if (index == external.size()) external.push_back(cid);
+      references.emplace_back(2, (u32)index);
+    }
+    Writer lw;                                                    // Links::save_to  links.rs:65-76
+    write_header(lw, NODE_LINKS);
+    lw.u32be((u32)external.size());
+    for (auto& c : external) lw.buf.insert(lw.buf.end(), c.begin(), c.end());
+    u64 size_external = 7 + 4 + 36 * external.size();             // Links::size  links.rs:96-100
+    CidB external_cid = store.put(std::move(lw.buf), NODE_LINKS);
+    Writer w;                                                     // Superchunk::save_to  :683-707
+    w.byte(NODE_SUPERCHUNK);
+    w.u32be((u32)shape[0]); w.u32be((u32)shape[1]); w.u32be((u32)shape[2]);
+    w.u32be((u32)sidelen);
+    w.byte((u8)levels);
+    w.u32be((u32)chunks_sidelen);
+    w.u32be((u32)subsidelen);
+    w.byte((u8)fractional_bits);
+    w.byte((u8)encoding);
+    w.u32be((u32)references.size());
+    u64 ref_bytes = 0;
+    for (auto& r : references) {                                  // Reference::write_to  :840-855
+      w.byte((u8)r.first);
+      ref_bytes += 1;
+      if (r.first != 0) { w.u32be(r.second); ref_bytes += 4; }
+    }
+    w.buf.insert(w.buf.end(), external_cid.begin(), external_cid.end());
+    w.u32be(0);                                                   // n_local
+    max.write_to(w);
+    min.write_to(w);
+    R.body = std::move(w.buf);
+    R.data_size = 7 + 4 * 3 + 4 + 1 + 4 + 4 + 1 + 4 + ref_bytes + 36 + 4 + max.size() + min.size();  // :654-669
+    R.stats.external = external.size();
+    R.stats.size = R.data_size + size_external + sizes;          // :263
+    return R;
   }
   // sector model: chunks get offsets into their own serialization; the superchunk's own Dacs are counted against a
   // serialization of their own (they are part of the superchunk node, read like any other bytes)

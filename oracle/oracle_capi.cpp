@@ -538,6 +538,55 @@ int32_t dcdf_oracle_super_stored_bytes(const void* obj, uint64_t* nbytes) {
   });
 }
 
+// ---- storage side: what Superchunk::build + Resolver::save put into the store (testing.rs MemoryMapper)
+struct SavedObj {
+  MemoryStore store;
+  CidB root;
+  BuildStats stats;
+};
+int32_t dcdf_oracle_super_save(const void* obj, void** out) {
+  return guard([&] {
+    const Obj* o = static_cast<const Obj*>(obj);
+    auto* sv = new SavedObj();
+    SuperNode::Saved r = o->super->save(sv->store);
+    Writer w;
+    write_header(w, NODE_MMSTRUCT3);
+    w.bytes(r.body);
+    sv->root = cid_for_bytes(w.buf);
+    // the superchunk node itself is listed last (as the caller's resolver.save would store it)
+    sv->store.objects.emplace_back(sv->root, std::move(w.buf));
+    sv->store.types.push_back(NODE_SUPERCHUNK);
+    sv->stats = r.stats;
+    *out = sv;
+  });
+}
+int32_t dcdf_oracle_saved_free(void* p) { delete static_cast<SavedObj*>(p); return OK; }
+int32_t dcdf_oracle_saved_count(const void* p, uint32_t* n) { *n = (uint32_t)static_cast<const SavedObj*>(p)->store.objects.size(); return OK; }
+int32_t dcdf_oracle_saved_node(const void* p, uint32_t i, uint8_t* cid, int32_t* type, uint8_t* bytes, uint64_t cap, uint64_t* len) {
+  return guard([&] {
+    const SavedObj* sv = static_cast<const SavedObj*>(p);
+    if (i >= sv->store.objects.size()) fail(BAD_ARG, "node index out of range");
+    const auto& o = sv->store.objects[i];
+    if (cid) memcpy(cid, o.first.data(), 36);
+    if (type) *type = sv->store.types[i];
+    if (len) *len = o.second.size();
+    if (bytes && cap >= o.second.size()) memcpy(bytes, o.second.data(), o.second.size());
+  });
+}
+int32_t dcdf_oracle_saved_stats(const void* p, uint64_t* size, uint32_t* elided, uint32_t* external, uint32_t* snapshots, uint32_t* logs) {
+  const SavedObj* sv = static_cast<const SavedObj*>(p);
+  *size = sv->stats.size; *elided = (uint32_t)sv->stats.elided; *external = (uint32_t)sv->stats.external;
+  *snapshots = (uint32_t)sv->stats.snapshots; *logs = (uint32_t)sv->stats.logs;
+  return OK;
+}
+int32_t dcdf_oracle_sha256(const uint8_t* p, uint64_t n, uint8_t* out32) {
+  OSha256 h;
+  h.update(p, (usize)n);
+  auto d = h.finish();
+  memcpy(out32, d.data(), 32);
+  return OK;
+}
+
 // ---- CPU baseline helper: encode `n_units` independent [T,r,c] sub-arrays of one strided raster with
 // `threads` host threads (the reference itself never spawns: superchunk.rs:123-188; threads=1 is faithful).
 // Returns total serialized bytes and elapsed seconds.

@@ -336,6 +336,11 @@ class SuperH(_Handle):
         _check(lib().dcdf_oracle_super_get_batch(self.ptr, C.c_uint64(len(irc)), _p(irc), _p(out), _p(bits)))
         return out, bits
 
+    def save(self):
+        h = C.c_void_p()
+        _check(lib().dcdf_oracle_super_save(self.ptr, C.byref(h)))
+        return SavedH(h.value)
+
     def window_raw(self, start, end, top, bottom, left, right):
         cube = (C.c_int64 * 6)(start, end, top, bottom, left, right)
         out = np.zeros((abs(end - start), abs(bottom - top), abs(right - left)), np.int64)
@@ -378,6 +383,44 @@ class SuperH(_Handle):
         out = np.zeros((abs(end - start), abs(bottom - top), abs(right - left)), np.float32)
         _check(lib().dcdf_oracle_super_window_f32(self.ptr, cube, _p(out)))
         return out
+
+
+class SavedH(_Handle):
+    """What Superchunk::build + Resolver::save store (testing.rs MemoryMapper): objects in first-save order."""
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().dcdf_oracle_saved_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+    def nodes(self):
+        n = C.c_uint32()
+        lib().dcdf_oracle_saved_count(self.ptr, C.byref(n))
+        out = []
+        for i in range(n.value):
+            cid = np.zeros(36, np.uint8)
+            t, ln = C.c_int32(), C.c_uint64()
+            _check(lib().dcdf_oracle_saved_node(self.ptr, i, _p(cid), C.byref(t), None, C.c_uint64(0), C.byref(ln)))
+            buf = np.zeros(max(ln.value, 1), np.uint8)
+            _check(lib().dcdf_oracle_saved_node(self.ptr, i, _p(cid), C.byref(t), _p(buf), C.c_uint64(ln.value), C.byref(ln)))
+            out.append((bytes(cid), t.value, bytes(buf[:ln.value])))
+        return out
+
+    def stats(self):
+        size = C.c_uint64()
+        el, ex, sn, lg = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib().dcdf_oracle_saved_stats(self.ptr, C.byref(size), C.byref(el), C.byref(ex), C.byref(sn), C.byref(lg))
+        return dict(size=size.value, elided=el.value, external=ex.value, snapshots=sn.value, logs=lg.value)
+
+
+def sha256(data):
+    b = np.frombuffer(bytes(data), dtype=np.uint8) if len(data) else np.zeros(1, np.uint8)
+    out = np.zeros(32, np.uint8)
+    lib().dcdf_oracle_sha256(_p(b), C.c_uint64(len(data)), _p(out))
+    return bytes(out)
 
 
 def superchunk_build(a, levels, k=2, fractional_bits=0, round_=False, compute_bits=True):
