@@ -469,27 +469,3 @@ class Superchunk(_Queryable):
             self.close()
         except Exception:
             pass
-
-
-class MMArray3:
-    """The typed facade the reference's users see (mmarray.rs:135-536; PyMMArray3F32 py-dcdf/src/lib.rs:497-538):
-    shape / get / cell / window, plus search (absent from the reference's Python bindings)."""
-
-    def __init__(self, superchunk):
-        self._sc = superchunk
-
-    @property
-    def shape(self):
-        return list(self._sc.shape)
-
-    def get(self, instant, row, col):
-        return self._sc.get(instant, row, col)
-
-    def cell(self, start, end, row, col):
-        return self._sc.cell(start, end, row, col)
-
-    def window(self, start, end, top, bottom, left, right):
-        return self._sc.window(start, end, top, bottom, left, right)
-
-    def search(self, start, end, top, bottom, left, right, lower, upper):
-        return self._sc.search(start, end, top, bottom, left, right, lower, upper)

@@ -83,13 +83,14 @@ def raster_slice(t0, t1, rows, cols, *, seed=0xDCDF0002, frac_bits=4, base=280, 
     return out
 
 
-def raster(instants, rows, cols, *, slice_instants=64, out=None, **kw):
-    """Whole [instants, rows, cols] raster, generated slice by slice (optionally into `out`)."""
+def raster(instants, rows, cols, *, slice_instants=64, out=None, t_start=0, **kw):
+    """Whole [instants, rows, cols] raster of instants t_start .. t_start + instants, generated slice by slice
+    (optionally into `out`)."""
     device = kw.get("device", "cpu")
     dtype = kw.get("dtype", torch.float32)
     if out is None:
         out = torch.empty((instants, rows, cols), device=device, dtype=dtype)
     for t0 in range(0, instants, slice_instants):
         t1 = min(t0 + slice_instants, instants)
-        out[t0:t1] = raster_slice(t0, t1, rows, cols, **kw)
+        out[t0:t1] = raster_slice(t_start + t0, t_start + t1, rows, cols, **kw)
     return out
