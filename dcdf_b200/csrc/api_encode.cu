@@ -149,12 +149,13 @@ void launch_encode_v4(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   ctx->launches++;
 }
 // Full f32 tiles that qualify for the small fast-path kernel (encode_v5.cuh; list 5, filled by k_finalize_tree).
+template <bool FULL>
 void launch_encode_v5(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   constexpr int G = 6;  // tiles per CTA, one CTA per SM
   const u32 stage_limit = std::min<u32>(ctx->opt.stage_limit, (u32)E5_POOL);
   const size_t smem = sizeof(E5Smem) * G;
-  CK(cudaFuncSetAttribute(k_encode_v5<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_encode_v5<G><<<(grid + G - 1) / G, E5_THREADS * G, smem, ctx->stream>>>(P, stage_limit, ctx->opt.fast_sync_mask);
+  CK(cudaFuncSetAttribute(k_encode_v5<G, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_encode_v5<G, FULL><<<(grid + G - 1) / G, E5_THREADS * G, smem, ctx->stream>>>(P, stage_limit, ctx->opt.fast_sync_mask);
   CK(cudaGetLastError());
   ctx->launches++;
 }
@@ -163,8 +164,11 @@ void launch_encode_v5(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
 template <typename InT>
 void launch_encode(dcdf_ctx* ctx, const EncParams& P, u32 grid, int list) {
   if (grid == 0) return;
-  if (list == 5) {
-    if (sizeof(InT) == 4) launch_encode_v5(ctx, P, grid);  // k_finalize_tree only fills the list for f32 input
+  if (list >= 5) {
+    if (sizeof(InT) == 4) {  // k_finalize_tree only fills these lists for f32 input
+      if (list == 5) launch_encode_v5<true>(ctx, P, grid);
+      else launch_encode_v5<false>(ctx, P, grid);
+    }
     return;
   }
   const bool force_v2 = ctx->opt.encode_tiles256 != 0;
@@ -238,7 +242,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
   ctx->istats.reserve(sizeof(InstStats) * (size_t)n_units * job.t_max);
   ctx->slices.reserve(sizeof(SliceDesc) * n_slices + 2 * sizeof(u64) * n_tables);
   ctx->sstate.reserve(sizeof(SliceState) * n_slices);
-  ctx->order.reserve(sizeof(u32) * (6 * (size_t)n_units + 8));
+  ctx->order.reserve(sizeof(u32) * (7 * (size_t)n_units + 8));
   ctx->pieces.reserve(sizeof(Piece) * (n_pieces + 2 * (size_t)n_tables));
   ctx->results.reserve(sizeof(UnitResult) * n_units);
   ctx->stored.reserve(n_units);
@@ -426,7 +430,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     time_begin(ctx, KT_ENCODE);
     CK(cudaEventRecord(ctx->fork_ev, st));  // clipped-tile lists run on the auxiliary stream beside the full-tile lists
     CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));
-    for (int list = 5; list >= 0; list--) {  // the fast-path list (most units of a typical raster) goes first
+    for (int list = 6; list >= 0; list--) {  // the fast-path lists (most units of a typical raster) go first
       EP.order = FP.order + (size_t)list * n_units;
       EP.order_count = d_counts + list;
       switch (job.encoding) {
@@ -888,10 +892,10 @@ int32_t dcdf_ctx_get_stat(const dcdf_ctx* ctx, const char* name, int64_t* value)
   if (!ctx || !name || !value) return DCDF_ERR_BAD_ARG;
   const std::string n(name);
   const uint32_t* c = ctx->last_list_counts;
-  if (n == "encode_units_fast") *value = c[5];
+  if (n == "encode_units_fast") *value = (int64_t)c[5] + c[6];
   else if (n == "encode_units_general") *value = (int64_t)c[0] + c[1] + c[2] + c[3] + c[4];
   else if (n == "encode_units_wide") *value = (int64_t)c[2] + c[3];
-  else if (n == "encode_units_clipped") *value = (int64_t)c[1] + c[3] + c[4];
+  else if (n == "encode_units_clipped") *value = (int64_t)c[1] + c[3] + c[4] + c[6];
   else return DCDF_ERR_BAD_ARG;
   return DCDF_OK;
 }

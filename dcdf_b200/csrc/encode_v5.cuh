@@ -187,14 +187,33 @@ __device__ __noinline__ void e5_top_bytes(u8* b0, u8* b1, u8* b2, u8* b3, const 
 
 // to_fixed (a3) of an exact, finite, small value: n * 2^(bits+1) is an integer below 2^22, so adding 1.5 * 2^23
 // leaves it in the low mantissa bits (fixed.rs:59-70: trunc(2 * shifted) + 1).
-DCDF_DEVINL int e5_conv(float x, float scale2) { return __float_as_int(__fmaf_rn(x, scale2, 12582912.0f)) - (0x4B400000 - 1); }
+DCDF_DEVINL int e5_conv(float x, float scale2) {
+  const int f = __float_as_int(__fmaf_rn(x, scale2, 12582912.0f)) - (0x4B400000 - 1);
+  return x != x ? 0 : f;  // NaN -> 0 (fixed.rs:35-37)
+}
 
 // One level-4 node (4x4 cells at pn, row stride sr) as four quads (x, y = upper row; z, w = lower row).
-DCDF_DEVINL void e5_load_node(const float* pn, i64 sr, uint4 (&raw)[4]) {
+// Clipped tiles (FULL == false): rl / cl = rows / columns of the node that lie inside the raster (may be <= 0); cells
+// outside are not read and become None (E4_NONE, as in encode_v4.cuh: excluded from min / max, 0 in an entry).
+template <bool FULL>
+DCDF_DEVINL void e5_load_node(const float* pn, i64 sr, uint4 (&raw)[4], int rl, int cl) {
 #pragma unroll
-  for (int r = 0; r < 4; r++) raw[r] = __ldg(reinterpret_cast<const uint4*>(pn + (i64)r * sr));
+  for (int r = 0; r < 4; r++) {
+    if (FULL || (r < rl && cl >= 4)) {
+      raw[r] = __ldg(reinterpret_cast<const uint4*>(pn + (i64)r * sr));
+    } else {
+      raw[r] = make_uint4(0, 0, 0, 0);
+      if (r < rl) {
+        const float* pr = pn + (i64)r * sr;
+        if (cl > 0) raw[r].x = __float_as_uint(__ldg(pr));
+        if (cl > 1) raw[r].y = __float_as_uint(__ldg(pr + 1));
+        if (cl > 2) raw[r].z = __float_as_uint(__ldg(pr + 2));
+      }
+    }
+  }
 }
-DCDF_DEVINL void e5_quads(const uint4 (&raw)[4], float scale2, int4 (&q)[4]) {
+template <bool FULL>
+DCDF_DEVINL void e5_quads(const uint4 (&raw)[4], float scale2, int4 (&q)[4], int rl, int cl) {
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     const uint4 u = raw[2 * h], l = raw[2 * h + 1];
@@ -202,9 +221,25 @@ DCDF_DEVINL void e5_quads(const uint4 (&raw)[4], float scale2, int4 (&q)[4]) {
                          e5_conv(__uint_as_float(l.x), scale2), e5_conv(__uint_as_float(l.y), scale2));
     q[2 * h + 1] = make_int4(e5_conv(__uint_as_float(u.z), scale2), e5_conv(__uint_as_float(u.w), scale2),
                              e5_conv(__uint_as_float(l.z), scale2), e5_conv(__uint_as_float(l.w), scale2));
+    if (!FULL) {
+      const bool ru = 2 * h < rl, rw = 2 * h + 1 < rl;
+      if (!(ru && cl > 0)) q[2 * h].x = E4_NONE;
+      if (!(ru && cl > 1)) q[2 * h].y = E4_NONE;
+      if (!(rw && cl > 0)) q[2 * h].z = E4_NONE;
+      if (!(rw && cl > 1)) q[2 * h].w = E4_NONE;
+      if (!(ru && cl > 2)) q[2 * h + 1].x = E4_NONE;
+      if (!(ru && cl > 3)) q[2 * h + 1].y = E4_NONE;
+      if (!(rw && cl > 2)) q[2 * h + 1].z = E4_NONE;
+      if (!(rw && cl > 3)) q[2 * h + 1].w = E4_NONE;
+    }
   }
 }
 DCDF_DEVINL const float* e5_node_ptr(const float* pt, i64 sr, int a) { return pt + (i64)(4 * (a >> 1)) * sr + 4 * (a & 1); }
+// differences that become DAC entries: a max of a node without cells counts as 0 (`None => 0`, snapshot.rs:122-130,
+// log.rs:128-135); min entries only exist for internal nodes, whose min is a value
+template <bool FULL>
+DCDF_DEVINL int e5_dx(int a, int b) { return e4_sub(e4_o0<FULL>(a), e4_o0<FULL>(b)); }
+DCDF_DEVINL int e5_dn(int a, int b) { return e4_sub(a, b); }
 
 // low bytes of four values as one word, and the zigzag codes of four signed bytes at once (dac.rs:134-137 on values in
 // -128..127: (b << 1) ^ (b >> 7) per byte; the carries of p + p land in the cleared low bits)
@@ -220,13 +255,14 @@ DCDF_DEVINL void e5_store_word(u8* p, u32 w) {
 // quads, then the four quad max entries, then the min entries of the internal quads -- the order in which their second
 // bytes sit in DAC level 1 (dac.rs:109-121).  Log: cells of the instant come from a second (L2-resident) read of the
 // node, the snapshot's from shared memory.  Snapshot: the emission pass has just stored the cells in shared memory.
+template <bool FULL>
 __device__ __noinline__ void e5_long_node(bool as_snapshot, const float* pn, i64 sr, float scale2, const int4* scell, int2 n4, u32 in5a,
-                                          u8* xb1, u8* nb1, u32* pos /* lx1, rx1, rn1 */) {
+                                          u8* xb1, u8* nb1, u32* pos /* lx1, rx1, rn1 */, int rl, int cl) {
   int4 q[4];
   if (!as_snapshot) {
     uint4 raw[4];
-    e5_load_node(pn, sr, raw);
-    e5_quads(raw, scale2, q);
+    e5_load_node<FULL>(pn, sr, raw, rl, cl);
+    e5_quads<FULL>(raw, scale2, q, rl, cl);
   }
   u32 lx1 = pos[0], rx1 = pos[1], rn1 = pos[2];
   u32 zx[4], zn[4];
@@ -234,13 +270,14 @@ __device__ __noinline__ void e5_long_node(bool as_snapshot, const float* pn, i64
   for (int b = 0; b < 4; b++) {
     const int4 s = scell[b * E5_THREADS];
     const int4 t = as_snapshot ? s : q[b];
-    const int qmax = max(max(t.x, t.y), max(t.z, t.w)), qmin = min(min(t.x, t.y), min(t.z, t.w));
-    const int sqmax = max(max(s.x, s.y), max(s.z, s.w)), sqmin = min(min(s.x, s.y), min(s.z, s.w));
-    zx[b] = zigzag32(as_snapshot ? n4.x - qmax : qmax - sqmax);
-    zn[b] = zigzag32(as_snapshot ? qmin - n4.y : qmin - sqmin);
+    int qmax, qmin, sqmax, sqmin;
+    e4_qmm<FULL>(t, qmax, qmin);
+    e4_qmm<FULL>(s, sqmax, sqmin);
+    zx[b] = zigzag32(as_snapshot ? e5_dx<FULL>(n4.x, qmax) : e5_dx<FULL>(qmax, sqmax));
+    zn[b] = zigzag32(as_snapshot ? e5_dn(qmin, n4.y) : e5_dn(qmin, sqmin));
     if ((in5a >> (3 - b)) & 1u) {
-      const u32 z0 = zigzag32(as_snapshot ? qmax - t.x : t.x - s.x), z1 = zigzag32(as_snapshot ? qmax - t.y : t.y - s.y);
-      const u32 z2 = zigzag32(as_snapshot ? qmax - t.z : t.z - s.z), z3 = zigzag32(as_snapshot ? qmax - t.w : t.w - s.w);
+      const u32 z0 = zigzag32(as_snapshot ? e5_dx<FULL>(qmax, t.x) : e4_sub(t.x, s.x)), z1 = zigzag32(as_snapshot ? e5_dx<FULL>(qmax, t.y) : e4_sub(t.y, s.y));
+      const u32 z2 = zigzag32(as_snapshot ? e5_dx<FULL>(qmax, t.z) : e4_sub(t.z, s.z)), z3 = zigzag32(as_snapshot ? e5_dx<FULL>(qmax, t.w) : e4_sub(t.w, s.w));
       if (z0 > 0xffu) xb1[lx1++] = (u8)(z0 >> 8);
       if (z1 > 0xffu) xb1[lx1++] = (u8)(z1 >> 8);
       if (z2 > 0xffu) xb1[lx1++] = (u8)(z2 >> 8);
@@ -263,7 +300,7 @@ DCDF_DEVINL void e5_tile_sync(int slot) { asm volatile("bar.sync %0, 64;" ::"r"(
 // what they share is the instruction stream: one CTA-wide barrier per instant keeps all 2G warps of the SM inside the
 // same stretch of code, so instruction-cache lines fetched for one warp are hits for the others (with unsynchronised
 // CTAs the kernel spent a quarter of its issue slots waiting for instruction fetches).
-template <int G>
+template <int G, bool FULL>
 __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams P, const u32 stage_limit, const int sync_mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int slot = threadIdx.x / E5_THREADS;
@@ -289,10 +326,18 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
   const float* const base = static_cast<const float*>(P.data) + unit.base + (i64)(8 * (int)morton_row(tid)) * sr + 8 * (int)morton_col(tid);
   const bool owner2 = (lane & 3) == 0;
   const int k1 = tid >> 4;  // own level-1 node
+  // rows / columns of the raster left from the origin of the thread's level-4 node a (clipped tiles)
+  const int rl8 = unit.rows - 8 * (int)morton_row(tid), cl8 = unit.cols - 8 * (int)morton_col(tid);
+#define E5_RL(a) (rl8 - 4 * ((a) >> 1))
+#define E5_CL(a) (cl8 - 4 * ((a) & 1))
 
   {  // the emission image starts out all zero; every copy-out re-zeroes what it used
     uint4* z = reinterpret_cast<uint4*>(S.pool);
     for (int i = tid; i < (E5_POOL + 16) / 16; i += E5_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (!FULL) {  // cells outside the raster are None in the snapshot image from the start
+    for (int q = 0; q < 16; q++) S.cell[q][tid] = make_int4(E4_NONE, E4_NONE, E4_NONE, E4_NONE);
+    for (int a = 0; a < 4; a++) S.l4s[a][tid] = make_int2(E4_NONE, INT32_MAX);
   }
 
   u32 err = 0;
@@ -308,7 +353,8 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
     const float* const pt = base + (i64)inst * P.stride_t;
     if (inst + 1 < unit.instants) {  // the next instant's cells on their way into L2 (the tiles of a CTA all load at once)
 #pragma unroll
-      for (int r = 0; r < 8; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + P.stride_t + (i64)r * sr));
+      for (int r = 0; r < 8; r++)
+        if (FULL || (r < rl8 && cl8 > 0)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + P.stride_t + (i64)r * sr));
     }
     const bool forced = first || n_logs == 254u;  // chunk.rs:62 (Block caps logs at 254)
 
@@ -337,15 +383,15 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
       t3max = INT32_MIN; t3min = INT32_MAX;
       u5 = 0; u4 = 0;
       uint4 raw[4];
-      e5_load_node(e5_node_ptr(pt, sr, 0), sr, raw);
+      e5_load_node<FULL>(e5_node_ptr(pt, sr, 0), sr, raw, E5_RL(0), E5_CL(0));
       if (pass == 0) {
         // ---------------- load, convert, differences, flags, length classes, payload
         eq3 = true;
 #pragma unroll 1
         for (int a = 0; a < 4; a++) {
           int4 q[4];
-          e5_quads(raw, scale2, q);
-          if (a < 3) e5_load_node(e5_node_ptr(pt, sr, a + 1), sr, raw);
+          e5_quads<FULL>(raw, scale2, q, E5_RL(a), E5_CL(a));
+          if (a < 3) e5_load_node<FULL>(e5_node_ptr(pt, sr, a + 1), sr, raw, E5_RL(a + 1), E5_CL(a + 1));
           const int2 s4 = S.l4s[a][tid];
           int amax = INT32_MIN, amin = INT32_MAX, dfirst = 0;
           bool aeq = true;
@@ -355,12 +401,13 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
 #pragma unroll
           for (int b = 0; b < 4; b++) {
             const int4 t = q[b], sq = S.cell[4 * a + b][tid];
-            const int qmax = max(max(t.x, t.y), max(t.z, t.w)), qmin = min(min(t.x, t.y), min(t.z, t.w));
-            const int sqmax = max(max(sq.x, sq.y), max(sq.z, sq.w)), sqmin = min(min(sq.x, sq.y), min(sq.z, sq.w));
-            const int d0 = t.x - sq.x, d1 = t.y - sq.y, d2 = t.z - sq.z, d3 = t.w - sq.w;
-            const int ex = qmax - sqmax, en = qmin - sqmin;
+            int qmax, qmin, sqmax, sqmin;
+            e4_qmm<FULL>(t, qmax, qmin);
+            e4_qmm<FULL>(sq, sqmax, sqmin);
+            const int d0 = e4_sub(t.x, sq.x), d1 = e4_sub(t.y, sq.y), d2 = e4_sub(t.z, sq.z), d3 = e4_sub(t.w, sq.w);  // None - None = 0 (log.rs:751)
+            const int ex = e5_dx<FULL>(qmax, sqmax), en = e5_dn(qmin, sqmin);
             const bool e5 = (((d1 ^ d0) | (d2 ^ d0) | (d3 ^ d0)) == 0);  // all four leaf diffs equal (log.rs:780-806)
-            if (qmax == qmin) u5n |= 1u << (3 - b);
+            if (e4_unif<FULL>(qmax, qmin)) u5n |= 1u << (3 - b);
             if (e5) e5n |= 1u << (3 - b);
             u32 leafw = e5_zz4(e5_low4(d0, d1, d2, d3));
             exw = __byte_perm(exw, (u32)ex, b == 0 ? 0x3214 : b == 1 ? 0x3240 : b == 2 ? 0x3410 : 0x4210);
@@ -392,16 +439,16 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
           L.mq |= (qx << (12 - 4 * a)) | (qn << (28 - 4 * a));
           u5 |= u5n << (12 - 4 * a);
           eq5 |= e5n << (12 - 4 * a);
-          if (amax == amin) u4 |= 1u << (3 - a);
+          if (e4_unif<FULL>(amax, amin)) u4 |= 1u << (3 - a);
           if (aeq) eq4 |= 1u << (3 - a);
-          if (e4_longer<1>(amax - s4.x)) L.mu |= 1u << (3 - a);
-          if (e4_longer<1>(amin - s4.y)) L.mu |= 1u << (7 - a);
+          if (e4_longer<1>(e5_dx<FULL>(amax, s4.x))) L.mu |= 1u << (3 - a);
+          if (e4_longer<1>(e5_dn(amin, s4.y))) L.mu |= 1u << (7 - a);
           t3max = max(t3max, amax); t3min = min(t3min, amin);
           if (a == 0) diff3 = dfirst;
           eq3 = eq3 && aeq && dfirst == diff3;
         }
-        if (e4_longer<1>(t3max - s3max)) L.mu |= 1u << 8;
-        if (e4_longer<1>(t3min - s3min)) L.mu |= 1u << 9;
+        if (e4_longer<1>(e5_dx<FULL>(t3max, s3max))) L.mu |= 1u << 8;
+        if (e4_longer<1>(e5_dn(t3min, s3min))) L.mu |= 1u << 9;
       } else {
         // ---------------- Snapshot entry masks of levels 6 and 5 (snapshot.rs:122-147: parent_max - child_max,
         // child_min - parent_min); the uniform flags and the level-4 records come out the same as in pass 0
@@ -409,39 +456,37 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
 #pragma unroll 1
         for (int a = 0; a < 4; a++) {
           int4 q[4];
-          e5_quads(raw, scale2, q);
-          if (a < 3) e5_load_node(e5_node_ptr(pt, sr, a + 1), sr, raw);
+          e5_quads<FULL>(raw, scale2, q, E5_RL(a), E5_CL(a));
+          if (a < 3) e5_load_node<FULL>(e5_node_ptr(pt, sr, a + 1), sr, raw, E5_RL(a + 1), E5_CL(a + 1));
           int qmax[4], qmin[4];
 #pragma unroll
-          for (int b = 0; b < 4; b++) {
-            qmax[b] = max(max(q[b].x, q[b].y), max(q[b].z, q[b].w));
-            qmin[b] = min(min(q[b].x, q[b].y), min(q[b].z, q[b].w));
-          }
+          for (int b = 0; b < 4; b++) e4_qmm<FULL>(q[b], qmax[b], qmin[b]);
           const int amax = max(max(qmax[0], qmax[1]), max(qmax[2], qmax[3])), amin = min(min(qmin[0], qmin[1]), min(qmin[2], qmin[3]));
           u32 leaf16 = 0, qx = 0, qn = 0, u5n = 0;
 #pragma unroll
           for (int b = 0; b < 4; b++) {
             const int4 t = q[b];
-            if (qmax[b] == qmin[b]) u5n |= 1u << (3 - b);
-            if (((u32)(qmax[b] - qmin[b]) | (u32)(amax - qmax[b]) | (u32)(qmin[b] - amin)) > 127u) {  // all differences are >= 0
-              if (e4_longer<1>(qmax[b] - t.x)) leaf16 |= 1u << (15 - 4 * b);
-              if (e4_longer<1>(qmax[b] - t.y)) leaf16 |= 1u << (14 - 4 * b);
-              if (e4_longer<1>(qmax[b] - t.z)) leaf16 |= 1u << (13 - 4 * b);
-              if (e4_longer<1>(qmax[b] - t.w)) leaf16 |= 1u << (12 - 4 * b);
-              if (e4_longer<1>(amax - qmax[b])) qx |= 1u << (3 - b);
-              if (e4_longer<1>(qmin[b] - amin)) qn |= 1u << (3 - b);
+            if (e4_unif<FULL>(qmax[b], qmin[b])) u5n |= 1u << (3 - b);
+            // full tiles: every difference is >= 0 and below the quad's / node's range; clipped: a cell outside counts as 0
+            if (!FULL || ((u32)(qmax[b] - qmin[b]) | (u32)(amax - qmax[b]) | (u32)(qmin[b] - amin)) > 127u) {
+              if (e4_longer<1>(e5_dx<FULL>(qmax[b], t.x))) leaf16 |= 1u << (15 - 4 * b);
+              if (e4_longer<1>(e5_dx<FULL>(qmax[b], t.y))) leaf16 |= 1u << (14 - 4 * b);
+              if (e4_longer<1>(e5_dx<FULL>(qmax[b], t.z))) leaf16 |= 1u << (13 - 4 * b);
+              if (e4_longer<1>(e5_dx<FULL>(qmax[b], t.w))) leaf16 |= 1u << (12 - 4 * b);
+              if (e4_longer<1>(e5_dx<FULL>(amax, qmax[b]))) qx |= 1u << (3 - b);
+              if (e4_longer<1>(e5_dn(qmin[b], amin))) qn |= 1u << (3 - b);
             }
           }
           S.l4t[a][tid] = make_int2(amax, amin);
           C.ml |= (u64)leaf16 << (48 - 16 * a);
           C.mq |= (qx << (12 - 4 * a)) | (qn << (28 - 4 * a));
           u5 |= u5n << (12 - 4 * a);
-          if (amax == amin) u4 |= 1u << (3 - a);
+          if (e4_unif<FULL>(amax, amin)) u4 |= 1u << (3 - a);
           t3max = max(t3max, amax); t3min = min(t3min, amin);
         }
-        if ((u32)(t3max - t3min) > 32767u) err |= EF_BAD_FORMAT;  // not eligible
+        if (t3max != E4_NONE && (u32)e4_sub(t3max, t3min) > 32767u) err |= EF_BAD_FORMAT;  // not eligible
       }
-      u3 = t3max == t3min;
+      u3 = e4_unif<FULL>(t3max, t3min);
 
       // ---------------- levels 2 and 1 with shuffles (4 resp. 16 consecutive lanes)
       t2max = max(t3max, shfl_xor(t3max, 1)); t2max = max(t2max, shfl_xor(t2max, 2));
@@ -449,19 +494,19 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
       const int diff2 = shfl(diff3, lane & ~3);
       const u32 ok3 = __ballot_sync(0xffffffffu, eq3 && diff3 == diff2);
       eq2 = ((ok3 >> (lane & ~3)) & 0xfu) == 0xfu;
-      u2 = t2max == t2min;
+      u2 = e4_unif<FULL>(t2max, t2min);
       t1max = max(t2max, shfl_xor(t2max, 4)); t1max = max(t1max, shfl_xor(t1max, 8));
       t1min = min(t2min, shfl_xor(t2min, 4)); t1min = min(t1min, shfl_xor(t1min, 8));
       const int diff1 = shfl(diff2, lane & ~15);
       const u32 ok2 = __ballot_sync(0xffffffffu, eq2 && diff2 == diff1);
       const bool eq1 = ((ok2 >> (lane & ~15)) & 0xffffu) == 0xffffu;
-      const bool u1 = t1max == t1min;
+      const bool u1 = e4_unif<FULL>(t1max, t1min);
 
       // structure flags: snapshot internal = !uniform (snapshot.rs:133); log internal = !uniform && !equal (log.rs:137-152)
       C.in5 = ~u5 & 0xffffu; C.in4 = ~u4 & 0xfu; C.in3 = !u3; C.in2 = !u2; C.in1 = !u1;
       if (pass == 0) {
-        if (e4_longer<1>(t2max - s2max)) L.mu |= 1u << 10;
-        if (e4_longer<1>(t2min - s2min)) L.mu |= 1u << 11;
+        if (e4_longer<1>(e5_dx<FULL>(t2max, s2max))) L.mu |= 1u << 10;
+        if (e4_longer<1>(e5_dn(t2min, s2min))) L.mu |= 1u << 11;
         L.in5 = ~u5 & ~eq5 & 0xffffu; L.in4 = ~u4 & ~eq4 & 0xfu; L.in3 = !u3 && !eq3; L.in2 = !u2 && !eq2; L.in1 = !u1 && !eq1;
         e5_count(L, owner2, wl);
       } else {
@@ -469,13 +514,13 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
 #pragma unroll
         for (int a = 0; a < 4; a++) {
           const int2 n4 = S.l4t[a][tid];
-          if (e4_longer<1>(t3max - n4.x)) C.mu |= 1u << (3 - a);
-          if (e4_longer<1>(n4.y - t3min)) C.mu |= 1u << (7 - a);
+          if (e4_longer<1>(e5_dx<FULL>(t3max, n4.x))) C.mu |= 1u << (3 - a);
+          if (e4_longer<1>(e5_dn(n4.y, t3min))) C.mu |= 1u << (7 - a);
         }
-        if (e4_longer<1>(t2max - t3max)) C.mu |= 1u << 8;
-        if (e4_longer<1>(t3min - t2min)) C.mu |= 1u << 9;
-        if (e4_longer<1>(t1max - t2max)) C.mu |= 1u << 10;
-        if (e4_longer<1>(t2min - t1min)) C.mu |= 1u << 11;
+        if (e4_longer<1>(e5_dx<FULL>(t2max, t3max))) C.mu |= 1u << 8;
+        if (e4_longer<1>(e5_dn(t3min, t2min))) C.mu |= 1u << 9;
+        if (e4_longer<1>(e5_dx<FULL>(t1max, t2max))) C.mu |= 1u << 10;
+        if (e4_longer<1>(e5_dn(t2min, t1min))) C.mu |= 1u << 11;
       }
       e5_count(C, owner2, ws);  // pass 0: structure only (the masks are still empty) -> the lower bound
 
@@ -492,7 +537,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
       }
       if ((lane & 15) == 0) {
         S.rec1[k1] = make_int4(t1max, t1min, diff1, eq1 ? 1 : 0);
-        if (pass == 0) S.ent1[k1] = make_int2(t1max - s1max, t1min - s1min);
+        if (pass == 0) S.ent1[k1] = make_int2(e5_dx<FULL>(t1max, s1max), e5_dn(t1min, s1min));
       }
       e5_tile_sync(slot);  // B1
 
@@ -512,7 +557,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
       l_in1 = 0; s_in1 = 0;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const bool un = n1max[k] == n1min[k];
+        const bool un = e4_unif<FULL>(n1max[k], n1min[k]);
         if (!un) s_in1 |= 1u << (3 - k);
         if (!un && !((n1flags >> k) & 1u)) l_in1 |= 1u << (3 - k);
       }
@@ -526,7 +571,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
       const bool as_log = pass == 0;
       int c_e1max[4], c_e1min[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) { c_e1max[k] = as_log ? l_e1max[k] : t0max - n1max[k]; c_e1min[k] = as_log ? l_e1min[k] : n1min[k] - t0min; }
+      for (int k = 0; k < 4; k++) { c_e1max[k] = as_log ? l_e1max[k] : e5_dx<FULL>(t0max, n1max[k]); c_e1min[k] = as_log ? l_e1min[k] : e5_dn(n1min[k], t0min); }
       E5Tot Tc;
       e5_totals(Tc, S, as_log ? 1 : 0, as_log ? l_in0 : s_in0, as_log ? l_in1 : s_in1, c_e1max, c_e1min, as_log ? t0max - s0max : t0max,
                 as_log ? t0min - s0min : t0min);
@@ -553,7 +598,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
     W.ml = as_snapshot ? C.ml : L.ml; W.mq = as_snapshot ? C.mq : L.mq; W.mu = as_snapshot ? C.mu : L.mu;
     int e1x[4], e1n[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) { e1x[k] = as_snapshot ? t0max - n1max[k] : l_e1max[k]; e1n[k] = as_snapshot ? n1min[k] - t0min : l_e1min[k]; }
+    for (int k = 0; k < 4; k++) { e1x[k] = as_snapshot ? e5_dx<FULL>(t0max, n1max[k]) : l_e1max[k]; e1n[k] = as_snapshot ? e5_dn(n1min[k], t0min) : l_e1min[k]; }
     const int e0x = as_snapshot ? t0max : t0max - s0max, e0n = as_snapshot ? t0min : t0min - s0min;
     const u32 nm_len = T.nm_len, n_int = T.n_int, I0 = T.I0, I1 = T.I1;
     const bool in0 = as_snapshot ? s_in0 : l_in0;
@@ -727,7 +772,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             if ((in1m >> (3 - k)) & 1u) en[nn++] = e1n[k];
-            else { accE = (accE << 1) | ((!(n1max[k] == n1min[k]) && ((n1flags >> k) & 1u)) ? 1u : 0u); nE++; }
+            else { accE = (accE << 1) | ((!e4_unif<FULL>(n1max[k], n1min[k]) && ((n1flags >> k) & 1u)) ? 1u : 0u); nE++; }
           }
           e5_top_bits(nw0, nw1, nw2, en, nn);
           if (!as_snapshot) e5_or_bits(eq_words, 0, accE, nE);
@@ -745,7 +790,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
       u8* dst5 = xb0 + Pn5 + 4u * R4;
       u8* dmn = nb0 + Mn5 + R5;
       uint4 raw[4];
-      if (as_snapshot) e5_load_node(e5_node_ptr(pt, sr, 0), sr, raw);
+      if (as_snapshot) e5_load_node<FULL>(e5_node_ptr(pt, sr, 0), sr, raw, E5_RL(0), E5_CL(0));
 #pragma unroll 1
       for (int a = 0; a < 4; a++) {
         const int2 n4 = S.l4t[a][tid];
@@ -756,20 +801,22 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
           // quads and leaves of the Snapshot from a pass over the tile, which also installs the instant as the snapshot
           // image the following Logs are built against (even when nothing can be emitted: the sizes must stay exact)
           int4 q[4];
-          e5_quads(raw, scale2, q);
-          if (a < 3) e5_load_node(e5_node_ptr(pt, sr, a + 1), sr, raw);
+          e5_quads<FULL>(raw, scale2, q, E5_RL(a), E5_CL(a));
+          if (a < 3) e5_load_node<FULL>(e5_node_ptr(pt, sr, a + 1), sr, raw, E5_RL(a + 1), E5_CL(a + 1));
           S.l4s[a][tid] = n4;
           zxw = 0; znw = 0;
 #pragma unroll
           for (int b = 0; b < 4; b++) {
             const int4 t = q[b];
             S.cell[4 * a + b][tid] = t;
-            const int qmax = max(max(t.x, t.y), max(t.z, t.w)), qmin = min(min(t.x, t.y), min(t.z, t.w));
-            zxw |= (zigzag32(n4.x - qmax) & 0xffu) << (8 * b);
-            znw |= (zigzag32(qmin - n4.y) & 0xffu) << (8 * b);
+            int qmax, qmin;
+            e4_qmm<FULL>(t, qmax, qmin);
+            zxw |= (zigzag32(e5_dx<FULL>(n4.x, qmax)) & 0xffu) << (8 * b);
+            znw |= (zigzag32(e5_dn(qmin, n4.y)) & 0xffu) << (8 * b);
             if (alive && ((in5a >> (3 - b)) & 1u))
               e5_store_word(dst6 + 4u * (u32)__popc(in5a >> (4 - b)),
-                            e5_pack4(zigzag32(qmax - t.x), zigzag32(qmax - t.y), zigzag32(qmax - t.z), zigzag32(qmax - t.w)));
+                            e5_pack4(zigzag32(e5_dx<FULL>(qmax, t.x)), zigzag32(e5_dx<FULL>(qmax, t.y)), zigzag32(e5_dx<FULL>(qmax, t.z)),
+                                     zigzag32(e5_dx<FULL>(qmax, t.w))));
           }
         } else {
           // quads and leaves of the Log from the payload of the fused pass
@@ -790,7 +837,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
         const u32 ml16 = (u32)(W.ml >> (48 - 16 * a)) & 0xffffu;
         const u32 lq = ((W.mq >> (12 - 4 * a)) & 0xfu) | (((W.mq >> (28 - 4 * a)) & 0xfu) & in5a);
         if ((ml16 & (e4_expand4(in5a) & 0xffffu)) | lq)
-          e5_long_node(as_snapshot, e5_node_ptr(pt, sr, a), sr, scale2, &S.cell[4 * a][tid], n4, in5a, xb1, nb1, pos);
+          e5_long_node<FULL>(as_snapshot, e5_node_ptr(pt, sr, a), sr, scale2, &S.cell[4 * a][tid], n4, in5a, xb1, nb1, pos, E5_RL(a), E5_CL(a));
       }
     }
     if (emit) {
@@ -802,8 +849,8 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
           const int2 n4 = S.l4t[a][tid];
           // the Snapshot pass has already installed l4s = l4t, and a Snapshot's entries do not refer to it
           const int2 s4 = as_snapshot ? make_int2(0, 0) : S.l4s[a][tid];
-          zx[a] = zigzag32(as_snapshot ? t3max - n4.x : n4.x - s4.x);
-          zn[a] = zigzag32(as_snapshot ? n4.y - t3min : n4.y - s4.y);
+          zx[a] = zigzag32(as_snapshot ? e5_dx<FULL>(t3max, n4.x) : e5_dx<FULL>(n4.x, s4.x));
+          zn[a] = zigzag32(as_snapshot ? e5_dn(n4.y, t3min) : e5_dn(n4.y, s4.y));
         }
         e5_store_word(xb0 + Pn4 + 4u * R3, e5_pack4(zx[0], zx[1], zx[2], zx[3]));
         u8* dmn = nb0 + Mn4 + R4;
@@ -821,21 +868,21 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
         }
       }
       if (x3) {
-        const u32 zx = zigzag32(as_snapshot ? t2max - t3max : t3max - s3max);
+        const u32 zx = zigzag32(as_snapshot ? e5_dx<FULL>(t2max, t3max) : e5_dx<FULL>(t3max, s3max));
         xb0[Pn3 + 4u * R2p + (u32)(tid & 3)] = (u8)zx;
         if (zx > 0xffu) e5_hi(xb1, zx, bx3 + e4_f3(pre[1]));
         if (W.in3) {
-          const u32 zn = zigzag32(as_snapshot ? t3min - t2min : t3min - s3min);
+          const u32 zn = zigzag32(as_snapshot ? e5_dn(t3min, t2min) : e5_dn(t3min, s3min));
           nb0[Mn3 + R3] = (u8)zn;
           if (zn > 0xffu) e5_hi(nb1, zn, bn3 + e4_f3(pre[3]));
         }
       }
       if (x2 && owner2) {
-        const u32 zx = zigzag32(as_snapshot ? t1max - t2max : t2max - s2max);
+        const u32 zx = zigzag32(as_snapshot ? e5_dx<FULL>(t1max, t2max) : e5_dx<FULL>(t2max, s2max));
         xb0[Pn2 + 4u * R1 + (u32)((tid >> 2) & 3)] = (u8)zx;
         if (zx > 0xffu) e5_hi(xb1, zx, bx2 + e4_f2(pre[1]));
         if (W.in2) {
-          const u32 zn = zigzag32(as_snapshot ? t2min - t1min : t2min - s2min);
+          const u32 zn = zigzag32(as_snapshot ? e5_dn(t2min, t1min) : e5_dn(t2min, s2min));
           nb0[Mn2 + R2own] = (u8)zn;
           if (zn > 0xffu) e5_hi(nb1, zn, bn2 + e4_f2(pre[3]));
         }
@@ -854,8 +901,8 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
           e5_top_bytes(nb0, nb1, out + DN.bytes[2], out + DN.bytes[3], en, nn);
         }
         out[0] = 2;  // k
-        store_be32(out + 1, 64u);  // rows
-        store_be32(out + 5, 64u);  // cols
+        store_be32(out + 1, (u32)unit.rows);
+        store_be32(out + 5, (u32)unit.cols);
         store_be32(out + 9, 64u);  // sidelen
         out[DX.hdr[0] - 1] = (u8)DX.levels;
         out[DN.hdr[0] - 1] = (u8)DN.levels;
@@ -955,6 +1002,8 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
   }
   err = __reduce_or_sync(0xffffffffu, err);
   if (lane == 0 && err) atomicOr(P.err, err);
+#undef E5_RL
+#undef E5_CL
 }
 
 }  // namespace dcdf

@@ -971,12 +971,17 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
         }
         const bool full = unit.rows == 64 && unit.cols == 64 && unit.lo == 0;
         if (full) flags |= UF_FULL;
-        // k_encode_v5 (encode_v5.cuh): full f32 tiles whose to_fixed is exact, without NaN, every fixed value below
+        // k_encode_v5 (encode_v5.cuh): f32 tiles with a 64-side tree whose to_fixed is exact, every fixed value below
         // 2^22 in magnitude and all of them within 32767 of each other -> every entry below the root takes <= 2 bytes
         bool fast = false;
-        if (P.allow_fast && !can_elide && full && narrow && P.encoding == 32 && (flags & UF_EXACT) && !any_nan && has) {
+        if (P.allow_fast && !can_elide && unit.lo == 0 && narrow && P.encoding == 32 && (flags & UF_EXACT) && has) {
           const double sc = ldexp(1.0, cbits + 1);
-          fast = (rmax - rmin) * sc <= 32767.0 && fabs(rmax) * sc < 4194303.0 && fabs(rmin) * sc < 4194303.0;
+          // fixed = 2 v 2^bits + 1 for values, 0 for NaN: every code of the unit within 32767 of every other one
+          double lo = rmin * sc + 1.0, hi = rmax * sc + 1.0;
+          if (any_nan) { lo = fmin(lo, 0.0); hi = fmax(hi, 0.0); }
+          fast = hi - lo <= 32767.0 && fabs(hi) < 4194303.0 && fabs(lo) < 4194303.0;
+          // clipped tiles: an entry next to a cell outside the raster is the max itself (snapshot.rs:122-130 with None => 0)
+          if (!full) fast = fast && fabs(hi) <= 32767.0 && fabs(lo) <= 32767.0;
         }
         unit.bits = cbits;
         unit.flags = flags;
@@ -984,8 +989,8 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
         P.stored[u] = can_elide ? 0 : 1;
         if (!can_elide) {
           u32 list = (narrow ? 0u : 2u) + (full ? 0u : 1u);
-          if (fast) list = 5u;
           if (narrow && !full && unit.lo == 0) list = 4u;  // clipped, but still a 64-side tree: k_encode_v4<.., false>
+          if (fast) list = full ? 5u : 6u;                  // k_encode_v5<.., true / false>
           P.order[(size_t)list * P.order_pitch + atomicAdd(&P.order_counts[list], 1u)] = u;
         }
       }

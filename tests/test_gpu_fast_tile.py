@@ -128,16 +128,17 @@ def test_fast_tiles_log_cap(ctx):
 
 
 def test_tiles_that_must_not_take_the_fast_path(ctx):
-    """NaN cells, a value range above 32767 fixed units, values above 2^22, data that needs rounding: each disqualifies
-    only its own tile; the neighbours still go through the fast path and everything must stay exact."""
+    """A value range above 32767 fixed units, values above 2^22, data that needs rounding: each disqualifies only its
+    own tile; the neighbours (one of them with NaN cells, which the fast path handles) still go through the fast path
+    and everything must stay exact."""
     rng = np.random.default_rng(64)
     data = _tiles(_frames(rng, "dense", T=8))
-    data[3, 5, 70] = np.nan                                    # tile (0, 1): NaN
+    data[3, 5, 70] = np.nan                                    # tile (0, 1): NaN (code 0 stays within 32767 of the values)
     data[:, 64:, :64] += np.float32(3000.0)                    # tile (1, 0): range 3000 * 32 > 32767 against ...
     data[2, 64:, :64] -= np.float32(3000.0)                    # ... one instant back at the old level
     data[:, 64:, 64:] += np.float32(200000.0)                  # tile (1, 1): fixed values above 2^22
     _check_superchunk(ctx, data, [1, 6]).close()
-    assert ctx.get_stat("encode_units_fast") == (0 if ctx.general else 1) and ctx.get_stat("encode_units_general") == (4 if ctx.general else 3)
+    assert ctx.get_stat("encode_units_fast") == (0 if ctx.general else 2) and ctx.get_stat("encode_units_general") == (4 if ctx.general else 2)
     noisy = _tiles(_frames(rng, "sparse", T=6)) * np.float32(0.3)   # full mantissas: Round without rounding fails ...
     _check_superchunk(ctx, noisy, [1, 6], fractional_bits=5, round_=True).close()   # ... with it, to_fixed rounds (not exact)
 
@@ -159,3 +160,52 @@ def test_fast_path_strided_device_input(ctx):
         for slot, c in enumerate(child):
             assert chunks[slot] == ref.node_bytes(int(c)), (r0, c0, slot)
         sc.close()
+
+
+@pytest.mark.parametrize("rows,cols", [(150, 200), (129, 191), (190, 130), (64, 100), (100, 64)])
+def test_fast_clipped_tiles_and_nan(ctx, rows, cols):
+    """Clipped tiles that keep a 64-side tree (cells outside the raster are None) and NaN cells (code 0) through the fast
+    path: temperature-like values (|fixed| <= 32767 so that an entry next to a None cell still fits two bytes), NaN
+    sprinkled, NaN blocks, an all-NaN instant, whole-field offsets, sparse changes."""
+    rng = np.random.default_rng(rows * 1000 + cols)
+    base = rng.integers(4000, 4300, (rows, cols))
+    frames = [base]
+    for i in range(1, 11):
+        f = frames[-1].copy()
+        if i % 5 == 0:
+            f = rng.integers(4000, 9000, (rows, cols))
+        elif i % 5 == 1:
+            f = f + 3
+        else:
+            m = rng.random((rows, cols)) < 0.05
+            f[m] += rng.integers(-200, 200, m.sum())
+        frames.append(f)
+    data = (np.stack(frames) / 16.0).astype(np.float32)
+    levels = [max(1, int(np.ceil(np.log2(max(rows, cols)))) - 6), 6]
+    sc = _check_superchunk(ctx, data, levels)
+    n_fast = ctx.get_stat("encode_units_fast")
+    if not ctx.general and cols % 4 == 0:                                  # rows of four cells must be 16-byte aligned for the fast path
+        assert n_fast >= ((rows + 63) // 64) * ((cols + 63) // 64) - 1       # all but (at most) a corner tile with a smaller tree
+    if cols % 4:
+        assert n_fast == 0
+    assert np.array_equal(sc.window(0, 11, 0, rows, 0, cols), data)
+    sc.close()
+    nan = data.copy()
+    nan[rng.random(nan.shape) < 0.03] = np.nan
+    nan[2:5, 10:40, 20:90] = np.nan
+    nan[7] = np.nan
+    sc = _check_superchunk(ctx, nan, levels)
+    if not ctx.general:
+        assert ctx.get_stat("encode_units_fast") == n_fast
+    assert np.array_equal(sc.window(0, 11, 0, rows, 0, cols), nan, equal_nan=True)
+    sc.close()
+
+
+def test_fast_nan_ocean_precipitation_like(ctx):
+    """configs[2]'s shape of data: clamped at 0, 60 % NaN in 16x16 blocks -- fast path with NaN codes and many uniform /
+    equal sub-trees."""
+    from dcdf_b200 import synth
+    data = synth.raster_slice(0, 20, 200, 260, hourly=False, nan_ocean=True).numpy()
+    sc = _check_superchunk(ctx, data, [3, 6], chunk_size=8)
+    assert ctx.general or ctx.get_stat("encode_units_fast") > 0
+    sc.close()
