@@ -394,10 +394,7 @@ void run_encode(dcdf_ctx* ctx, EncodeJob& job, EncodeOut& out, bool want_pieces)
     TP.units = ctx->units.as<EncUnit>();
     TP.ustats = SP.ustats; TP.istats = SP.istats; TP.t_max = job.t_max;
     TP.encoding = job.encoding; TP.round = job.round; TP.req_bits = job.req_bits;
-    // k_encode_v5 reads rows of four cells with 128-bit loads
-    TP.allow_fast = job.encoding == DCDF_ENC_F32 && !ctx->opt.no_fast_encode && job.strides[2] == 1 && job.strides[1] % 4 == 0 &&
-                    job.strides[0] % 4 == 0 && ((uintptr_t)job.dev_data & 15) == 0;
-    for (const auto& u : job.units) if (u.base % 4 != 0) { TP.allow_fast = 0; break; }
+    TP.allow_fast = job.encoding == DCDF_ENC_F32 && !ctx->opt.no_fast_encode && job.strides[2] == 1;  // k_encode_v5 reads rows of four cells
     TP.tbl_min = d_tbl_min; TP.tbl_max = d_tbl_max;
     TP.order = FP.order; TP.order_pitch = FP.order_pitch; TP.order_counts = FP.order_counts;
     TP.stored = FP.stored; TP.err = d_err;

@@ -196,11 +196,16 @@ DCDF_DEVINL int e5_conv(float x, float scale2) {
 // Clipped tiles (FULL == false): rl / cl = rows / columns of the node that lie inside the raster (may be <= 0); cells
 // outside are not read and become None (E4_NONE, as in encode_v4.cuh: excluded from min / max, 0 in an entry).
 template <bool FULL>
-DCDF_DEVINL void e5_load_node(const float* pn, i64 sr, uint4 (&raw)[4], int rl, int cl) {
+DCDF_DEVINL void e5_load_node(const float* pn, i64 sr, uint4 (&raw)[4], int rl, int cl, bool vec) {
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     if (FULL || (r < rl && cl >= 4)) {
-      raw[r] = __ldg(reinterpret_cast<const uint4*>(pn + (i64)r * sr));
+      const float* pr = pn + (i64)r * sr;
+      if (vec) {
+        raw[r] = __ldg(reinterpret_cast<const uint4*>(pr));
+      } else {  // rows that are not 16-byte aligned (e.g. 1405 columns): four 32-bit loads
+        raw[r] = make_uint4(__float_as_uint(__ldg(pr)), __float_as_uint(__ldg(pr + 1)), __float_as_uint(__ldg(pr + 2)), __float_as_uint(__ldg(pr + 3)));
+      }
     } else {
       raw[r] = make_uint4(0, 0, 0, 0);
       if (r < rl) {
@@ -257,11 +262,11 @@ DCDF_DEVINL void e5_store_word(u8* p, u32 w) {
 // node, the snapshot's from shared memory.  Snapshot: the emission pass has just stored the cells in shared memory.
 template <bool FULL>
 __device__ __noinline__ void e5_long_node(bool as_snapshot, const float* pn, i64 sr, float scale2, const int4* scell, int2 n4, u32 in5a,
-                                          u8* xb1, u8* nb1, u32* pos /* lx1, rx1, rn1 */, int rl, int cl) {
+                                          u8* xb1, u8* nb1, u32* pos /* lx1, rx1, rn1 */, int rl, int cl, bool vec) {
   int4 q[4];
   if (!as_snapshot) {
     uint4 raw[4];
-    e5_load_node<FULL>(pn, sr, raw, rl, cl);
+    e5_load_node<FULL>(pn, sr, raw, rl, cl, vec);
     e5_quads<FULL>(raw, scale2, q, rl, cl);
   }
   u32 lx1 = pos[0], rx1 = pos[1], rn1 = pos[2];
@@ -302,6 +307,7 @@ DCDF_DEVINL void e5_tile_sync(int slot) { asm volatile("bar.sync %0, 64;" ::"r"(
 // CTAs the kernel spent a quarter of its issue slots waiting for instruction fetches).
 template <int G, bool FULL>
 __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams P, const u32 stage_limit, const int sync_mask) {
+  const bool vec = ((P.stride_r | P.stride_t) & 3) == 0 && (((uintptr_t)P.data) & 15) == 0;  // every row of four cells is 16-byte aligned
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int slot = threadIdx.x / E5_THREADS;
   E5Smem& S = *reinterpret_cast<E5Smem*>(smem_raw + (size_t)slot * sizeof(E5Smem));
@@ -383,7 +389,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
       t3max = INT32_MIN; t3min = INT32_MAX;
       u5 = 0; u4 = 0;
       uint4 raw[4];
-      e5_load_node<FULL>(e5_node_ptr(pt, sr, 0), sr, raw, E5_RL(0), E5_CL(0));
+      e5_load_node<FULL>(e5_node_ptr(pt, sr, 0), sr, raw, E5_RL(0), E5_CL(0), vec);
       if (pass == 0) {
         // ---------------- load, convert, differences, flags, length classes, payload
         eq3 = true;
@@ -391,7 +397,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
         for (int a = 0; a < 4; a++) {
           int4 q[4];
           e5_quads<FULL>(raw, scale2, q, E5_RL(a), E5_CL(a));
-          if (a < 3) e5_load_node<FULL>(e5_node_ptr(pt, sr, a + 1), sr, raw, E5_RL(a + 1), E5_CL(a + 1));
+          if (a < 3) e5_load_node<FULL>(e5_node_ptr(pt, sr, a + 1), sr, raw, E5_RL(a + 1), E5_CL(a + 1), vec);
           const int2 s4 = S.l4s[a][tid];
           int amax = INT32_MIN, amin = INT32_MAX, dfirst = 0;
           bool aeq = true;
@@ -457,7 +463,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
         for (int a = 0; a < 4; a++) {
           int4 q[4];
           e5_quads<FULL>(raw, scale2, q, E5_RL(a), E5_CL(a));
-          if (a < 3) e5_load_node<FULL>(e5_node_ptr(pt, sr, a + 1), sr, raw, E5_RL(a + 1), E5_CL(a + 1));
+          if (a < 3) e5_load_node<FULL>(e5_node_ptr(pt, sr, a + 1), sr, raw, E5_RL(a + 1), E5_CL(a + 1), vec);
           int qmax[4], qmin[4];
 #pragma unroll
           for (int b = 0; b < 4; b++) e4_qmm<FULL>(q[b], qmax[b], qmin[b]);
@@ -790,7 +796,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
       u8* dst5 = xb0 + Pn5 + 4u * R4;
       u8* dmn = nb0 + Mn5 + R5;
       uint4 raw[4];
-      if (as_snapshot) e5_load_node<FULL>(e5_node_ptr(pt, sr, 0), sr, raw, E5_RL(0), E5_CL(0));
+      if (as_snapshot) e5_load_node<FULL>(e5_node_ptr(pt, sr, 0), sr, raw, E5_RL(0), E5_CL(0), vec);
 #pragma unroll 1
       for (int a = 0; a < 4; a++) {
         const int2 n4 = S.l4t[a][tid];
@@ -802,7 +808,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
           // image the following Logs are built against (even when nothing can be emitted: the sizes must stay exact)
           int4 q[4];
           e5_quads<FULL>(raw, scale2, q, E5_RL(a), E5_CL(a));
-          if (a < 3) e5_load_node<FULL>(e5_node_ptr(pt, sr, a + 1), sr, raw, E5_RL(a + 1), E5_CL(a + 1));
+          if (a < 3) e5_load_node<FULL>(e5_node_ptr(pt, sr, a + 1), sr, raw, E5_RL(a + 1), E5_CL(a + 1), vec);
           S.l4s[a][tid] = n4;
           zxw = 0; znw = 0;
 #pragma unroll
@@ -837,7 +843,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
         const u32 ml16 = (u32)(W.ml >> (48 - 16 * a)) & 0xffffu;
         const u32 lq = ((W.mq >> (12 - 4 * a)) & 0xfu) | (((W.mq >> (28 - 4 * a)) & 0xfu) & in5a);
         if ((ml16 & (e4_expand4(in5a) & 0xffffu)) | lq)
-          e5_long_node<FULL>(as_snapshot, e5_node_ptr(pt, sr, a), sr, scale2, &S.cell[4 * a][tid], n4, in5a, xb1, nb1, pos, E5_RL(a), E5_CL(a));
+          e5_long_node<FULL>(as_snapshot, e5_node_ptr(pt, sr, a), sr, scale2, &S.cell[4 * a][tid], n4, in5a, xb1, nb1, pos, E5_RL(a), E5_CL(a), vec);
       }
     }
     if (emit) {

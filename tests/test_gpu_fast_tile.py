@@ -144,7 +144,7 @@ def test_tiles_that_must_not_take_the_fast_path(ctx):
 
 
 def test_fast_path_strided_device_input(ctx):
-    """A device-resident view whose rows are 16-byte aligned qualifies; one that is not falls back."""
+    """Device-resident views: rows 16-byte aligned (128-bit loads) and not (32-bit loads)."""
     import torch
     from dcdf_b200 import Superchunk
     rng = np.random.default_rng(65)
@@ -184,10 +184,8 @@ def test_fast_clipped_tiles_and_nan(ctx, rows, cols):
     levels = [max(1, int(np.ceil(np.log2(max(rows, cols)))) - 6), 6]
     sc = _check_superchunk(ctx, data, levels)
     n_fast = ctx.get_stat("encode_units_fast")
-    if not ctx.general and cols % 4 == 0:                                  # rows of four cells must be 16-byte aligned for the fast path
+    if not ctx.general:                                                    # 191 columns: rows not 16-byte aligned -> 32-bit loads
         assert n_fast >= ((rows + 63) // 64) * ((cols + 63) // 64) - 1       # all but (at most) a corner tile with a smaller tree
-    if cols % 4:
-        assert n_fast == 0
     assert np.array_equal(sc.window(0, 11, 0, rows, 0, cols), data)
     sc.close()
     nan = data.copy()
