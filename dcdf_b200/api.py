@@ -192,14 +192,29 @@ class _Queryable:
     def get(self, instant, row, col, raw=False):
         return self.get_batch([[instant, row, col]], raw)[0]
 
-    def cell_batch(self, queries, raw=False):
+    def cell_batch(self, queries, raw=False, out=None, flat=False):
+        """Chunk / Superchunk::fill_cell for n x (start, end, row, col).  `out`: optional destination (a numpy array or
+        a torch tensor, e.g. pinned host memory or device memory) for all series back to back; flat=True returns
+        (out, offsets) instead of one view per series."""
         q = np.ascontiguousarray(queries, dtype=np.int64).reshape(-1, 4)
         lens = np.abs(q[:, 1] - q[:, 0]).astype(np.uint64)
         off = np.zeros(len(q) + 1, np.uint64)
         np.cumsum(lens, out=off[1:])
-        out = _out_array(int(off[-1]), self.encoding, raw)
-        self.ctx.check(self._fn("cell_batch")(self.ctx._h, self._h, len(q), _ptr(q), _ptr(off), _ptr(out),
-                                              ENC_I64 if raw else self.encoding, MEM_HOST))
+        mem = MEM_HOST
+        if out is None:
+            out = _out_array(int(off[-1]), self.encoding, raw)
+            ptr = _ptr(out)
+        elif _is_torch(out):
+            _check_out(out, int(off[-1]), self.encoding, raw)
+            _order_after_torch(self.ctx, out)
+            ptr, mem = C.c_void_p(out.data_ptr()), (MEM_DEVICE if out.is_cuda else MEM_HOST)
+        else:
+            _check_out(out, int(off[-1]), self.encoding, raw)
+            ptr = _ptr(out)
+        self.ctx.check(self._fn("cell_batch")(self.ctx._h, self._h, len(q), _ptr(q), _ptr(off), ptr,
+                                              ENC_I64 if raw else self.encoding, mem))
+        if flat:
+            return out, off
         return [out[int(off[i]):int(off[i + 1])] for i in range(len(q))]
 
     def cell(self, start, end, row, col, raw=False):

@@ -352,7 +352,6 @@ void do_cell_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const int64_t* q, c
   if (n == 0) return;
   if (!q || !out_off) api_fail(DCDF_ERR_BAD_ARG, "null queries");
   const OutSpec os = out_spec(out_encoding, mb->Q.encoding);
-  if (mem != DCDF_MEM_HOST) api_fail(DCDF_ERR_BAD_ARG, "cell_batch takes host query arrays (results may stay on the device via window_batch)");
   std::vector<i64> qq(q, q + 4 * n);
   i64 longest = 1;
   for (uint64_t i = 0; i < n; i++) {

@@ -71,26 +71,30 @@ void validate_array(const dcdf_array3* a) {
     api_fail(DCDF_ERR_BAD_ARG, "bad encoding %d", a->encoding);
   for (int i = 0; i < 3; i++) {
     if (a->shape[i] <= 0) api_fail(DCDF_ERR_BAD_ARG, "empty array axis %d", i);
-    if (a->strides[i] < 0) api_fail(DCDF_ERR_BAD_ARG, "negative strides are not supported");
   }
   if (a->mem != DCDF_MEM_HOST && a->mem != DCDF_MEM_DEVICE) api_fail(DCDF_ERR_BAD_ARG, "bad mem kind");
 }
 
-// Returns a device pointer for the array (copying a host view's spanned extent if needed).
+// Returns a device pointer for element [0, 0, 0] of the array (copying a host view's spanned extent if needed; strides
+// may be negative, as in a reversed ndarray view: mmbuffer.rs:573-594).
 const void* stage_input(dcdf_ctx* ctx, const dcdf_array3* a) {
   if (a->mem == DCDF_MEM_DEVICE) return a->base;
-  size_t span = 1;
-  for (int i = 0; i < 3; i++) span += (size_t)(a->shape[i] - 1) * (size_t)a->strides[i];
-  size_t bytes = span * elem_size(a->encoding);
+  int64_t lo = 0, hi = 0;  // lowest / highest element offset the view touches
+  for (int i = 0; i < 3; i++) {
+    const int64_t ext = (a->shape[i] - 1) * a->strides[i];
+    if (ext < 0) lo += ext; else hi += ext;
+  }
+  const size_t es = elem_size(a->encoding);
+  const size_t bytes = (size_t)(hi - lo + 1) * es;
   ctx->input_copy.reserve(bytes);
   // One host-to-device engine per GPU: uploads of different contexts are queued first come first served and each one
   // runs at the full link rate, so the kernels and downloads of one context overlap the upload of the next instead of
   // all contexts uploading (and then computing) in lockstep.
   static std::mutex upload_mutex[64];
   std::lock_guard<std::mutex> lock(upload_mutex[ctx->device & 63]);
-  CK(cudaMemcpyAsync(ctx->input_copy.p, a->base, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->input_copy.p, static_cast<const char*>(a->base) + lo * (int64_t)es, bytes, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  return ctx->input_copy.p;
+  return static_cast<const char*>(ctx->input_copy.p) - lo * (int64_t)es;
 }
 
 struct EncodeJob {
@@ -155,7 +159,7 @@ void launch_encode_v5(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   const u32 stage_limit = std::min<u32>(ctx->opt.stage_limit, (u32)E5_POOL);
   const size_t smem = sizeof(E5Smem) * G;
   CK(cudaFuncSetAttribute(k_encode_v5<G, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_encode_v5<G, FULL><<<(grid + G - 1) / G, E5_THREADS * G, smem, ctx->stream>>>(P, stage_limit, ctx->opt.fast_sync_mask);
+  k_encode_v5<G, FULL><<<(grid + G - 1) / G, E5_THREADS * G, smem, FULL ? ctx->stream : ctx->aux_stream>>>(P, stage_limit, ctx->opt.fast_sync_mask);
   CK(cudaGetLastError());
   ctx->launches++;
 }

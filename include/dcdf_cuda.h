@@ -145,7 +145,8 @@ int32_t dcdf_chunk_block_instants(dcdf_ctx* ctx, const dcdf_chunk* chunk, uint32
 int32_t dcdf_chunk_get_batch(dcdf_ctx* ctx, const dcdf_chunk* chunk, uint64_t n, const int64_t* irc, void* out,
                              int32_t out_encoding, int32_t mem);
 /* Chunk::fill_cell  chunk.rs:135-148, batched: q = n x (start,end,row,col); out_off[n+1] gives the
- * element offset of each series in `out` (exclusive prefix sum of end-start, computed by the caller). */
+ * element offset of each series in `out` (exclusive prefix sum of end-start, computed by the caller).
+ * q and out_off are host arrays; `mem` says where `out` lives (pinned host memory receives at the full PCIe rate). */
 int32_t dcdf_chunk_cell_batch(dcdf_ctx* ctx, const dcdf_chunk* chunk, uint64_t n, const int64_t* q,
                               const uint64_t* out_off, void* out, int32_t out_encoding, int32_t mem);
 /* Chunk::fill_window  chunk.rs:152-158: out is a dense [instants, rows, cols] array */

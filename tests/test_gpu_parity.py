@@ -120,6 +120,24 @@ def test_chunk_build_strided_view_and_device_input(ctx):
     dev = torch.from_numpy(big).cuda()
     got = Chunk.build(ctx, dev[2:11, 5:50, 3:60], fractional_bits=3)
     _diff(got.write_to(), ref.serialize(), "strided device view")
+    # reversed ndarray views have negative strides (mmbuffer.rs:573-594 slices any ArrayViewMut3)
+    for rev in (np.s_[::-1], np.s_[:, ::-1], np.s_[:, :, ::-1], np.s_[::-1, ::-2, ::-1]):
+        v = big[rev]
+        ref = orc.chunk_build(np.ascontiguousarray(v), fractional_bits=3)
+        _diff(Chunk.build(ctx, v, fractional_bits=3).write_to(), ref.serialize(), f"negative strides {rev}")
+    from dcdf_b200 import Superchunk, synth
+    field = synth.raster_slice(0, 9, 150, 200).numpy()
+    for rev in (np.s_[::-1], np.s_[:, ::-1, ::-1]):
+        v = field[rev]
+        sc = Superchunk.build(ctx, v, [2, 6])
+        refs = orc.superchunk_build(np.ascontiguousarray(v), [2, 6])
+        kinds, child = refs.node_refs(0)
+        chunks = sc.chunk_bytes(0)
+        for slot, c in enumerate(child):
+            if kinds[slot]:
+                _diff(chunks[slot], refs.node_bytes(int(c)), f"superchunk over a reversed view, slot {slot}")
+        assert np.array_equal(sc.window(0, 9, 0, 150, 0, 200), v)
+        sc.close()
 
 
 @pytest.mark.parametrize("shape", [(5, 65, 65), (4, 70, 130), (3, 200, 300), (6, 128, 128), (3, 1, 100)])
