@@ -690,8 +690,8 @@ def run_c5(args):
         data = synth.raster(t1i - t0i, rows, cols, device=dev, seed=0xDCDF0005, t_start=t0i)
         torch.cuda.synchronize()
         if not warmed:
-            for _ in range(max(1, args.warmup)):
-                Superchunk.build(ctx, data[:CHUNK_SIZE], levels, compute_bits=True, chunk_size=CHUNK_SIZE).close()
+            for _ in range(max(1, args.warmup)):  # full-size: scratch, arena and result pools reach their final sizes here
+                Superchunk.build(ctx, data, levels, compute_bits=True, chunk_size=CHUNK_SIZE).close()
             warmed = True
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -760,7 +760,7 @@ def main():
     ap.add_argument("--cpu-windows", type=int, default=192)
     ap.add_argument("--variant-instants", type=int, default=512)
     ap.add_argument("--c3-instants", type=int, default=14610)
-    ap.add_argument("--c5-slab-slices", type=int, default=17)
+    ap.add_argument("--c5-slab-slices", type=int, default=18)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

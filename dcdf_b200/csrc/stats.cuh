@@ -806,7 +806,20 @@ struct TreeParams {
   u32* err;
 };
 
-// one CTA per slice; nodes in index order (parents first); one thread per child of the current node
+// order-preserving map of a double onto unsigned integers (shared-memory atomicMin / atomicMax over raw extrema)
+DCDF_DEVINL unsigned long long dbl_key(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+DCDF_DEVINL double key_dbl(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+// one CTA per slice; nodes in index order (parents first).  Per node: the per-instant table entries are computed by one
+// thread per (child, instant) -- a child of the root of a deep tree covers hundreds of leaf tiles -- and folded per child
+// through shared memory; then one thread per child classifies it.
+constexpr int kTreeBatch = 1024;  // children of one node handled per round
 __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n_slices) {
   const u32 s = blockIdx.x;
   if (s >= n_slices) return;
@@ -818,6 +831,8 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
   u32 err = 0;
   u32 n_el = 0, n_st = 0;
   __shared__ int s_slice_failed;
+  __shared__ unsigned long long s_rmin[kTreeBatch], s_rmax[kTreeBatch];
+  __shared__ u8 s_keep[kTreeBatch], s_nan[kTreeBatch];  // some instant has min != max; some cell is NaN
   if (tid == 0) {
     // slice-level compute_fractional_bits (dataset.rs:842): resolve the exact pass and surface its panic, which comes
     // before anything Superchunk::build raises
@@ -844,32 +859,25 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
     i64* tmin = P.tbl_min + sd.table_base + (u64)nd.tbl_off * (u64)sd.instants;
     i64* tmax = P.tbl_max + sd.table_base + (u64)nd.tbl_off * (u64)sd.instants;
     if (alive && !nd.levels_ok) err |= EF_BAD_LEVELS;
-    for (u32 c = tid; c < nd.n_children; c += blockDim.x) {
-      const TreeChild ch = P.children[nd.first_child + c];
-      if (!alive) {
-        if (ch.kind == 1) {
-          const u32 u = sd.unit_base + (u32)ch.index;
-          EncUnit unit = P.units[u];
-          unit.flags |= UF_SKIP;
-          P.units[u] = unit;
-          P.stored[u] = 0;
+   for (u32 c_base = 0; c_base < nd.n_children; c_base += kTreeBatch) {
+    const u32 c_end = min(nd.n_children, c_base + (u32)kTreeBatch);
+    for (u32 i = tid; i < c_end - c_base; i += blockDim.x) {
+      s_rmin[i] = dbl_key(INFINITY); s_rmax[i] = dbl_key(-INFINITY);
+      s_keep[i] = 0; s_nan[i] = 0;
+    }
+    __syncthreads();
+    // ---- per (child, instant): table entries (superchunk.rs:140-151,192-198)
+    if (alive) {
+      const u32 n_items = (c_end - c_base) * (u32)sd.instants;
+      for (u32 item = tid; item < n_items; item += blockDim.x) {
+        const u32 ci = item % (c_end - c_base), c = c_base + ci;
+        const int t = (int)(item / (c_end - c_base));
+        const TreeChild ch = P.children[nd.first_child + c];
+        if (ch.kind == 0) {  // entirely outside the raster: Elided with (0,0) per instant (superchunk.rs:134-139)
+          tmin[(u64)t * nd.n_children + c] = 0; tmax[(u64)t * nd.n_children + c] = 0;
+          continue;
         }
-        continue;
-      }
-      if (ch.kind == 0) {  // entirely outside the raster: Elided with (0,0) per instant (superchunk.rs:134-139)
-        for (int t = 0; t < sd.instants; t++) { tmin[(u64)t * nd.n_children + c] = 0; tmax[(u64)t * nd.n_children + c] = 0; }
-        continue;
-      }
-      // region statistics: combine the leaf tiles the child covers
-      bool has = false, nonfinite = false;
-      double vmax = -INFINITY, vneg = 0.0;
-      int fnn = 0, fng = 0;
-      i64 imax = INT64_MIN, imin = INT64_MAX;
-      bool can_elide = true;
-      bool any_nan = false;                        // some cell of some instant is NaN
-      double rmin = INFINITY, rmax = -INFINITY;    // raw extrema over every instant (fast-path eligibility)
-      const i64 region_cols = (i64)(ch.gc1 - ch.gc0) * P.leaf_side;
-      for (int t = 0; t < sd.instants; t++) {
+        const i64 region_cols = (i64)(ch.gc1 - ch.gc0) * P.leaf_side;
         double mn = INFINITY, mx = -INFINITY;
         i64 lmn = INT64_MAX, lmx = INT64_MIN;
         u64 first = ~0ull, last = 0;
@@ -901,8 +909,8 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
         i64 fmn, fmx;
         if (is_float) {
           const bool all_nan = first == ~0ull;
-          any_nan = any_nan || all_nan || last != 0;
-          rmin = fmin(rmin, mn); rmax = fmax(rmax, mx);
+          if (all_nan || last != 0) s_nan[ci] = 1;
+          if (!all_nan) { atomicMin(&s_rmin[ci], dbl_key(mn)); atomicMax(&s_rmax[ci], dbl_key(mx)); }
           const bool quirk = !all_nan && last > first;  // mmbuffer.rs:485-487
           if (P.encoding == 32) {
             fmn = (all_nan || quirk) ? 0 : to_fixed_dev<float>((float)mn, nbits, round, err);
@@ -916,8 +924,31 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
         }
         tmin[(u64)t * nd.n_children + c] = fmn;
         tmax[(u64)t * nd.n_children + c] = fmx;
-        can_elide = can_elide && fmn == fmx;  // superchunk.rs:145-147
+        if (fmn != fmx) s_keep[ci] = 1;  // superchunk.rs:145-147
       }
+    }
+    __syncthreads();
+    // ---- per child: classification
+    for (u32 c = c_base + tid; c < c_end; c += blockDim.x) {
+      const TreeChild ch = P.children[nd.first_child + c];
+      if (!alive) {
+        if (ch.kind == 1) {
+          const u32 u = sd.unit_base + (u32)ch.index;
+          EncUnit unit = P.units[u];
+          unit.flags |= UF_SKIP;
+          P.units[u] = unit;
+          P.stored[u] = 0;
+        }
+        continue;
+      }
+      if (ch.kind == 0) continue;
+      bool has = false, nonfinite = false;
+      double vmax = -INFINITY, vneg = 0.0;
+      int fnn = 0, fng = 0;
+      i64 imax = INT64_MIN, imin = INT64_MAX;
+      const bool can_elide = s_keep[c - c_base] == 0;
+      const bool any_nan = s_nan[c - c_base] != 0;  // some cell of some instant is NaN
+      const double rmin = key_dbl(s_rmin[c - c_base]), rmax = key_dbl(s_rmax[c - c_base]);  // raw extrema over every instant (fast-path eligibility)
       // unit-level summaries over the covered tiles (for compute_fractional_bits of the child, :167)
       for (int gr = ch.gr0; gr < ch.gr1; gr++)
         for (int gc = ch.gc0; gc < ch.gc1; gc++) {
@@ -995,7 +1026,8 @@ __global__ void __launch_bounds__(256) k_finalize_tree(const TreeParams P, u32 n
         }
       }
     }
-    __syncthreads();  // node states written by this node's children are read by later nodes
+    __syncthreads();  // node states written by this node's children are read by later nodes; the shared accumulators are reused
+   }
   }
   if (n_el) atomicAdd(&P.state[s].n_elided, n_el);
   if (n_st) atomicAdd(&P.state[s].n_stored, n_st);
