@@ -78,8 +78,7 @@ struct E5Tot {
 };
 // Block totals of one candidate and the entry counts of its two DACs (snapshot.rs:71-79, log.rs:77-86): below the
 // level-1 nodes nothing is longer than two bytes, so DAC levels 2 and 3 only hold bytes of the root / level-1 entries.
-DCDF_DEVINL void e5_totals(E5Tot& T, const E5Smem& S, int cand, bool in0, u32 in1m, const int (&e1max)[4], const int (&e1min)[4],
-                           int e0max, int e0min) {
+DCDF_DEVINL void e5_totals(E5Tot& T, const E5Smem& S, int cand, bool in0, u32 in1m, const u32 (&topx)[4], const u32 (&topn)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; i++) T.tot[i] = in0 ? S.wt[0][cand][i] + S.wt[1][cand][i] : 0u;
   T.I0 = in0 ? 1u : 0u;
@@ -91,19 +90,32 @@ DCDF_DEVINL void e5_totals(E5Tot& T, const E5Smem& S, int cand, bool in0, u32 in
   T.cmin[0] = T.n_int;
 #pragma unroll
   for (int j = 1; j < 4; j++) {
-    u32 tm = e4_longer_j(e0max, j) ? 1u : 0u, tn = 0;
-    if (in0) {
-      tn = e4_longer_j(e0min, j) ? 1u : 0u;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        tm += e4_longer_j(e1max[k], j) ? 1u : 0u;
-        tn += (((in1m >> (3 - k)) & 1u) && e4_longer_j(e1min[k], j)) ? 1u : 0u;
-      }
-    }
-    T.cmax[j] = tm + (j == 1 ? e4_fsum(T.tot[1]) + T.tot[2] : 0u);
-    T.cmin[j] = tn + (j == 1 ? e4_fsum(T.tot[3]) : 0u);
+    T.cmax[j] = topx[j] + (j == 1 ? e4_fsum(T.tot[1]) + T.tot[2] : 0u);
+    T.cmin[j] = topn[j] + (j == 1 ? e4_fsum(T.tot[3]) : 0u);
   }
 }
+
+// The root's and the level-1 nodes' entries of one DAC, one per lane: lane 0 = root, lane 1 + k = level-1 node k.  They
+// are the first entries of the DAC in BFS order, hence the first ones of every DAC level they reach: entry -> zigzag
+// code, byte length, position on each level, and the number of top entries per level (dac.rs:109-121).
+struct E5Top {
+  u32 z;
+  int len;       // 0: the entry does not exist
+  u32 pos[4];    // position of the entry's byte j on DAC level j
+  u32 n[4];      // top entries that reach level j
+};
+DCDF_DEVINL void e5_top(E5Top& t, bool valid, int e, u32 lane) {
+  t.z = zigzag32(e);
+  t.len = valid ? 1 + (e4_longer<1>(e) ? 1 : 0) + (e4_longer<2>(e) ? 1 : 0) + (e4_longer<3>(e) ? 1 : 0) : 0;
+  const u32 lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const u32 m = __ballot_sync(0xffffffffu, t.len > j);
+    t.pos[j] = (u32)__popc(m & lt);
+    t.n[j] = (u32)__popc(m);
+  }
+}
+DCDF_DEVINL int e5_lane5(u32 lane, int v0, const int (&v)[4]) { return lane == 0 ? v0 : lane == 1 ? v[0] : lane == 2 ? v[1] : lane == 3 ? v[2] : v[3]; }
 // Number of max-DAC entries longer than one byte that precede this thread's entries of tree level `level` (2..6).
 DCDF_DEVINL u32 e5_base_x(const E5Tot& T, const u32 (&pre)[4], int level) {
   const u32 t = T.tot[1], p = pre[1];
@@ -579,8 +591,14 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
 #pragma unroll
       for (int k = 0; k < 4; k++) { c_e1max[k] = as_log ? l_e1max[k] : e5_dx<FULL>(t0max, n1max[k]); c_e1min[k] = as_log ? l_e1min[k] : e5_dn(n1min[k], t0min); }
       E5Tot Tc;
-      e5_totals(Tc, S, as_log ? 1 : 0, as_log ? l_in0 : s_in0, as_log ? l_in1 : s_in1, c_e1max, c_e1min, as_log ? t0max - s0max : t0max,
-                as_log ? t0min - s0min : t0min);
+      {
+        const bool c_in0 = as_log ? l_in0 : s_in0;
+        const u32 c_in1 = as_log ? l_in1 : s_in1;
+        E5Top tx, tn;
+        e5_top(tx, lane == 0 || (c_in0 && lane < 5), e5_lane5(lane, as_log ? t0max - s0max : t0max, c_e1max), lane);
+        e5_top(tn, c_in0 && (lane == 0 || (lane < 5 && ((c_in1 >> (4 - lane)) & 1u))), e5_lane5(lane, as_log ? t0min - s0min : t0min, c_e1min), lane);
+        e5_totals(Tc, S, as_log ? 1 : 0, c_in0, c_in1, tx.n, tn.n);
+      }
       const u32 size = 13u + bitmap_size(Tc.nm_len) + (as_log ? bitmap_size(Tc.nm_len - Tc.n_int) : 0u) + e4_dac_size(Tc.cmax) + e4_dac_size(Tc.cmin);
       if (as_log) {
         T = Tc;
@@ -610,6 +628,13 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
     const bool in0 = as_snapshot ? s_in0 : l_in0;
     const u32 in1m = as_snapshot ? s_in1 : l_in1;
     const int cand = as_snapshot ? 0 : 1;
+    // this warp's share of the root / level-1 entries: warp 0 the max DAC, warp 1 the min DAC (lane j = entry j)
+    E5Top top;
+    {
+      const bool mn = warp == 1;
+      const bool valid = mn ? (in0 && (lane == 0 || (lane < 5 && ((in1m >> (4 - lane)) & 1u)))) : (lane == 0 || (in0 && lane < 5));
+      e5_top(top, valid, mn ? e5_lane5(lane, e0n, e1n) : e5_lane5(lane, e0x, e1x), lane);
+    }
     const bool staged = my_size <= stage_limit;
     if (tid == 0) {
       const u64 need = ((u64)my_size + 15ull) & ~15ull;
@@ -761,27 +786,27 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
         }
         if ((W.mu >> 10) & 1u) e5_or_bit(xw0, pos);
       }
-      if (tid == 0) {
-        // root and level-1 nodes: nodemap, equal, continuation bits of every DAC level
-        u8* const xw1 = e4_words_of(out, DX.hdr[1], T.cmax[1]);
-        u8* const xw2 = e4_words_of(out, DX.hdr[2], T.cmax[2]);
-        u8* const nw1 = e4_words_of(out, DN.hdr[1], T.cmin[1]);
-        u8* const nw2 = e4_words_of(out, DN.hdr[2], T.cmin[2]);
-        int ex[5] = {e0x, e1x[0], e1x[1], e1x[2], e1x[3]};
-        e5_top_bits(xw0, xw1, xw2, ex, in0 ? 5 : 1);
+      // root and level-1 nodes.  Continuation bits of their DAC entries: warp 0 takes the max DAC, warp 1 the min DAC,
+      // one lane per entry (at most five); nodemap and `equal` bits of these nodes: one thread.
+      {
+        u8* const tw0 = warp == 0 ? xw0 : nw0;
+        u8* const tw1 = warp == 0 ? e4_words_of(out, DX.hdr[1], T.cmax[1]) : e4_words_of(out, DN.hdr[1], T.cmin[1]);
+        u8* const tw2 = warp == 0 ? e4_words_of(out, DX.hdr[2], T.cmax[2]) : e4_words_of(out, DN.hdr[2], T.cmin[2]);
+        if (top.len > 1) e5_or_bit(tw0, top.pos[0]);
+        if (top.len > 2) e5_or_bit(tw1, top.pos[1]);
+        if (top.len > 3) e5_or_bit(tw2, top.pos[2]);
+      }
+      if (tid == E5_THREADS - 1) {
         if (in0) {
           e5_or_bits(nm_words, 0, 0x10u | in1m, 5);
-          int en[5];
-          int nn = 1;
-          en[0] = e0n;
-          u32 accE = 0; int nE = 0;
+          if (!as_snapshot) {
+            u32 accE = 0; int nE = 0;
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            if ((in1m >> (3 - k)) & 1u) en[nn++] = e1n[k];
-            else { accE = (accE << 1) | ((!e4_unif<FULL>(n1max[k], n1min[k]) && ((n1flags >> k) & 1u)) ? 1u : 0u); nE++; }
+            for (int k = 0; k < 4; k++) {
+              if (!((in1m >> (3 - k)) & 1u)) { accE = (accE << 1) | ((!e4_unif<FULL>(n1max[k], n1min[k]) && ((n1flags >> k) & 1u)) ? 1u : 0u); nE++; }
+            }
+            e5_or_bits(eq_words, 0, accE, nE);
           }
-          e5_top_bits(nw0, nw1, nw2, en, nn);
-          if (!as_snapshot) e5_or_bits(eq_words, 0, accE, nE);
         } else if (!as_snapshot && !u0 && eq0) {
           e5_or_bit(eq_words, 0);
         }
@@ -893,25 +918,26 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
           if (zn > 0xffu) e5_hi(nb1, zn, bn2 + e4_f2(pre[3]));
         }
       }
-      if (tid == 0) {
-        // root and level-1 entries (any length), structure header
-        int ex[5] = {e0x, e1x[0], e1x[1], e1x[2], e1x[3]};
-        e5_top_bytes(xb0, xb1, out + DX.bytes[2], out + DX.bytes[3], ex, in0 ? 5 : 1);
-        if (in0) {
-          int en[5];
-          int nn = 1;
-          en[0] = e0n;
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            if ((in1m >> (3 - k)) & 1u) en[nn++] = e1n[k];
-          e5_top_bytes(nb0, nb1, out + DN.bytes[2], out + DN.bytes[3], en, nn);
+      {  // root and level-1 entries (any length): the same lanes as in phase A
+        u8* const tb0 = warp == 0 ? xb0 : nb0;
+        u8* const tb1 = warp == 0 ? xb1 : nb1;
+        u8* const tb2 = out + (warp == 0 ? DX.bytes[2] : DN.bytes[2]);
+        u8* const tb3 = out + (warp == 0 ? DX.bytes[3] : DN.bytes[3]);
+        if (top.len > 0) tb0[top.pos[0]] = (u8)top.z;
+        if (top.len > 1) tb1[top.pos[1]] = (u8)(top.z >> 8);
+        if (top.len > 2) tb2[top.pos[2]] = (u8)(top.z >> 16);
+        if (top.len > 3) tb3[top.pos[3]] = (u8)(top.z >> 24);
+      }
+      if (warp == 1 && lane >= 16) {  // structure header (snapshot.rs:48-52 / log.rs:53-58): k, shape, sidelen; DAC level counts
+        const u32 i = lane - 16u;
+        if (i < 13u) {
+          const u32 word = i < 5u ? (u32)unit.rows : i < 9u ? (u32)unit.cols : 64u;
+          out[i] = i == 0 ? (u8)2 : (u8)(word >> (8u * ((12u - i) & 3u)));
+        } else if (i == 13u) {
+          out[DX.hdr[0] - 1] = (u8)DX.levels;
+        } else if (i == 14u) {
+          out[DN.hdr[0] - 1] = (u8)DN.levels;
         }
-        out[0] = 2;  // k
-        store_be32(out + 1, (u32)unit.rows);
-        store_be32(out + 5, (u32)unit.cols);
-        store_be32(out + 9, 64u);  // sidelen
-        out[DX.hdr[0] - 1] = (u8)DX.levels;
-        out[DN.hdr[0] - 1] = (u8)DN.levels;
       }
     }
     e5_tile_sync(slot);  // B2
