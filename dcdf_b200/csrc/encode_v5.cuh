@@ -166,37 +166,6 @@ DCDF_DEVINL void e5_or_bit(u8* bytes, u32 bitpos) {
   const u32 g = bitpos + 8u * (u32)(A & 3u);
   e4_red_or(reinterpret_cast<u32*>(A & ~(uintptr_t)3) + (g >> 5), e4_bswap(0x80000000u >> (g & 31u)));
 }
-// bits of `src` at the positions where `sel` is set, packed to the right in order (both MSB-first over n entries)
-DCDF_DEVINL u32 e5_compress(u32 src, u32 sel, int n) {
-  u32 out = 0;
-#pragma unroll
-  for (int i = 4; i >= 0; i--)
-    if (i < n && ((sel >> i) & 1u)) out = (out << 1) | ((src >> i) & 1u);
-  return out;
-}
-// The first entries of a DAC are the root's and the level-1 nodes' (BFS order), so their continuation bits are the
-// first bits of every level's bitmap: three short runs per DAC instead of one call per bit.  e[i], i < n (n <= 5).
-__device__ __noinline__ void e5_top_bits(u8* w0, u8* w1, u8* w2, const int* e, int n) {
-  u32 m1 = 0, m2 = 0, m3 = 0;  // entry i = bit n-1-i: longer than 1 / 2 / 3 bytes
-  for (int i = 0; i < n; i++) {
-    m1 = (m1 << 1) | (e4_longer<1>(e[i]) ? 1u : 0u);
-    m2 = (m2 << 1) | (e4_longer<2>(e[i]) ? 1u : 0u);
-    m3 = (m3 << 1) | (e4_longer<3>(e[i]) ? 1u : 0u);
-  }
-  e5_or_bits(w0, 0, m1, n);
-  if (m2) e5_or_bits(w1, 0, e5_compress(m2, m1, n), __popc(m1));
-  if (m3) e5_or_bits(w2, 0, e5_compress(m3, m2, n), __popc(m2));
-}
-// ... and their bytes are the first bytes of every level (dac.rs:109-121)
-__device__ __noinline__ void e5_top_bytes(u8* b0, u8* b1, u8* b2, u8* b3, const int* e, int n) {
-  u32 r1 = 0, r2 = 0, r3 = 0;
-  for (int i = 0; i < n; i++) {
-    const u32 z = zigzag32(e[i]);
-    b0[i] = (u8)z;
-    if (z > 0xffu) e4_emit_hi(b1, b2, b3, z, r1, r2, r3);
-  }
-}
-
 // to_fixed (a3) of an exact, finite, small value: n * 2^(bits+1) is an integer below 2^22, so adding 1.5 * 2^23
 // leaves it in the low mantissa bits (fixed.rs:59-70: trunc(2 * shifted) + 1).
 DCDF_DEVINL int e5_conv(float x, float scale2) {
@@ -636,13 +605,19 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
       e5_top(top, valid, mn ? e5_lane5(lane, e0n, e1n) : e5_lane5(lane, e0x, e1x), lane);
     }
     const bool staged = my_size <= stage_limit;
+    // The piece's place in the arena: the atomic's round trip is long, so a staged structure only looks at the answer
+    // when its image is complete (a warp stalls at the first instruction that needs a pending result).
+    u64 my_off = 0;
+    auto publish_piece = [&]() {
+      S.piece_off = my_off;
+      Piece pc;
+      pc.off = my_off; pc.size = my_size; pc.kind = as_snapshot ? 1u : 0u;
+      P.pieces[unit.piece_base + inst] = pc;
+    };
     if (tid == 0) {
       const u64 need = ((u64)my_size + 15ull) & ~15ull;
-      const u64 off = atomicAdd(P.arena_head, (unsigned long long)need);
-      S.piece_off = off;
-      Piece pc;
-      pc.off = off; pc.size = my_size; pc.kind = as_snapshot ? 1u : 0u;
-      P.pieces[unit.piece_base + inst] = pc;
+      my_off = atomicAdd(P.arena_head, (unsigned long long)need);
+      if (!staged) publish_piece();
     }
     // stream layout (snapshot.rs:48-58 / log.rs:53-64)
     const u32 eq_len = nm_len - n_int;
@@ -983,6 +958,7 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
         }
       }
     }
+    if (decltype(in_shared)::value && tid == 0) publish_piece();
     e5_tile_sync(slot);  // B3
 
     // ================= copy-out (re-aligning by `shift` bytes) and re-zero the image =================
