@@ -103,6 +103,52 @@ __device__ __noinline__ Quad<V> dac_get4_slow(const u8* chunk, const DacDir* d, 
   }
   return q;
 }
+// Four consecutive entries idx .. idx + 3 <= len0 of which some are longer than one byte (nib: continuation bits of
+// level 0, bit 3 = entry idx).  The entries that continue sit next to each other on the next level as well, so every
+// level costs ONE rank over the serialized directory (bitmap.rs:186-212) for the whole group, not one per entry
+// (dac.rs:80-93 per entry would).
+template <typename V>
+__device__ __noinline__ Quad<V> dac_get4_multi(const u8* chunk, const DacDir* d, u32 idx, u32 nib) {
+  u64 n0, n1, n2, n3;
+  {
+    const u32 len = d->len[0], words = d->base[0] + 8u + 4u * (len / 128u);
+    const u8* b = chunk + words + 4u * ((len + 31u) / 32u) + idx;
+    n0 = b[0]; n1 = b[1]; n2 = b[2]; n3 = b[3];
+  }
+  u32 cont = nib & 15u;  // bit 3 - i: entry i continues on the next level
+  u32 p = idx;           // position of the group's first entry on the current level
+  const u32 nl = d->n_levels;
+#pragma unroll 1
+  for (u32 j = 1; j < nl && cont; j++) {
+    const BitMapRef up{chunk, d->len[j - 1], d->base[j - 1]};
+    // the first continuing entry of the group sits at p + (entries before it that stopped); ones before it = ones before p
+    // only if nothing between p and it is set, which holds: the entries in between did not continue
+    const u32 r = up.rank(p);
+    const u32 len = d->len[j], words = d->base[j] + 8u + 4u * (len / 128u);
+    const u8* bytes = chunk + words + 4u * ((len + 31u) / 32u);
+    const u8* more = chunk + words;
+    const bool last = j + 1u >= nl;
+    u32 next = 0, k = 0;
+    const u32 sh = 8u * j;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if ((cont >> (3 - i)) & 1u) {
+        const u32 pos = r + k;
+        k++;
+        if (pos < len) {  // malformed input guard
+          const u64 byte = bytes[pos];
+          if (i == 0) n0 |= byte << sh; else if (i == 1) n1 |= byte << sh; else if (i == 2) n2 |= byte << sh; else n3 |= byte << sh;
+          if (!last && ((more[pos >> 3] >> (7u - (pos & 7u))) & 1u)) next |= 1u << (3 - i);
+        }
+      }
+    }
+    cont = next;
+    p = r;
+  }
+  Quad<V> q;
+  q.c[0] = (V)unzigzag64(n0); q.c[1] = (V)unzigzag64(n1); q.c[2] = (V)unzigzag64(n2); q.c[3] = (V)unzigzag64(n3);
+  return q;
+}
 template <typename V>
 DCDF_DEVINL void dac_get4(const Dac4& m, u32 idx, V (&d)[4]) {
   u32 nib = 1;
@@ -116,7 +162,7 @@ DCDF_DEVINL void dac_get4(const Dac4& m, u32 idx, V (&d)[4]) {
 #pragma unroll
     for (int i = 0; i < 4; i++) d[i] = unzz8<V>(b[i]);
   } else {
-    const Quad<V> q = dac_get4_slow<V>(m.chunk, m.d, idx);
+    const Quad<V> q = idx + 4u <= m.len0 ? dac_get4_multi<V>(m.chunk, m.d, idx, nib) : dac_get4_slow<V>(m.chunk, m.d, idx);
 #pragma unroll
     for (int i = 0; i < 4; i++) d[i] = q.c[i];
   }
