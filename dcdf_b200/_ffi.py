@@ -116,6 +116,7 @@ def _declare(lib):
         "dcdf_saved_count": (i32, [vp, _P(u32)]),
         "dcdf_saved_node": (i32, [vp, u32, vp, _P(i32), _P(u64)]),
         "dcdf_saved_node_bytes": (i32, [vp, vp, u32, vp, u64, i32]),
+        "dcdf_saved_all_bytes": (i32, [vp, vp, vp, u64, vp]),
         "dcdf_saved_stats": (i32, [vp, _P(BuildStats)]),
         "dcdf_superchunk_open": (i32, [vp, u32, vp, FETCH_FN, vp, _P(vp)]),
     }

@@ -383,14 +383,17 @@ class Superchunk(_Queryable):
         try:
             n = C.c_uint32()
             self.ctx.check(lib.dcdf_saved_count(h, C.byref(n)))
+            offs = np.zeros(n.value + 1, np.uint64)
+            self.ctx.check(lib.dcdf_saved_all_bytes(self.ctx._h, h, None, 0, _ptr(offs)))
+            buf = np.empty(max(int(offs[-1]), 1), np.uint8)
+            self.ctx.check(lib.dcdf_saved_all_bytes(self.ctx._h, h, _ptr(buf), int(offs[-1]), _ptr(offs)))  # one transfer
+            view = memoryview(buf)
             nodes = []
+            cid = np.zeros(_ffi.CID_BYTES, np.uint8)
+            t, size = C.c_int32(), C.c_uint64()
             for i in range(n.value):
-                cid = np.zeros(_ffi.CID_BYTES, np.uint8)
-                t, size = C.c_int32(), C.c_uint64()
                 self.ctx.check(lib.dcdf_saved_node(h, i, _ptr(cid), C.byref(t), C.byref(size)))
-                buf = np.empty(max(size.value, 1), np.uint8)
-                self.ctx.check(lib.dcdf_saved_node_bytes(self.ctx._h, h, i, _ptr(buf), size.value, MEM_HOST))
-                nodes.append((cid.tobytes(), t.value, buf[:size.value].tobytes()))
+                nodes.append((cid.tobytes(), t.value, bytes(view[int(offs[i]):int(offs[i + 1])])))
             st = BuildStats()
             self.ctx.check(lib.dcdf_saved_stats(h, C.byref(st)))
             stats = dict(size=st.size, elided=st.elided, local=st.local, external=st.external, snapshots=st.snapshots, logs=st.logs)

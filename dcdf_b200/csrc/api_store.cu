@@ -128,7 +128,7 @@ void ensure_digests(dcdf_ctx* ctx, const dcdf_superchunk* scc) {
   ctx->query_in.reserve(sizeof(HashJob) * jobs.size());
   ctx->query_out.reserve(32 * jobs.size());
   CK(cudaMemcpyAsync(ctx->query_in.p, jobs.data(), sizeof(HashJob) * jobs.size(), cudaMemcpyHostToDevice, st));
-  k_sha256<<<(unsigned)((jobs.size() + 63) / 64), 64, 0, st>>>(sc->chunk_blob, ctx->query_in.as<HashJob>(), (u32)jobs.size(), ctx->query_out.as<u8>());
+  k_sha256<<<(unsigned)((jobs.size() + 31) / 32), 32, 0, st>>>(sc->chunk_blob, ctx->query_in.as<HashJob>(), (u32)jobs.size(), ctx->query_out.as<u8>());
   CK(cudaGetLastError());
   ctx->launches++;
   std::vector<uint8_t> dig(32 * jobs.size());
@@ -326,6 +326,29 @@ int32_t dcdf_saved_node_bytes(dcdf_ctx* ctx, const dcdf_saved* s, uint32_t i, ui
     if (n.dev_len)
       CK(cudaMemcpyAsync(dst + n.bytes.size(), s->sc->chunk_blob + n.dev_off, n.dev_len, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                          ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int32_t dcdf_saved_all_bytes(dcdf_ctx* ctx, const dcdf_saved* s, uint8_t* dst, uint64_t cap, uint64_t* offsets) {
+  return guarded(ctx, [&] {
+    if (!s || !offsets) api_fail(DCDF_ERR_BAD_ARG, "null saved object / offsets");
+    uint64_t total = 0;
+    for (size_t i = 0; i < s->nodes.size(); i++) {
+      const SavedNode& n = s->nodes[i];
+      offsets[i] = total;
+      total += n.bytes.size() + n.dev_len;
+    }
+    offsets[s->nodes.size()] = total;
+    if (!dst) return;
+    if (cap < total) api_fail(DCDF_ERR_BAD_ARG, "destination too small: need %llu bytes", (unsigned long long)total);
+    // every device-resident part is queued without waiting in between; one wait at the end
+    for (size_t i = 0; i < s->nodes.size(); i++) {
+      const SavedNode& n = s->nodes[i];
+      uint8_t* d = dst + offsets[i];
+      if (!n.bytes.empty()) memcpy(d, n.bytes.data(), n.bytes.size());
+      if (n.dev_len) CK(cudaMemcpyAsync(d + n.bytes.size(), s->sc->chunk_blob + n.dev_off, n.dev_len, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
   });
 }

@@ -247,6 +247,10 @@ int32_t dcdf_saved_count(const dcdf_saved* saved, uint32_t* n_nodes);
 int32_t dcdf_saved_node(const dcdf_saved* saved, uint32_t i, uint8_t* cid /* DCDF_CID_BYTES */, int32_t* node_type, uint64_t* size);
 /* The stored bytes of object i (header included), into host or device memory. */
 int32_t dcdf_saved_node_bytes(dcdf_ctx* ctx, const dcdf_saved* saved, uint32_t i, uint8_t* dst, uint64_t cap, int32_t mem);
+/* Every object's stored bytes back to back in object order (what a StoreWrite loop would write, mapper.rs:19-38) with one
+ * wait for all device-to-host transfers; offsets[i] .. offsets[i + 1] is object i (offsets has n_nodes + 1 entries).  dst == NULL only
+ * fills offsets (offsets[n_nodes] = bytes needed). */
+int32_t dcdf_saved_all_bytes(dcdf_ctx* ctx, const dcdf_saved* saved, uint8_t* dst, uint64_t cap, uint64_t* offsets);
 int32_t dcdf_saved_stats(const dcdf_saved* saved, dcdf_build_stats* stats);
 
 /* Mapper::load stand-in (mapper.rs:10-38): hand out the stored bytes of a node; they must stay valid until the call that

@@ -158,3 +158,26 @@ def test_open_rejects_damaged_or_missing_objects(ctx):
             Superchunk.open(ctx, [root], st)
         assert e.value.code == code, (what, e.value)
     Superchunk.open(ctx, [root], store).close()
+
+
+def test_single_object_fetch_matches_the_bulk_transfer(ctx):
+    """dcdf_saved_node_bytes (one object, host or device destination) against dcdf_saved_all_bytes."""
+    import ctypes as C
+    from dcdf_b200 import Superchunk, _ffi
+    rng = np.random.default_rng(5)
+    data = (rng.integers(0, 50, (24, 100, 130)) / 4).astype(np.float32)
+    sc = Superchunk.build(ctx, data, [2, 6], compute_bits=True, chunk_size=8)
+    nodes, _ = sc.save(1)
+    lib = ctx._lib
+    h = C.c_void_p()
+    ctx.check(lib.dcdf_superchunk_save(ctx._h, sc._h, 1, C.byref(h)))
+    try:
+        for i in (0, len(nodes) // 2, len(nodes) - 1):
+            buf = np.zeros(len(nodes[i][2]), np.uint8)
+            ctx.check(lib.dcdf_saved_node_bytes(ctx._h, h, i, buf.ctypes.data_as(C.c_void_p), len(buf), 0))
+            assert buf.tobytes() == nodes[i][2]
+        small = np.zeros(3, np.uint8)
+        assert lib.dcdf_saved_node_bytes(ctx._h, h, 0, small.ctypes.data_as(C.c_void_p), 3, 0) != 0   # destination too small
+    finally:
+        lib.dcdf_saved_free(h)
+    sc.close()
