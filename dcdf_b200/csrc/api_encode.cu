@@ -153,9 +153,23 @@ void launch_encode_v4(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   ctx->launches++;
 }
 // Full f32 tiles that qualify for the small fast-path kernel (encode_v5.cuh; list 5, filled by k_finalize_tree).
+// Measurement variants (ctx option fast_variant): 1 = four tiles per CTA, 2 = four tiles per CTA with the instant's tile
+// staged in shared memory by bulk copies behind an mbarrier (the TMA unit's 1-D form).
+template <int G, bool BULK>
+void launch_encode_v5_variant(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
+  const u32 stage_limit = std::min<u32>(ctx->opt.stage_limit, (u32)E5_POOL);
+  const size_t smem = (sizeof(E5Smem) + (BULK ? sizeof(E5Bulk) : 0)) * G;
+  CK(cudaFuncSetAttribute(k_encode_v5<G, true, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_encode_v5<G, true, BULK><<<(grid + G - 1) / G, E5_THREADS * G, smem, ctx->stream>>>(P, stage_limit, ctx->opt.fast_sync_mask);
+  CK(cudaGetLastError());
+  ctx->launches++;
+}
 template <bool FULL>
 void launch_encode_v5(dcdf_ctx* ctx, const EncParams& P, u32 grid) {
   constexpr int G = 6;  // tiles per CTA, one CTA per SM
+  if (FULL && ctx->opt.fast_variant == 1) return launch_encode_v5_variant<4, false>(ctx, P, grid);
+  if (FULL && ctx->opt.fast_variant == 2 && ((P.stride_r | P.stride_t) & 3) == 0 && (((uintptr_t)P.data + 4 * 0) & 15) == 0)
+    return launch_encode_v5_variant<4, true>(ctx, P, grid);
   const u32 stage_limit = std::min<u32>(ctx->opt.stage_limit, (u32)E5_POOL);
   const size_t smem = sizeof(E5Smem) * G;
   CK(cudaFuncSetAttribute(k_encode_v5<G, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -877,6 +891,7 @@ int32_t dcdf_ctx_set_option(dcdf_ctx* ctx, const char* name, int64_t value) {
   else if (n == "encode_tiles256") ctx->opt.encode_tiles256 = value != 0;
   else if (n == "no_fast_encode") ctx->opt.no_fast_encode = value != 0;
   else if (n == "fast_sync_mask") ctx->opt.fast_sync_mask = (int)value;
+  else if (n == "fast_variant") ctx->opt.fast_variant = (int)value;
   else if (n == "window_cells") ctx->opt.window_cells = value != 0;
   else if (n == "window_wide") ctx->opt.window_wide = value != 0;
   else if (n == "search_dfs") ctx->opt.search_dfs = value != 0;

@@ -177,12 +177,15 @@ DCDF_DEVINL int e5_conv(float x, float scale2) {
 // Clipped tiles (FULL == false): rl / cl = rows / columns of the node that lie inside the raster (may be <= 0); cells
 // outside are not read and become None (E4_NONE, as in encode_v4.cuh: excluded from min / max, 0 in an entry).
 template <bool FULL>
-DCDF_DEVINL void e5_load_node(const float* pn, i64 sr, uint4 (&raw)[4], int rl, int cl, bool vec) {
+DCDF_DEVINL void e5_load_node(const float* pn, i64 sr, uint4 (&raw)[4], int rl, int cl, int vec) {
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     if (FULL || (r < rl && cl >= 4)) {
       const float* pr = pn + (i64)r * sr;
-      if (vec) {
+      if (vec == 2) {  // the instant's tile sits in shared memory (bulk-copy variant)
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw[r].x), "=r"(raw[r].y), "=r"(raw[r].z), "=r"(raw[r].w)
+                     : "r"((u32)__cvta_generic_to_shared(pr)));
+      } else if (vec) {
         raw[r] = __ldg(reinterpret_cast<const uint4*>(pr));
       } else {  // rows that are not 16-byte aligned (e.g. 1405 columns): four 32-bit loads
         raw[r] = make_uint4(__float_as_uint(__ldg(pr)), __float_as_uint(__ldg(pr + 1)), __float_as_uint(__ldg(pr + 2)), __float_as_uint(__ldg(pr + 3)));
@@ -243,7 +246,7 @@ DCDF_DEVINL void e5_store_word(u8* p, u32 w) {
 // node, the snapshot's from shared memory.  Snapshot: the emission pass has just stored the cells in shared memory.
 template <bool FULL>
 __device__ __noinline__ void e5_long_node(bool as_snapshot, const float* pn, i64 sr, float scale2, const int4* scell, int2 n4, u32 in5a,
-                                          u8* xb1, u8* nb1, u32* pos /* lx1, rx1, rn1 */, int rl, int cl, bool vec) {
+                                          u8* xb1, u8* nb1, u32* pos /* lx1, rx1, rn1 */, int rl, int cl, int vec) {
   int4 q[4];
   if (!as_snapshot) {
     uint4 raw[4];
@@ -279,6 +282,35 @@ __device__ __noinline__ void e5_long_node(bool as_snapshot, const float* pn, i64
   pos[0] = lx1; pos[1] = rx1; pos[2] = rn1;
 }
 
+// mbarrier + bulk copy (the TMA unit's 1-D form) for the BULK variant of the kernel
+DCDF_DEVINL u32 e5_smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+DCDF_DEVINL void e5_mbar_init(unsigned long long* b, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(e5_smem_u32(b)), "r"(count) : "memory");
+}
+DCDF_DEVINL void e5_mbar_expect_tx(unsigned long long* b, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(e5_smem_u32(b)), "r"(bytes) : "memory");
+}
+DCDF_DEVINL void e5_mbar_wait(unsigned long long* b, u32 parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "E5_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra E5_DONE;\n\t"
+      "bra E5_WAIT;\n\t"
+      "E5_DONE:\n\t}" ::"r"(e5_smem_u32(b)), "r"(parity) : "memory");
+}
+DCDF_DEVINL void e5_bulk_g2s(void* smem, const void* g, u32 bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(e5_smem_u32(smem)),
+               "l"(g), "r"(bytes), "r"(e5_smem_u32(b))
+               : "memory");
+}
+// BULK variant: the instant's 64x64 f32 tile, row-major, filled by 64 bulk copies (one row each) behind an mbarrier
+struct E5Bulk {
+  __align__(16) float raw[64 * 64];
+  __align__(8) unsigned long long mbar;
+  unsigned long long pad_;
+};
+
 // barrier over the 64 threads of one tile (named barrier 1 + tile slot; barrier 0 stays the CTA-wide one)
 DCDF_DEVINL void e5_tile_sync(int slot) { asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory"); }
 
@@ -286,12 +318,21 @@ DCDF_DEVINL void e5_tile_sync(int slot) { asm volatile("bar.sync %0, 64;" ::"r"(
 // what they share is the instruction stream: one CTA-wide barrier per instant keeps all 2G warps of the SM inside the
 // same stretch of code, so instruction-cache lines fetched for one warp are hits for the others (with unsynchronised
 // CTAs the kernel spent a quarter of its issue slots waiting for instruction fetches).
-template <int G, bool FULL>
+template <int G, bool FULL, bool BULK>
+DCDF_DEVINL void e5_body(const EncParams& P, const u32 stage_limit, const int sync_mask);
+template <int G, bool FULL, bool BULK = false>
 __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams P, const u32 stage_limit, const int sync_mask) {
-  const bool vec = ((P.stride_r | P.stride_t) & 3) == 0 && (((uintptr_t)P.data) & 15) == 0;  // every row of four cells is 16-byte aligned
+  e5_body<G, FULL, BULK>(P, stage_limit, sync_mask);
+}
+template <int G, bool FULL, bool BULK>
+DCDF_DEVINL void e5_body(const EncParams& P, const u32 stage_limit, const int sync_mask) {
+  // every row of four cells is 16-byte aligned -> 128-bit loads; BULK (host checked the alignment): loads from the staged tile
+  const int vec = BULK ? 2 : (((P.stride_r | P.stride_t) & 3) == 0 && (((uintptr_t)P.data) & 15) == 0) ? 1 : 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int slot = threadIdx.x / E5_THREADS;
-  E5Smem& S = *reinterpret_cast<E5Smem*>(smem_raw + (size_t)slot * sizeof(E5Smem));
+  constexpr size_t kSlab = sizeof(E5Smem) + (BULK ? sizeof(E5Bulk) : 0);
+  E5Smem& S = *reinterpret_cast<E5Smem*>(smem_raw + (size_t)slot * kSlab);
+  E5Bulk& SB = *reinterpret_cast<E5Bulk*>(smem_raw + (size_t)slot * kSlab + sizeof(E5Smem));  // only touched when BULK
 
   const u32 n_order = *P.order_count;
   if (blockIdx.x * (u32)G >= n_order) return;
@@ -308,9 +349,24 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
   }
   const int tid = threadIdx.x % E5_THREADS, lane = tid & 31, warp = tid >> 5;
   const float scale2 = (float)((i64)2 << unit.bits);
-  const i64 sr = P.stride_r;
+  const i64 sr = BULK ? 64 : P.stride_r;
   // the thread's 8x8 block
-  const float* const base = static_cast<const float*>(P.data) + unit.base + (i64)(8 * (int)morton_row(tid)) * sr + 8 * (int)morton_col(tid);
+  const float* const base = BULK ? SB.raw + (8 * (int)morton_row(tid)) * 64 + 8 * (int)morton_col(tid)
+                                 : static_cast<const float*>(P.data) + unit.base + (i64)(8 * (int)morton_row(tid)) * sr + 8 * (int)morton_col(tid);
+  // BULK: thread r fetches row r of the tile (256 bytes) of one instant
+  const float* const my_row = static_cast<const float*>(P.data) + unit.base + (i64)tid * P.stride_r;
+  auto fetch_instant = [&](int t) {
+    if (tid == 0) e5_mbar_expect_tx(&SB.mbar, 64u * 256u);
+    e5_bulk_g2s(SB.raw + 64 * tid, my_row + (i64)t * P.stride_t, 256u, &SB.mbar);
+  };
+  if (BULK) {
+    if (tid == 0) {
+      e5_mbar_init(&SB.mbar, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    e5_tile_sync(slot);
+    if (unit.instants > 0) fetch_instant(0);
+  }
   const bool owner2 = (lane & 3) == 0;
   const int k1 = tid >> 4;  // own level-1 node
   // rows / columns of the raster left from the origin of the thread's level-4 node a (clipped tiles)
@@ -337,8 +393,9 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
     if ((inst & sync_mask) == 0) __syncthreads();  // all tiles of the CTA start the instant together (shared instruction stream)
     if (inst >= unit.instants) continue;
     const bool first = inst == 0;
-    const float* const pt = base + (i64)inst * P.stride_t;
-    if (inst + 1 < unit.instants) {  // the next instant's cells on their way into L2 (the tiles of a CTA all load at once)
+    const float* const pt = BULK ? base : base + (i64)inst * P.stride_t;
+    if (BULK) e5_mbar_wait(&SB.mbar, (u32)inst & 1u);  // the instant's tile has landed
+    if (!BULK && inst + 1 < unit.instants) {  // the next instant's cells on their way into L2 (the tiles of a CTA all load at once)
 #pragma unroll
       for (int r = 0; r < 8; r++)
         if (FULL || (r < rl8 && cl8 > 0)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + P.stride_t + (i64)r * sr));
@@ -916,6 +973,8 @@ __global__ void __launch_bounds__(E5_THREADS * G, 1) k_encode_v5(const EncParams
       }
     }
     e5_tile_sync(slot);  // B2
+    // BULK: nobody reads the staged tile any more -> the next instant's rows start coming in behind the rank directories
+    if (BULK && inst + 1 < unit.instants) fetch_instant(inst + 1);
 
     if (emit) {
       // ================= bitmap headers and rank directories: index[b] = ones in bits [0, 128(b+1))  (bitmap.rs:97-104)

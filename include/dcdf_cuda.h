@@ -88,6 +88,9 @@ int32_t dcdf_ctx_set_stream(dcdf_ctx* ctx, void* cuda_stream);
  *   "arena_hint"  <bytes>   first size of the encoder's output arena (grown and retried when it overflows)
  *   "no_fast_encode" 0|1    eligible full f32 tiles through the general encoder instead of the fast-path kernel
  *   "encode_tiles256" 0|1   full 64x64 tiles through the 256-thread tile encoder
+ *   "fast_variant" 0|1|2    fast-path kernel launches for A/B runs: 1 = four tiles per CTA (255 registers), 2 = four tiles
+ *                           per CTA with every instant's tile staged in shared memory by bulk copies behind an mbarrier
+ *   "fast_sync_mask" <m>    fast-path kernel: the tiles of a CTA re-align every (m + 1) instants (default 3)
  *   "window_cells" 0|1      windows through the per-cell walker (the path of trees larger than 64x64)
  *   "window_wide" 0|1       64-bit tile expansion even when every DAC code fits three bytes
  *   "search_dfs" 0|1        depth-first search kernel instead of the tile search

@@ -21,6 +21,9 @@ for i in range(4):
     best = min(best, ms)
     n = ctx.get_stat("encode_units_fast"), ctx.get_stat("encode_units_general")
     tb = sc.total_bytes()
+    if i == 3:
+        out = sc.window(0, min(T, 128), 0, 704, 0, 1408, out=torch.empty_like(data[:min(T, 128)]))
+        ok = bool(torch.equal(out, data[:min(T, 128)]))
     sc.close()
 units = (T + 63) // 64 * 242
-print(f"encode ms {best:.3f}  units fast/general {n}  tile-instants/ms {242 * T / best:.0f}  bytes {tb}  ratio {tb / data.numel() / 4:.3f}")
+print(f"encode ms {best:.3f}  units fast/general {n}  tile-instants/ms {242 * T / best:.0f}  bytes {tb}  ratio {tb / data.numel() / 4:.3f}  round trip {ok}")

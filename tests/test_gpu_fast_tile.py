@@ -12,16 +12,19 @@ from test_gpu_parity import _check_superchunk
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["staged", "direct", "general"])
+@pytest.fixture(scope="module", params=["staged", "direct", "general", "bulk"])
 def ctx(request):
     """staged: default; direct: stage_limit = 0 sends every structure straight into the arena; general: the same
-    inputs through the general encoder (no_fast_encode), which must give the same bytes."""
+    inputs through the general encoder (no_fast_encode), which must give the same bytes; bulk: the measurement variant
+    that stages every instant's tile in shared memory with bulk copies behind an mbarrier (fast_variant = 2)."""
     from dcdf_b200 import Context
     c = Context(0)
     if request.param == "direct":
         c.set_option("stage_limit", 0)
     if request.param == "general":
         c.set_option("no_fast_encode", 1)
+    if request.param == "bulk":
+        c.set_option("fast_variant", 2)
     c.general = request.param == "general"
     yield c
     c.close()
