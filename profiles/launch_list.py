@@ -5,7 +5,7 @@ agg = {}
 for r in rows:
     name, val, unit = r[4], float(r[14].replace(",", "")), r[13]
     us = val / 1e3 if unit in ("ns", "nsecond") else val * 1e3 if unit in ("ms", "msecond") else val
-    m = re.search(r"dcdf::(\w+(?:<[^(]*>)?)", name)
+    m = re.search(r"(?:dcdf::)?\b(kb?_\w+(?:<[^(]*>)?)", name)  # this library's kernels are k_* / kb_* (with or without the namespace)
     key = "dcdf::" + m.group(1) if m else "torch kernels (synthetic generator / comparison, not part of the path)"
     a = agg.setdefault(key, [0.0, 0])
     a[0] += us; a[1] += 1

@@ -7,11 +7,14 @@ from dcdf_b200 import Context, Superchunk, synth, _ffi
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 704
 kw = {}
 opts = []
+R, Cc = 704, 1408
 for a in sys.argv[2:]:
     k, v = a.split("=")
     if k in ("noise_every", "noise_mask"): kw[k] = int(v)
+    elif k == "rows": R = int(v)
+    elif k == "cols": Cc = int(v)
     else: opts.append((k, int(v)))
-data = synth.raster(T, 704, 1408, device="cuda", **kw)
+data = synth.raster(T, R, Cc, device="cuda", **kw)
 ctx = Context(0)
 for k, v in opts: ctx.set_option(k, v)
 best = 1e9
@@ -22,8 +25,8 @@ for i in range(4):
     n = ctx.get_stat("encode_units_fast"), ctx.get_stat("encode_units_general")
     tb = sc.total_bytes()
     if i == 3:
-        out = sc.window(0, min(T, 128), 0, 704, 0, 1408, out=torch.empty_like(data[:min(T, 128)]))
+        out = sc.window(0, min(T, 128), 0, R, 0, Cc, out=torch.empty_like(data[:min(T, 128)]))
         ok = bool(torch.equal(out, data[:min(T, 128)]))
     sc.close()
-units = (T + 63) // 64 * 242
-print(f"encode ms {best:.3f}  units fast/general {n}  tile-instants/ms {242 * T / best:.0f}  bytes {tb}  ratio {tb / data.numel() / 4:.3f}  round trip {ok}")
+n_tiles = ((R + 63) // 64) * ((Cc + 63) // 64)
+print(f"encode ms {best:.3f}  units fast/general {n}  tile-instants/ms {n_tiles * T / best:.0f}  bytes {tb}  ratio {tb / data.numel() / 4:.3f}  round trip {ok}")
