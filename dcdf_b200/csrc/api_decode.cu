@@ -363,11 +363,35 @@ void do_cell_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const int64_t* q, c
     longest = std::max(longest, e - s);
   }
   const size_t total = out_off[n];
+  // Series of one subchunk are walked next to each other (the kernel takes queries in array order): at any instant they
+  // descend the same structure, so its upper levels are read from DRAM once and then from L2.  Only the order of the work
+  // changes: every series still lands at its own out_off.
+  std::vector<uint32_t> order(n);
+  for (uint64_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+  if (n > 1 && n <= 0xffffffffull) {
+    const i64 cs = mb->Q.chunks_sidelen;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      const i64 ra = qq[4 * a + 2], ca = qq[4 * a + 3], rb = qq[4 * b + 2], cb = qq[4 * b + 3];
+      const i64 ta = (ra / cs) * (i64)mb->Q.subsidelen + ca / cs, tb = (rb / cs) * (i64)mb->Q.subsidelen + cb / cs;
+      if (ta != tb) return ta < tb;
+      if (ra != rb) return ra < rb;
+      if (ca != cb) return ca < cb;
+      return a < b;
+    });
+  }
+  std::vector<i64> qs(4 * n);
+  std::vector<u64> bases(n + 1);
+  for (uint64_t j = 0; j < n; j++) {
+    const uint32_t i = order[j];
+    for (int k = 0; k < 4; k++) qs[4 * j + k] = qq[4 * i + k];
+    bases[j] = out_off[i];
+  }
+  bases[n] = out_off[n];
   ctx->query_in.reserve(sizeof(i64) * 4 * n + sizeof(u64) * (n + 1));
   i64* d_q = ctx->query_in.as<i64>();
   u64* d_off = reinterpret_cast<u64*>(d_q + 4 * n);
-  CK(cudaMemcpyAsync(d_q, qq.data(), sizeof(i64) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_off, out_off, sizeof(u64) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_q, qs.data(), sizeof(i64) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_off, bases.data(), sizeof(u64) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
   OutTarget ot = out_begin(ctx, out, os.esize * total, mem);
   dim3 grid((unsigned)std::min<i64>((longest + 127) / 128, 1024), (unsigned)std::min<uint64_t>(n, 65535));
   tbegin(ctx, KT_CELL);
@@ -375,7 +399,7 @@ void do_cell_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const int64_t* q, c
   CK(cudaGetLastError());
   ctx->launches++;
   tend(ctx, KT_CELL);
-  out_end(ctx, ot);  // qq stays alive until here
+  out_end(ctx, ot);  // qs / bases stay alive until here
   tcollect(ctx, KT_CELL);
 }
 

@@ -96,14 +96,37 @@ struct BitMapRef {
     const u32 w = be32_at(chunk, words_off() + 4u * (i >> 5));
     return (w >> (31u - (i & 31u))) & 1u;
   }
-  DCDF_DEVINL u32 rank(u32 i) const {  // bitmap.rs:186-212: ones in [0, i)
-    const u32 block = i / 128u;
-    u32 count = block > 0 ? be32_at(chunk, base + 8u + 4u * (block - 1u)) : 0u;
-    const u32 wo = words_off();
-    const u32 end = i >> 5;
-    for (u32 w = block * 4u; w < end; w++) count += __popc(be32_at(chunk, wo + 4u * w));
-    const u32 left = i & 31u;
-    if (left) count += __popc(be32_at(chunk, wo + 4u * end) >> (32u - left));
+  // bitmap.rs:186-212: ones in [0, i).  The directory entry and the (up to four) words of i's 128-bit block are all
+  // requested before the first of them is used -- a warp stalls at the first instruction that needs a pending load, so a
+  // loop that adds one word at a time pays up to five memory round trips where this pays one.  `on` = false: no load, 0.
+  DCDF_DEVINL u32 rank(u32 i, bool on = true) const {
+    const u32 block = i >> 7, rel = i & 127u;
+    const uintptr_t a = (uintptr_t)(chunk + words_off() + 16u * block);
+    const u32* w = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+    const u32 sh = (u32)(a & 3) * 8u;
+    const u32 nw = on ? (rel + 31u) >> 5 : 0u;            // words of the block with bits below i
+    const u32 n_ld = nw + ((sh && nw) ? 1u : 0u);          // aligned words they lie in
+    const uintptr_t ai = (uintptr_t)(chunk + base + 8u + 4u * (block - 1u));
+    const u32* wi = reinterpret_cast<const u32*>(ai & ~(uintptr_t)3);
+    const u32 shi = (u32)(ai & 3) * 8u;
+    const bool want_idx = on && block > 0;
+    u32 i0 = 0, i1 = 0, x0 = 0, x1 = 0, x2 = 0, x3 = 0, x4 = 0;
+    if (want_idx) i0 = wi[0];
+    if (want_idx && shi) i1 = wi[1];
+    if (n_ld > 0) x0 = w[0];
+    if (n_ld > 1) x1 = w[1];
+    if (n_ld > 2) x2 = w[2];
+    if (n_ld > 3) x3 = w[3];
+    if (n_ld > 4) x4 = w[4];
+    u32 count = __byte_perm(shi ? __funnelshift_r(i0, i1, shi) : i0, 0, 0x0123);
+    const u32 b0 = __byte_perm(sh ? __funnelshift_r(x0, x1, sh) : x0, 0, 0x0123), b1 = __byte_perm(sh ? __funnelshift_r(x1, x2, sh) : x1, 0, 0x0123);
+    const u32 b2 = __byte_perm(sh ? __funnelshift_r(x2, x3, sh) : x2, 0, 0x0123), b3 = __byte_perm(sh ? __funnelshift_r(x3, x4, sh) : x3, 0, 0x0123);
+    // the first min(rel - 32k, 32) bits of word k
+    const u32 r = on ? rel : 0u;
+    count += __popc(b0 & (u32)(0xffffffff00000000ull >> min(r, 32u)));
+    count += __popc(b1 & (u32)(0xffffffff00000000ull >> min(r > 32u ? r - 32u : 0u, 32u)));
+    count += __popc(b2 & (u32)(0xffffffff00000000ull >> min(r > 64u ? r - 64u : 0u, 32u)));
+    count += __popc(b3 & (u32)(0xffffffff00000000ull >> (r > 96u ? r - 96u : 0u)));
     return count;
   }
   DCDF_DEVINL u32 rank0(u32 i) const { return i - rank(i); }
@@ -141,9 +164,11 @@ struct DacFast {
   BitsFast more0;
   DacRef slow;
   bool empty;  // no levels at all: every lookup yields 0 (dac.rs:80-93)
-  DCDF_DEVINL i64 get(u32 index) const {
-    if (empty) return 0;
-    if (!more0.get(index)) return unzigzag64((u64)bytes0[index]);
+  // `on` = false: no load, 0.  The continuation bit and the byte are requested together.
+  DCDF_DEVINL i64 get(u32 index, bool on = true) const {
+    if (empty || !on) return 0;
+    const u32 byte = bytes0[index];
+    if (!more0.get(index)) return unzigzag64((u64)byte);
     return slow.get(index);
   }
   // Same lookup in the expansion's value type: a one-byte code decodes in 32-bit arithmetic.
@@ -345,16 +370,18 @@ DCDF_DEVINL i64 log_get(const ChunkView& cv, const InstDir& l, const InstDir& s,
     sl >>= 1;
     if (sl == 0) return max_t + max_s;  // malformed input guard
     const u32 child = (row / sl) * 2u + (col / sl);
-    if (has_s) {
-      is = 1u + nm_s.rank(is) * 4u + child;
-      max_s -= mx_s.get(is);
-    }
-    if (has_t) {
-      it = 1u + nm_t.rank(it) * 4u + child;
-      max_t = mx_t.get(it);
-    }
-    const bool leaf_t = has_t ? (it >= l.nm_len || !nm_t.get(it)) : true;
-    const bool leaf_s = has_s ? (is >= s.nm_len || !nm_s.get(is)) : true;
+    // the two trees are descended side by side: both ranks in one round trip, then everything that hangs off the new
+    // indices (entry, continuation bit, nodemap bit of either tree) in a second one
+    const u32 rs = nm_s.rank(is, has_s), rt = nm_t.rank(it, has_t);
+    if (has_s) is = 1u + rs * 4u + child;
+    if (has_t) it = 1u + rt * 4u + child;
+    const bool in_t = has_t && it < l.nm_len, in_s = has_s && is < s.nm_len;
+    const bool bit_t = in_t ? nm_t.get(it) : false, bit_s = in_s ? nm_s.get(is) : false;
+    const i64 es = mx_s.get(is, has_s), et = mx_t.get(it, has_t);
+    max_s -= es;
+    if (has_t) max_t = et;
+    const bool leaf_t = !bit_t;
+    const bool leaf_s = !bit_s;
     if (leaf_t && leaf_s) return max_t + max_s;
     if (leaf_s) {
       has_s = false;
