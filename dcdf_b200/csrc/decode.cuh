@@ -465,7 +465,7 @@ __global__ void k_get_batch(const QuerySet Q, const i64* irc, u64 n, void* out, 
 }
 
 // Chunk::fill_cell batched: queries (start,end,row,col); one thread per (query, instant), grid.y = query
-__global__ void k_cell_batch(const QuerySet Q, const i64* q, const u64* out_off, u64 n, void* out, int raw) {
+__global__ void __launch_bounds__(128, 9) k_cell_batch(const QuerySet Q, const i64* q, const u64* out_off, u64 n, void* out, int raw) {
   for (u64 qi = blockIdx.y; qi < n; qi += gridDim.y) {
     const i64 start = q[4 * qi], end = q[4 * qi + 1], row = q[4 * qi + 2], col = q[4 * qi + 3];
     const u64 base = out_off[qi];

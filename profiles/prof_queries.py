@@ -9,7 +9,7 @@ data = synth.raster(T, R, C, device="cuda")
 ctx = Context(0)
 sc = Superchunk.build(ctx, data, [5, 6], compute_bits=True, chunk_size=64)
 rng = np.random.default_rng(7)
-nq = 4096
+nq = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 q = np.stack([np.zeros(nq, np.int64), np.full(nq, T, np.int64), rng.integers(0, R, nq), rng.integers(0, C, nq)], axis=1)
 sc.cell_batch(q[:64])
 series = sc.cell_batch(q)
