@@ -347,20 +347,27 @@ void do_get_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const int64_t* irc, 
   if (mem == DCDF_MEM_DEVICE) check_err_word(ctx, mb->d.err, "get_batch");  // host queries were checked above
 }
 
+uint32_t spread1by1_host(uint32_t v) {  // common.cuh: spread1by1
+  v &= 0x0000ffffu;
+  v = (v | (v << 8)) & 0x00ff00ffu;
+  v = (v | (v << 4)) & 0x0f0f0f0fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+
 void do_cell_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const int64_t* q, const uint64_t* out_off, void* out,
                    int32_t out_encoding, int32_t mem) {
   if (n == 0) return;
   if (!q || !out_off) api_fail(DCDF_ERR_BAD_ARG, "null queries");
   const OutSpec os = out_spec(out_encoding, mb->Q.encoding);
   std::vector<i64> qq(q, q + 4 * n);
-  i64 longest = 1;
   for (uint64_t i = 0; i < n; i++) {
     if (qq[4 * i] > qq[4 * i + 1]) std::swap(qq[4 * i], qq[4 * i + 1]);
     const i64 s = qq[4 * i], e = qq[4 * i + 1], r = qq[4 * i + 2], c = qq[4 * i + 3];
     if (s < 0 || e > mb->Q.shape[0] || r < 0 || r >= mb->Q.shape[1] || c < 0 || c >= mb->Q.shape[2])
       api_fail(DCDF_ERR_OUT_OF_BOUNDS, "cell series %llu out of bounds", (unsigned long long)i);
     if ((uint64_t)(e - s) != out_off[i + 1] - out_off[i]) api_fail(DCDF_ERR_BAD_ARG, "out_off does not match the series lengths");
-    longest = std::max(longest, e - s);
   }
   const size_t total = out_off[n];
   // Series of one subchunk are walked next to each other (the kernel takes queries in array order): at any instant they
@@ -369,37 +376,115 @@ void do_cell_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const int64_t* q, c
   std::vector<uint32_t> order(n);
   for (uint64_t i = 0; i < n; i++) order[i] = (uint32_t)i;
   if (n > 1 && n <= 0xffffffffull) {
-    const i64 cs = mb->Q.chunks_sidelen;
+    const i64 cs0 = mb->Q.chunks_sidelen;
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
       const i64 ra = qq[4 * a + 2], ca = qq[4 * a + 3], rb = qq[4 * b + 2], cb = qq[4 * b + 3];
-      const i64 ta = (ra / cs) * (i64)mb->Q.subsidelen + ca / cs, tb = (rb / cs) * (i64)mb->Q.subsidelen + cb / cs;
+      const i64 ta = (ra / cs0) * (i64)mb->Q.subsidelen + ca / cs0, tb = (rb / cs0) * (i64)mb->Q.subsidelen + cb / cs0;
       if (ta != tb) return ta < tb;
       if (ra != rb) return ra < rb;
       if (ca != cb) return ca < cb;
       return a < b;
     });
   }
-  std::vector<i64> qs(4 * n);
-  std::vector<u64> bases(n + 1);
-  for (uint64_t j = 0; j < n; j++) {
-    const uint32_t i = order[j];
-    for (int k = 0; k < 4; k++) qs[4 * j + k] = qq[4 * i + k];
-    bases[j] = out_off[i];
+  // Tiles that at least `cell_tile_min` series of the batch fall into are decoded once per instant by the tile decoder
+  // (k_cell_tiles4) and hand out the asked-for cells; the other series take the per-cell walk.  A second series on a cell
+  // that is already listed (same cell, other instants) also takes the walk.
+  const i64 cs = mb->Q.chunks_sidelen;
+  const uint32_t tile_min = ctx->opt.cell_tile_min;
+  const bool tiles_ok = tile_min > 0 && mb->max_sidelen <= 64 && n <= 0xffffffffull;
+  std::vector<i64> qs;                 // walker: queries in walk order
+  std::vector<u64> bases;
+  std::vector<uint16_t> masks;         // tile path: 256 entries per dense tile (asked-for cells of every 4x4 block)
+  std::vector<CellRef> refs;
+  std::vector<SeriesJob> jobs;
+  qs.reserve(4 * n); bases.reserve(n + 1);
+  i64 longest = 1;
+  auto tile_of = [&](uint32_t i) { return (qq[4 * i + 2] / cs) * (i64)mb->Q.subsidelen + qq[4 * i + 3] / cs; };
+  auto walk = [&](uint32_t i) {
+    for (int k = 0; k < 4; k++) qs.push_back(qq[4 * i + k]);
+    bases.push_back(out_off[i]);
+    longest = std::max(longest, qq[4 * i + 1] - qq[4 * i]);
+  };
+  for (uint64_t j0 = 0; j0 < n;) {
+    uint64_t j1 = j0 + 1;
+    const i64 tile = tile_of(order[j0]);
+    while (j1 < n && tile_of(order[j1]) == tile) j1++;
+    if (!tiles_ok || j1 - j0 < tile_min) {
+      for (uint64_t j = j0; j < j1; j++) walk(order[j]);
+      j0 = j1;
+      continue;
+    }
+    const uint32_t tile_idx = (uint32_t)(masks.size() / DT_THREADS);
+    const uint32_t ref_first = (uint32_t)refs.size();
+    masks.resize(masks.size() + DT_THREADS, 0);
+    uint16_t* mk = masks.data() + (size_t)tile_idx * DT_THREADS;
+    i64 t_min = INT64_MAX, t_max = INT64_MIN;
+    i64 prev_r = -1, prev_c = -1;
+    for (uint64_t j = j0; j < j1; j++) {
+      const uint32_t i = order[j];
+      const i64 s_ = qq[4 * i], e_ = qq[4 * i + 1], r = qq[4 * i + 2] % cs, c = qq[4 * i + 3] % cs;
+      if (e_ <= s_) continue;                                  // empty series: nothing to write
+      if (r == prev_r && c == prev_c) { walk(i); continue; }   // same cell again
+      prev_r = r; prev_c = c;
+      const uint32_t p = spread1by1_host((uint32_t)(c >> 2)) | (spread1by1_host((uint32_t)(r >> 2)) << 1);
+      const uint32_t bit = 4u * (2u * (((uint32_t)r >> 1) & 1u) + (((uint32_t)c >> 1) & 1u)) + 2u * ((uint32_t)r & 1u) + ((uint32_t)c & 1u);
+      mk[p] |= (uint16_t)(1u << bit);
+      refs.push_back(CellRef{out_off[i], s_, e_, 16u * p + bit, 0u});
+      t_min = std::min(t_min, s_); t_max = std::max(t_max, e_);
+    }
+    const uint32_t ref_count = (uint32_t)refs.size() - ref_first;
+    if (ref_count) {
+      const uint32_t slot = (uint32_t)tile;
+      for (i64 sl = t_min / mb->Q.chunk_size; sl <= (t_max - 1) / mb->Q.chunk_size; sl++)
+        jobs.push_back(SeriesJob{(uint32_t)sl, slot, tile_idx, ref_first, ref_count, 0u, t_min, t_max});
+    }
+    j0 = j1;
   }
-  bases[n] = out_off[n];
-  ctx->query_in.reserve(sizeof(i64) * 4 * n + sizeof(u64) * (n + 1));
-  i64* d_q = ctx->query_in.as<i64>();
-  u64* d_off = reinterpret_cast<u64*>(d_q + 4 * n);
-  CK(cudaMemcpyAsync(d_q, qs.data(), sizeof(i64) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_off, bases.data(), sizeof(u64) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+  const uint64_t n_walk = bases.size();
+  bases.push_back(out_off[n]);
   OutTarget ot = out_begin(ctx, out, os.esize * total, mem);
-  dim3 grid((unsigned)std::min<i64>((longest + 127) / 128, 1024), (unsigned)std::min<uint64_t>(n, 65535));
+  // uploads first, then the timed kernels
+  TileSeriesParams TP;
+  if (!jobs.empty()) {
+    const size_t b_masks = sizeof(uint16_t) * masks.size(), b_refs = sizeof(CellRef) * refs.size(), b_jobs = sizeof(SeriesJob) * jobs.size();
+    ctx->query_aux.reserve(b_masks + 16);
+    ctx->query_aux2.reserve(b_refs + b_jobs + 32);
+    CellRef* d_refs = ctx->query_aux2.as<CellRef>();
+    SeriesJob* d_jobs = reinterpret_cast<SeriesJob*>(ctx->query_aux2.as<u8>() + ((b_refs + 15) & ~size_t(15)));
+    CK(cudaMemcpyAsync(ctx->query_aux.p, masks.data(), b_masks, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_refs, refs.data(), b_refs, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_jobs, jobs.data(), b_jobs, cudaMemcpyHostToDevice, ctx->stream));
+    TP.Q = mb->Q; TP.jobs = d_jobs; TP.n_jobs = jobs.size(); TP.masks = ctx->query_aux.as<uint16_t>(); TP.refs = d_refs;
+    TP.out = ot.dev; TP.raw = os.raw;
+  }
+  i64* d_q = nullptr;
+  u64* d_off = nullptr;
+  if (n_walk) {
+    ctx->query_in.reserve(sizeof(i64) * 4 * n_walk + sizeof(u64) * (n_walk + 1));
+    d_q = ctx->query_in.as<i64>();
+    d_off = reinterpret_cast<u64*>(d_q + 4 * n_walk);
+    CK(cudaMemcpyAsync(d_q, qs.data(), sizeof(i64) * 4 * n_walk, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_off, bases.data(), sizeof(u64) * (n_walk + 1), cudaMemcpyHostToDevice, ctx->stream));
+  }
   tbegin(ctx, KT_CELL);
-  k_cell_batch<<<grid, 128, 0, ctx->stream>>>(mb->Q, d_q, d_off, n, ot.dev, os.raw);
-  CK(cudaGetLastError());
-  ctx->launches++;
+  if (!jobs.empty()) {
+    const bool narrow = mb->max_dac_levels <= 3 && !ctx->opt.window_wide;
+    if (narrow) CK(cudaFuncSetAttribute(k_cell_tiles4<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Series4Smem<int32_t>)));
+    else CK(cudaFuncSetAttribute(k_cell_tiles4<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Series4Smem<i64>)));
+    const unsigned grid = (unsigned)std::min<u64>(jobs.size(), (u64)ctx->sm_count * 64);
+    if (narrow) k_cell_tiles4<int32_t><<<grid, DT_THREADS, sizeof(Series4Smem<int32_t>), ctx->stream>>>(TP);
+    else k_cell_tiles4<i64><<<grid, DT_THREADS, sizeof(Series4Smem<i64>), ctx->stream>>>(TP);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (n_walk) {
+    dim3 grid((unsigned)std::min<i64>((longest + 127) / 128, 1024), (unsigned)std::min<uint64_t>(n_walk, 65535));
+    k_cell_batch<<<grid, 128, 0, ctx->stream>>>(mb->Q, d_q, d_off, n_walk, ot.dev, os.raw);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
   tend(ctx, KT_CELL);
-  out_end(ctx, ot);  // qs / bases stay alive until here
+  out_end(ctx, ot);  // the host vectors stay alive until here
   tcollect(ctx, KT_CELL);
 }
 

@@ -91,9 +91,9 @@ DCDF_DEVINL u32 top_slot() { return S_::PRIVATE_TOP ? threadIdx.x >> 5 : 0u; }
 
 // Cells of this thread's 4x4 block for one instant, given the state of its level L-2 node: mode 0 internal (r = rank1 of
 // the node, its quads start at BFS index 1 + 4r), 1 uniform (value = pay), 2 equal (value = pay + snapshot cell).
-template <typename V, typename S_>
+template <typename V, typename S_, typename OUT>
 DCDF_DEVINL void block4(const Dac4& mx, const u8* eq, u32 eq_len, const RankTab& T, u32 nm_len, u32 mode, V pay, u32 r, u32 p, u32 oQ,
-                       const S_& S, const QuadOut& O) {
+                       const S_& S, const OUT& O) {
   const int R0 = 4 * (int)morton_row(p), C0 = 4 * (int)morton_col(p);
   if (!O.touches(R0, C0, 4)) return;
   const bool fast = O.vec4 && O.inside(R0, C0, 4);
@@ -148,8 +148,8 @@ DCDF_DEVINL void block4(const Dac4& mx, const u8* eq, u32 eq_len, const RankTab&
 
 // Snapshot at `chunk + d.off`: every thread walks to its level L-2 node, writes the snapshot values of its ancestors,
 // of its four quads and of its sixteen cells; with `emit` the cells also go to the window (the instant is the snapshot).
-template <typename V, typename S_>
-DCDF_DEVINL void snapshot4(const u8* chunk, const InstDir& d, int L, S_& S, bool emit, const QuadOut& O) {
+template <typename V, typename S_, typename OUT>
+DCDF_DEVINL void snapshot4(const u8* chunk, const InstDir& d, int L, S_& S, bool emit, const OUT& O) {
   const u32 p = threadIdx.x;
   RankTab& T = S.tab[threadIdx.x >> 5];
   const u32 nm_len = d.nm_len;
@@ -203,12 +203,12 @@ DCDF_DEVINL void snapshot4(const u8* chunk, const InstDir& d, int L, S_& S, bool
     for (int i = 0; i < 4; i++) q.c[i] = qv.c[c] - dd[i];
     reinterpret_cast<Quad<V>*>(S.cells)[4u * p + (u32)c] = q;
   }
-  if (emit) block4<V, S_>(mx, chunk, 0u, T, nm_len, 2u, (V)0, 0u, p, off3(L - 1), S, O);  // "equal to the snapshot, offset 0"
+  if (emit) block4<V, S_, OUT>(mx, chunk, 0u, T, nm_len, 2u, (V)0, 0u, p, off3(L - 1), S, O);  // "equal to the snapshot, offset 0"
 }
 
 // Log at `chunk + d.off` against the snapshot pyramid in S: walk to the level L-2 node, then the block's cells.
-template <typename V, typename S_>
-DCDF_DEVINL void log4(const u8* chunk, const InstDir& d, int L, S_& S, const QuadOut& O) {
+template <typename V, typename S_, typename OUT>
+DCDF_DEVINL void log4(const u8* chunk, const InstDir& d, int L, S_& S, const OUT& O) {
   const u32 p = threadIdx.x;
   RankTab& T = S.tab[threadIdx.x >> 5];
   const u32 nm_len = d.nm_len;
@@ -252,17 +252,17 @@ DCDF_DEVINL void log4(const u8* chunk, const InstDir& d, int L, S_& S, const Qua
       }
     }
   }
-  block4<V, S_>(mx, eq, d.eq_len, T, nm_len, mode, pay, r, p, off3(L - 1), S, O);
+  block4<V, S_, OUT>(mx, eq, d.eq_len, T, nm_len, mode, pay, r, p, off3(L - 1), S, O);
 }
 
-template <typename V, typename S_>
-DCDF_DEVINL void instant4(const u8* chunk, const InstDir& d, bool is_snap, bool emit, int L, S_& S, const QuadOut& O) {
-  if (is_snap) snapshot4<V, S_>(chunk, d, L, S, emit, O);
-  else log4<V, S_>(chunk, d, L, S, O);
+template <typename V, typename S_, typename OUT>
+DCDF_DEVINL void instant4(const u8* chunk, const InstDir& d, bool is_snap, bool emit, int L, S_& S, const OUT& O) {
+  if (is_snap) snapshot4<V, S_, OUT>(chunk, d, L, S, emit, O);
+  else log4<V, S_, OUT>(chunk, d, L, S, O);
 }
-template <typename V, typename S_>
-__device__ __noinline__ void instant4_global(const u8* chunk, const InstDir* d, bool is_snap, bool emit, int L, S_* S, const QuadOut* O) {
-  instant4<V, S_>(chunk, *d, is_snap, emit, L, *S, *O);
+template <typename V, typename S_, typename OUT>
+__device__ __noinline__ void instant4_global(const u8* chunk, const InstDir* d, bool is_snap, bool emit, int L, S_* S, const OUT* O) {
+  instant4<V, S_, OUT>(chunk, *d, is_snap, emit, L, *S, *O);
 }
 
 // Start the copy of a structure and of its directory entry into staging half b.
@@ -355,10 +355,10 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_window_t
       __syncthreads();
       u32 delta;
       if (staged4<V>(chunk, S.dir[2], delta)) {
-        instant4<V, Tile4Smem<V>>(S.stage[1] + (int32_t)delta, S.dir[2], true, false, L, S, O);
+        instant4<V, Tile4Smem<V>, QuadOut>(S.stage[1] + (int32_t)delta, S.dir[2], true, false, L, S, O);
       } else {
         const QuadOut O2 = O;
-        instant4_global<V, Tile4Smem<V>>(chunk, &S.dir[2], true, false, L, &S, &O2);
+        instant4_global<V, Tile4Smem<V>, QuadOut>(chunk, &S.dir[2], true, false, L, &S, &O2);
       }
       __syncthreads();
     }
@@ -384,10 +384,127 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_window_t
       const bool is_snap = D.snap == ti;
       u32 delta;
       if (staged4<V>(chunk, D, delta)) {
-        instant4<V, Tile4Smem<V>>(S.stage[b] + (int32_t)delta, D, is_snap, true, L, S, O);
+        instant4<V, Tile4Smem<V>, QuadOut>(S.stage[b] + (int32_t)delta, D, is_snap, true, L, S, O);
       } else {
         const QuadOut O2 = O;  // only the copy has its address taken
-        instant4_global<V, Tile4Smem<V>>(chunk, &D, is_snap, true, L, &S, &O2);
+        instant4_global<V, Tile4Smem<V>, QuadOut>(chunk, &D, is_snap, true, L, &S, &O2);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Cell series of a tile that many series of one batch fall into (Chunk::fill_cell chunk.rs:133-150, superchunk.rs:353-400):
+// decode the tile's instants once with the window decoder's per-thread walk into an image of the tile in shared memory,
+// then let the CTA hand every asked-for cell to its series.  A root-to-leaf walk per (series, instant) reads the same
+// structure once per series; from some dozens of series per tile on, expanding it once is cheaper.  One CTA per (time
+// slice, tile); blocks of the tile without an asked-for cell are not decoded.
+struct SeriesJob {
+  u32 slice, slot;
+  u32 tile;          // index into `masks` (256 entries per tile)
+  u32 ref_first, ref_count;
+  u32 pad_;
+  i64 t_min, t_max;  // union of the instants the tile's series cover
+};
+struct TileSeriesParams {
+  QuerySet Q;
+  const SeriesJob* jobs;
+  u64 n_jobs;
+  const uint16_t* masks;
+  const CellRef* refs;
+  void* out;
+  int raw;
+};
+template <typename V>
+struct Series4Smem {
+  Tile4Smem<V> T;
+  __align__(16) V img[4096];  // the instant being served, Morton order (img[16 * block + 4 * quad + cell])
+};
+
+template <typename V>
+__global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 3 : 2) k_cell_tiles4(const TileSeriesParams P) {
+  extern __shared__ __align__(16) unsigned char dt4_smem_raw[];
+  Series4Smem<V>& SS = *reinterpret_cast<Series4Smem<V>*>(dt4_smem_raw);
+  Tile4Smem<V>& S = SS.T;
+  const QuerySet& Q = P.Q;
+  const int tid = threadIdx.x;
+  for (u64 ji = blockIdx.x; ji < P.n_jobs; ji += gridDim.x) {
+    const SeriesJob J = P.jobs[ji];
+    const SliceMeta sm = Q.slices[J.slice];
+    const i64 t_lo = max(J.t_min, sm.t0), t_hi = min(J.t_max, sm.t0 + (i64)sm.instants);
+    if (t_hi <= t_lo) continue;
+    const int32_t u = Q.slot_unit[sm.slot_base + J.slot];
+    const UnitMeta m = u >= 0 ? Q.units[u] : UnitMeta{};
+    const bool stored = u >= 0 && m.stored;
+    const CellRef* refs = P.refs + J.ref_first;
+    // the thread's first reference stays in registers for the whole job (tiles with up to 256 series need no other)
+    const bool have0 = (u32)tid < J.ref_count;
+    const CellRef r0 = have0 ? refs[tid] : CellRef{0, 0, 0, 0, 0};
+    CellOut co;
+    if (!stored) {
+      // Elided: one value per instant from the max table, parent's fractional bits (superchunk.rs:325-330)
+      const SlotDesc sdsc = Q.slot_desc[sm.slot_base + J.slot];
+      co.init(Q, P.out, P.raw, sdsc.bits);
+      for (u32 k = (u32)tid; k < J.ref_count; k += DT_THREADS) {
+        const CellRef r = k == (u32)tid ? r0 : refs[k];
+        for (i64 t = max(t_lo, r.start); t < min(t_hi, r.end); t++)
+          co.put(r.base + (u64)(t - r.start), (i64)Q.tbl_max[sdsc.tbl0 + (u64)(t - sm.t0) * sdsc.stride]);
+      }
+      continue;
+    }
+    co.init(Q, P.out, P.raw, m.bits);
+    SeriesOut<V> O;
+    O.img = SS.img + 16 * tid;
+    O.mask = P.masks[(u64)J.tile * DT_THREADS + (u64)tid];
+    const u8* chunk = Q.blob + m.blob_off;
+    const InstDir* dir = Q.dir + m.dir_base;
+    const int L = 31 - __clz(m.sidelen);
+    const u32 ti0 = (u32)(t_lo - sm.t0), n_t = (u32)(t_hi - t_lo);
+    __syncthreads();  // the previous job's readers are done with the staging buffers and the image
+    const u32 snap0 = dir[ti0].snap;
+    if (snap0 != ti0) {
+      // the series start inside a block: expand the block's snapshot first
+      prefetch_dir4<V, Tile4Smem<V>>(dir + snap0, S, 2);
+      prefetch4<V, Tile4Smem<V>>(chunk, dir[snap0].off, dir[snap0].size, S, 1);
+      cp_async_wait_all();
+      __syncthreads();
+      {  // once per job at most: through the out-of-line copy of the decoder (it accepts staged bytes as well)
+        u32 delta;
+        const bool st = staged4<V>(chunk, S.dir[2], delta);
+        const SeriesOut<V> O2 = O;
+        instant4_global<V, Tile4Smem<V>, SeriesOut<V>>(st ? S.stage[1] + (int32_t)delta : chunk, &S.dir[2], true, false, L, &S, &O2);
+      }
+      __syncthreads();
+    }
+    prefetch_dir4<V, Tile4Smem<V>>(dir + ti0, S, 0);
+    prefetch4<V, Tile4Smem<V>>(chunk, dir[ti0].off, dir[ti0].size, S, 0);
+    if (n_t > 1) prefetch_dir4<V, Tile4Smem<V>>(dir + ti0 + 1, S, 1);
+    u32 rs = 0;  // i % 3
+    for (u32 i = 0; i < n_t; i++) {
+      const int b = (int)(i & 1u);
+      const u32 ti = ti0 + i;
+      const u32 slot1 = rs == 2 ? 0u : rs + 1u, slot2 = slot1 == 2 ? 0u : slot1 + 1u;
+      cp_async_wait_all();
+      __syncthreads();  // structure i and directory entry i+1 have landed; everyone is done with instant i-1 and its image
+      if (i + 1 < n_t) {
+        prefetch4<V, Tile4Smem<V>>(chunk, S.dir[slot1].off, S.dir[slot1].size, S, b ^ 1);
+        if (i + 2 < n_t) prefetch_dir4<V, Tile4Smem<V>>(dir + ti + 2, S, slot2);
+      }
+      const InstDir& D = S.dir[rs];
+      rs = slot1;
+      const bool is_snap = D.snap == ti;
+      u32 delta;
+      if (staged4<V>(chunk, D, delta)) {
+        instant4<V, Tile4Smem<V>, SeriesOut<V>>(S.stage[b] + (int32_t)delta, D, is_snap, true, L, S, O);
+      } else {
+        const SeriesOut<V> O2 = O;  // only the copy has its address taken
+        instant4_global<V, Tile4Smem<V>, SeriesOut<V>>(chunk, &D, is_snap, true, L, &S, &O2);
+      }
+      __syncthreads();  // the image of instant i is complete
+      const i64 t = t_lo + (i64)i;
+      for (u32 k = (u32)tid; k < J.ref_count; k += DT_THREADS) {
+        const CellRef r = k == (u32)tid ? r0 : refs[k];
+        if (t >= r.start && t < r.end) co.put(r.base + (u64)(t - r.start), SS.img[r.cell]);
       }
     }
   }

@@ -226,6 +226,36 @@ struct QuadOut {
   }
 };
 
+// Cell series through the tile decoder (k_cell_tiles4): the cells of a tile that some series of the batch asks for.
+struct CellRef {
+  u64 base;        // output element of the series' first instant
+  i64 start, end;  // the series covers instants [start, end)
+  u32 cell;        // 16 * block + 4 * quad + cell: block = Morton index of the 4x4 block, quad = 2 * (row / 2) + col / 2 and
+  u32 pad_;        // cell = 2 * (row & 1) + (col & 1) inside the block -- the order the block decoder produces values in
+};
+// Same interface as QuadOut towards the block decoder: the values of the blocks that hold an asked-for cell go to an image
+// of the tile in shared memory (one instant), from which the CTA then serves every series of the tile.
+template <typename V>
+struct SeriesOut {
+  V* img;     // the thread's 16 cells: img[4 * quad + cell]
+  u32 mask;   // asked-for cells of the block (bit 4 * quad + cell); 0: nothing to decode
+  static constexpr bool vec4 = false;
+  DCDF_DEVINL bool touches(int, int, int) const { return mask != 0; }
+  DCDF_DEVINL bool inside(int, int, int) const { return false; }
+  DCDF_DEVINL void put(int r0, int c0, const V (&v)[4]) const {  // the 2x2 quad at (r0, c0): only its place inside the block matters
+    const u32 quad = 2u * (((u32)r0 >> 1) & 1u) + (((u32)c0 >> 1) & 1u);
+    Quad<V> q;
+#pragma unroll
+    for (int i = 0; i < 4; i++) q.c[i] = v[i];
+    reinterpret_cast<Quad<V>*>(img)[quad] = q;
+  }
+  DCDF_DEVINL void put_pair(bool, int r0, int c0, const V (&a)[4], const V (&b)[4]) const {
+    if (!(mask & (0xffu << (8u * (((u32)r0 >> 1) & 1u))))) return;  // nothing asked for in this half of the block
+    put(r0, c0, a);
+    put(r0, c0 + 2, b);
+  }
+};
+
 // The `equal` bits of the children that stop here are consecutive: child c's bit is at e0 + (non-internal children
 // before c), e0 = idx0 - rank1(idx0) (rank0(idx + 1) - 1, log.rs:265).  Returns a 16-bit window starting at e0's byte.
 DCDF_DEVINL u32 eq_window(const u8* eq, u32 e0) {

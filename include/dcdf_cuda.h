@@ -91,6 +91,8 @@ int32_t dcdf_ctx_set_stream(dcdf_ctx* ctx, void* cuda_stream);
  *   "fast_variant" 0|1|2    fast-path kernel launches for A/B runs: 1 = four tiles per CTA (255 registers), 2 = four tiles
  *                           per CTA with every instant's tile staged in shared memory by bulk copies behind an mbarrier
  *   "fast_sync_mask" <m>    fast-path kernel: the tiles of a CTA re-align every (m + 1) instants (default 3)
+ *   "cell_tile_min" <n>     cell series: a tile that at least n series of a batch fall into is decoded once per instant by
+ *                           the tile decoder instead of one root-to-leaf walk per (series, instant) (default 64, the measured break-even; 0 = never)
  *   "window_cells" 0|1      windows through the per-cell walker (the path of trees larger than 64x64)
  *   "window_wide" 0|1       64-bit tile expansion even when every DAC code fits three bytes
  *   "search_dfs" 0|1        depth-first search kernel instead of the tile search

@@ -7,6 +7,9 @@ from dcdf_b200 import Context, Superchunk, synth, _ffi
 T, R, C = int(sys.argv[1]) if len(sys.argv) > 1 else 512, 721, 1440
 data = synth.raster(T, R, C, device="cuda")
 ctx = Context(0)
+for a in sys.argv[3:]:
+    k, v = a.split("=")
+    ctx.set_option(k, int(v))
 sc = Superchunk.build(ctx, data, [5, 6], compute_bits=True, chunk_size=64)
 rng = np.random.default_rng(7)
 nq = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
