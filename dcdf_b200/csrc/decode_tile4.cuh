@@ -353,12 +353,12 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_window_t
       prefetch4<V, Tile4Smem<V>>(chunk, dir[snap0].off, dir[snap0].size, S, 1);
       cp_async_wait_all();
       __syncthreads();
-      u32 delta;
-      if (staged4<V>(chunk, S.dir[2], delta)) {
-        instant4<V, Tile4Smem<V>, QuadOut>(S.stage[1] + (int32_t)delta, S.dir[2], true, false, L, S, O);
-      } else {
+      {  // once per job at most: through the out-of-line copy of the decoder (it accepts staged bytes as well), so that the
+         // kernel holds ONE inlined copy of it
+        u32 delta;
+        const bool st = staged4<V>(chunk, S.dir[2], delta);
         const QuadOut O2 = O;
-        instant4_global<V, Tile4Smem<V>, QuadOut>(chunk, &S.dir[2], true, false, L, &S, &O2);
+        instant4_global<V, Tile4Smem<V>, QuadOut>(st ? S.stage[1] + (int32_t)delta : chunk, &S.dir[2], true, false, L, &S, &O2);
       }
       __syncthreads();
     }
