@@ -593,10 +593,13 @@ void do_search_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
   CK(cudaMemcpyAsync(d_jb, job_base.data(), sizeof(u64) * (n + 1), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_lo, lower, sizeof(i64) * n, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_hi, upper, sizeof(i64) * n, cudaMemcpyHostToDevice, st));
-  ctx->query_aux.reserve(sizeof(u64) * (2 * n_jobs + 2) + sizeof(u64) * (n + 1));
+  const u64 n_scan_chunks = (n_jobs + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  ctx->query_aux.reserve(sizeof(u64) * (2 * n_jobs + 2) + sizeof(u64) * (n + 1) + sizeof(u64) * (2 * n_scan_chunks + 2));
   u64* d_counts = ctx->query_aux.as<u64>();
   u64* d_offsets = d_counts + n_jobs;
   u64* d_pick = d_offsets + n_jobs + 1;
+  u64* d_sums = d_pick + n + 1;
+  u64* d_sum_off = d_sums + n_scan_chunks;
   SearchParams SP;
   SP.Q = mb->Q;
   SP.cubes = d_c; SP.job_base = d_jb; SP.n_queries = n; SP.n_jobs = n_jobs;
@@ -639,8 +642,79 @@ void do_search_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
     CK(cudaFuncSetAttribute(k_search_tiles4<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Search4Smem<i64>)));
     CK(cudaFuncSetAttribute(k_search_tiles4<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Search4Smem<int32_t>)));
   }
+  // Counting pass with shared decodes (k_count_tiles4) when the windows of the batch overlap: every (time slice, tile) some
+  // window touches is decoded once for all of them.  Worth it from a few windows per touched tile on (ctx option
+  // "search_share_min", default 3; the per-window kernel prunes by the window's own band, which a shared decode cannot).
+  bool shared_count = false;
+  TileCountParams TC;
+  unsigned cgrid = 0;
+  std::vector<CountEntry> entries;
+  std::vector<CountJob> cjobs;
+  // (a call that also wants the cells keeps the per-window counting pass: its cached findings make the writing pass cheap)
+  if (tiles && (!out_irc || ctx->opt.search_share_min == 1) && ctx->opt.search_share_min > 0 && cs <= 64 && mb->Q.chunk_size <= 0xffff) {
+    const i64 ct = mb->Q.chunk_size;
+    const u64 n_slots = mb->Q.n_slots, n_keys = (u64)mb->Q.n_slices * n_slots;
+    std::vector<uint32_t> key_count(n_keys + 1, 0);
+    u64 n_ent = 0;
+    auto for_each_entry = [&](auto&& fn) {
+      for (uint64_t q = 0; q < n; q++) {
+        const CubeDev& c = cubes[q];
+        if (!(c.end > c.start && c.bottom > c.top && c.right > c.left)) continue;
+        const i64 cr0 = c.top / cs, cc0 = c.left / cs, cr1 = (c.bottom - 1) / cs, cc1 = (c.right - 1) / cs;
+        const i64 ncc = cc1 - cc0 + 1, T_all = c.end - c.start;
+        for (i64 sl = c.start / ct; sl <= (c.end - 1) / ct; sl++)
+          for (i64 cr = cr0; cr <= cr1; cr++)
+            for (i64 cc = cc0; cc <= cc1; cc++) {
+              const u64 key = (u64)sl * n_slots + (u64)(cr * mb->Q.subsidelen + cc);
+              fn(q, c, sl, cr, cc, (cr - cr0) * ncc + (cc - cc0), T_all, key);
+            }
+      }
+    };
+    for_each_entry([&](uint64_t, const CubeDev&, i64, i64, i64, i64, i64, u64 key) { key_count[key + 1]++; n_ent++; });
+    u64 touched = 0;
+    for (u64 k = 0; k < n_keys; k++) touched += key_count[k + 1] ? 1 : 0;
+    if (touched && n_ent >= (u64)ctx->opt.search_share_min * touched && n_ent <= 0xffffffffull) {
+      shared_count = true;
+      std::vector<u64> key_off(n_keys + 1, 0);
+      for (u64 k = 0; k < n_keys; k++) key_off[k + 1] = key_off[k] + key_count[k + 1];
+      entries.resize(n_ent);
+      std::vector<u64> fill(key_off.begin(), key_off.end() - 1);
+      for_each_entry([&](uint64_t q, const CubeDev& c, i64 sl, i64 cr, i64 cc, i64 sub, i64 T_all, u64 key) {
+        CountEntry E;
+        i64 lo = lower[q], hi = upper[q];
+        if (lo > hi) std::swap(lo, hi);  // helpers.rs:7-16 via chunk.rs:214
+        E.lower = lo; E.upper = hi;
+        const i64 s0 = sl * ct, t_lo = std::max(c.start, s0), t_hi = std::min(c.end, s0 + ct);
+        E.t0 = (uint16_t)(t_lo - s0); E.t1 = (uint16_t)(t_hi - s0);
+        E.cnt_base = (i64)job_base[q] + sub * T_all + (s0 - c.start);
+        const i64 top = cr * cs, left = cc * cs;
+        E.top = (uint8_t)(std::max(top, c.top) - top); E.bottom = (uint8_t)(std::min(top + cs, c.bottom) - top);
+        E.left = (uint8_t)(std::max(left, c.left) - left); E.right = (uint8_t)(std::min(left + cs, c.right) - left);
+        entries[fill[key]++] = E;
+      });
+      for (u64 k = 0; k < n_keys; k++)
+        for (u64 e0 = key_off[k]; e0 < key_off[k + 1]; e0 += CT_MAX)
+          cjobs.push_back(CountJob{(uint32_t)(k / n_slots), (uint32_t)(k % n_slots), (uint32_t)e0,
+                                   (uint32_t)std::min<u64>(CT_MAX, key_off[k + 1] - e0)});
+      const size_t b_ent = sizeof(CountEntry) * entries.size(), b_jobs = sizeof(CountJob) * cjobs.size();
+      ctx->search_cache.reserve(b_ent + b_jobs + 32);
+      CountEntry* d_ent = ctx->search_cache.as<CountEntry>();
+      CountJob* d_cj = reinterpret_cast<CountJob*>(ctx->search_cache.as<u8>() + ((b_ent + 15) & ~size_t(15)));
+      CK(cudaMemcpyAsync(d_ent, entries.data(), b_ent, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(d_cj, cjobs.data(), b_jobs, cudaMemcpyHostToDevice, st));
+      TC.Q = mb->Q; TC.jobs = d_cj; TC.n_jobs = cjobs.size(); TC.entries = d_ent; TC.counts = d_counts;
+      cgrid = (unsigned)std::min<u64>(cjobs.size(), (u64)ctx->sm_count * 64);
+      if (narrow) CK(cudaFuncSetAttribute(k_count_tiles4<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Count4Smem<int32_t>)));
+      else CK(cudaFuncSetAttribute(k_count_tiles4<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Count4Smem<i64>)));
+      TS.hit_cache = nullptr;  // the shared counting pass keeps no per-thread findings; the buffer holds its entries
+    }
+  }
   auto launch_search = [&](int write) {
-    if (tiles) {
+    if (tiles && !write && shared_count) {
+      CK(cudaMemsetAsync(d_counts, 0, sizeof(u64) * n_jobs, st));
+      if (narrow) k_count_tiles4<int32_t><<<cgrid, DT_THREADS, sizeof(Count4Smem<int32_t>), st>>>(TC);
+      else k_count_tiles4<i64><<<cgrid, DT_THREADS, sizeof(Count4Smem<i64>), st>>>(TC);
+    } else if (tiles) {
       if (!write) CK(cudaMemsetAsync(d_counts, 0, sizeof(u64) * n_jobs, st));  // the counting pass adds per warp
       if (narrow) k_search_tiles4<int32_t><<<tgrid, DT_THREADS, sizeof(Search4Smem<int32_t>), st>>>(TS);
       else k_search_tiles4<i64><<<tgrid, DT_THREADS, sizeof(Search4Smem<i64>), st>>>(TS);
@@ -651,7 +725,15 @@ void do_search_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
   tbegin(ctx, KT_SEARCH);
   launch_search(0);
   CK(cudaGetLastError());
-  k_scan_u64<<<1, 1024, 0, st>>>(d_counts, n_jobs, d_offsets);
+  if (n_jobs <= 4u * SCAN_CHUNK) {
+    k_scan_u64<<<1, 1024, 0, st>>>(d_counts, n_jobs, d_offsets);
+  } else {
+    const unsigned nb = (unsigned)((n_jobs + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    k_scan_sums<<<nb, 1024, 0, st>>>(d_counts, n_jobs, d_sums);
+    k_scan_u64<<<1, 1024, 0, st>>>(d_sums, nb, d_sum_off);
+    k_scan_apply<<<nb, 1024, 0, st>>>(d_counts, n_jobs, d_sum_off, d_offsets);
+    ctx->launches += 2;
+  }
   CK(cudaGetLastError());
   k_pick_u64<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(d_offsets, d_jb, n + 1, d_pick);
   CK(cudaGetLastError());

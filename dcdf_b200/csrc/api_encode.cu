@@ -892,6 +892,7 @@ int32_t dcdf_ctx_set_option(dcdf_ctx* ctx, const char* name, int64_t value) {
   else if (n == "no_fast_encode") ctx->opt.no_fast_encode = value != 0;
   else if (n == "fast_sync_mask") ctx->opt.fast_sync_mask = (int)value;
   else if (n == "fast_variant") ctx->opt.fast_variant = (int)value;
+  else if (n == "search_share_min") ctx->opt.search_share_min = (uint32_t)std::max<int64_t>(value, 0);
   else if (n == "cell_tile_min") ctx->opt.cell_tile_min = (uint32_t)std::max<int64_t>(value, 0);
   else if (n == "window_cells") ctx->opt.window_cells = value != 0;
   else if (n == "window_wide") ctx->opt.window_wide = value != 0;

@@ -783,6 +783,63 @@ __global__ void __launch_bounds__(1024) k_scan_u64(const u64* in, u64 n, u64* ou
   if (tid == 0) out[n] = carry_s;
 }
 
+// The same scan over many CTAs for long inputs (a search batch has one count per (window, subchunk, instant)): sums of
+// 8192-element chunks -> k_scan_u64 over the sums -> every chunk scanned from its offset.
+constexpr int SCAN_CHUNK = 8192;
+__global__ void __launch_bounds__(1024) k_scan_sums(const u64* in, u64 n, u64* sums) {
+  __shared__ u64 wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u64 base = (u64)blockIdx.x * SCAN_CHUNK;
+  u64 s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_CHUNK / 1024; k++) {
+    const u64 i = base + (u64)k * 1024u + (u64)tid;
+    if (i < n) s += in[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) wsum[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    u64 w = wsum[lane];
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+    if (lane == 0) sums[blockIdx.x] = w;
+  }
+}
+__global__ void __launch_bounds__(1024) k_scan_apply(const u64* in, u64 n, const u64* chunk_off, u64* out) {
+  __shared__ u64 wsum[32];
+  __shared__ u64 carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = chunk_off[blockIdx.x];
+  __syncthreads();
+  const u64 base0 = (u64)blockIdx.x * SCAN_CHUNK;
+  for (int k = 0; k < SCAN_CHUNK / 1024; k++) {
+    const u64 i = base0 + (u64)k * 1024u + (u64)tid;
+    const u64 v = i < n ? in[i] : 0ull;
+    u64 x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      u64 y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      u64 w = wsum[lane], xs = w;
+      for (int o = 1; o < 32; o <<= 1) {
+        u64 y = __shfl_up_sync(0xffffffffu, xs, o);
+        if (lane >= o) xs += y;
+      }
+      wsum[lane] = xs - w;
+    }
+    __syncthreads();
+    const u64 carry = carry_s;
+    if (i < n) out[i] = carry + wsum[warp] + x - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + wsum[warp] + x;
+    __syncthreads();
+  }
+  if (blockIdx.x == gridDim.x - 1 && tid == 0) out[n] = chunk_off[gridDim.x];
+}
+
 // flat to_fixed / from_fixed (fixed.rs:31-86)
 template <typename F>
 __global__ void k_to_fixed(const F* in, u64 n, int bits, int round, i64* out, u32* err) {

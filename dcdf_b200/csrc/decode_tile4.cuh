@@ -219,7 +219,7 @@ DCDF_DEVINL void log4(const u8* chunk, const InstDir& d, int L, S_& S, const OUT
   V pay = dac_get1<V>(mx, 0);
   if (!(T.W[0] >> 31)) {
     // log.rs:180-186: a single-node log is uniform unless its equal bit says "snapshot + constant"
-    const bool uniform = S.single[top_slot<S_>()] || !bit_at(eq, 0);
+    const bool uniform = S.single[top_slot<S_>()] || (!OUT::search_quirk && !bit_at(eq, 0));
     mode = uniform ? 1u : 2u;
     if (uniform) pay += sup_at(S, 0, 0);
   }
@@ -507,6 +507,194 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 3 : 2) k_cell_til
         if (t >= r.start && t < r.end) co.put(r.base + (u64)(t - r.start), SS.img[r.cell]);
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Counting pass of a value-range search batch whose windows overlap (Chunk::iter_search / Superchunk::search counts,
+// chunk.rs:213-228, superchunk.rs:464-585): one CTA per (time slice, tile) decodes every instant ONCE and counts the hits
+// of every window that touches the tile there, instead of one decode per (window, tile).  counts[] has one slot per
+// (window, subchunk, instant), exactly as the per-window kernel fills it; each slot belongs to one CTA (plain stores).
+struct CountJob {
+  u32 slice, slot;
+  u32 ent_first, ent_count;  // ent_count <= CT_MAX
+};
+struct TileCountParams {
+  QuerySet Q;
+  const CountJob* jobs;
+  u64 n_jobs;
+  const CountEntry* entries;
+  u64* counts;               // zeroed by the caller
+};
+template <typename V>
+struct Count4Smem {
+  Tile4Smem<V> T;
+  CountShared<V> C;
+};
+
+template <typename V>
+__global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_count_tiles4(const TileCountParams P) {
+  extern __shared__ __align__(16) unsigned char dt4_smem_raw[];
+  Count4Smem<V>& SS = *reinterpret_cast<Count4Smem<V>*>(dt4_smem_raw);
+  Tile4Smem<V>& S = SS.T;
+  CountShared<V>& C = SS.C;
+  const QuerySet& Q = P.Q;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (u64 ji = blockIdx.x; ji < P.n_jobs; ji += gridDim.x) {
+    const CountJob J = P.jobs[ji];
+    const SliceMeta sm = Q.slices[J.slice];
+    const int32_t u = Q.slot_unit[sm.slot_base + J.slot];
+    const UnitMeta m = u >= 0 ? Q.units[u] : UnitMeta{};
+    const bool stored = u >= 0 && m.stored;
+    __syncthreads();  // the previous job is done with the entries, the counters and the staging buffers
+    if (tid < (int)J.ent_count) {
+      const CountEntry E = P.entries[J.ent_first + (u32)tid];
+      C.ent[tid] = E;
+      C.cnt[0][tid] = 0; C.cnt[1][tid] = 0;
+      C.keep[tid] = 1;
+      // the band in the expansion's type: values outside V's range cannot occur
+      const i64 vlo = sizeof(V) == 4 ? (i64)INT32_MIN : INT64_MIN, vhi = sizeof(V) == 4 ? (i64)INT32_MAX : INT64_MAX;
+      const bool empty = E.lower > vhi || E.upper < vlo || E.lower > E.upper;
+      C.lo[tid] = empty ? (V)1 : (V)max(E.lower, vlo);
+      C.hi[tid] = empty ? (V)0 : (V)min(E.upper, vhi);
+    }
+    if (tid == 0) C.n = J.ent_count;
+    __syncthreads();
+    if (Q.tbl_min) {
+      // Superchunk::search only looks into a subchunk when its min / max entries say that some instant of the window can
+      // have cells in range (superchunk.rs:480-493), at every level of a nested superchunk: one warp per entry
+      const SlotDesc sd = Q.slot_desc[sm.slot_base + J.slot];
+      for (u32 e = (u32)warp; e < J.ent_count; e += DT_WARPS) {
+        const CountEntry& E = C.ent[e];
+        i64 lo = E.lower, hi = E.upper;
+        if (lo > hi) { const i64 x = lo; lo = hi; hi = x; }
+        bool ok = true;
+        for (int lv = 0; lv <= sd.n_up; lv++)
+          ok = ok && __any_sync(0xffffffffu, slot_has_cells_part(Q, sd, (i64)E.t0, (i64)E.t1, lo, hi, lane, 32, lv));
+        if (lane == 0 && !ok) C.keep[e] = 0;
+      }
+      __syncthreads();
+    }
+    // slice-local instants any kept entry covers
+    u32 t_lo = 0xffffffffu, t_hi = 0;
+    unsigned long long mine = 0ull;
+    const int R0 = 4 * (int)morton_row((u32)tid), C0 = 4 * (int)morton_col((u32)tid);
+    for (u32 e = 0; e < J.ent_count; e++) {
+      if (!C.keep[e]) continue;
+      const CountEntry& E = C.ent[e];
+      t_lo = min(t_lo, (u32)E.t0); t_hi = max(t_hi, (u32)E.t1);
+      if (R0 + 4 > (int)E.top && R0 < (int)E.bottom && C0 + 4 > (int)E.left && C0 < (int)E.right) mine |= 1ull << e;
+    }
+    if (t_hi <= t_lo) continue;  // CTA-uniform
+    if (!stored) {
+      // Elided subchunk: one value per instant from the max table (superchunk.rs:541-559)
+      const SlotDesc sdsc = Q.slot_desc[sm.slot_base + J.slot];
+      for (u32 e = (u32)tid; e < J.ent_count; e += DT_THREADS) {
+        if (!C.keep[e]) continue;
+        const CountEntry E = C.ent[e];
+        const u64 area = (u64)(E.bottom - E.top) * (u64)(E.right - E.left);
+        for (u32 t = E.t0; t < E.t1; t++) {
+          const i64 v = Q.tbl_max[sdsc.tbl0 + (u64)t * sdsc.stride];
+          if (E.lower <= v && v <= E.upper) P.counts[E.cnt_base + (i64)t] = area;
+        }
+      }
+      continue;
+    }
+    const u8* chunk = Q.blob + m.blob_off;
+    const InstDir* dir = Q.dir + m.dir_base;
+    const int L = 31 - __clz(m.sidelen);
+    CountOut<V> O;
+    O.C = &C; O.mine = mine; O.R0 = R0; O.C0 = C0; O.t = t_lo; O.buf = 0; O.single_log = false; O.e_root = 0;
+    const u32 ti0 = t_lo, n_t = t_hi - t_lo;
+    const u32 snap0 = dir[ti0].snap;
+    // the block's snapshot is expanded first when the first instant is a Log; every Snapshot on the way leaves its root's
+    // min / max for the single-node-Log rule
+    auto snapshot_root = [&](const u8* base, const InstDir& D) {
+      if (tid == 0) {
+        const Dac4 mx = dac4_of(base, &D.max), mn = dac4_of(base, &D.min);
+        const V vmax = dac_get1<V>(mx, 0);
+        const bool internal = D.nm_len > 0 && bit_at(bitmap_bits(base, D.nm_len, D.nm_base), 0);
+        C.smax0 = vmax;
+        C.smin0 = internal ? dac_get1<V>(mn, 0) : vmax;  // the root's min entry is the absolute minimum (snapshot.rs:139-141)
+      }
+    };
+    if (snap0 != ti0) {
+      prefetch_dir4<V, Tile4Smem<V>>(dir + snap0, S, 2);
+      prefetch4<V, Tile4Smem<V>>(chunk, dir[snap0].off, dir[snap0].size, S, 1);
+      cp_async_wait_all();
+      __syncthreads();
+      {
+        u32 delta;
+        const bool st = staged4<V>(chunk, S.dir[2], delta);
+        const u8* base = st ? S.stage[1] + (int32_t)delta : chunk;
+        snapshot_root(base, S.dir[2]);
+        const CountOut<V> O2 = O;
+        instant4_global<V, Tile4Smem<V>, CountOut<V>>(base, &S.dir[2], true, false, L, &S, &O2);
+      }
+      __syncthreads();
+    }
+    prefetch_dir4<V, Tile4Smem<V>>(dir + ti0, S, 0);
+    prefetch4<V, Tile4Smem<V>>(chunk, dir[ti0].off, dir[ti0].size, S, 0);
+    if (n_t > 1) prefetch_dir4<V, Tile4Smem<V>>(dir + ti0 + 1, S, 1);
+    u32 rs = 0;  // i % 3
+    // entries that cover an instant: one bit per entry, built one instant ahead by the first two warps (read after the
+    // barrier at the top of that instant)
+    auto mark_active = [&](u32 t_next, u32 parity) {
+      if (tid < CT_MAX) {
+        const bool on = tid < (int)J.ent_count && C.keep[tid] && t_next >= (u32)C.ent[tid].t0 && t_next < (u32)C.ent[tid].t1;
+        const u32 w = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) reinterpret_cast<u32*>(&C.act[parity])[warp] = w;
+      }
+    };
+    mark_active(ti0, 0u);
+    // counters of instant i - 1 go to counts[] while instant i is decoded (nobody adds to them any more)
+    auto flush = [&](u32 t_done, u32 b) {
+      if (tid < (int)J.ent_count) {
+        const u32 c = C.cnt[b][tid];
+        if (c) {
+          const CountEntry& E = C.ent[tid];
+          P.counts[E.cnt_base + (i64)t_done] = (u64)c;
+          C.cnt[b][tid] = 0;
+        }
+      }
+    };
+    for (u32 i = 0; i < n_t; i++) {
+      const int b = (int)(i & 1u);
+      const u32 ti = ti0 + i;
+      const u32 slot1 = rs == 2 ? 0u : rs + 1u, slot2 = slot1 == 2 ? 0u : slot1 + 1u;
+      cp_async_wait_all();
+      __syncthreads();  // structure i and directory entry i+1 have landed; everyone is done with instant i-1
+      if (i + 1 < n_t) {
+        prefetch4<V, Tile4Smem<V>>(chunk, S.dir[slot1].off, S.dir[slot1].size, S, b ^ 1);
+        if (i + 2 < n_t) prefetch_dir4<V, Tile4Smem<V>>(dir + ti + 2, S, slot2);
+      }
+      if (i > 0) flush(ti - 1u, (u32)(b ^ 1));
+      if (i + 1 < n_t) mark_active(ti + 1u, (u32)(b ^ 1));
+      const InstDir& D = S.dir[rs];
+      rs = slot1;
+      const bool is_snap = D.snap == ti;
+      u32 delta;
+      const bool st = staged4<V>(chunk, D, delta);
+      const u8* base = st ? S.stage[b] + (int32_t)delta : chunk;
+      O.t = ti; O.buf = (u32)b;
+      O.single_log = false;
+      if (is_snap) {
+        // written by thread 0 now, read by Logs after the next barrier; this instant itself does not use it
+        snapshot_root(base, D);
+      } else {
+        const bool internal = D.nm_len > 0 && bit_at(bitmap_bits(base, D.nm_len, D.nm_base), 0);
+        O.single_log = !internal;
+        O.e_root = dac_get1<V>(dac4_of(base, &D.max), 0);
+      }
+      if (st) {
+        instant4<V, Tile4Smem<V>, CountOut<V>>(base, D, is_snap, true, L, S, O);
+      } else {
+        const CountOut<V> O2 = O;  // only the copy has its address taken
+        instant4_global<V, Tile4Smem<V>, CountOut<V>>(chunk, &D, is_snap, true, L, &S, &O2);
+      }
+    }
+    __syncthreads();
+    flush(ti0 + n_t - 1u, (u32)((n_t - 1u) & 1u));
   }
 }
 

@@ -182,6 +182,7 @@ DCDF_DEVINL u32 below(u32 inb, int c) { return __popc(inb & ((1u << c) - 1u)); }
 
 // Where the cells of the current (window, tile, instant) go.
 struct QuadOut {
+  static constexpr bool search_quirk = false;
   CellOut co;
   u64 base;       // element index of tile cell (0, 0) at this instant
   i64 pitch;      // window columns
@@ -237,6 +238,7 @@ struct CellRef {
 // of the tile in shared memory (one instant), from which the CTA then serves every series of the tile.
 template <typename V>
 struct SeriesOut {
+  static constexpr bool search_quirk = false;
   V* img;     // the thread's 16 cells: img[4 * quad + cell]
   u32 mask;   // asked-for cells of the block (bit 4 * quad + cell); 0: nothing to decode
   static constexpr bool vec4 = false;
@@ -253,6 +255,91 @@ struct SeriesOut {
     if (!(mask & (0xffu << (8u * (((u32)r0 >> 1) & 1u))))) return;  // nothing asked for in this half of the block
     put(r0, c0, a);
     put(r0, c0 + 2, b);
+  }
+};
+
+// Value-range COUNTS of many windows over one tile (k_count_tiles4): the windows of a batch that touch the tile in this time
+// slice share one decode of every instant.  An entry = one (window, tile): its rectangle inside the tile, its band, the
+// instants of the slice it covers and where its per-instant counts go.
+struct CountEntry {
+  i64 cnt_base;          // counts[cnt_base + t] for the slice-local instant t
+  i64 lower, upper;
+  uint16_t t0, t1;       // slice-local instants [t0, t1)
+  u8 top, bottom, left, right;  // tile coordinates, exclusive ends (<= 64)
+};
+constexpr int CT_MAX = 64;  // entries per job (a tile touched by more windows is split into several jobs)
+template <typename V>
+struct CountShared {
+  CountEntry ent[CT_MAX];
+  V lo[CT_MAX], hi[CT_MAX];  // the entry's band in the expansion's value type (clamped; lo > hi: no value can match)
+  u32 cnt[2][CT_MAX];   // hits of the instant being decoded / of the previous one (flushed while the next one is decoded)
+  u32 keep[CT_MAX];     // 0: pruned by the superchunk's min / max tables (superchunk.rs:480-493)
+  unsigned long long act[2];  // entries that cover the instant being decoded (by instant parity)
+  V smin0, smax0;       // root of the block's snapshot
+  u32 n;
+};
+// Same interface as QuadOut towards the block decoder: the values of one half of the thread's block are tested against
+// every entry whose rectangle touches the block.  The hit SET of the reference's traversal (snapshot.rs:310-421,
+// log.rs:519-702) is "value inside the band" because every node test uses exact bounds -- with one exception that is
+// reproduced here: for a Log that is a single node the traversal tests the root with min_t = 0 (the empty min Dac,
+// log.rs:527-548) and from there on reads the Log as "snapshot + root entry" whether or not its `equal` bit is set
+// (SURVEY App. B #15).  log4 builds those values (search_quirk); the root test is applied per entry below.
+template <typename V>
+struct CountOut {
+  static constexpr bool search_quirk = true;
+  static constexpr bool vec4 = false;
+  CountShared<V>* C;
+  unsigned long long mine;  // entries whose rectangle touches the thread's block
+  int R0, C0;               // the block's origin
+  u32 t;                    // slice-local instant
+  u32 buf;                  // counter set / activity mask of this instant
+  bool single_log;          // the instant is a single-node Log
+  V e_root;                 // ... and its root entry
+  DCDF_DEVINL bool touches(int, int, int) const { return mine != 0ull; }
+  DCDF_DEVINL bool inside(int, int, int) const { return false; }
+  DCDF_DEVINL void put_pair(bool, int r0, int c0, const V (&a)[4], const V (&b)[4]) const {
+    unsigned long long m = mine & C->act[buf];
+    if (!m) return;
+    // the strip's own range first: most bands miss it or hold all of it
+    const V vmin = min(min(min(a[0], a[1]), min(a[2], a[3])), min(min(b[0], b[1]), min(b[2], b[3])));
+    const V vmax = max(max(max(a[0], a[1]), max(a[2], a[3])), max(max(b[0], b[1]), max(b[2], b[3])));
+    while (m) {
+      const int e = __ffsll((long long)m) - 1;
+      m &= m - 1ull;
+      const V lo = C->lo[e], hi = C->hi[e];
+      bool all = false, none = false;
+      if (single_log) {  // the traversal's root test (log.rs:527-548 with min_t = 0)
+        const CountEntry& E = C->ent[e];
+        const i64 mn = (i64)C->smin0, mx = (i64)C->smax0 + (i64)e_root;
+        all = mn >= E.lower && mx <= E.upper;
+        none = !all && (mn > E.upper || mx < E.lower);
+      }
+      if (none || (!all && (vmax < lo || vmin > hi))) continue;
+      // cells of this 2x4 strip inside the entry's rectangle: bits 0..3 = a, 4..7 = b (cell = 2 * (row & 1) + (col & 1))
+      const uchar4 rc = *reinterpret_cast<const uchar4*>(&C->ent[e].top);  // top, bottom, left, right
+      const u32 rowm = ((r0 >= (int)rc.x && r0 < (int)rc.y) ? 0x33u : 0u) | ((r0 + 1 >= (int)rc.x && r0 + 1 < (int)rc.y) ? 0xccu : 0u);
+      const u32 colm = ((c0 >= (int)rc.z && c0 < (int)rc.w) ? 0x05u : 0u) | ((c0 + 1 >= (int)rc.z && c0 + 1 < (int)rc.w) ? 0x0au : 0u) |
+                       ((c0 + 2 >= (int)rc.z && c0 + 2 < (int)rc.w) ? 0x50u : 0u) | ((c0 + 3 >= (int)rc.z && c0 + 3 < (int)rc.w) ? 0xa0u : 0u);
+      const u32 in = rowm & colm;
+      if (!in) continue;
+      u32 hit = in;
+      if (!all && !(vmin >= lo && vmax <= hi)) {
+        hit = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (a[i] >= lo && a[i] <= hi) hit |= 1u << i;
+          if (b[i] >= lo && b[i] <= hi) hit |= 16u << i;
+        }
+        hit &= in;
+      }
+      if (hit) atomicAdd(&C->cnt[buf][e], (u32)__popc(hit));
+    }
+  }
+  DCDF_DEVINL void put(int r0, int c0, const V (&v)[4]) const {  // trees of side 2: one quad at (0, 0)
+    // the second quad of the strip lies outside every rectangle of a 2x2 tile (right <= 2); it repeats the first one so
+    // that the strip's range is the quad's
+    CountOut o = *this;
+    o.put_pair(false, r0, c0, v, v);
   }
 };
 

@@ -120,6 +120,7 @@ struct dcdf_ctx {
     uint32_t cell_tile_min = 64;         // cell series: tiles with at least this many series of a batch are decoded by the tile decoder (0: never)
     int window_cells = 0;                // windows through the per-cell walker (the path of trees larger than 64x64)
     int window_wide = 0;                 // 64-bit expansion even when every DAC code fits three bytes
+    uint32_t search_share_min = 3;       // value-range search: shared decodes for the counting pass from this many windows per touched (slice, tile) on (0: never)
     int search_dfs = 0;                  // depth-first search kernel instead of the tile search
     int search_no_cache = 0;             // the search's writing pass recomputes instead of reading cached findings
     int trace = 0;                       // host-side phase times of the encode pipeline on stderr (adds stream syncs)

@@ -95,6 +95,8 @@ int32_t dcdf_ctx_set_stream(dcdf_ctx* ctx, void* cuda_stream);
  *                           the tile decoder instead of one root-to-leaf walk per (series, instant) (default 64, the measured break-even; 0 = never)
  *   "window_cells" 0|1      windows through the per-cell walker (the path of trees larger than 64x64)
  *   "window_wide" 0|1       64-bit tile expansion even when every DAC code fits three bytes
+ *   "search_share_min" <n>  value-range search: when the windows of a batch overlap (>= n windows per touched (time slice, tile)
+ *                           on average; default 3, 0 = never) the counting pass decodes every touched tile once for all of them
  *   "search_dfs" 0|1        depth-first search kernel instead of the tile search
  *   "search_no_cache" 0|1   search's writing pass recomputes instead of reading the counting pass's findings
  *   "trace" 0|1             host-side phase times of the encode pipeline on stderr

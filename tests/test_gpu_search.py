@@ -17,10 +17,16 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["default", "shared", "per_window"])
+def ctx(request):
+    """shared: the counting pass always decodes every touched (time slice, tile) once for all windows of the batch
+    (search_share_min = 1); per_window: never; default: from three windows per touched tile on."""
     from dcdf_b200 import Context
     c = Context(0)
+    if request.param == "shared":
+        c.set_option("search_share_min", 1)
+    if request.param == "per_window":
+        c.set_option("search_share_min", 0)
     yield c
     c.close()
 
@@ -148,3 +154,30 @@ def test_superchunk_search_prunes_with_the_superchunk_min_max_like_the_reference
         for a, b in zip(mine, series):
             assert np.array_equal(a, b)
         got.close()
+
+
+def test_single_node_logs_follow_the_reference_traversal(ctx):
+    """SURVEY Appendix B #15 through every counting path: a Log that is one node (the tile is uniform, or equal to its
+    snapshot plus a constant, at that instant) is tested by the reference with min_t = 0 at the root and read as
+    "snapshot + root entry" below it.  Counts and cells against the oracle for many bands, several windows per call."""
+    import fixtures as fx
+    from dcdf_b200 import Superchunk
+    rng = np.random.default_rng(5)
+    a = fx.array8_3()
+    frames = [a[0], np.full((8, 8), 5, np.int64), a[0] + 3, a[0] - 2, np.full((8, 8), -4, np.int64), a[1], np.full((8, 8), 9, np.int64), a[1] + 1]
+    data = np.stack([np.tile(f, (2, 2)) for f in frames])          # four 8x8 subchunks with the same history
+    data[:, 8:, 8:] += 1
+    got, ref = Superchunk.build(ctx, data, [1, 3]), orc.superchunk_build(data, [1, 3])
+    T = len(frames)
+    cubes, los, his = [], [], []
+    for lo in range(-8, 14, 2):
+        for width in (0, 1, 3, 20):
+            t0 = int(rng.integers(0, T - 1))
+            r0, c0 = int(rng.integers(0, 14)), int(rng.integers(0, 14))
+            cubes.append([t0, int(rng.integers(t0 + 1, T + 1)), r0, int(rng.integers(r0 + 1, 17)), c0, int(rng.integers(c0 + 1, 17))])
+            los.append(lo); his.append(lo + width)
+    counts, cells = got.search_batch(cubes, los, his)
+    rcounts, rcells, _ = ref.search_batch(cubes, los, his)
+    assert counts.tolist() == rcounts.tolist()
+    assert np.array_equal(cells, rcells)
+    got.close()
