@@ -390,7 +390,7 @@ def search_leg(ctx, sc, T, rows, cols, n_windows, peak, sectors_per_window, valu
         algo = 32.0 * sectors_per_window * ns + 24.0 * float(c2.sum())
         res["roofline"] = {"bound": "hbm", "achieved": algo / (k_full * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                            "frac": algo / (k_full * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes": int(algo),
-                           "kernel": "k_search_tiles4<int> (count + write passes)",
+                           "kernel": "k_search_tiles4<int> (count + write passes of the windows whose cells are wanted; the count-only leg runs k_count_tiles4)",
                            "model": f"sector model: 32 B x {sectors_per_window:.0f} distinct sectors per window (oracle, sample slice) x {ns} windows + 24 B per match"}
     return res
 
