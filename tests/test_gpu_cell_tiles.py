@@ -89,3 +89,15 @@ def test_dense_series_plain_chunk_and_small_trees(ctx):
         T, R, C = shape
         _check(ch, data, _queries(rng, T, R, C, 400))
         ch.close()
+
+
+def test_dense_series_nested_superchunk(ctx):
+    """Three k2_levels entries (superchunks inside a superchunk, BASELINE configs[4]'s shape of tree)."""
+    from dcdf_b200 import Superchunk
+    rng = np.random.default_rng(14)
+    T, R, C = 24, 200, 230
+    data = (rng.integers(0, 64, (T, R, C)) / 4).astype(np.float32)
+    data[:, 128:192, 64:128] = 1.25           # an elided leaf
+    sc = Superchunk.build(ctx, data, [1, 1, 6], compute_bits=True, chunk_size=8)
+    _check(sc, data, _queries(rng, T, R, C, 6000))
+    sc.close()
