@@ -368,7 +368,7 @@ def search_leg(ctx, sc, T, rows, cols, n_windows, peak, sectors_per_window, valu
     vmin, vmax = value_range
     band = max(1, int((vmax - vmin) * 0.05))
     lo_v = rng.integers(vmin, vmax, n_windows)
-    sc.search_batch(cubes[:256], lo_v[:256], lo_v[:256] + band, want_cells=False)
+    sc.search_batch(cubes, lo_v, lo_v + band, want_cells=False)  # warm-up at full size: the per-job count buffers grow here, not inside the timed call
     t0 = time.perf_counter()
     counts, _ = sc.search_batch(cubes, lo_v, lo_v + band, want_cells=False)  # counting pass: 10^5 windows hold ~10^9 matches
     t_count = time.perf_counter() - t0
