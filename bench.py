@@ -387,6 +387,12 @@ def search_leg(ctx, sc, T, rows, cols, n_windows, peak, sectors_per_window, valu
            "with_cells": {"windows": ns, "matches": int(c2.sum()), "kernel_ms_both_passes": k_full, "windows_per_s_e2e": ns / t_full,
                           "windows_per_s_kernel": ns / (k_full * 1e-3), "cells_scanned_per_s_kernel": vol_s / (k_full * 1e-3)}}
     if sectors_per_window:
+        # count-only leg: the windows overlap, so the bytes that have to move are every encoded byte once at most
+        algo_c = min(32.0 * sectors_per_window * n_windows, float(sc.total_bytes())) + 8.0 * n_windows
+        res["count_roofline"] = {"bound": "hbm", "achieved": algo_c / (k_count * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": algo_c / (k_count * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes": int(algo_c),
+                                 "kernel": "k_count_tiles4<int> + the scan of the per-job counts",
+                                 "model": "min(sector model x windows, every encoded byte once) + 8 B per window"}
         algo = 32.0 * sectors_per_window * ns + 24.0 * float(c2.sum())
         res["roofline"] = {"bound": "hbm", "achieved": algo / (k_full * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                            "frac": algo / (k_full * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes": int(algo),
