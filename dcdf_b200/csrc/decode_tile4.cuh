@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_count_ti
     const InstDir* dir = Q.dir + m.dir_base;
     const int L = 31 - __clz(m.sidelen);
     CountOut<V> O;
-    O.C = &C; O.mine = mine; O.R0 = R0; O.C0 = C0; O.t = t_lo; O.buf = 0; O.single_log = false; O.e_root = 0;
+    O.C = &C; O.mine = mine; O.R0 = R0; O.C0 = C0; O.t = t_lo; O.buf = 0; O.is_log = false; O.min_t = 0; O.e_root = 0;
     const u32 ti0 = t_lo, n_t = t_hi - t_lo;
     const u32 snap0 = dir[ti0].snap;
     // the block's snapshot is expanded first when the first instant is a Log; every Snapshot on the way leaves its root's
@@ -613,9 +613,9 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_count_ti
       if (tid == 0) {
         const Dac4 mx = dac4_of(base, &D.max), mn = dac4_of(base, &D.min);
         const V vmax = dac_get1<V>(mx, 0);
-        const bool internal = D.nm_len > 0 && bit_at(bitmap_bits(base, D.nm_len, D.nm_base), 0);
         C.smax0 = vmax;
-        C.smin0 = internal ? dac_get1<V>(mn, 0) : vmax;  // the root's min entry is the absolute minimum (snapshot.rs:139-141)
+        C.smin0 = dac_get1<V>(mn, 0);  // the root's min entry is the absolute minimum (snapshot.rs:139-141); a single-node
+                                       // Snapshot has no min Dac and the reference reads 0 from it (dac.rs:80-93)
       }
     };
     if (snap0 != ti0) {
@@ -677,14 +677,13 @@ __global__ void __launch_bounds__(DT_THREADS, sizeof(V) == 4 ? 4 : 2) k_count_ti
       const bool st = staged4<V>(chunk, D, delta);
       const u8* base = st ? S.stage[b] + (int32_t)delta : chunk;
       O.t = ti; O.buf = (u32)b;
-      O.single_log = false;
+      O.is_log = !is_snap;
       if (is_snap) {
         // written by thread 0 now, read by Logs after the next barrier; this instant itself does not use it
         snapshot_root(base, D);
       } else {
-        const bool internal = D.nm_len > 0 && bit_at(bitmap_bits(base, D.nm_len, D.nm_base), 0);
-        O.single_log = !internal;
         O.e_root = dac_get1<V>(dac4_of(base, &D.max), 0);
+        O.min_t = dac_get1<V>(dac4_of(base, &D.min), 0);
       }
       if (st) {
         instant4<V, Tile4Smem<V>, CountOut<V>>(base, D, is_snap, true, L, S, O);

@@ -281,9 +281,11 @@ struct CountShared {
 // Same interface as QuadOut towards the block decoder: the values of one half of the thread's block are tested against
 // every entry whose rectangle touches the block.  The hit SET of the reference's traversal (snapshot.rs:310-421,
 // log.rs:519-702) is "value inside the band" because every node test uses exact bounds -- with one exception that is
-// reproduced here: for a Log that is a single node the traversal tests the root with min_t = 0 (the empty min Dac,
-// log.rs:527-548) and from there on reads the Log as "snapshot + root entry" whether or not its `equal` bit is set
-// (SURVEY App. B #15).  log4 builds those values (search_quirk); the root test is applied per entry below.
+// reproduced here: a Log's ROOT is tested with min = snapshot.min.get(0) + log.min.get(0) and max = snapshot.max.get(0) +
+// log.max.get(0) (log.rs:527-548), and an empty min Dac yields 0 (dac.rs:80-93).  So a Log over a single-node Snapshot, and
+// a Log that is a single node itself, are tested against a wrong lower bound; a single-node Log is
+// moreover read as "snapshot + root entry" whether or not its `equal` bit is set.  log4 builds those values
+// (search_quirk); the root test is applied per entry below, to every Log instant (it changes nothing when it is exact).
 template <typename V>
 struct CountOut {
   static constexpr bool search_quirk = true;
@@ -293,8 +295,8 @@ struct CountOut {
   int R0, C0;               // the block's origin
   u32 t;                    // slice-local instant
   u32 buf;                  // counter set / activity mask of this instant
-  bool single_log;          // the instant is a single-node Log
-  V e_root;                 // ... and its root entry
+  bool is_log;              // the instant is a Log: the reference's root test applies
+  V min_t, e_root;          // its root entries (min Dac: 0 when empty)
   DCDF_DEVINL bool touches(int, int, int) const { return mine != 0ull; }
   DCDF_DEVINL bool inside(int, int, int) const { return false; }
   DCDF_DEVINL void put_pair(bool, int r0, int c0, const V (&a)[4], const V (&b)[4]) const {
@@ -308,9 +310,9 @@ struct CountOut {
       m &= m - 1ull;
       const V lo = C->lo[e], hi = C->hi[e];
       bool all = false, none = false;
-      if (single_log) {  // the traversal's root test (log.rs:527-548 with min_t = 0)
+      if (is_log) {  // the traversal's root test (log.rs:527-548)
         const CountEntry& E = C->ent[e];
-        const i64 mn = (i64)C->smin0, mx = (i64)C->smax0 + (i64)e_root;
+        const i64 mn = (i64)C->smin0 + (i64)min_t, mx = (i64)C->smax0 + (i64)e_root;
         all = mn >= E.lower && mx <= E.upper;
         none = !all && (mn > E.upper || mx < E.lower);
       }
