@@ -21,3 +21,14 @@ def test_batch_kernels_agree_with_the_per_query_kernels(seed):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run(seed, 9)
+
+
+@pytest.mark.parametrize("seed,fast", [(1, False), (11, True)])
+def test_encoder_bytes_on_temporal_patterns(seed, fast):
+    """profiles/tools/stress_encode.py: Superchunk::build byte for byte against the oracle on rasters with uniform
+    instants, constant offsets between instants, NaNs, clipped tiles, nested trees and 64-bit values; fast = f32 rasters with
+    64-side leaves and long slices, most of whose units take the fast-path encoder."""
+    spec = importlib.util.spec_from_file_location("stress_encode", os.path.join(ROOT, "profiles", "tools", "stress_encode.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(seed, 6, fast)
