@@ -71,7 +71,26 @@ def run(seed, n_cases):
         ok_c = bool(np.array_equal(fa, fb, equal_nan=True))
         want = np.concatenate([data[a:b, r, c] for a, b, r, c in q]) if nq else fa
         ok_i = bool(np.array_equal(fa, want, equal_nan=True))
-        print(f"case {case}: {kind} levels {levels} {T}x{R}x{C} chunk_size {cs}: search {ok_s} ({int(ca.sum())} hits)  cells {ok_c} input {ok_i}", flush=True)
+        # hits WITH cells (count + write passes of the per-window kernel) against the oracle, order included: windows
+        # inside one time slice, two-level trees (for nested ones the reference's order is region-major)
+        ok_o = True
+        if len(levels) == 2:
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
+            import oracle_lib as orc
+            sl = int(rng.integers(0, (T + cs - 1) // cs))
+            s0, s1 = sl * cs, min(T, (sl + 1) * cs)
+            ref = orc.superchunk_build(data[s0:s1], levels, **({"compute_bits": True} if kind == "f32" else {}))
+            k = 12
+            a_ = rng.integers(0, s1 - s0, k); b_ = np.minimum(s1 - s0, a_ + rng.integers(1, s1 - s0 + 1, k))
+            loc = np.stack([a_, b_, r0[:k], r1[:k], c0[:k], c1[:k]], axis=1)
+            glob = loc.copy(); glob[:, 0] += s0; glob[:, 1] += s0
+            gc, gcells = scs["plain"].search_batch(glob, lo[:k], hi[:k])
+            rc, rcells, _ = ref.search_batch(loc, lo[:k], hi[:k])
+            if rcells is not None and len(rcells):
+                rcells = rcells.copy(); rcells[:, 0] += s0
+            ok_o = gc.tolist() == rc.tolist() and (int(gc.sum()) == 0 or bool(np.array_equal(gcells, rcells)))
+        print(f"case {case}: {kind} levels {levels} {T}x{R}x{C} chunk_size {cs}: search {ok_s} ({int(ca.sum())} hits)  cells {ok_c} input {ok_i} oracle order {ok_o}", flush=True)
+        ok_s = ok_s and ok_o
         if not (ok_s and ok_c and ok_i):
             bad = np.nonzero(ca != cb)[0][:5]
             print("first differing windows", bad, cubes[bad].tolist(), lo[bad].tolist(), hi[bad].tolist(), "shared", ca[bad].tolist(), "per window", cb[bad].tolist())
