@@ -181,3 +181,35 @@ def test_single_node_logs_follow_the_reference_traversal(ctx):
     assert counts.tolist() == rcounts.tolist()
     assert np.array_equal(cells, rcells)
     got.close()
+
+
+def test_logs_over_a_single_node_snapshot_follow_the_reference_root_test(ctx):
+    """A block whose Snapshot is one node (the tile is uniform at that instant): the reference tests the root of every Log of
+    the block with snapshot.min.get(0) + log.min.get(0), and the empty min Dac of a single-node Snapshot reads 0
+    (log.rs:527-548, dac.rs:80-93) -- bands below the wrong bound find nothing, bands above it may find everything.  Counts
+    and cells against the oracle in every counting mode."""
+    import fixtures as fx
+    from dcdf_b200 import Superchunk
+    rng = np.random.default_rng(6)
+    a = fx.array8_3()
+    frames = [np.full((8, 8), -13, np.int64), a[0] - 40, a[0] - 41, a[1] - 40, np.full((8, 8), 7, np.int64), a[0] - 39, a[1] + 50, a[0] - 40]
+    data = np.stack([np.tile(f, (2, 2)) for f in frames])
+    data[:, 8:, :8] -= 3
+    got, ref = Superchunk.build(ctx, data, [1, 3]), orc.superchunk_build(data, [1, 3])
+    T = len(frames)
+    cubes, los, his = [], [], []
+    for lo in range(-60, 70, 5):
+        for width in (0, 4, 12, 200):
+            t0 = int(rng.integers(0, T - 1))
+            r0, c0 = int(rng.integers(0, 14)), int(rng.integers(0, 14))
+            cubes.append([t0, int(rng.integers(t0 + 1, T + 1)), r0, int(rng.integers(r0 + 1, 17)), c0, int(rng.integers(c0 + 1, 17))])
+            los.append(lo); his.append(lo + width)
+    cubes.append([0, T, 0, 16, 0, 16]); los.append(-30); his.append(1000)
+    cubes.append([0, T, 0, 16, 0, 16]); los.append(-1000); his.append(-36)     # everything below a bound
+    counts, cells = got.search_batch(cubes, los, his)
+    only_counts, _ = got.search_batch(cubes, los, his, want_cells=False)
+    rcounts, rcells, _ = ref.search_batch(cubes, los, his)
+    assert counts.tolist() == rcounts.tolist()
+    assert only_counts.tolist() == rcounts.tolist()
+    assert np.array_equal(cells, rcells)
+    got.close()
