@@ -71,6 +71,13 @@ def run(seed, n_cases):
         ok_c = bool(np.array_equal(fa, fb, equal_nan=True))
         want = np.concatenate([data[a:b, r, c] for a, b, r, c in q]) if nq else fa
         ok_i = bool(np.array_equal(fa, want, equal_nan=True))
+        # windows and single cells against the input
+        wflat, woff = scs["plain"].window_batch(cubes[:60])
+        ok_w = all(bool(np.array_equal(wflat[int(woff[i]):int(woff[i + 1])], data[a:b, r_a:r_b, c_a:c_b].ravel(), equal_nan=True))
+                   for i, (a, b, r_a, r_b, c_a, c_b) in enumerate(cubes[:60]))
+        irc = np.stack([rng.integers(0, T, 2000), rng.integers(0, R, 2000), rng.integers(0, C, 2000)], axis=1)
+        ok_g = bool(np.array_equal(scs["plain"].get_batch(irc), data[irc[:, 0], irc[:, 1], irc[:, 2]], equal_nan=True))
+        ok_i = ok_i and ok_w and ok_g
         # hits WITH cells (count + write passes of the per-window kernel) against the oracle, order included: windows
         # inside one time slice, two-level trees (for nested ones the reference's order is region-major)
         ok_o = True
