@@ -201,15 +201,34 @@ DCDF_DEVINL void e5_load_node(const float* pn, i64 sr, uint4 (&raw)[4], int rl, 
     }
   }
 }
+// ... without the NaN test: a NaN comes out as as_int(NaN) - (0x4B400000 - 1) > 2^29, far above any eligible value
+DCDF_DEVINL int e5_conv_raw(float x, float scale2) { return __float_as_int(__fmaf_rn(x, scale2, 12582912.0f)) - (0x4B400000 - 1); }
+DCDF_DEVINL int e5_nan0(u32 bits, int f) { return (bits & 0x7fffffffu) > 0x7f800000u ? 0 : f; }
 template <bool FULL>
 DCDF_DEVINL void e5_quads(const uint4 (&raw)[4], float scale2, int4 (&q)[4], int rl, int cl) {
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     const uint4 u = raw[2 * h], l = raw[2 * h + 1];
-    q[2 * h] = make_int4(e5_conv(__uint_as_float(u.x), scale2), e5_conv(__uint_as_float(u.y), scale2),
-                         e5_conv(__uint_as_float(l.x), scale2), e5_conv(__uint_as_float(l.y), scale2));
-    q[2 * h + 1] = make_int4(e5_conv(__uint_as_float(u.z), scale2), e5_conv(__uint_as_float(u.w), scale2),
-                             e5_conv(__uint_as_float(l.z), scale2), e5_conv(__uint_as_float(l.w), scale2));
+    q[2 * h] = make_int4(e5_conv_raw(__uint_as_float(u.x), scale2), e5_conv_raw(__uint_as_float(u.y), scale2),
+                         e5_conv_raw(__uint_as_float(l.x), scale2), e5_conv_raw(__uint_as_float(l.y), scale2));
+    q[2 * h + 1] = make_int4(e5_conv_raw(__uint_as_float(u.z), scale2), e5_conv_raw(__uint_as_float(u.w), scale2),
+                             e5_conv_raw(__uint_as_float(l.z), scale2), e5_conv_raw(__uint_as_float(l.w), scale2));
+  }
+  // NaN -> 0 (fixed.rs:35-37), looked for once per node instead of once per cell: the largest of the sixteen values
+  {
+    const int m01 = max(max(max(q[0].x, q[0].y), max(q[0].z, q[0].w)), max(max(q[1].x, q[1].y), max(q[1].z, q[1].w)));
+    const int m23 = max(max(max(q[2].x, q[2].y), max(q[2].z, q[2].w)), max(max(q[3].x, q[3].y), max(q[3].z, q[3].w)));
+    if (max(m01, m23) > (1 << 28)) {
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const uint4 u = raw[2 * h], l = raw[2 * h + 1];
+        q[2 * h] = make_int4(e5_nan0(u.x, q[2 * h].x), e5_nan0(u.y, q[2 * h].y), e5_nan0(l.x, q[2 * h].z), e5_nan0(l.y, q[2 * h].w));
+        q[2 * h + 1] = make_int4(e5_nan0(u.z, q[2 * h + 1].x), e5_nan0(u.w, q[2 * h + 1].y), e5_nan0(l.z, q[2 * h + 1].z), e5_nan0(l.w, q[2 * h + 1].w));
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
     if (!FULL) {
       const bool ru = 2 * h < rl, rw = 2 * h + 1 < rl;
       if (!(ru && cl > 0)) q[2 * h].x = E4_NONE;
@@ -235,8 +254,10 @@ DCDF_DEVINL int e5_dn(int a, int b) { return e4_sub(a, b); }
 DCDF_DEVINL u32 e5_low4(int a, int b, int c, int d) { return __byte_perm(__byte_perm((u32)a, (u32)b, 0x0040), __byte_perm((u32)c, (u32)d, 0x0040), 0x5410); }
 DCDF_DEVINL u32 e5_zz4(u32 p) { return ((p + p) & 0xfefefefeu) ^ (((p >> 7) & 0x01010101u) * 0xffu); }
 DCDF_DEVINL u32 e5_pack4(u32 z0, u32 z1, u32 z2, u32 z3) { return (z0 & 0xffu) | ((z1 & 0xffu) << 8) | ((z2 & 0xffu) << 16) | (z3 << 24); }
+// ALIGNED: the staged image is shifted so that every group of four sibling entries starts on a word (the caller knows)
+template <bool ALIGNED = false>
 DCDF_DEVINL void e5_store_word(u8* p, u32 w) {
-  if ((((uintptr_t)p) & 3u) == 0) *reinterpret_cast<u32*>(p) = w;
+  if (ALIGNED || (((uintptr_t)p) & 3u) == 0) *reinterpret_cast<u32*>(p) = w;
   else { p[0] = (u8)w; p[1] = (u8)(w >> 8); p[2] = (u8)(w >> 16); p[3] = (u8)(w >> 24); }
 }
 
@@ -877,7 +898,7 @@ DCDF_DEVINL void e5_body(const EncParams& P, const u32 stage_limit, const int sy
             zxw |= (zigzag32(e5_dx<FULL>(n4.x, qmax)) & 0xffu) << (8 * b);
             znw |= (zigzag32(e5_dn(qmin, n4.y)) & 0xffu) << (8 * b);
             if (alive && ((in5a >> (3 - b)) & 1u))
-              e5_store_word(dst6 + 4u * (u32)__popc(in5a >> (4 - b)),
+              e5_store_word<decltype(in_shared)::value>(dst6 + 4u * (u32)__popc(in5a >> (4 - b)),
                             e5_pack4(zigzag32(e5_dx<FULL>(qmax, t.x)), zigzag32(e5_dx<FULL>(qmax, t.y)), zigzag32(e5_dx<FULL>(qmax, t.z)),
                                      zigzag32(e5_dx<FULL>(qmax, t.w))));
           }
@@ -887,11 +908,11 @@ DCDF_DEVINL void e5_body(const EncParams& P, const u32 stage_limit, const int sy
           if (alive) {
 #pragma unroll
             for (int b = 0; b < 4; b++)
-              if ((in5a >> (3 - b)) & 1u) e5_store_word(dst6 + 4u * (u32)__popc(in5a >> (4 - b)), S.leaf[4 * a + b][tid]);
+              if ((in5a >> (3 - b)) & 1u) e5_store_word<decltype(in_shared)::value>(dst6 + 4u * (u32)__popc(in5a >> (4 - b)), S.leaf[4 * a + b][tid]);
           }
         }
         if (!alive) continue;
-        e5_store_word(dst5, zxw);
+        e5_store_word<decltype(in_shared)::value>(dst5, zxw);
         dst5 += 4;
         dst6 += 4u * (u32)__popc(in5a);
 #pragma unroll
@@ -915,7 +936,7 @@ DCDF_DEVINL void e5_body(const EncParams& P, const u32 stage_limit, const int sy
           zx[a] = zigzag32(as_snapshot ? e5_dx<FULL>(t3max, n4.x) : e5_dx<FULL>(n4.x, s4.x));
           zn[a] = zigzag32(as_snapshot ? e5_dn(n4.y, t3min) : e5_dn(n4.y, s4.y));
         }
-        e5_store_word(xb0 + Pn4 + 4u * R3, e5_pack4(zx[0], zx[1], zx[2], zx[3]));
+        e5_store_word<decltype(in_shared)::value>(xb0 + Pn4 + 4u * R3, e5_pack4(zx[0], zx[1], zx[2], zx[3]));
         u8* dmn = nb0 + Mn4 + R4;
         if (W.mu & 0xffu) {
 #pragma unroll
