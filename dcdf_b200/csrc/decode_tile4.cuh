@@ -78,8 +78,9 @@ DCDF_DEVINL u32 tab_bits4(const RankTab& T, u32 idx) {  // bits idx .. idx+3 as 
   return __brev(__funnelshift_l(T.W[w + 1u], T.W[w], idx & 31u)) & 15u;
 }
 
-// Snapshot value of node pk of level k: levels 0 and 1 are shared between warps, every warp keeps its own copy so that
-// no warp ever reads what another one wrote (k_window_tiles5 lets warps drift apart by more than one instant).
+// Snapshot value of node pk of level k.  Levels 0 and 1 are shared between warps; a layout with PRIVATE_TOP keeps a copy
+// per warp so that no warp ever reads what another one wrote (needed by a decoder whose warps drift apart by more than one
+// instant -- the bulk-copy ring measured in round 1; every shipped layout has PRIVATE_TOP = false).
 template <typename S_>
 DCDF_DEVINL auto& sup_at(S_& S, int k, u32 pk) {
   if (!S_::PRIVATE_TOP) return S.sup[off3(k) + pk];

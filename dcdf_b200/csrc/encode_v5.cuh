@@ -116,30 +116,6 @@ DCDF_DEVINL void e5_top(E5Top& t, bool valid, int e, u32 lane) {
   }
 }
 DCDF_DEVINL int e5_lane5(u32 lane, int v0, const int (&v)[4]) { return lane == 0 ? v0 : lane == 1 ? v[0] : lane == 2 ? v[1] : lane == 3 ? v[2] : v[3]; }
-// Number of max-DAC entries longer than one byte that precede this thread's entries of tree level `level` (2..6).
-DCDF_DEVINL u32 e5_base_x(const E5Tot& T, const u32 (&pre)[4], int level) {
-  const u32 t = T.tot[1], p = pre[1];
-  u32 b = T.cmax[1] - e4_fsum(t) - T.tot[2];  // root and level-1 entries come first
-  if (level == 2) return b + e4_f2(p);
-  b += e4_f2(t);
-  if (level == 3) return b + e4_f3(p);
-  b += e4_f3(t);
-  if (level == 4) return b + e4_f4(p);
-  b += e4_f4(t);
-  if (level == 5) return b + e4_f5(p);
-  return b + e4_f5(t) + pre[2];
-}
-DCDF_DEVINL u32 e5_base_n(const E5Tot& T, const u32 (&pre)[4], int level) {
-  const u32 t = T.tot[3], p = pre[3];
-  u32 b = T.cmin[1] - e4_fsum(t);
-  if (level == 2) return b + e4_f2(p);
-  b += e4_f2(t);
-  if (level == 3) return b + e4_f3(p);
-  b += e4_f3(t);
-  if (level == 4) return b + e4_f4(p);
-  return b + e4_f4(t) + e4_f5(p);
-}
-
 // second byte of a two-byte code (DAC level 1): rare, out of line; returns the next position
 __device__ __noinline__ u32 e5_hi(u8* b1, u32 z, u32 r1) {
   b1[r1] = (u8)(z >> 8);
@@ -166,13 +142,6 @@ DCDF_DEVINL void e5_or_bit(u8* bytes, u32 bitpos) {
   const u32 g = bitpos + 8u * (u32)(A & 3u);
   e4_red_or(reinterpret_cast<u32*>(A & ~(uintptr_t)3) + (g >> 5), e4_bswap(0x80000000u >> (g & 31u)));
 }
-// to_fixed (a3) of an exact, finite, small value: n * 2^(bits+1) is an integer below 2^22, so adding 1.5 * 2^23
-// leaves it in the low mantissa bits (fixed.rs:59-70: trunc(2 * shifted) + 1).
-DCDF_DEVINL int e5_conv(float x, float scale2) {
-  const int f = __float_as_int(__fmaf_rn(x, scale2, 12582912.0f)) - (0x4B400000 - 1);
-  return x != x ? 0 : f;  // NaN -> 0 (fixed.rs:35-37)
-}
-
 // One level-4 node (4x4 cells at pn, row stride sr) as four quads (x, y = upper row; z, w = lower row).
 // Clipped tiles (FULL == false): rl / cl = rows / columns of the node that lie inside the raster (may be <= 0); cells
 // outside are not read and become None (E4_NONE, as in encode_v4.cuh: excluded from min / max, 0 in an entry).
@@ -201,7 +170,9 @@ DCDF_DEVINL void e5_load_node(const float* pn, i64 sr, uint4 (&raw)[4], int rl, 
     }
   }
 }
-// ... without the NaN test: a NaN comes out as as_int(NaN) - (0x4B400000 - 1) > 2^29, far above any eligible value
+// to_fixed (a3) of an exact, finite, small value: n * 2^(bits+1) is an integer below 2^22, so adding 1.5 * 2^23
+// leaves it in the low mantissa bits (fixed.rs:59-70: trunc(2 * shifted) + 1).  Without the NaN test: a NaN comes out as
+// as_int(NaN) - (0x4B400000 - 1) > 2^29, far above any eligible value (e5_quads looks for it once per node).
 DCDF_DEVINL int e5_conv_raw(float x, float scale2) { return __float_as_int(__fmaf_rn(x, scale2, 12582912.0f)) - (0x4B400000 - 1); }
 DCDF_DEVINL int e5_nan0(u32 bits, int f) { return (bits & 0x7fffffffu) > 0x7f800000u ? 0 : f; }
 template <bool FULL>
