@@ -10,9 +10,10 @@
   MMArray3.shape/get/cell/window   py-dcdf/src/lib.rs:497-538 (PyMMArray3F32), mmarray.rs:357-400
   search with float bounds         mmarray.rs:407-417 is todo!() upstream; chunk.rs:213-228 takes fixed-point bounds
 
-The store is any mapping CID (bytes) -> stored node bytes; datasets, coordinates and the Span node format stay with the
-host application (out of scope): a Variable here keeps the list of its slices' superchunk CIDs,
-which is what the reference's span tree resolves to.
+The store is any mapping CID (bytes) -> stored node bytes.  The slices' superchunk CIDs are kept in the reference's span
+tree (dcdf_b200/span.py: stored Span nodes, `Variable.cid` = the root span, dataset.rs:880-987), so a variable written here
+can be re-opened from its serialized form (`write_to` / `Variable.load`, dataset.rs:1012-1075); the flat lists below are
+what that tree resolves to, kept for routing.  Datasets and coordinates stay with the host application.
 """
 import collections
 import functools
@@ -21,6 +22,7 @@ import threading
 import numpy as np
 
 from . import _ffi
+from . import span as _span
 from .api import DcdfError, Superchunk
 
 
@@ -138,8 +140,10 @@ class MMArray3:
 class Variable(MMArray3):
     """One variable of a dataset: a time series of rasters stored as one superchunk per `chunk_size` instants."""
 
-    def __init__(self, ctx, store, k2_levels, chunk_size=64, round=None, span_size=8, dtype=np.float32, cache_bytes=1 << 30):
-        self.ctx, self.store = ctx, store
+    def __init__(self, ctx, store, k2_levels, chunk_size=64, round=None, span_size=8, dtype=np.float32, cache_bytes=1 << 30,
+                 name="data"):
+        self.ctx, self.store, self.name = ctx, store, str(name)
+        self.tree = None           # span tree (created with the first append, when the raster shape is known)
         self.k2_levels, self.chunk_size, self.round, self.span_size = tuple(k2_levels), int(chunk_size), round, int(span_size)
         self.dtype = np.dtype(dtype)
         self.roots = []            # CID of every time slice's superchunk node, in time order
@@ -159,7 +163,12 @@ class Variable(MMArray3):
         if tuple(data.shape[1:]) != (self.rows or data.shape[1], self.cols or data.shape[2]):
             raise ValueError("shape of the appended raster does not match the variable")
         self.rows, self.cols = int(data.shape[1]), int(data.shape[2])
+        if self.tree is None:      # Dataset::add_variable saves one empty span (dataset.rs:127-129)
+            self.tree = _span.SpanTree(self.store, self.rows, self.cols, self.chunk_size, self.span_size,
+                                       _span.ENCODINGS[self.dtype.name])
+        update = False
         if self.roots and self.instants[-1] < self.chunk_size:
+            update = True
             T = self.shape[0]
             tail = self.window(T - self.instants[-1], T, 0, self.rows, 0, self.cols)
             if is_t:
@@ -179,12 +188,76 @@ class Variable(MMArray3):
                     self.store[cid] = b
                 info = sc.info(s)
                 self.roots.append(nodes[-1][0])
+                self.tree.append(nodes[-1][0], int(info.shape[0]), update=update)   # span.update for the re-encoded tail
+                update = False
                 self.instants.append(int(info.shape[0]))
                 self.slice_bits.append(int(info.fractional_bits))
                 self.stats.append(stats)
         finally:
             sc.close()
+        self.tree.commit()         # Variable::save_spans
         return self
+
+    # ------------------------------------------------------------------ stored form
+    @property
+    def cid(self):
+        """CID of the root span (Variable.cid, dataset.rs:58); None before the first append."""
+        return self.tree.commit() if self.tree is not None else None
+
+    def write_to(self):
+        """The variable as it sits inside a Dataset node (dataset.rs:1018-1040): name, rounding, span_size, chunk_size,
+        k2_levels, encoding, CID of the root span."""
+        if self.tree is None:
+            raise ValueError("nothing appended yet: the root span needs the raster shape")
+        name = self.name.encode()
+        if len(name) > 255:
+            raise ValueError("name longer than 255 bytes")            # write_str: one length byte (extio.rs:260-265)
+        b = bytes([len(name)]) + name
+        b += bytes([1, self.round]) if self.round is not None else b"\x00"
+        b += self.span_size.to_bytes(4, "big") + self.chunk_size.to_bytes(4, "big") + bytes([len(self.k2_levels)])
+        for lv in self.k2_levels:
+            b += int(lv).to_bytes(4, "big")
+        return b + bytes([_span.ENCODINGS[self.dtype.name]]) + self.cid
+
+    @classmethod
+    def load(cls, ctx, store, stored, cache_bytes=1 << 30):
+        """Variable::load_from (dataset.rs:1042-1075) + a walk of the span tree down to the slices' superchunk nodes."""
+        stored = bytes(stored)
+        try:
+            n = stored[0]
+            name, p = stored[1:1 + n].decode(), 1 + n
+            rnd = None
+            if stored[p] == 1:
+                rnd, p = stored[p + 1], p + 1
+            p += 1
+            span_size, chunk_size = int.from_bytes(stored[p:p + 4], "big"), int.from_bytes(stored[p + 4:p + 8], "big")
+            nk, p = stored[p + 8], p + 9
+            k2 = [int.from_bytes(stored[p + 4 * i:p + 4 * i + 4], "big") for i in range(nk)]
+            p += 4 * nk
+            enc, root = stored[p], stored[p + 1:p + 1 + _span.CID_BYTES]
+            if len(root) != _span.CID_BYTES or len(stored) != p + 1 + _span.CID_BYTES:
+                raise IndexError
+        except IndexError:
+            raise DcdfError(6, "truncated or oversized Variable record") from None
+        dtypes = {v: k for k, v in _span.ENCODINGS.items()}
+        if enc not in dtypes:
+            raise DcdfError(6, f"unknown encoding {enc}")
+        v = cls(ctx, store, k2, chunk_size=chunk_size, round=rnd, span_size=span_size, dtype=np.dtype(dtypes[enc]),
+                cache_bytes=cache_bytes, name=name)
+        top = _span.Span.from_bytes(bytes(store[root]))
+        v.rows, v.cols = top.rows, top.cols
+        v.tree = _span.SpanTree(store, top.rows, top.cols, chunk_size, span_size, enc, root=root)
+        for cid in v.tree.chunks():
+            instants, rows, cols, bits, cenc = _span.superchunk_header(bytes(store[cid]))
+            if (rows, cols, cenc) != (top.rows, top.cols, enc):
+                raise DcdfError(6, "a time slice does not match its variable")
+            v.roots.append(cid)
+            v.instants.append(instants)
+            v.slice_bits.append(bits)
+            v.stats.append(None)
+        if sum(v.instants) != top.instants:
+            raise DcdfError(6, "span tree and time slices disagree on the number of instants")
+        return v
 
     # ------------------------------------------------------------------ geometry / routing
     @property

@@ -42,7 +42,25 @@ def test_append_with_tail_reencode_equals_one_build(ctx):
     with pytest.raises(DcdfError) as e:
         va.window(0, 123, 0, 150, 0, 200)
     assert e.value.code == 5
-    va.close(); vb.close()
+    # the span tree (dataset.rs:880-987): three appends with two tail updates end at the root one append builds, and at
+    # the root the step-by-step restatement of the reference reaches from the same chunk CIDs
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    import span_oracle as so
+    assert va.cid == vb.cid and store_b[vb.cid] == store_a[va.cid]
+    ov = so.OVariable({}, [150, 200], 16, 3, 32)
+    ov.append(list(zip(vb.roots, vb.instants)), False)
+    assert ov.cid == vb.cid
+    # re-open from the stored record in a fresh object (Variable::load_from, dataset.rs:1042-1075) and carry on appending
+    vc = Variable.load(ctx, store_a, va.write_to())
+    assert (vc.roots, vc.instants, vc.slice_bits, vc.shape) == (va.roots, va.instants, va.slice_bits, va.shape)
+    assert np.array_equal(vc.window(100, 122, 0, 150, 0, 200), data[100:122])
+    more = synth.raster_slice(122, 142, 150, 200).numpy()
+    vc.append(more)
+    vb.append(more)
+    assert vc.cid == vb.cid and vc.roots == vb.roots and vc.instants == [16] * 8 + [14]
+    assert np.array_equal(vc.window(110, 142, 0, 150, 0, 200), np.concatenate([data, more])[110:142])
+    va.close(); vb.close(); vc.close()
 
 
 def test_device_cache_is_lru_by_bytes_and_reloads_from_the_store(ctx):

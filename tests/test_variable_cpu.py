@@ -41,3 +41,115 @@ def test_getitem_follows_the_reference_dispatch():
         assert np.array_equal(got[0], a[idx][0])                                  # _Slice forwards indexing
     with pytest.raises(IndexError):
         v[1, 2, 3, 4]
+
+
+def _fake_superchunk_node(i, instants, rows, cols, bits, enc=32):
+    import struct
+    return bytes([0xDC, 0xE0, 0, 0, 0, 1, 2, 5]) + struct.pack(">IIIIBIIBB", instants, rows, cols, 64, 2, 16, 4, bits, enc) + b"%d" % i
+
+
+def test_variable_record_round_trip_through_the_span_tree():
+    """write_to / load (dataset.rs:1018-1075) and the walk of the span tree, on stand-in superchunk nodes (no GPU)."""
+    from dcdf_b200 import span as sp
+    from dcdf_b200.api import DcdfError
+    from dcdf_b200.variable import Variable
+    store = {}
+    v = Variable(None, store, [2, 2], chunk_size=20, round=2, span_size=3, name="dates")       # dataset.rs:1256
+    with pytest.raises(ValueError):
+        v.write_to()
+    v.rows, v.cols = 16, 16
+    v.tree = sp.SpanTree(store, 16, 16, 20, 3, sp.ENCODINGS["float32"])
+    lengths = [20] * 10 + [7]
+    for i, n in enumerate(lengths):
+        b = _fake_superchunk_node(i, n, 16, 16, 2 + i % 3)
+        cid = sp.cid_of(b)
+        store[cid] = b
+        v.tree.append(cid, n)
+        v.roots.append(cid); v.instants.append(n); v.slice_bits.append(2 + i % 3); v.stats.append(None)
+    rec = v.write_to()
+    assert rec[:6] == b"\x05dates" and rec[6:8] == b"\x01\x02"
+    assert rec[8:16] == (3).to_bytes(4, "big") + (20).to_bytes(4, "big") and rec[16] == 2
+    assert rec[17:25] == (2).to_bytes(4, "big") * 2 and rec[25] == 32 and rec[26:] == v.cid and len(rec) == 26 + 36
+    w = Variable.load(None, store, rec)
+    assert (w.name, w.round, w.span_size, w.chunk_size, w.k2_levels, w.dtype) == ("dates", 2, 3, 20, (2, 2), np.float32)
+    assert (w.roots, w.instants, w.slice_bits) == (v.roots, v.instants, v.slice_bits)
+    assert w.shape == [207, 16, 16] and w.cid == v.cid and w.tree.tail() == (v.roots[-1], 7)
+    u = Variable(None, store, [2, 2], chunk_size=20, round=None, span_size=3, name="apples")
+    u.rows, u.cols, u.tree = 16, 16, v.tree
+    assert Variable.load(None, store, u.write_to()).round is None
+    for bad in (rec[:-1], rec + b"\x00", rec[:25] + b"\x07" + rec[26:]):
+        with pytest.raises(DcdfError):
+            Variable.load(None, store, bad)
+
+
+class _StubSuperchunk:
+    """Stands in for api.Superchunk so that the host logic of Variable.append (tail re-encode, span tree, cache groups)
+    runs without a GPU: a 'stored superchunk node' here is the real 35-byte header followed by the raw raster."""
+
+    def __init__(self, slices):
+        self.slices = slices
+
+    @classmethod
+    def build(cls, ctx, data, k2_levels, fractional_bits=0, round=False, compute_bits=True, chunk_size=64):
+        data = np.asarray(data, np.float32)
+        return cls([data[a:a + chunk_size] for a in range(0, data.shape[0], chunk_size)])
+
+    @property
+    def n_slices(self):
+        return len(self.slices)
+
+    def save(self, s):
+        from dcdf_b200 import span as sp
+        a = self.slices[s]
+        node = _fake_superchunk_node(0, a.shape[0], a.shape[1], a.shape[2], 3)[:35] + a.tobytes()
+        return [(sp.cid_of(node), 5, node)], None
+
+    def info(self, s):
+        import types
+        return types.SimpleNamespace(shape=list(self.slices[s].shape), fractional_bits=3)
+
+    @classmethod
+    def open(cls, ctx, cids, store):
+        out = []
+        for c in cids:
+            n, r, cc = (int.from_bytes(store[c][8 + 4 * i:12 + 4 * i], "big") for i in range(3))
+            out.append(np.frombuffer(store[c][35:], np.float32).reshape(n, r, cc))
+        return cls(out)
+
+    def window(self, a, b, t, bm, l, r):
+        return np.concatenate(self.slices)[a:b, t:bm, l:r]
+
+    def total_bytes(self):
+        return sum(s.nbytes for s in self.slices)
+
+    def close(self):
+        pass
+
+
+def test_append_drives_the_span_tree_like_the_reference(monkeypatch):
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    import span_oracle as so
+    from dcdf_b200 import variable as var
+    monkeypatch.setattr(var, "Superchunk", _StubSuperchunk)
+    rng = np.random.default_rng(5)
+    data = rng.standard_normal((61, 6, 7)).astype(np.float32)
+    store = {}
+    v = var.Variable(None, store, [1, 2], chunk_size=4, span_size=2)
+    ov = so.OVariable({}, [6, 7], 4, 2, 32)
+    cuts = [0, 3, 4, 13, 14, 30, 31, 61]
+    for a, b in zip(cuts, cuts[1:]):
+        had_tail = ov.tail_data() is not None
+        n_keep = len(v.roots) - (1 if had_tail else 0)
+        v.append(data[a:b])
+        ov.append(list(zip(v.roots[n_keep:], v.instants[n_keep:])), had_tail)    # the reference's walk on the same chunk CIDs
+        assert v.cid == ov.cid, (a, b)
+        assert v.shape == [b, 6, 7] and np.array_equal(v.window(0, b, 0, 6, 0, 7), data[:b])
+    assert v.instants == [4] * 15 + [1]
+    one = var.Variable(None, {}, [1, 2], chunk_size=4, span_size=2)
+    one.append(data)
+    assert one.cid == v.cid                                      # the tree does not depend on how the instants arrived
+    w = var.Variable.load(None, store, v.write_to())
+    assert w.roots == v.roots and np.array_equal(w.window(7, 50, 2, 3, 3, 4)[:, 0, 0], data[7:50, 2, 3])
+    w.append(data[:5])
+    assert w.instants == [4] * 16 + [2] and w.shape[0] == 66
