@@ -198,6 +198,19 @@ class Variable(MMArray3):
         self.tree.commit()         # Variable::save_spans
         return self
 
+    def fork(self):
+        """A second handle on the same stored state (the reference clones a Variable before it appends to it,
+        dataset.rs:269-276): appending to the fork leaves this one as it is.  The device cache is shared."""
+        v = Variable(self.ctx, self.store, self.k2_levels, chunk_size=self.chunk_size, round=self.round, span_size=self.span_size,
+                     dtype=self.dtype, cache_bytes=self.cache.cache_bytes, name=self.name)
+        v.cache = self.cache
+        v.roots, v.instants, v.slice_bits, v.stats = list(self.roots), list(self.instants), list(self.slice_bits), list(self.stats)
+        v.rows, v.cols = self.rows, self.cols
+        if self.tree is not None:
+            v.tree = _span.SpanTree(self.store, self.rows, self.cols, self.chunk_size, self.span_size,
+                                    _span.ENCODINGS[self.dtype.name], root=self.tree.commit())
+        return v
+
     # ------------------------------------------------------------------ stored form
     @property
     def cid(self):

@@ -43,9 +43,7 @@ def test_getitem_follows_the_reference_dispatch():
         v[1, 2, 3, 4]
 
 
-def _fake_superchunk_node(i, instants, rows, cols, bits, enc=32):
-    import struct
-    return bytes([0xDC, 0xE0, 0, 0, 0, 1, 2, 5]) + struct.pack(">IIIIBIIBB", instants, rows, cols, 64, 2, 16, 4, bits, enc) + b"%d" % i
+from stub_superchunk import StubSuperchunk as _StubSuperchunk, fake_superchunk_node as _fake_superchunk_node  # noqa: E402
 
 
 def test_variable_record_round_trip_through_the_span_tree():
@@ -80,50 +78,6 @@ def test_variable_record_round_trip_through_the_span_tree():
     for bad in (rec[:-1], rec + b"\x00", rec[:25] + b"\x07" + rec[26:]):
         with pytest.raises(DcdfError):
             Variable.load(None, store, bad)
-
-
-class _StubSuperchunk:
-    """Stands in for api.Superchunk so that the host logic of Variable.append (tail re-encode, span tree, cache groups)
-    runs without a GPU: a 'stored superchunk node' here is the real 35-byte header followed by the raw raster."""
-
-    def __init__(self, slices):
-        self.slices = slices
-
-    @classmethod
-    def build(cls, ctx, data, k2_levels, fractional_bits=0, round=False, compute_bits=True, chunk_size=64):
-        data = np.asarray(data, np.float32)
-        return cls([data[a:a + chunk_size] for a in range(0, data.shape[0], chunk_size)])
-
-    @property
-    def n_slices(self):
-        return len(self.slices)
-
-    def save(self, s):
-        from dcdf_b200 import span as sp
-        a = self.slices[s]
-        node = _fake_superchunk_node(0, a.shape[0], a.shape[1], a.shape[2], 3)[:35] + a.tobytes()
-        return [(sp.cid_of(node), 5, node)], None
-
-    def info(self, s):
-        import types
-        return types.SimpleNamespace(shape=list(self.slices[s].shape), fractional_bits=3)
-
-    @classmethod
-    def open(cls, ctx, cids, store):
-        out = []
-        for c in cids:
-            n, r, cc = (int.from_bytes(store[c][8 + 4 * i:12 + 4 * i], "big") for i in range(3))
-            out.append(np.frombuffer(store[c][35:], np.float32).reshape(n, r, cc))
-        return cls(out)
-
-    def window(self, a, b, t, bm, l, r):
-        return np.concatenate(self.slices)[a:b, t:bm, l:r]
-
-    def total_bytes(self):
-        return sum(s.nbytes for s in self.slices)
-
-    def close(self):
-        pass
 
 
 def test_append_drives_the_span_tree_like_the_reference(monkeypatch):
