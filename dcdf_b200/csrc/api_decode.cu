@@ -548,9 +548,9 @@ void do_window_batch(dcdf_ctx* ctx, MetaBlock* mb, uint64_t n, const dcdf_cube* 
     return;
   }
   const unsigned gy = (unsigned)std::min<uint64_t>(n, 65535);
-  const unsigned gx = (unsigned)std::max<i64>(1, std::min<i64>((biggest + 255) / 256, std::max<i64>(1, (i64)ctx->sm_count * 16 / gy)));
+  const unsigned gx = (unsigned)std::max<i64>(1, std::min<i64>((biggest / 8 + 127) / 128, std::max<i64>(1, (i64)ctx->sm_count * 32 / gy)));
   tbegin(ctx, KT_WINDOW);
-  k_window_cells<<<dim3(gx, gy), 256, 0, ctx->stream>>>(mb->Q, d_c, d_off, n, ot.dev, os.raw);
+  k_window_blocks<<<dim3(gx, gy), 128, 0, ctx->stream>>>(mb->Q, d_c, d_off, n, ot.dev, os.raw);
   CK(cudaGetLastError());
   ctx->launches++;
   tend(ctx, KT_WINDOW);

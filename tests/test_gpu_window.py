@@ -151,3 +151,25 @@ def test_other_window_kernels_stay_bit_exact(option):
         assert _same(_canon(w), _canon(data[c[0]:c[1], c[2]:c[3], c[4]:c[5]])), c
     sc.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("rows,cols", [(2, 2), (1, 2), (3, 3), (4, 4), (5, 7), (8, 8), (17, 9), (33, 20), (64, 64), (100, 130), (256, 256)])
+def test_block_walker_every_tree_depth(rows, cols):
+    """k_window_blocks (one thread per 4x4 block, the descent shared by its cells): the kernel of trees larger than 64x64,
+    forced onto the small ones too; raw fixed values against the oracle's fill_window, windows clipped at every block phase."""
+    from dcdf_b200 import Chunk, Context
+    ctx = Context(0)
+    ctx.set_option("window_cells", 1)
+    T = 14
+    data = _field(T, rows, cols, 77 + rows * 100 + cols, nan_frac=0.08 if rows * cols > 8 else 0.0, flat=rows >= 8)
+    got = Chunk.build(ctx, data, fractional_bits=4)
+    ref = orc.chunk_build(data, fractional_bits=4)
+    assert got.write_to() == ref.serialize()
+    wins = [(0, T, 0, rows, 0, cols), (1, T, 0, rows, 0, cols), (T - 1, T, rows - 1, rows, cols - 1, cols),
+            (3, 9, rows // 3, rows, cols // 2, cols), (5, 6, 0, max(1, rows - 1), 0, max(1, cols - 1))]
+    for k in range(1, 8):                                   # every phase of the 4x4 block grid on both edges
+        wins.append((2, 7, min(k, rows - 1), max(min(k, rows - 1) + 1, rows - k % 3), min(7 - k, cols - 1), max(min(7 - k, cols - 1) + 1, cols - k % 4)))
+    for (a, b, t, bo, l, r) in wins:
+        assert np.array_equal(got.window(a, b, t, bo, l, r, raw=True), ref.window(a, b, t, bo, l, r)), (a, b, t, bo, l, r)
+    got.close()
+    ctx.close()
