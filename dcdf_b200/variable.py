@@ -166,35 +166,37 @@ class Variable(MMArray3):
         if self.tree is None:      # Dataset::add_variable saves one empty span (dataset.rs:127-129)
             self.tree = _span.SpanTree(self.store, self.rows, self.cols, self.chunk_size, self.span_size,
                                        _span.ENCODINGS[self.dtype.name])
-        update = False
-        if self.roots and self.instants[-1] < self.chunk_size:
-            update = True
+        if int(data.shape[0]) == 0:
+            return self            # the loop of Variable::append does not run (dataset.rs:838)
+        update = bool(self.roots) and self.instants[-1] < self.chunk_size
+        if update:
             T = self.shape[0]
             tail = self.window(T - self.instants[-1], T, 0, self.rows, 0, self.cols)
             if is_t:
                 data = torch.cat([torch.from_numpy(tail).to(data.device), data], dim=0)
             else:
                 data = np.concatenate([tail, np.asarray(data, dtype=self.dtype)], axis=0)
-            old = self.roots.pop()
-            self.instants.pop(); self.slice_bits.pop(); self.stats.pop()
-            self.cache.invalidate([old])
         bits = self.round if self.round is not None else 0
         sc = Superchunk.build(self.ctx, data, list(self.k2_levels), fractional_bits=bits, round=self.round is not None,
                               compute_bits=True, chunk_size=self.chunk_size)
-        try:
+        new = []                   # nothing of the variable changes until every slice is built and saved (a data error
+        try:                       # -- NaN-only input, precision loss -- leaves it as it was)
             for s in range(sc.n_slices):
                 nodes, stats = sc.save(s)
                 for cid, _, b in nodes:
                     self.store[cid] = b
                 info = sc.info(s)
-                self.roots.append(nodes[-1][0])
-                self.tree.append(nodes[-1][0], int(info.shape[0]), update=update)   # span.update for the re-encoded tail
-                update = False
-                self.instants.append(int(info.shape[0]))
-                self.slice_bits.append(int(info.fractional_bits))
-                self.stats.append(stats)
+                new.append((nodes[-1][0], int(info.shape[0]), int(info.fractional_bits), stats))
         finally:
             sc.close()
+        if update:
+            old = self.roots.pop()
+            self.instants.pop(); self.slice_bits.pop(); self.stats.pop()
+            self.cache.invalidate([old])
+        for cid, n, fb, stats in new:
+            self.tree.append(cid, n, update=update)   # Span::update for the re-encoded tail, Span::append after it
+            update = False
+            self.roots.append(cid); self.instants.append(n); self.slice_bits.append(fb); self.stats.append(stats)
         self.tree.commit()         # Variable::save_spans
         return self
 

@@ -107,3 +107,75 @@ def test_append_drives_the_span_tree_like_the_reference(monkeypatch):
     assert w.roots == v.roots and np.array_equal(w.window(7, 50, 2, 3, 3, 4)[:, 0, 0], data[7:50, 2, 3])
     w.append(data[:5])
     assert w.instants == [4] * 16 + [2] and w.shape[0] == 66
+
+
+def test_a_failed_append_leaves_the_variable_as_it_was(monkeypatch):
+    from dcdf_b200 import variable as var
+    from dcdf_b200.api import DcdfError
+
+    class Failing(_StubSuperchunk):
+        @classmethod
+        def build(cls, ctx, data, *a, **k):
+            if np.isnan(np.asarray(data)).any():
+                raise DcdfError(1, "non-finite value")             # fixed.rs:40
+            return super().build(ctx, data, *a, **k)
+
+    monkeypatch.setattr(var, "Superchunk", Failing)
+    data = np.arange(10 * 4 * 4, dtype=np.float32).reshape(10, 4, 4)
+    v = var.Variable(None, {}, [1, 1], chunk_size=4, span_size=2)
+    v.append(data[:6])
+    before = (list(v.roots), list(v.instants), v.cid, v.tree.tail())
+    bad = data[6:].copy()
+    bad[1, 2, 3] = np.nan
+    with pytest.raises(DcdfError):
+        v.append(bad)
+    assert (v.roots, v.instants, v.cid, v.tree.tail()) == before
+    assert np.array_equal(v.window(0, 6, 0, 4, 0, 4), data[:6])
+    assert v.append(data[6:6]).shape == [6, 4, 4] and v.cid == before[2]   # nothing to append: nothing changes
+    v.append(data[6:])
+    assert v.instants == [4, 4, 2] and np.array_equal(v.window(0, 10, 0, 4, 0, 4), data)
+
+
+def test_cache_is_lru_by_bytes_and_loads_once_under_concurrent_requests(monkeypatch):
+    """cache.rs:37-232 semantics on the device-resident cache, with a stand-in for the opened handle."""
+    import threading
+    import time
+    from dcdf_b200 import variable as var
+    opened, closed = [], []
+
+    class Handle:
+        def __init__(self, key):
+            self.key = key
+
+        def total_bytes(self):
+            return 100
+
+        def close(self):
+            closed.append(self.key)
+
+    class Opener:
+        @staticmethod
+        def open(ctx, cids, store):
+            time.sleep(0.02)                                        # a load in flight while other threads ask for the key
+            opened.append(tuple(cids))
+            return Handle(tuple(cids))
+
+    monkeypatch.setattr(var, "Superchunk", Opener)
+    cache = var.ChunkCache(None, {}, cache_bytes=250)              # room for two handles
+    got = []
+    threads = [threading.Thread(target=lambda: got.append(cache.get([b"a"]))) for _ in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert len(opened) == 1 and len({id(h) for h in got}) == 1 and (cache.hits, cache.misses) == (7, 1)
+    cache.get([b"b"])
+    cache.get([b"a"])                                               # a is now the most recently used
+    cache.get([b"c"])                                               # 300 bytes > 250: the least recently used (b) goes
+    assert closed == [(b"b",)] and cache.evictions == 1 and cache.resident_bytes == 200
+    cache.get([b"b"])
+    assert closed == [(b"b",), (b"a",)] and opened.count((b"b",)) == 2
+    cache.invalidate([b"c"])
+    assert closed[-1] == (b"c",) and cache.resident_bytes == 100
+    cache.close()
+    assert cache.resident_bytes == 0 and sorted(closed)[-1] == (b"c",)
