@@ -118,7 +118,7 @@ struct dcdf_ctx {
     int fast_sync_mask = 3;              // k_encode_v5: the tiles of a CTA re-align every (mask + 1) instants (measured: 0 / 1 / 3 / never = 46.1 / 47.0 / 48.0 / 45.9 k tile-instants per ms)
     int encode_tiles256 = 0;             // full tiles through the 256-thread tile encoder instead of the 64-thread one
     uint32_t cell_tile_min = 64;         // cell series: tiles with at least this many series of a batch are decoded by the tile decoder (0: never)
-    int window_cells = 0;                // windows through the per-cell walker (the path of trees larger than 64x64)
+    int window_cells = 0;                // windows through the 4x4-block walker (the path of trees larger than 64x64)
     int window_wide = 0;                 // 64-bit expansion even when every DAC code fits three bytes
     uint32_t search_share_min = 3;       // value-range search: shared decodes for the counting pass from this many windows per touched (slice, tile) on (0: never)
     int search_dfs = 0;                  // depth-first search kernel instead of the tile search

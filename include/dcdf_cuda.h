@@ -93,7 +93,7 @@ int32_t dcdf_ctx_set_stream(dcdf_ctx* ctx, void* cuda_stream);
  *   "fast_sync_mask" <m>    fast-path kernel: the tiles of a CTA re-align every (m + 1) instants (default 3)
  *   "cell_tile_min" <n>     cell series: a tile that at least n series of a batch fall into is decoded once per instant by
  *                           the tile decoder instead of one root-to-leaf walk per (series, instant) (default 64, the measured break-even; 0 = never)
- *   "window_cells" 0|1      windows through the per-cell walker (the path of trees larger than 64x64)
+ *   "window_cells" 0|1      windows through the 4x4-block walker k_window_blocks (the path of trees larger than 64x64)
  *   "window_wide" 0|1       64-bit tile expansion even when every DAC code fits three bytes
  *   "search_share_min" <n>  value-range search: when the windows of a batch overlap (>= n windows per touched (time slice, tile)
  *                           on average; default 3, 0 = never) the counting pass decodes every touched tile once for all of them
