@@ -673,6 +673,13 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------ configs[4]
+def _c5_span(n_slices, world, rank):
+    """Slices [s0, s1) of the year that `rank` encodes and decodes: contiguous spans of ceil(n_slices / world) slices, so
+    every slice belongs to exactly one rank (the last ranks may get fewer, or none when world does not divide)."""
+    per = (n_slices + world - 1) // world
+    return min(n_slices, rank * per), min(n_slices, (rank + 1) * per)
+
+
 def run_c5(args):
     """One 1801x3600 hourly year, k2_levels [2,4,6], as contiguous time spans over the N ranks (strong scaling).  A rank
     walks its span slab by slab (a slab = up to 17 slices, 28 GB raw, generated on the device, untimed): encode, then
@@ -684,8 +691,7 @@ def run_c5(args):
     rows, cols, levels = 1801, 3600, [2, 4, 6]
     T_year = args.instants
     n_slices = (T_year + CHUNK_SIZE - 1) // CHUNK_SIZE
-    per = (n_slices + world - 1) // world
-    s0, s1 = rank * per, min(n_slices, (rank + 1) * per)
+    s0, s1 = _c5_span(n_slices, world, rank)
     ctx = Context(local)
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)

@@ -43,3 +43,16 @@ def test_reference_arm_extra_ranks_exit_without_work(monkeypatch, capsys):
     monkeypatch.setenv("RANK", "1")
     bench.run_reference(type("A", (), dict(gpus=2, steps=1, warmup=0, ref_rows=8))())
     assert capsys.readouterr().out == ""
+
+
+def test_c5_time_spans_cover_the_year_exactly_once():
+    """bench.py --config c5 (north_star's multi-GPU statement): the 137 slices of one year dealt as contiguous spans."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for n_slices in (1, 7, 8, 137, 229):
+        for world in (1, 2, 4, 8):
+            spans = [bench._c5_span(n_slices, world, r) for r in range(world)]
+            covered = [s for a, b in spans for s in range(a, b)]
+            assert covered == list(range(n_slices)), (n_slices, world)
+            assert max(b - a for a, b in spans) == -(-n_slices // world)        # the slowest rank's share sets the time
+            assert all(0 <= a <= b <= n_slices for a, b in spans)
