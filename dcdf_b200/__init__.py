@@ -10,5 +10,6 @@ from ._ffi import build_library as build  # noqa: F401
 from .api import Chunk, Context, DcdfError, Superchunk  # noqa: F401
 from .variable import ChunkCache, MMArray3, Variable  # noqa: F401
 from .dataset import Coordinate, Dataset  # noqa: F401
+from .store import DirStore  # noqa: F401
 
-__all__ = ["build", "Chunk", "ChunkCache", "Context", "Coordinate", "Dataset", "DcdfError", "MMArray3", "Superchunk", "Variable"]
+__all__ = ["build", "Chunk", "ChunkCache", "Context", "Coordinate", "Dataset", "DcdfError", "DirStore", "MMArray3", "Superchunk", "Variable"]
