@@ -109,3 +109,21 @@ def test_python_test_suite_of_the_reference_on_the_host_logic(monkeypatch):
         ov.append(list(zip(v.roots, v.instants)), False)
         assert ov.cid == v.cid, v.name
         assert sum(v.instants) == test_data[v.name].shape[0]
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64, np.float32, np.float64])
+def test_range_vectors_of_the_reference(dtype):
+    """range.rs:144-260: IntRange / FloatRange (-20, 5, 30) against (-20..130).step_by(5): get, every symmetric slice,
+    and both out-of-bounds panics."""
+    data = np.arange(-20, 130, 5).astype(dtype)
+    rng = Coordinate.range("r", -20, 5, 30, dtype)
+    assert len(rng) == 30 and rng.slice(0, 30).shape == (30,)
+    for i in range(30):
+        assert rng.get(i) == data[i] and type(rng.get(i)) is dtype
+    for i in range(15):
+        got = rng.slice(i, 30 - i)
+        assert got.dtype == dtype and np.array_equal(got, data[i:30 - i])
+    with pytest.raises(DcdfError):
+        rng.get(30)
+    with pytest.raises(DcdfError):
+        rng.slice(29, 31)
