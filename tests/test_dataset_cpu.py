@@ -127,3 +127,26 @@ def test_range_vectors_of_the_reference(dtype):
         rng.get(30)
     with pytest.raises(DcdfError):
         rng.slice(29, 31)
+
+
+def test_python_test_suite_of_the_reference_over_oracle_written_nodes(monkeypatch):
+    """The same flow with the CPU oracle as the codec: every stored object -- subchunks, Links, superchunk nodes, spans,
+    the dataset -- is reference-format bytes, rounding variables included, and the host logic reads all of it back."""
+    from oracle_superchunk import OracleSuperchunk
+    from dcdf_b200 import variable as var
+    monkeypatch.setattr(var, "Superchunk", OracleSuperchunk)
+    store = {}
+    ds, test_data, cid = flow.populate(None, store, rounds=True)
+    flow.check_metadata(ds)
+    final = Dataset.load(None, store, ds.commit())
+    flow.check_queries(final, test_data)
+    kinds = {}
+    for b in store.values():                                            # what the DAG is made of (node.rs:9-15)
+        k = ("dataset",) if b[6] == 0 else ("links",) if b[6] == 1 else ("mmstruct3", b[7])
+        kinds[k] = kinds.get(k, 0) + 1
+    assert kinds[("dataset",)] == 2 and kinds[("links",)] >= 1
+    roots = {r for v in final.variables for r in v.roots}              # the rasters repeat every 60 instants: equal slices
+    assert kinds[("mmstruct3", 5)] >= len(roots) >= 12                 # are ONE object (content addressing de-duplicates)
+    assert kinds[("mmstruct3", 3)] >= 6 and kinds[("mmstruct3", 4)] >= 1
+    for v in final.variables:
+        assert v.fractional_bits == (2 if v.round is not None else (0 if v.dtype.kind == "i" else 3)), v.name
